@@ -1,0 +1,335 @@
+/*
+ * rs_oracle.c -- CPU restatement of the reference's prover hot path, in plain C.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+ * load this library; the product (ringsnark_b200/librsgpu.so) never links, loads or calls it.
+ *
+ * PARITY PINNED: every function here is checked in tests/test_oracle.py against outputs of the unmodified
+ * reference (SEAL 4.1.1 + SEAL-Polytools + ringSNARK headers compiled from /root/reference by
+ * oracle/Makefile.ref), committed as .rsgv files under tests/golden, and against SEAL's own NTT known-answer test.
+ *
+ * Each function cites the reference file:line it restates (paths relative to /root/reference).
+ * Arithmetic is deliberately naive (unsigned __int128 and %): the reference always returns canonical
+ * residues in [0, p), so only the mathematical function matters.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+static inline uint64_t mulmod(uint64_t a, uint64_t b, uint64_t p) { return (uint64_t)(((u128)a * b) % p); }
+static inline uint64_t addmod(uint64_t a, uint64_t b, uint64_t p) { uint64_t s = a + b; return s >= p ? s - p : s; }
+static inline uint64_t submod(uint64_t a, uint64_t b, uint64_t p) { return a >= b ? a - b : a + p - b; }
+static uint64_t powmod(uint64_t a, uint64_t e, uint64_t p) {
+  uint64_t r = 1 % p;
+  a %= p;
+  while (e) { if (e & 1) r = mulmod(r, a, p); a = mulmod(a, a, p); e >>= 1; }
+  return r;
+}
+/* depends/SEAL/native/src/seal/util/uintarithsmallmod.h (try_invert_uint_mod): inverse or failure. p prime here. */
+int ro_try_invert(uint64_t a, uint64_t p, uint64_t *inv) {
+  a %= p;
+  if (a == 0) return 0;
+  *inv = powmod(a, p - 2, p);
+  return 1;
+}
+uint64_t ro_mulmod(uint64_t a, uint64_t b, uint64_t p) { return mulmod(a % p, b % p, p); }
+
+static uint32_t reverse_bits(uint32_t x, int bits) {
+  uint32_t r = 0;
+  for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+  return r;
+}
+static int ilog2(size_t n) { int l = 0; while (((size_t)1 << l) < n) l++; return l; }
+
+/*
+ * Minimal primitive 2N-th root of unity mod p.
+ * depends/SEAL/native/src/seal/util/numth.cpp:386-412 (try_minimal_primitive_root): take any primitive root r of
+ * order `degree`, then walk r, r^3, r^5, ... (all primitive degree-th roots) and keep the smallest.
+ * numth.cpp:353-384 finds the starting root by random sampling; the minimum does not depend on that choice.
+ */
+uint64_t ro_minimal_primitive_root(uint64_t degree, uint64_t p) {
+  if ((p - 1) % degree != 0) return 0;
+  uint64_t root = 0;
+  for (uint64_t g = 2; g < p; g++) {
+    uint64_t r = powmod(g, (p - 1) / degree, p);
+    if (powmod(r, degree / 2, p) == p - 1) { root = r; break; }
+  }
+  uint64_t gen_sq = mulmod(root, root, p), cur = root, best = root;
+  for (uint64_t i = 0; i < degree / 2; i++) {
+    if (cur < best) best = cur;
+    cur = mulmod(cur, gen_sq, p);
+  }
+  return best;
+}
+
+/* depends/SEAL/native/src/seal/util/ntt.cpp:240-299 (NTTTables::initialize): psi powers in bit-reversed slots;
+ * inverse powers in the "reverse_bits(i-1)+1" order consumed sequentially by transform_from_rev. */
+static void build_tables(int logn, uint64_t p, uint64_t *roots, uint64_t *inv_roots, uint64_t *inv_n) {
+  size_t n = (size_t)1 << logn;
+  uint64_t psi = ro_minimal_primitive_root(2 * n, p), ipsi = 0;
+  ro_try_invert(psi, p, &ipsi);
+  uint64_t pw = psi;
+  for (size_t i = 1; i < n; i++) { roots[reverse_bits((uint32_t)i, logn)] = pw; pw = mulmod(pw, psi, p); }
+  roots[0] = 1;
+  pw = ipsi;
+  for (size_t i = 1; i < n; i++) { inv_roots[reverse_bits((uint32_t)(i - 1), logn) + 1] = pw; pw = mulmod(pw, ipsi, p); }
+  inv_roots[0] = 1;
+  ro_try_invert((uint64_t)n % p, p, inv_n);
+}
+
+/* Forward negacyclic NTT, natural order in -> bit-reversed order out, canonical residues.
+ * depends/SEAL/native/src/seal/util/ntt.cpp:407-436 + util/dwthandler.h:94-190 (transform_to_rev, Cooley-Tukey,
+ * roots consumed sequentially from index 1). */
+void ro_ntt_forward(uint64_t *a, size_t n, uint64_t p) {
+  int logn = ilog2(n);
+  uint64_t *roots = malloc(n * 8), *iroots = malloc(n * 8), inv_n;
+  build_tables(logn, p, roots, iroots, &inv_n);
+  size_t gap = n >> 1, ri = 0;
+  for (size_t m = 1; m < n; m <<= 1, gap >>= 1) {
+    size_t off = 0;
+    for (size_t i = 0; i < m; i++, off += gap << 1) {
+      uint64_t r = roots[++ri];
+      for (size_t j = 0; j < gap; j++) {
+        uint64_t u = a[off + j], v = mulmod(a[off + j + gap], r, p);
+        a[off + j] = addmod(u, v, p);
+        a[off + j + gap] = submod(u, v, p);
+      }
+    }
+  }
+  free(roots); free(iroots);
+}
+
+/* Inverse negacyclic NTT, bit-reversed in -> natural out, scaled by n^-1.
+ * depends/SEAL/native/src/seal/util/ntt.cpp:452-474 + util/dwthandler.h:202-330 (transform_from_rev,
+ * Gentleman-Sande; the n^-1 factor is merged into the last stage, same product). */
+void ro_ntt_inverse(uint64_t *a, size_t n, uint64_t p) {
+  int logn = ilog2(n);
+  uint64_t *roots = malloc(n * 8), *iroots = malloc(n * 8), inv_n;
+  build_tables(logn, p, roots, iroots, &inv_n);
+  size_t gap = 1, ri = 0;
+  for (size_t m = n >> 1; m >= 1; m >>= 1, gap <<= 1) {
+    size_t off = 0;
+    for (size_t i = 0; i < m; i++, off += gap << 1) {
+      uint64_t r = iroots[++ri];
+      for (size_t j = 0; j < gap; j++) {
+        uint64_t u = a[off + j], v = a[off + j + gap];
+        a[off + j] = addmod(u, v, p);
+        a[off + j + gap] = mulmod(submod(u, v, p), r, p);
+      }
+    }
+    if (m == 1) break;
+  }
+  for (size_t i = 0; i < n; i++) a[i] = mulmod(a[i], inv_n, p);
+  free(roots); free(iroots);
+}
+
+/* depends/SEAL/native/src/seal/batchencoder.cpp:64-88 (populate_matrix_reps_index_map): slot k of the batched
+ * vector lives at coefficient index map[k] of the NTT-domain plaintext; generator 3 of (Z/2N)^*. */
+void ro_batch_index_map(size_t N, uint64_t *map) {
+  int logn = ilog2(N);
+  size_t row = N >> 1, m = N << 1;
+  uint64_t gen = 3, pos = 1;
+  for (size_t i = 0; i < row; i++) {
+    uint64_t i1 = (pos - 1) >> 1, i2 = (m - pos - 1) >> 1;
+    map[i] = reverse_bits((uint32_t)i1, logn);
+    map[row | i] = reverse_bits((uint32_t)i2, logn);
+    pos = (pos * gen) & (m - 1);
+  }
+}
+
+/* depends/SEAL/native/src/seal/batchencoder.cpp:110-149 (BatchEncoder::encode(vector<uint64_t>)):
+ * values[k] -> coefficient map[k], the other N_E - nvals slots zero, then inverse NTT mod t. */
+void ro_batch_encode(const uint64_t *vals, size_t nvals, size_t N_E, uint64_t t, uint64_t *out) {
+  uint64_t *map = malloc(N_E * 8);
+  ro_batch_index_map(N_E, map);
+  memset(out, 0, N_E * 8);
+  for (size_t k = 0; k < nvals; k++) out[map[k]] = vals[k];
+  ro_ntt_inverse(out, N_E, t);
+  free(map);
+}
+
+/* depends/SEAL/native/src/seal/evaluator.cpp:2174-2265 (transform_to_ntt_inplace(Plaintext)):
+ * centred lift v -> v (v < ceil(t/2), context.cpp:329) or v + (Q - t), reduced into every Q_l
+ * (fast path evaluator.cpp:2243-2259, slow multi-word path :2220-2242; both equal the expression below),
+ * then one forward NTT per Q_l.  out is [L_E][N_E]. */
+void ro_plain_lift_ntt(const uint64_t *plain, size_t N_E, uint64_t t, const uint64_t *Q, size_t L_E, uint64_t *out) {
+  uint64_t thr = (t + 1) >> 1;
+  for (size_t l = 0; l < L_E; l++) {
+    uint64_t q = Q[l], tm = t % q;
+    uint64_t *o = out + l * N_E;
+    for (size_t i = 0; i < N_E; i++) {
+      uint64_t v = plain[i], r = v % q;
+      if (v >= thr) r = submod(r, tm, q); /* v + (Q - t) == v - t (mod Q_l) */
+      o[i] = r;
+    }
+    ro_ntt_forward(o, N_E, q);
+  }
+}
+
+/* depends/SEAL-Polytools/src/poly_arith.cpp:147-153 (SealPoly::is_zero), bug included:
+ * `*mm == 0 && !memcmp(mm, mm + 1, size - 1)` compares BYTES although size counts words, so it proves only
+ * that bytes [0, size + 7) are zero. */
+int ro_is_zero_quirk(const uint64_t *w, size_t size) {
+  if (size == 0) return 1;
+  if (w[0] != 0) return 0;
+  return memcmp(w, w + 1, size - 1) == 0;
+}
+
+/* depends/SEAL-Polytools/src/poly_arith.cpp:155-162 (SealPoly::is_equal): memcmp over size BYTES. */
+int ro_is_equal_quirk(const uint64_t *a, const uint64_t *b, size_t size) { return memcmp(a, b, size) == 0; }
+
+/*
+ * EncodingElem::inner_product, ringsnark/seal/seal_ring.tcc:361-433 with operator*= :509-548 and operator+= :479-507,
+ * on flat words.  crs: [T][L_R][2][L_E][N_E]; coeff: [T][L_R][N_R] (dense words of to_poly());
+ * tag[i]: 0 = skip (is_zero() true), 1 = scalar one (ciphertext used unchanged, :525-528), 2 = general.
+ * out: [L_R][2][L_E][N_E].  Returns the number of summed terms (0 => the reference returns an EMPTY element).
+ * Per general term and ring limb j: batch-encode limb j mod q_j (a11), lift + NTT (a12/a13), dyadic product with
+ * both ciphertext polynomials (a14, util/polyarithsmallmod.cpp:226-284), modular add (a15, evaluator.cpp:217-231).
+ */
+size_t ro_inner_product(const uint64_t *crs, const uint64_t *coeff, const uint8_t *tag, size_t T, size_t N_R, size_t L_R,
+                        const uint64_t *q, size_t N_E, size_t L_E, const uint64_t *Q, uint64_t *out) {
+  size_t per_ct = 2 * L_E * N_E, per_enc = L_R * per_ct, used = 0;
+  uint64_t *plain = malloc(N_E * 8), *pntt = malloc(L_E * N_E * 8);
+  memset(out, 0, per_enc * 8);
+  for (size_t i = 0; i < T; i++) {
+    if (tag[i] == 0) continue;
+    used++;
+    for (size_t j = 0; j < L_R; j++) {
+      const uint64_t *ct = crs + i * per_enc + j * per_ct;
+      uint64_t *acc = out + j * per_ct;
+      if (tag[i] == 2) {
+        ro_batch_encode(coeff + (i * L_R + j) * N_R, N_R, N_E, q[j], plain);
+        ro_plain_lift_ntt(plain, N_E, q[j], Q, L_E, pntt);
+      }
+      for (size_t k = 0; k < 2; k++)
+        for (size_t l = 0; l < L_E; l++) {
+          const uint64_t *c = ct + (k * L_E + l) * N_E;
+          uint64_t *a = acc + (k * L_E + l) * N_E;
+          for (size_t x = 0; x < N_E; x++) {
+            uint64_t term = tag[i] == 2 ? mulmod(c[x], pntt[l * N_E + x], Q[l]) : c[x];
+            a[x] = addmod(a[x], term, Q[l]);
+          }
+        }
+    }
+  }
+  free(plain); free(pntt);
+  return used;
+}
+
+/* EncodingElem::operator+= on two non-empty elements: evaluator.cpp:217-231 (add_poly_coeffmod per limb). */
+void ro_enc_add(uint64_t *acc, const uint64_t *other, size_t L_R, size_t N_E, size_t L_E, const uint64_t *Q) {
+  for (size_t j = 0; j < L_R; j++)
+    for (size_t k = 0; k < 2; k++)
+      for (size_t l = 0; l < L_E; l++) {
+        size_t off = ((j * 2 + k) * L_E + l) * N_E;
+        for (size_t x = 0; x < N_E; x++) acc[off + x] = addmod(acc[off + x], other[off + x], Q[l]);
+      }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Witness map, one slot at a time (every slot of every ring limb is an independent copy of the same
+ * computation over Z_p).
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* ringsnark/util/polynomials.tcc:9-43 (interpolate) on the domain x_j = j (util/evaluation_domain.tcc:7-13):
+ * s[] = coefficients of the master polynomial, phi_j = Z'(x_j) by Horner, f = y_j / phi_j, synthetic division. */
+static void interpolate_slot(size_t n, const uint64_t *y, uint64_t p, uint64_t *coeffs, uint64_t *s) {
+  for (size_t k = 0; k < n; k++) { coeffs[k] = 0; s[k] = 0; }
+  s[n - 1] = submod(0, 0 % p, p); /* -x[0] = 0 */
+  for (size_t i = 1; i < n; i++) {
+    uint64_t xi = i % p;
+    for (size_t j = n - i - 1; j < n - 1; j++) s[j] = submod(s[j], mulmod(xi, s[j + 1], p), p);
+    s[n - 1] = submod(s[n - 1], xi, p);
+  }
+  for (size_t j = 0; j < n; j++) {
+    uint64_t xj = j % p, phi = n % p;
+    for (size_t k = n - 1; k > 0; k--) { phi = mulmod(phi, xj, p); phi = addmod(phi, mulmod(s[k], k % p, p), p); }
+    uint64_t inv = 0;
+    ro_try_invert(phi, p, &inv);
+    uint64_t ff = mulmod(y[j], inv, p), b = 1 % p;
+    for (size_t k = n; k-- > 0;) {
+      coeffs[k] = addmod(coeffs[k], mulmod(b, ff, p), p);
+      b = mulmod(b, xj, p);
+      b = addmod(b, s[k], p);
+    }
+  }
+}
+
+/* ringsnark/util/evaluation_domain.tcc:53-60 (vanishing_polynomial): Z(x) = prod_{i<n} (x - i); n+1 coefficients. */
+void ro_vanishing(size_t n, uint64_t p, uint64_t *Z) {
+  memset(Z, 0, (n + 1) * 8);
+  Z[0] = 1 % p; /* running product, degree i after i factors */
+  for (size_t i = 0; i < n; i++) {
+    uint64_t neg = submod(0, i % p, p);
+    for (size_t k = i + 2; k-- > 0;) { /* new[k] = old[k-1] - i * old[k] */
+      uint64_t lower = k ? Z[k - 1] : 0;
+      uint64_t same = k <= i ? mulmod(Z[k], neg, p) : 0;
+      Z[k] = addmod(same, lower, p);
+    }
+  }
+}
+
+/* One interpolation for a whole vector of ring elements. y, coeffs: [n][L_R][N_R]. */
+void ro_interpolate(size_t n, const uint64_t *y, size_t N_R, size_t L_R, const uint64_t *q, uint64_t *coeffs) {
+  size_t W = N_R * L_R;
+#pragma omp parallel
+  {
+    uint64_t *ys = malloc(n * 8), *cs = malloc(n * 8), *s = malloc(n * 8);
+#pragma omp for schedule(static)
+    for (size_t w = 0; w < W; w++) {
+      uint64_t p = q[w / N_R];
+      for (size_t k = 0; k < n; k++) ys[k] = y[k * W + w];
+      interpolate_slot(n, ys, p, cs, s);
+      for (size_t k = 0; k < n; k++) coeffs[k * W + w] = cs[k];
+    }
+    free(ys); free(cs); free(s);
+  }
+}
+
+/*
+ * r1cs_to_qrp_witness_map, ringsnark/reductions/r1cs_to_qrp/r1cs_to_qrp.tcc:148-259, non-ZK call
+ * (d1 = d2 = d3 = 0 as in groth16.tcc:82-84), values only:
+ *   aA, aB, aC = interpolate(full evaluations)            :216-223
+ *   prod = aA * aB (schoolbook, polynomials.tcc:61-66), diff = prod - aC (:68-73, :237-243)
+ *   H = diff / Z  (long division by the monic Z, polynomials.tcc:75-81, evaluation_domain.tcc:80-84)
+ * lenA, lenB, lenC are the operand lengths AFTER Boost's normalize() as the reference sees them (trailing elements
+ * for which RingElem::operator== says "== 0", i.e. the is_equal prefix quirk) -- computed by the caller with
+ * ro_is_equal_quirk on whole ring elements; trailing coefficients beyond them are treated as zero.
+ * yfull: [3][n][W]; H out: [n-1][W] (coefficients the reference adds into coefficients_for_H[0..n-2]).
+ */
+void ro_witness_H(size_t n, const uint64_t *aA, const uint64_t *aB, const uint64_t *aC, size_t lenA, size_t lenB,
+                  size_t lenC, size_t N_R, size_t L_R, const uint64_t *q, uint64_t *H, size_t *H_len_out) {
+  size_t W = N_R * L_R;
+  size_t Hn = n >= 1 ? n - 1 : 0;
+  memset(H, 0, Hn * W * 8);
+  size_t lenP = (lenA && lenB) ? lenA + lenB - 1 : 0;
+  size_t lenD = lenP > lenC ? lenP : lenC;
+  /* quotient length: |diff| - |Z| + 1 with |Z| = n + 1, or empty when |diff| < |Z| */
+  size_t lenQ = lenD >= n + 1 ? lenD - (n + 1) + 1 : 0;
+  if (H_len_out) *H_len_out = lenQ;
+  if (!lenQ) return;
+#pragma omp parallel
+  {
+    uint64_t *a = malloc(n * 8), *b = malloc(n * 8), *u = malloc((2 * n + 1) * 8), *Z = malloc((n + 1) * 8);
+    uint64_t lastp = 0;
+#pragma omp for schedule(static)
+    for (size_t w = 0; w < W; w++) {
+      uint64_t p = q[w / N_R];
+      if (p != lastp) { ro_vanishing(n, p, Z); lastp = p; }
+      for (size_t k = 0; k < n; k++) { a[k] = k < lenA ? aA[k * W + w] : 0; b[k] = k < lenB ? aB[k * W + w] : 0; }
+      memset(u, 0, (2 * n + 1) * 8);
+      for (size_t i = 0; i < lenB; i++)
+        for (size_t j = 0; j < lenA; j++) u[i + j] = addmod(u[i + j], mulmod(a[j], b[i], p), p);
+      for (size_t k = 0; k < lenC; k++) u[k] = submod(u[k], aC[k * W + w], p);
+      /* Knuth long division by monic Z (degree n): q[k] = u[n+k]; u[j] -= q[k] Z[j-k] */
+      for (size_t k = lenQ; k-- > 0;) {
+        uint64_t qk = u[n + k];
+        if (k < Hn) H[k * W + w] = qk;
+        for (size_t j = n + k; j-- > k;) u[j] = submod(u[j], mulmod(qk, Z[j - k], p), p);
+      }
+    }
+    free(a); free(b); free(u); free(Z);
+  }
+}

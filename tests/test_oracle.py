@@ -1,0 +1,140 @@
+"""Pins the C oracle (oracle/rs_oracle.c) to the unmodified reference: golden dumps produced by
+oracle/_ref/ref_harness (SEAL 4.1.1 + ringSNARK compiled from /root/reference; generator script
+tests/golden/regen.sh) and SEAL's own NTT known-answer test.  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from rsgv import Case
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.rsgv")))
+IDS = [os.path.basename(g)[:-5] for g in GOLD]
+
+
+def test_golden_present():
+    assert len(GOLD) >= 4
+
+
+def test_seal_ntt_known_answer():
+    # depends/SEAL/native/tests/seal/util/ntt.cpp:75-101: NTT of (1, 1) mod 0xffffffffffc0001 at n = 2
+    out = O.ntt_forward(np.array([1, 1], dtype=np.uint64), 0xFFFFFFFFFFC0001)
+    assert [int(x) for x in out] == [288794978602139553, 864126526004445282]
+
+
+def test_ntt_round_trip():
+    # depends/SEAL/native/tests/seal/util/ntt.cpp:103-133
+    p = 0xFFFFFFFFFFC0001
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, p, size=1024, dtype=np.uint64)
+    assert np.array_equal(O.ntt_inverse(O.ntt_forward(a, p), p), a)
+
+
+@pytest.fixture(scope="module", params=GOLD, ids=IDS)
+def case(request):
+    return Case(request.param)
+
+
+def test_roots_and_raw_ntt(case):
+    d = case.d
+    assert O.minimal_primitive_root(2 * case.N_E, int(case.Q[0])) == int(d["kat_root_Q0"][0])
+    assert O.minimal_primitive_root(2 * case.N_E, int(case.q[0])) == int(d["kat_root_q0"][0])
+    assert np.array_equal(O.ntt_forward(d["kat_ntt_in"], case.Q[0]), d["kat_ntt_fwd_Q0"])
+    assert np.array_equal(O.ntt_inverse(d["kat_intt_in"], case.q[0]), d["kat_intt_inv_q0"])
+
+
+def test_batch_encode_and_lift(case):
+    words, _, _ = case.ring("kat_elem")
+    pc = case.d["kat_plain_coeff"].reshape(case.L_R, case.N_E)
+    pn = case.d["kat_plain_ntt"].reshape(case.L_R, case.L_E, case.N_E)
+    for j in range(case.L_R):
+        limb = words[0][j * case.N_R:(j + 1) * case.N_R]
+        enc = O.batch_encode(limb, case.N_E, case.q[j])
+        assert np.array_equal(enc, pc[j])
+        assert np.array_equal(O.plain_lift_ntt(enc, case.q[j], case.Q), pn[j])
+
+
+def test_multiply_plain(case):
+    words, _, _ = case.ring("kat_elem")
+    crs, _ = case.enc("crs_s_pows")
+    out, used = O.inner_product(crs[0:1], words[0:1], np.array([O.TAG_GENERAL], dtype=np.uint8),
+                                case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)
+    assert used == 1
+    assert np.array_equal(out, case.d["kat_mul_plain"])
+
+
+def _ip(case, crs, name):
+    words, tag, scalar = case.ring(name)
+    tags = O.term_tags(words, tag, scalar)
+    return O.inner_product(crs[:len(tags)], words, tags, case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)
+
+
+def test_inner_products_and_proof(case):
+    s_pows, _ = case.enc("crs_s_pows")
+    delta_ts, _ = case.enc("crs_delta_ts")
+    delta_mid, _ = case.enc("crs_delta_mid")
+    ip, ip_size = case.enc("ip")
+    order = [(s_pows, "wit_A_io"), (s_pows, "wit_A_mid"), (s_pows, "wit_B_io"), (s_pows, "wit_B_mid"),
+             (delta_ts, "wit_H"), (delta_mid, "auxiliary_input")]
+    mine = []
+    for k, (crs, name) in enumerate(order):
+        out, used = _ip(case, crs, name)
+        empty_ref = int(ip_size[k][0]) == 2 ** 64 - 1
+        assert (used == 0) == empty_ref, (name, used)
+        if used:
+            assert np.array_equal(out, ip[k]), name
+        mine.append((out, used))
+    # groth16.tcc:89-112: A = ip0 + ip1 + alpha, B = ip2 + ip3 + beta, C = ip4 + ip5
+    proof, _ = case.enc("proof")
+    alpha, _ = case.enc("crs_alpha")
+    beta, _ = case.enc("crs_beta")
+
+    def total(parts):
+        acc = None
+        for w, used in parts:
+            if used:
+                acc = w if acc is None else O.enc_add(acc, w, case.L_R, case.N_E, case.L_E, case.Q)
+        return acc
+
+    A = total([mine[0], mine[1], (alpha[0], 1)])
+    B = total([mine[2], mine[3], (beta[0], 1)])
+    Cc = total([mine[4], mine[5]])
+    assert np.array_equal(A, proof[0]) and np.array_equal(B, proof[1]) and np.array_equal(Cc, proof[2])
+    assert int(case.d["verified"][0]) == 1
+
+
+def test_witness_map(case):
+    n = case.n
+    for p in range(case.L_R):
+        Z = O.vanishing(n, case.q[p])
+        zw, _, _ = case.ring("wit_Z")
+        assert np.array_equal(zw[:, p * case.N_R], Z)
+    got = {}
+    for poly in "ABC":
+        for part in ("io", "mid", "full"):
+            y, _, _ = case.ring(f"eval_{poly}_{part}")
+            got[(poly, part)] = O.interpolate(y, case.N_R, case.L_R, case.q)
+            if part != "full":
+                ref, _, _ = case.ring(f"wit_{poly}_{part}")
+                assert np.array_equal(got[(poly, part)], ref), (poly, part)
+    H, hl = O.witness_H(got[("A", "full")], got[("B", "full")], got[("C", "full")], case.N_R, case.L_R, case.q)
+    ref, tag, _ = case.ring("wit_H")
+    assert ref.shape[0] == n + 1
+    assert hl == n - 1
+    assert np.array_equal(H, ref[:n - 1])
+    assert not ref[n - 1:].any()          # two trailing scalar zeros in non-ZK mode
+
+
+def test_is_zero_quirk():
+    w = np.zeros(64, dtype=np.uint64)
+    assert O.is_zero_quirk(w)
+    w[63] = 5
+    assert O.is_zero_quirk(w)              # only bytes [0, size+7) are inspected (poly_arith.cpp:147-153)
+    w[8] = 1 << 56
+    assert O.is_zero_quirk(w)              # byte 71 = top byte of word 8 is outside the compared window
+    w[8] = 1
+    assert not O.is_zero_quirk(w)
+    w[8] = 0; w[7] = 1 << 63
+    assert not O.is_zero_quirk(w)
