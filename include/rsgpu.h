@@ -1,0 +1,128 @@
+/*
+ * rsgpu.h -- C ABI of the B200-native prover backend for zkFHE/ringSNARK (librsgpu.so).
+ *
+ * The reference has no FFI: its boundary is the C++ template concept RingT / EncT that
+ * ringsnark/zk_proof_systems, ringsnark/reductions and ringsnark/util require.
+ * This header is what a backend header pair (ringsnark_b200/cpp/ringsnark/seal_gpu/seal_ring.hpp) binds to;
+ * every entry point names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C, opaque handles, plain pointers and sizes; no exceptions cross the boundary;
+ *   - every function returns RSG_OK (0) or a negative status; rsg_last_error() gives the thread-local text;
+ *   - all data are uint64 words holding canonical residues;
+ *   - ring element  : [L_R][N_R] words, limb-major            (depends/SEAL-Polytools/include/poly_arith.h:81-102)
+ *   - encoding      : [L_R][2][L_E][N_E] words, NTT form        (ringsnark/seal/seal_ring.hpp:225,
+ *                                                                depends/SEAL/native/src/seal/ciphertext.h:337-349)
+ *   - "h_" pointers are HOST memory, "d_" pointers are DEVICE memory of the context's GPU;
+ *   - thread-safe: concurrent calls on one context are serialised per stream slot (rinocchio.tcc:106-163
+ *     calls inner_product from 10 OpenMP sections);
+ *   - there is NO CPU fallback: without a usable CUDA device rsg_context_create fails with RSG_ERR_CUDA.
+ */
+#ifndef RSGPU_H
+#define RSGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSG_OK 0
+#define RSG_ERR_ARG (-1)       /* invalid argument (reference: std::invalid_argument) */
+#define RSG_ERR_CUDA (-2)      /* CUDA runtime failure / no device */
+#define RSG_ERR_STATE (-3)     /* context not set / handle misuse (reference: "context not set") */
+#define RSG_ERR_NOTINV (-4)    /* "element is not invertible in ring" (seal_ring.tcc:87-103) */
+#define RSG_ERR_UNSUPPORTED (-5)
+
+/* Per-term dispatch of EncodingElem::operator*= (seal_ring.tcc:509-548) decided by the host shim exactly as the
+ * reference does: is_zero() (incl. the SealPoly::is_zero prefix quirk) -> SKIP; scalar 1 -> ONE (ciphertext taken
+ * unchanged); anything else -> GENERAL (batch-encode, lift, NTT, dyadic product). */
+#define RSG_TERM_SKIP 0
+#define RSG_TERM_ONE 1
+#define RSG_TERM_GENERAL 2
+
+typedef struct rsg_context rsg_context;   /* replaces the statics of RingElem / EncodingElem (seal_ring.hpp:25,218-223) */
+typedef struct rsg_crs rsg_crs;           /* a vector<EncodingElem> laid out contiguously in HBM (groth16.hpp:14-20) */
+typedef struct rsg_ringvec rsg_ringvec;   /* a vector<RingElem> resident in HBM */
+
+const char *rsg_last_error(void);
+int rsg_device_count(void);
+
+/* RingElem::set_context + EncodingElem::set_context (seal_ring.hpp:52-58, 266-320).
+ * q[L_R] ring primes (= plaintext moduli t_j), Q[L_E] first-level ciphertext primes; every prime < 2^61 and
+ * == 1 mod 2*N_E.  NTT tables use SEAL's minimal primitive 2N-th root (util/numth.cpp:386-412). */
+int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, const uint64_t *q, size_t N_E, size_t L_E,
+                       const uint64_t *Q, int device);
+void rsg_context_destroy(rsg_context *ctx);
+int rsg_context_sync(rsg_context *ctx);
+/* Run every subsequent launch of this context on a caller-owned CUDA stream (cudaStream_t as void*). */
+int rsg_context_set_stream(rsg_context *ctx, void *cuda_stream);
+/* Kernels launched by this context since creation (the bench's "gpu_launches" claim). */
+uint64_t rsg_context_launch_count(const rsg_context *ctx);
+
+/* ---- CRS: vector<EncodingElem> produced by EncodingElem::encode (seal_ring.tcc:324-359) ---- */
+int rsg_crs_create(rsg_context *ctx, size_t n_elems, rsg_crs **out);                         /* uninitialised arena */
+int rsg_crs_upload(rsg_crs *crs, size_t first, size_t count, const uint64_t *h_words);       /* count encodings */
+int rsg_crs_download(const rsg_crs *crs, size_t first, size_t count, uint64_t *h_words);
+int rsg_crs_fill_uniform(rsg_crs *crs, uint64_t seed);   /* synthetic CRS: uniform residues, generated on device */
+uint64_t *rsg_crs_device_ptr(rsg_crs *crs);
+void rsg_crs_destroy(rsg_crs *crs);
+
+/* ---- vectors of ring elements ---- */
+int rsg_ringvec_create(rsg_context *ctx, size_t n_elems, rsg_ringvec **out);
+int rsg_ringvec_upload(rsg_ringvec *v, size_t first, size_t count, const uint64_t *h_words);
+int rsg_ringvec_download(const rsg_ringvec *v, size_t first, size_t count, uint64_t *h_words);
+int rsg_ringvec_fill_uniform(rsg_ringvec *v, uint64_t seed);
+uint64_t *rsg_ringvec_device_ptr(rsg_ringvec *v);
+size_t rsg_ringvec_size(const rsg_ringvec *v);
+void rsg_ringvec_destroy(rsg_ringvec *v);
+/* SealPoly::is_zero with its byte/word confusion (poly_arith.cpp:147-153): h_flags[i] = 1 iff bytes
+ * [0, L_R*N_R + 7) of element first+i are zero.  One kernel + one small copy for the whole range. */
+int rsg_ringvec_is_zero_prefix(const rsg_ringvec *v, size_t first, size_t count, uint8_t *h_flags);
+
+/* ---- hot path (b): EncodingElem::inner_product (seal_ring.tcc:361-433) ----
+ * out = sum over i in [0, count) with tag[i] != SKIP of crs[crs_first+i] (*) coeffs[coeff_first+i].
+ * h_out (host, may be NULL) and/or d_out (device, may be NULL) receive one encoding.  *n_used = number of summed
+ * terms; 0 means the reference returns an EMPTY EncodingElem and the outputs are all-zero words. */
+int rsg_inner_product(rsg_context *ctx, const rsg_crs *crs, size_t crs_first, const rsg_ringvec *coeffs,
+                      size_t coeff_first, size_t count, const uint8_t *h_tags, uint64_t *h_out, uint64_t *d_out,
+                      size_t *n_used);
+/* EncodingElem::operator+= for non-empty operands (seal_ring.tcc:479-507 -> evaluator.cpp:217-231). */
+int rsg_enc_add(rsg_context *ctx, uint64_t *d_acc, const uint64_t *d_other);
+/* Sum of `parts` encodings stored back to back (the kernel that follows the NCCL all-gather). */
+int rsg_enc_sum(rsg_context *ctx, const uint64_t *d_parts, size_t parts, uint64_t *d_out);
+
+/* ---- hot path (a): r1cs_to_qrp_witness_map (reductions/r1cs_to_qrp/r1cs_to_qrp.tcc:148-259) ----
+ * evals: 9*n ring elements, order A_mid,B_mid,C_mid,A_io,B_io,C_io,A_full,B_full,C_full (the outputs of
+ * linear_combination::evaluate, :175-219), each block n elements.
+ * coeffs: receives 6*n elements A_io,B_io,C_io,A_mid,B_mid,C_mid (qrp_witness order, qrp.hpp:171-181).
+ * H: receives n+1 elements: (A*B - C)/Z in [0, n-1), zeros at n-1 and n (non-ZK call of groth16.tcc:82-84).
+ * Interpolation on the domain {0..n-1} (util/polynomials.tcc:9-43), product and exact division by the monic
+ * Z (util/polynomials.tcc:61-81, util/evaluation_domain.tcc:53-84); all slot-parallel on the GPU. */
+int rsg_witness_map(rsg_context *ctx, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H);
+/* util/polynomials.tcc:9-43 on its own: vectors of n ring elements; `batch` vectors back to back. */
+int rsg_interpolate(rsg_context *ctx, size_t n, size_t batch, const rsg_ringvec *y, size_t y_first, rsg_ringvec *out,
+                    size_t out_first);
+/* util/evaluation_domain.tcc:53-60: coefficients of Z(x) = prod_{i<n}(x-i) mod each ring prime: h_Z[L_R][n+1]. */
+int rsg_vanishing(rsg_context *ctx, size_t n, uint64_t *h_Z);
+
+/* ---- low-level entry points used by tests and by the multi-GPU driver (device pointers) ---- */
+/* BatchEncoder::encode (batchencoder.cpp:110-149): count elements [L_R][N_R] -> plaintext coeffs [count][L_R][N_E] */
+int rsg_batch_encode(rsg_context *ctx, const uint64_t *d_ring, size_t count, uint64_t *d_plain);
+/* Evaluator::transform_to_ntt_inplace (evaluator.cpp:2174-2265): [count][L_R][N_E] -> [count][L_R][L_E][N_E] */
+int rsg_plain_to_ntt(rsg_context *ctx, const uint64_t *d_plain, size_t count, uint64_t *d_plain_ntt);
+/* util::ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey (util/ntt.cpp:407-474) over one prime of the context:
+ * which = 0 -> Q[idx], which = 1 -> q[idx]; batch polynomials of N_E words, in place. */
+int rsg_ntt(rsg_context *ctx, uint64_t *d_data, size_t batch, int which, size_t idx, int inverse);
+/* The streaming multiply-accumulate alone: d_plain_ntt indexed by h_pidx[i] (or ~0u for RSG_TERM_ONE terms). */
+int rsg_crs_lincomb(rsg_context *ctx, const uint64_t *d_crs, const uint32_t *h_term, const uint32_t *h_pidx,
+                    size_t n_terms, const uint64_t *d_plain_ntt, uint64_t *d_out);
+/* Timing hook: device milliseconds of the most recent kernels, by name, measured with CUDA events on the
+ * context's stream when profiling is enabled. */
+int rsg_context_enable_timing(rsg_context *ctx, int on);
+int rsg_context_last_timing(rsg_context *ctx, const char *kernel, float *ms, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSGPU_H */

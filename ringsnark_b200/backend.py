@@ -1,0 +1,195 @@
+"""Python mirror of the backend objects (thin; all computation happens in librsgpu.so on the GPU).
+
+Names follow the reference: a Context replaces the statics of RingElem/EncodingElem (ringsnark/seal/seal_ring.hpp:25,
+218-223), a Crs is a vector<EncodingElem> (groth16.hpp:14-20), a RingVec is a vector<RingElem>.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .capi import check, load_library
+
+TERM_SKIP, TERM_ONE, TERM_GENERAL = 0, 1, 2
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Context:
+    def __init__(self, N_R, q, N_E, Q, device=0):
+        self.lib = load_library()
+        self.N_R, self.N_E = int(N_R), int(N_E)
+        self.q, self.Q = _u64(q).copy(), _u64(Q).copy()
+        self.L_R, self.L_E = self.q.size, self.Q.size
+        self.ring_words = self.L_R * self.N_R
+        self.enc_words = self.L_R * 2 * self.L_E * self.N_E
+        h = C.c_void_p()
+        check(self.lib.rsg_context_create(C.byref(h), self.N_R, self.L_R, _ptr(self.q), self.N_E, self.L_E, _ptr(self.Q), device))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rsg_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.rsg_context_sync(self.h))
+
+    def set_stream(self, cuda_stream):
+        check(self.lib.rsg_context_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def launch_count(self):
+        return int(self.lib.rsg_context_launch_count(self.h))
+
+    def enable_timing(self, on=True):
+        check(self.lib.rsg_context_enable_timing(self.h, 1 if on else 0))
+
+    def timing(self, kernel=None):
+        ms, n = C.c_float(0), C.c_uint64(0)
+        check(self.lib.rsg_context_last_timing(self.h, kernel.encode() if kernel else None, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    # ---- factories
+    def crs(self, n):
+        return Crs(self, n)
+
+    def ringvec(self, n):
+        return RingVec(self, n)
+
+    def crs_from(self, words):
+        words = _u64(words).reshape(-1, self.enc_words)
+        c = Crs(self, words.shape[0])
+        c.upload(words)
+        return c
+
+    def ringvec_from(self, words):
+        words = _u64(words).reshape(-1, self.ring_words)
+        v = RingVec(self, words.shape[0])
+        v.upload(words)
+        return v
+
+    # ---- hot path (b)
+    def term_tags(self, vec, tag=None, scalar=None, first=0, count=None):
+        """The reference's per-term dispatch (seal_ring.tcc:390-396, 509-548). `tag`/`scalar` describe elements the
+        caller holds as scalars (RingElem variant); poly elements get SealPoly::is_zero's prefix test on the GPU."""
+        count = len(vec) - first if count is None else count
+        flags = vec.is_zero_prefix(first, count)
+        out = np.where(flags != 0, TERM_SKIP, TERM_GENERAL).astype(np.uint8)
+        if tag is not None:
+            for i in range(count):
+                if int(tag[i]) == 0:
+                    s = int(scalar[i])
+                    out[i] = TERM_SKIP if s == 0 else (TERM_ONE if s == 1 else TERM_GENERAL)
+        return out
+
+    def inner_product(self, crs, coeffs, tags, crs_first=0, coeff_first=0, to_host=True, d_out=None):
+        """EncodingElem::inner_product (seal_ring.tcc:361-433). Returns (words or None, n_used)."""
+        tags = np.ascontiguousarray(tags, dtype=np.uint8)
+        out = np.empty(self.enc_words, dtype=np.uint64) if to_host else None
+        used = C.c_size_t(0)
+        check(self.lib.rsg_inner_product(self.h, crs.h, crs_first, coeffs.h, coeff_first, tags.size, _ptr(tags),
+                                         _ptr(out) if to_host else None, C.c_void_p(d_out) if d_out else None, C.byref(used)))
+        return out, int(used.value)
+
+    # ---- hot path (a)
+    def witness_map(self, n, evals, coeffs=None, H=None):
+        coeffs = coeffs or RingVec(self, 6 * n)
+        H = H or RingVec(self, n + 1)
+        check(self.lib.rsg_witness_map(self.h, n, evals.h, coeffs.h, H.h))
+        return coeffs, H
+
+    def interpolate(self, n, y, batch=1, out=None, y_first=0, out_first=0):
+        out = out or RingVec(self, batch * n)
+        check(self.lib.rsg_interpolate(self.h, n, batch, y.h, y_first, out.h, out_first))
+        return out
+
+    def vanishing(self, n):
+        Z = np.zeros((self.L_R, n + 1), dtype=np.uint64)
+        check(self.lib.rsg_vanishing(self.h, n, _ptr(Z)))
+        return Z
+
+
+class _Arena:
+    def __len__(self):
+        return self.n
+
+
+class Crs(_Arena):
+    def __init__(self, ctx, n):
+        self.ctx, self.n = ctx, int(n)
+        h = C.c_void_p()
+        check(ctx.lib.rsg_crs_create(ctx.h, self.n, C.byref(h)))
+        self.h = h
+
+    def upload(self, words, first=0):
+        words = _u64(words).reshape(-1, self.ctx.enc_words)
+        check(self.ctx.lib.rsg_crs_upload(self.h, first, words.shape[0], _ptr(words)))
+
+    def download(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.empty((count, self.ctx.enc_words), dtype=np.uint64)
+        check(self.ctx.lib.rsg_crs_download(self.h, first, count, _ptr(out)))
+        return out
+
+    def fill_uniform(self, seed):
+        check(self.ctx.lib.rsg_crs_fill_uniform(self.h, seed))
+
+    def device_ptr(self):
+        return int(self.ctx.lib.rsg_crs_device_ptr(self.h) or 0)
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.rsg_crs_destroy(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+
+class RingVec(_Arena):
+    def __init__(self, ctx, n):
+        self.ctx, self.n = ctx, int(n)
+        h = C.c_void_p()
+        check(ctx.lib.rsg_ringvec_create(ctx.h, self.n, C.byref(h)))
+        self.h = h
+
+    def upload(self, words, first=0):
+        words = _u64(words).reshape(-1, self.ctx.ring_words)
+        check(self.ctx.lib.rsg_ringvec_upload(self.h, first, words.shape[0], _ptr(words)))
+
+    def download(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.empty((count, self.ctx.ring_words), dtype=np.uint64)
+        check(self.ctx.lib.rsg_ringvec_download(self.h, first, count, _ptr(out)))
+        return out
+
+    def fill_uniform(self, seed):
+        check(self.ctx.lib.rsg_ringvec_fill_uniform(self.h, seed))
+
+    def device_ptr(self):
+        return int(self.ctx.lib.rsg_ringvec_device_ptr(self.h) or 0)
+
+    def is_zero_prefix(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        flags = np.zeros(count, dtype=np.uint8)
+        check(self.ctx.lib.rsg_ringvec_is_zero_prefix(self.h, first, count, _ptr(flags)))
+        return flags
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.rsg_ringvec_destroy(self.h)
+            self.h = None
+        except Exception:
+            pass

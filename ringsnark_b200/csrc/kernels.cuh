@@ -1,0 +1,225 @@
+// CUDA kernels of the prover hot path (sm_100a).  See DESIGN.md for the roofline of each.
+//   k_encode_intt     BatchEncoder::encode            batchencoder.cpp:64-88,110-149 + util/ntt.cpp:452-474
+//   k_lift_fwd_ntt    transform_to_ntt_inplace        evaluator.cpp:2174-2265 + util/ntt.cpp:407-436
+//   k_crs_lincomb     multiply_plain_ntt + add_inplace evaluator.cpp:2135-2172,155-240 fused over all terms
+//   k_enc_sum         add_inplace over partial sums   evaluator.cpp:217-231
+//   k_is_zero_prefix  SealPoly::is_zero (with its bug) poly_arith.cpp:147-153
+//   k_ntt             raw forward / inverse NTT        util/ntt.cpp:407-474
+#pragma once
+#include "ntt.cuh"
+
+namespace rsg {
+
+constexpr int MAX_LR = 8;
+constexpr int MAX_LE = 16;
+
+// Read-only parameter block living in device global memory (one per context).
+struct DevParams {
+  uint32_t N_R, L_R, N_E, L_E, logN_E;
+  ModConst q[MAX_LR];
+  ModConst Q[MAX_LE];
+  const Twiddle *fwdQ[MAX_LE];   // forward tables mod Q_l
+  const Twiddle *invQ[MAX_LE];   // inverse tables mod Q_l (raw NTT entry point only)
+  const Twiddle *fwdq[MAX_LR];   // forward tables mod q_j (raw NTT entry point only)
+  const Twiddle *invq[MAX_LR];   // inverse tables mod q_j (batch encoder)
+  Twiddle invN_q[MAX_LR];        // N_E^-1 mod q_j
+  Twiddle invN_Q[MAX_LE];        // N_E^-1 mod Q_l
+  uint64_t thr[MAX_LR];          // ceil(q_j / 2): plain_upper_half_threshold (context.cpp:329)
+  uint64_t tmodQ[MAX_LR][MAX_LE];  // q_j mod Q_l
+  const uint32_t *index_map;     // matrix_reps_index_map_ (batchencoder.cpp:64-88), N_E entries
+};
+
+__device__ __forceinline__ uint64_t canon4(uint64_t x, uint64_t p) {  // [0,4p) -> [0,p)
+  const uint64_t two_p = p << 1;
+  x = x >= two_p ? x - two_p : x;
+  return x >= p ? x - p : x;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batch encode: ring limb (N_R slot values) -> plaintext polynomial coefficients mod t = q_j (N_E words).
+// grid (count, L_R); elem_idx (nullable) selects which ring element each block encodes.
+template <int LOGN>
+__global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict__ P, const uint64_t *__restrict__ ring,
+                                                     const uint32_t *__restrict__ elem_idx,
+                                                     uint64_t *__restrict__ plain) {
+  extern __shared__ uint64_t sm[];
+  constexpr uint32_t n = 1u << LOGN;
+  const uint32_t j = blockIdx.y, e = blockIdx.x;
+  const uint32_t N_R = P->N_R, L_R = P->L_R;
+  const uint32_t src_e = elem_idx ? elem_idx[e] : e;
+  const uint64_t *src = ring + ((size_t)src_e * L_R + j) * N_R;
+  const uint64_t p = P->q[j].p;
+  for (uint32_t i = threadIdx.x; i < padded_words(n); i += blockDim.x) sm[i] = 0;
+  __syncthreads();
+  const uint32_t *map = P->index_map;
+  for (uint32_t k = threadIdx.x; k < N_R; k += blockDim.x) sm[pad_idx(__ldg(map + k))] = src[k];
+  __syncthreads();
+  ntt_inverse_smem<LOGN>(sm, P->invq[j], p, 0, 0);
+  const Twiddle invn = P->invN_q[j];
+  uint64_t *dst = plain + ((size_t)e * L_R + j) * n;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = mul_shoup(sm[pad_idx(i)], invn, p);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Centred lift into Q_l + forward NTT.  grid (count, L_R, L_E).
+template <int LOGN>
+__global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
+                                                      uint64_t *__restrict__ out) {
+  extern __shared__ uint64_t sm[];
+  constexpr uint32_t n = 1u << LOGN;
+  const uint32_t e = blockIdx.x, j = blockIdx.y, l = blockIdx.z;
+  const uint32_t L_R = P->L_R, L_E = P->L_E;
+  const ModConst m = P->Q[l];
+  const uint64_t thr = P->thr[j], tm = P->tmodQ[j][l];
+  const uint64_t *src = plain + ((size_t)e * L_R + j) * n;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t v = src[i];
+    uint64_t r = reduce64(v, m);
+    if (v >= thr) r = sub_mod(r, tm, m.p);   // v + (Q - t)  ==  v - t  (mod Q_l)
+    sm[pad_idx(i)] = r;
+  }
+  __syncthreads();
+  ntt_forward_smem<LOGN>(sm, P->fwdQ[l], m.p, 0, 0);
+  uint64_t *dst = out + (((size_t)e * L_R + j) * L_E + l) * n;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = canon4(sm[pad_idx(i)], m.p);
+}
+
+// Raw NTT of `batch` polynomials in place; grid (batch).
+template <int LOGN, bool INVERSE>
+__global__ void __launch_bounds__(512) k_ntt(uint64_t *__restrict__ data, const Twiddle *__restrict__ tab, uint64_t p,
+                                             Twiddle invn) {
+  extern __shared__ uint64_t sm[];
+  constexpr uint32_t n = 1u << LOGN;
+  uint64_t *d = data + (size_t)blockIdx.x * n;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[pad_idx(i)] = d[i];
+  __syncthreads();
+  if (INVERSE) {
+    ntt_inverse_smem<LOGN>(sm, tab, p, 0, 0);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = mul_shoup(sm[pad_idx(i)], invn, p);
+  } else {
+    ntt_forward_smem<LOGN>(sm, tab, p, 0, 0);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = canon4(sm[pad_idx(i)], p);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The CRS linear combination: one coalesced, 128-bit-vectorised streaming pass over the CRS in HBM.
+//   partial[z][j][k][l][x] = sum_{t in split z} crs[term[t]][j][k][l][x] * pntt[pidx[t]][j][l][x]   mod Q_l
+// Each thread owns two adjacent x for one (j, l) and both ciphertext polynomials k = 0, 1: per term it loads
+// 3 x 16 B and issues 4 multiply-accumulates into 192-bit accumulators (one Barrett reduction per output word per
+// launch instead of one per term -- same canonical residue).
+// grid (N_E / (2*blockDim), L_R*L_E, splits).
+__device__ __forceinline__ ulonglong2 ld_stream(const uint64_t *p) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
+                                                     const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
+                                                     uint32_t n_terms, uint32_t terms_per_split,
+                                                     const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial) {
+  const uint32_t N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
+  const uint32_t x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const uint32_t j = blockIdx.y / L_E, l = blockIdx.y - j * L_E;
+  const uint32_t t0 = blockIdx.z * terms_per_split;
+  const uint32_t t1 = min(n_terms, t0 + terms_per_split);
+  const size_t poly = (size_t)N_E;                       // words per (k, l) row
+  const size_t ct_words = 2 * (size_t)L_E * poly;        // one ciphertext
+  const size_t enc_words = (size_t)L_R * ct_words;       // one encoding
+  const size_t c_off = (size_t)j * ct_words + (size_t)l * poly + x;          // k = 0 row inside an encoding
+  const size_t k_stride = (size_t)L_E * poly;
+  const size_t p_off = ((size_t)j * L_E + l) * poly + x;
+  const size_t p_stride = (size_t)L_R * L_E * poly;
+
+  Acc192 a00, a01, a10, a11;
+  a00.clear(); a01.clear(); a10.clear(); a11.clear();
+
+  uint32_t t = t0;
+  for (; t + UNROLL <= t1; t += UNROLL) {
+    ulonglong2 c0[UNROLL], c1[UNROLL], pp[UNROLL];
+    uint32_t pi[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const uint32_t ci = __ldg(term + t + u);
+      pi[u] = __ldg(pidx + t + u);
+      const uint64_t *c = crs + (size_t)ci * enc_words + c_off;
+      c0[u] = ld_stream(c);
+      c1[u] = ld_stream(c + k_stride);
+      if (pi[u] != 0xFFFFFFFFu) pp[u] = ld_stream(pntt + (size_t)pi[u] * p_stride + p_off);
+      else pp[u] = make_ulonglong2(1, 1);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      a00.mac(c0[u].x, pp[u].x);
+      a01.mac(c0[u].y, pp[u].y);
+      a10.mac(c1[u].x, pp[u].x);
+      a11.mac(c1[u].y, pp[u].y);
+    }
+  }
+  for (; t < t1; t++) {
+    const uint32_t ci = __ldg(term + t), pi = __ldg(pidx + t);
+    const uint64_t *c = crs + (size_t)ci * enc_words + c_off;
+    const ulonglong2 c0 = ld_stream(c), c1 = ld_stream(c + k_stride);
+    const ulonglong2 pp = pi != 0xFFFFFFFFu ? ld_stream(pntt + (size_t)pi * p_stride + p_off) : make_ulonglong2(1, 1);
+    a00.mac(c0.x, pp.x);
+    a01.mac(c0.y, pp.y);
+    a10.mac(c1.x, pp.x);
+    a11.mac(c1.y, pp.y);
+  }
+  const ModConst m = P->Q[l];
+  uint64_t *o = partial + (size_t)blockIdx.z * enc_words + c_off;
+  *reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(a00.reduce(m), a01.reduce(m));
+  *reinterpret_cast<ulonglong2 *>(o + k_stride) = make_ulonglong2(a10.reduce(m), a11.reduce(m));
+}
+
+// out[w] = sum_s parts[s][w] mod Q_l(w): the modular-add kernel (after split-K or after the NCCL all-gather).
+__global__ void __launch_bounds__(256) k_enc_sum(const DevParams *__restrict__ P, const uint64_t *__restrict__ parts,
+                                                 uint32_t n_parts, uint64_t *__restrict__ out) {
+  const uint32_t N_E = P->N_E, L_E = P->L_E;
+  const size_t enc_words = (size_t)P->L_R * 2 * L_E * N_E;
+  const size_t w = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (w >= enc_words) return;
+  const uint32_t l = (uint32_t)((w / N_E) % L_E);
+  const uint64_t p = P->Q[l].p;
+  ulonglong2 acc = *reinterpret_cast<const ulonglong2 *>(parts + w);
+  for (uint32_t s = 1; s < n_parts; s++) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(parts + (size_t)s * enc_words + w);
+    acc.x = add_mod(acc.x, v.x, p);
+    acc.y = add_mod(acc.y, v.y, p);
+  }
+  *reinterpret_cast<ulonglong2 *>(out + w) = acc;
+}
+
+// flags[e] = 1 iff bytes [0, W + 7) of element e are zero (W = words per element); one block per element.
+__global__ void __launch_bounds__(256) k_is_zero_prefix(const uint64_t *__restrict__ ring, uint32_t W,
+                                                        uint8_t *__restrict__ flags) {
+  const uint64_t *src = ring + (size_t)blockIdx.x * W;
+  const uint32_t bytes = W + 7, full = min(bytes / 8, W), rem = bytes % 8;
+  uint32_t nz = 0;
+  for (uint32_t i = threadIdx.x; i < full; i += blockDim.x) nz |= (src[i] != 0);
+  if (threadIdx.x == 0 && rem && full < W) nz |= ((src[full] & ((1ull << (8 * rem)) - 1)) != 0);
+  const int any = __syncthreads_or((int)nz);
+  if (threadIdx.x == 0) flags[blockIdx.x] = any ? 0 : 1;
+}
+
+// Counter-based uniform residues (synthetic CRS / ring elements): word w of row r uses modulus mods[r % n_mods].
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) k_fill_uniform(uint64_t *__restrict__ dst, size_t words, uint32_t row_words,
+                                                      const ModConst *__restrict__ mods, uint32_t n_mods,
+                                                      uint32_t rows_per_mod_cycle, uint64_t seed) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride) {
+    const size_t row = w / row_words;
+    const uint64_t p = mods[(row / rows_per_mod_cycle) % n_mods].p;
+    dst[w] = __umul64hi(splitmix64(seed ^ (w * 0xD1342543DE82EF95ull)), p);
+  }
+}
+
+}  // namespace rsg

@@ -1,0 +1,790 @@
+// librsgpu.so -- C ABI (include/rsgpu.h) over the sm_100a kernels.  Host side: context (NTT tables, Barrett
+// constants, batch-encoder index map), device arenas, launch logic.  No CPU fallback anywhere: every entry point
+// that computes runs CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rsgpu.h"
+#include "kernels.cuh"
+#include "witness.cuh"
+
+using namespace rsg;
+typedef unsigned __int128 u128;
+
+// ------------------------------------------------------------------------------------------------------------
+// errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(RSG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+extern "C" const char *rsg_last_error(void) { return g_err.c_str(); }
+extern "C" int rsg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host number theory (context creation only)
+static uint64_t h_mulmod(uint64_t a, uint64_t b, uint64_t p) { return (uint64_t)(((u128)a * b) % p); }
+static uint64_t h_powmod(uint64_t a, uint64_t e, uint64_t p) {
+  uint64_t r = 1 % p;
+  a %= p;
+  while (e) {
+    if (e & 1) r = h_mulmod(r, a, p);
+    a = h_mulmod(a, a, p);
+    e >>= 1;
+  }
+  return r;
+}
+static uint64_t h_inv(uint64_t a, uint64_t p) { return h_powmod(a, p - 2, p); }
+static bool h_is_prime(uint64_t p) {
+  if (p < 2) return false;
+  for (uint64_t s : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+    if (p % s == 0) return p == s;
+  }
+  uint64_t d = p - 1;
+  int r = 0;
+  while ((d & 1) == 0) { d >>= 1; r++; }
+  for (uint64_t a : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+    uint64_t x = h_powmod(a, d, p);
+    if (x == 1 || x == p - 1) continue;
+    bool comp = true;
+    for (int i = 1; i < r; i++) {
+      x = h_mulmod(x, x, p);
+      if (x == p - 1) { comp = false; break; }
+    }
+    if (comp) return false;
+  }
+  return true;
+}
+// SEAL's choice of psi: the smallest primitive `degree`-th root of unity (util/numth.cpp:386-412).
+static uint64_t h_minimal_primitive_root(uint64_t degree, uint64_t p) {
+  uint64_t root = 0;
+  for (uint64_t g = 2; g < p; g++) {
+    uint64_t r = h_powmod(g, (p - 1) / degree, p);
+    if (h_powmod(r, degree / 2, p) == p - 1) { root = r; break; }
+  }
+  uint64_t sq = h_mulmod(root, root, p), cur = root, best = root;
+  for (uint64_t i = 0; i < degree / 2; i++) {
+    if (cur < best) best = cur;
+    cur = h_mulmod(cur, sq, p);
+  }
+  return best;
+}
+static uint32_t h_bitrev(uint32_t x, int bits) {
+  uint32_t r = 0;
+  for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+  return r;
+}
+static Twiddle h_twiddle(uint64_t w, uint64_t p) {
+  Twiddle t;
+  t.w = w;
+  t.wq = (uint64_t)(((u128)w << 64) / p);
+  return t;
+}
+static ModConst h_modconst(uint64_t p) {
+  ModConst m;
+  m.p = p;
+  // floor(2^128 / p) = floor((2^128 - 1) / p) for odd p > 1
+  u128 all = ~(u128)0;
+  u128 ratio = all / p;
+  m.ratio0 = (uint64_t)ratio;
+  m.ratio1 = (uint64_t)(ratio >> 64);
+  m.r128 = (uint64_t)((all % p + 1) % p);
+  return m;
+}
+// fwd[(1<<s)+g] = psi^bitrev((1<<s)+g, logn) -- SEAL's root_powers_ (util/ntt.cpp:268-276); inv = element-wise inverse.
+static void h_tables(int logn, uint64_t p, std::vector<Twiddle> &fwd, std::vector<Twiddle> &inv) {
+  const size_t n = (size_t)1 << logn;
+  const uint64_t psi = h_minimal_primitive_root(2 * n, p), ipsi = h_inv(psi, p);
+  fwd.assign(n, h_twiddle(1, p));
+  inv.assign(n, h_twiddle(1, p));
+  uint64_t pw = 1, ipw = 1;
+  for (size_t i = 1; i < n; i++) {
+    pw = h_mulmod(pw, psi, p);
+    ipw = h_mulmod(ipw, ipsi, p);
+    const uint32_t k = h_bitrev((uint32_t)i, logn);
+    fwd[k] = h_twiddle(pw, p);
+    inv[k] = h_twiddle(ipw, p);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct TimingRec {
+  std::string name;
+  cudaEvent_t a, b;
+};
+
+struct WitnessTables {   // per constraint count n
+  uint64_t *d_Vinv = nullptr;   // [L_R][n][n]
+  uint64_t *d_T = nullptr;      // [L_R][n-1][n-1] upper-triangular Toeplitz of rev(Z)^-1
+  std::vector<uint64_t> h_Z;    // [L_R][n+1]
+};
+
+struct rsg_context {
+  int device = 0;
+  size_t N_R = 0, L_R = 0, N_E = 0, L_E = 0;
+  int logN = 0;
+  std::vector<uint64_t> q, Q;
+  DevParams hp;                 // host copy
+  DevParams *d_params = nullptr;
+  ModConst *d_modq = nullptr, *d_modQ = nullptr;
+  std::vector<void *> owned;    // device allocations freed at destroy
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::mutex mu;
+  uint64_t launches = 0;
+  bool timing = false;
+  std::vector<TimingRec> recs;
+  std::map<size_t, WitnessTables> wit;
+  // scratch (grown on demand)
+  uint64_t *d_plain = nullptr, *d_pntt = nullptr, *d_partial = nullptr;
+  size_t cap_plain = 0, cap_pntt = 0, cap_partial = 0;
+  uint32_t *d_term = nullptr, *d_pidx = nullptr, *d_eidx = nullptr;
+  size_t cap_term = 0, cap_pidx = 0, cap_eidx = 0;
+  uint64_t *d_out_scratch = nullptr;
+  size_t cap_out_scratch = 0;
+  uint8_t *d_flags = nullptr;
+  size_t cap_flags = 0;
+  size_t enc_words() const { return L_R * 2 * L_E * N_E; }
+  size_t ring_words() const { return L_R * N_R; }
+};
+struct rsg_crs {
+  rsg_context *ctx;
+  size_t n;
+  uint64_t *d;
+};
+struct rsg_ringvec {
+  rsg_context *ctx;
+  size_t n;
+  uint64_t *d;
+};
+
+struct LaunchScope {   // counts launches and optionally brackets them with events
+  rsg_context *c;
+  const char *name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(rsg_context *ctx, const char *nm) : c(ctx), name(nm) {
+    c->launches++;
+    if (c->timing) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (c->timing) {
+      cudaEventRecord(b, c->stream);
+      c->recs.push_back({name, a, b});
+    }
+  }
+};
+
+template <typename T>
+static int dev_alloc(rsg_context *c, T **p, size_t count, bool track = true) {
+  void *v = nullptr;
+  CUDA_TRY(cudaMalloc(&v, std::max<size_t>(count, 1) * sizeof(T)));
+  *p = (T *)v;
+  if (track) c->owned.push_back(v);
+  return RSG_OK;
+}
+template <typename T>
+static int ensure(rsg_context *c, T **p, size_t *cap, size_t need) {
+  if (*cap >= need) return RSG_OK;
+  if (*p) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaFree(*p));
+    *p = nullptr;
+  }
+  void *v = nullptr;
+  CUDA_TRY(cudaMalloc(&v, need * sizeof(T)));
+  *p = (T *)v;
+  *cap = need;
+  return RSG_OK;
+}
+template <typename T>
+static int upload_vec(rsg_context *c, const std::vector<T> &h, T **d) {
+  int rc = dev_alloc(c, d, h.size());
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return RSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, const uint64_t *q, size_t N_E, size_t L_E,
+                                  const uint64_t *Q, int device) {
+  if (!out || !q || !Q) return fail(RSG_ERR_ARG, "null argument");
+  if (N_E < 256 || N_E > 16384 || (N_E & (N_E - 1))) return fail(RSG_ERR_UNSUPPORTED, "N_E must be a power of two in [256, 16384]");
+  if (N_R == 0 || N_R > N_E || (N_R & (N_R - 1))) return fail(RSG_ERR_ARG, "N_R must be a power of two <= N_E");
+  if (L_R == 0 || L_R > (size_t)MAX_LR || L_E == 0 || L_E > (size_t)MAX_LE) return fail(RSG_ERR_ARG, "limb count out of range");
+  for (size_t i = 0; i < L_R + L_E; i++) {
+    uint64_t p = i < L_R ? q[i] : Q[i - L_R];
+    if (p >= (1ull << 61) || p < 2 * N_E || (p - 1) % (2 * N_E) != 0 || !h_is_prime(p))
+      return fail(RSG_ERR_ARG, "every modulus must be a prime < 2^61 with p = 1 mod 2*N_E");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(RSG_ERR_CUDA, "no CUDA device: librsgpu has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(RSG_ERR_ARG, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  rsg_context *c = new rsg_context();
+  c->device = device;
+  c->N_R = N_R; c->L_R = L_R; c->N_E = N_E; c->L_E = L_E;
+  while (((size_t)1 << c->logN) < N_E) c->logN++;
+  c->q.assign(q, q + L_R);
+  c->Q.assign(Q, Q + L_E);
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+
+  DevParams &hp = c->hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.N_R = (uint32_t)N_R; hp.L_R = (uint32_t)L_R; hp.N_E = (uint32_t)N_E; hp.L_E = (uint32_t)L_E; hp.logN_E = (uint32_t)c->logN;
+  std::vector<Twiddle> fwd, inv;
+  int rc;
+  for (size_t l = 0; l < L_E; l++) {
+    hp.Q[l] = h_modconst(Q[l]);
+    h_tables(c->logN, Q[l], fwd, inv);
+    Twiddle *d;
+    if ((rc = upload_vec(c, fwd, &d))) return rc;
+    hp.fwdQ[l] = d;
+    if ((rc = upload_vec(c, inv, &d))) return rc;
+    hp.invQ[l] = d;
+    hp.invN_Q[l] = h_twiddle(h_inv(N_E % Q[l], Q[l]), Q[l]);
+  }
+  for (size_t j = 0; j < L_R; j++) {
+    hp.q[j] = h_modconst(q[j]);
+    h_tables(c->logN, q[j], fwd, inv);
+    Twiddle *d;
+    if ((rc = upload_vec(c, fwd, &d))) return rc;
+    hp.fwdq[j] = d;
+    if ((rc = upload_vec(c, inv, &d))) return rc;
+    hp.invq[j] = d;
+    hp.invN_q[j] = h_twiddle(h_inv(N_E % q[j], q[j]), q[j]);
+    hp.thr[j] = (q[j] + 1) >> 1;
+    for (size_t l = 0; l < L_E; l++) hp.tmodQ[j][l] = q[j] % Q[l];
+  }
+  {  // batchencoder.cpp:64-88
+    std::vector<uint32_t> map(N_E);
+    const size_t row = N_E >> 1, m = N_E << 1;
+    uint64_t pos = 1;
+    for (size_t i = 0; i < row; i++) {
+      map[i] = h_bitrev((uint32_t)((pos - 1) >> 1), c->logN);
+      map[row | i] = h_bitrev((uint32_t)((m - pos - 1) >> 1), c->logN);
+      pos = (pos * 3) & (m - 1);
+    }
+    uint32_t *d;
+    if ((rc = upload_vec(c, map, &d))) return rc;
+    hp.index_map = d;
+  }
+  if ((rc = dev_alloc(c, &c->d_params, 1))) return rc;
+  CUDA_TRY(cudaMemcpy(c->d_params, &hp, sizeof(hp), cudaMemcpyHostToDevice));
+  {
+    std::vector<ModConst> mq(hp.q, hp.q + L_R), mQ(hp.Q, hp.Q + L_E);
+    if ((rc = upload_vec(c, mq, &c->d_modq))) return rc;
+    if ((rc = upload_vec(c, mQ, &c->d_modQ))) return rc;
+  }
+  *out = c;
+  return RSG_OK;
+}
+
+extern "C" void rsg_context_destroy(rsg_context *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (void *p : c->owned) cudaFree(p);
+  for (auto &kv : c->wit) { cudaFree(kv.second.d_Vinv); cudaFree(kv.second.d_T); }
+  cudaFree(c->d_plain); cudaFree(c->d_pntt); cudaFree(c->d_partial);
+  cudaFree(c->d_term); cudaFree(c->d_pidx); cudaFree(c->d_eidx); cudaFree(c->d_flags); cudaFree(c->d_out_scratch);
+  for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+extern "C" int rsg_context_sync(rsg_context *c) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
+}
+extern "C" int rsg_context_set_stream(rsg_context *c, void *s) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return RSG_OK;
+}
+extern "C" uint64_t rsg_context_launch_count(const rsg_context *c) { return c ? c->launches : 0; }
+extern "C" int rsg_context_enable_timing(rsg_context *c, int on) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  std::lock_guard<std::mutex> g(c->mu);
+  cudaStreamSynchronize(c->stream);
+  for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  c->recs.clear();
+  c->timing = on != 0;
+  return RSG_OK;
+}
+extern "C" int rsg_context_last_timing(rsg_context *c, const char *kernel, float *ms, uint64_t *launches) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float total = 0;
+  uint64_t n = 0;
+  for (auto &r : c->recs)
+    if (!kernel || r.name == kernel) {
+      float t = 0;
+      CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+      total += t;
+      n++;
+    }
+  if (ms) *ms = total;
+  if (launches) *launches = n;
+  return RSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// arenas
+extern "C" int rsg_crs_create(rsg_context *c, size_t n, rsg_crs **out) {
+  if (!c || !out) return fail(RSG_ERR_STATE, "context not set");
+  CUDA_TRY(cudaSetDevice(c->device));
+  rsg_crs *r = new rsg_crs{c, n, nullptr};
+  void *v = nullptr;
+  cudaError_t e = cudaMalloc(&v, std::max<size_t>(n, 1) * c->enc_words() * 8);
+  if (e != cudaSuccess) { delete r; return fail(RSG_ERR_CUDA, std::string("cudaMalloc CRS: ") + cudaGetErrorString(e)); }
+  r->d = (uint64_t *)v;
+  *out = r;
+  return RSG_OK;
+}
+extern "C" int rsg_crs_upload(rsg_crs *r, size_t first, size_t count, const uint64_t *h) {
+  if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "CRS range");
+  rsg_context *c = r->ctx;
+  CUDA_TRY(cudaMemcpyAsync(r->d + first * c->enc_words(), h, count * c->enc_words() * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
+}
+extern "C" int rsg_crs_download(const rsg_crs *r, size_t first, size_t count, uint64_t *h) {
+  if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "CRS range");
+  rsg_context *c = r->ctx;
+  CUDA_TRY(cudaMemcpyAsync(h, r->d + first * c->enc_words(), count * c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
+}
+static int fill_uniform(rsg_context *c, uint64_t *d, size_t words, uint32_t row_words, const ModConst *mods, uint32_t n_mods,
+                        uint64_t seed) {
+  std::lock_guard<std::mutex> g(c->mu);
+  LaunchScope ls(c, "k_fill_uniform");
+  k_fill_uniform<<<148 * 8, 256, 0, c->stream>>>(d, words, row_words, mods, n_mods, 1, seed);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+extern "C" int rsg_crs_fill_uniform(rsg_crs *r, uint64_t seed) {
+  if (!r) return fail(RSG_ERR_ARG, "null CRS");
+  rsg_context *c = r->ctx;
+  return fill_uniform(c, r->d, r->n * c->enc_words(), (uint32_t)c->N_E, c->d_modQ, (uint32_t)c->L_E, seed);
+}
+extern "C" uint64_t *rsg_crs_device_ptr(rsg_crs *r) { return r ? r->d : nullptr; }
+extern "C" void rsg_crs_destroy(rsg_crs *r) {
+  if (!r) return;
+  cudaStreamSynchronize(r->ctx->stream);
+  cudaFree(r->d);
+  delete r;
+}
+
+extern "C" int rsg_ringvec_create(rsg_context *c, size_t n, rsg_ringvec **out) {
+  if (!c || !out) return fail(RSG_ERR_STATE, "context not set");
+  CUDA_TRY(cudaSetDevice(c->device));
+  rsg_ringvec *r = new rsg_ringvec{c, n, nullptr};
+  void *v = nullptr;
+  cudaError_t e = cudaMalloc(&v, std::max<size_t>(n, 1) * c->ring_words() * 8);
+  if (e != cudaSuccess) { delete r; return fail(RSG_ERR_CUDA, std::string("cudaMalloc ringvec: ") + cudaGetErrorString(e)); }
+  r->d = (uint64_t *)v;
+  cudaMemsetAsync(r->d, 0, std::max<size_t>(n, 1) * c->ring_words() * 8, c->stream);
+  *out = r;
+  return RSG_OK;
+}
+extern "C" int rsg_ringvec_upload(rsg_ringvec *r, size_t first, size_t count, const uint64_t *h) {
+  if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "ringvec range");
+  rsg_context *c = r->ctx;
+  CUDA_TRY(cudaMemcpyAsync(r->d + first * c->ring_words(), h, count * c->ring_words() * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
+}
+extern "C" int rsg_ringvec_download(const rsg_ringvec *r, size_t first, size_t count, uint64_t *h) {
+  if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "ringvec range");
+  rsg_context *c = r->ctx;
+  CUDA_TRY(cudaMemcpyAsync(h, r->d + first * c->ring_words(), count * c->ring_words() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
+}
+extern "C" int rsg_ringvec_fill_uniform(rsg_ringvec *r, uint64_t seed) {
+  if (!r) return fail(RSG_ERR_ARG, "null ringvec");
+  rsg_context *c = r->ctx;
+  return fill_uniform(c, r->d, r->n * c->ring_words(), (uint32_t)c->N_R, c->d_modq, (uint32_t)c->L_R, seed);
+}
+extern "C" uint64_t *rsg_ringvec_device_ptr(rsg_ringvec *r) { return r ? r->d : nullptr; }
+extern "C" size_t rsg_ringvec_size(const rsg_ringvec *r) { return r ? r->n : 0; }
+extern "C" void rsg_ringvec_destroy(rsg_ringvec *r) {
+  if (!r) return;
+  cudaStreamSynchronize(r->ctx->stream);
+  cudaFree(r->d);
+  delete r;
+}
+
+extern "C" int rsg_ringvec_is_zero_prefix(const rsg_ringvec *r, size_t first, size_t count, uint8_t *h_flags) {
+  if (!r || first + count > r->n || !h_flags) return fail(RSG_ERR_ARG, "ringvec range");
+  if (!count) return RSG_OK;
+  rsg_context *c = r->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  int rc = ensure(c, &c->d_flags, &c->cap_flags, count);
+  if (rc) return rc;
+  {
+    LaunchScope ls(c, "k_is_zero_prefix");
+    k_is_zero_prefix<<<(unsigned)count, 256, 0, c->stream>>>(r->d + first * c->ring_words(), (uint32_t)c->ring_words(), c->d_flags);
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(h_flags, c->d_flags, count, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// NTT launch helpers
+static unsigned ntt_threads(int logn) { return (unsigned)std::max(32, std::min(512, (1 << logn) / 16)); }
+static size_t ntt_smem(int logn) { return (size_t)padded_words(1u << logn) * 8; }
+
+template <int LOGN>
+static int set_smem_attrs() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done[dev]) return RSG_OK;
+  const int bytes = (int)ntt_smem(LOGN);
+  CUDA_TRY(cudaFuncSetAttribute(k_encode_intt<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[dev] = true;
+  return RSG_OK;
+}
+
+#define DISPATCH_LOGN(logn, ...)                  \
+  switch (logn) {                                 \
+    case 8: { constexpr int LG = 8; __VA_ARGS__; } break;   \
+    case 9: { constexpr int LG = 9; __VA_ARGS__; } break;   \
+    case 10: { constexpr int LG = 10; __VA_ARGS__; } break; \
+    case 11: { constexpr int LG = 11; __VA_ARGS__; } break; \
+    case 12: { constexpr int LG = 12; __VA_ARGS__; } break; \
+    case 13: { constexpr int LG = 13; __VA_ARGS__; } break; \
+    case 14: { constexpr int LG = 14; __VA_ARGS__; } break; \
+    default: return fail(RSG_ERR_UNSUPPORTED, "unsupported N_E"); \
+  }
+
+static int launch_encode(rsg_context *c, const uint64_t *d_ring, const uint32_t *d_eidx, size_t count, uint64_t *d_plain) {
+  if (!count) return RSG_OK;
+  const unsigned th = ntt_threads(c->logN);
+  const size_t sm = ntt_smem(c->logN);
+  dim3 grid((unsigned)count, (unsigned)c->L_R);
+  LaunchScope ls(c, "k_encode_intt");
+  DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG>(); if (rc) return rc;
+                           k_encode_intt<LG><<<grid, th, sm, c->stream>>>(c->d_params, d_ring, d_eidx, d_plain); });
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count, uint64_t *d_pntt) {
+  if (!count) return RSG_OK;
+  const unsigned th = ntt_threads(c->logN);
+  const size_t sm = ntt_smem(c->logN);
+  // grid.x is the term index: up to 2^31-1
+  dim3 grid((unsigned)count, (unsigned)c->L_R, (unsigned)c->L_E);
+  LaunchScope ls(c, "k_lift_fwd_ntt");
+  DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG>(); if (rc) return rc;
+                           k_lift_fwd_ntt<LG><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+
+extern "C" int rsg_batch_encode(rsg_context *c, const uint64_t *d_ring, size_t count, uint64_t *d_plain) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  std::lock_guard<std::mutex> g(c->mu);
+  return launch_encode(c, d_ring, nullptr, count, d_plain);
+}
+extern "C" int rsg_plain_to_ntt(rsg_context *c, const uint64_t *d_plain, size_t count, uint64_t *d_pntt) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  std::lock_guard<std::mutex> g(c->mu);
+  return launch_lift_ntt(c, d_plain, count, d_pntt);
+}
+extern "C" int rsg_ntt(rsg_context *c, uint64_t *d, size_t batch, int which, size_t idx, int inverse) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  if ((which == 0 && idx >= c->L_E) || (which == 1 && idx >= c->L_R) || which < 0 || which > 1) return fail(RSG_ERR_ARG, "bad modulus index");
+  if (!batch) return RSG_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  const uint64_t p = which == 0 ? c->Q[idx] : c->q[idx];
+  const Twiddle *tab = which == 0 ? (inverse ? c->hp.invQ[idx] : c->hp.fwdQ[idx]) : (inverse ? c->hp.invq[idx] : c->hp.fwdq[idx]);
+  const Twiddle invn = which == 0 ? c->hp.invN_Q[idx] : c->hp.invN_q[idx];
+  const unsigned th = ntt_threads(c->logN);
+  const size_t sm = ntt_smem(c->logN);
+  LaunchScope ls(c, inverse ? "k_ntt_inv" : "k_ntt_fwd");
+  DISPATCH_LOGN(c->logN, {
+    int rc = set_smem_attrs<LG>();
+    if (rc) return rc;
+    if (inverse) k_ntt<LG, true><<<(unsigned)batch, th, sm, c->stream>>>(d, tab, p, invn);
+    else k_ntt<LG, false><<<(unsigned)batch, th, sm, c->stream>>>(d, tab, p, invn);
+  });
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// lincomb
+static int launch_lincomb(rsg_context *c, const uint64_t *d_crs, const uint32_t *h_term, const uint32_t *h_pidx, size_t n_terms,
+                          const uint64_t *d_pntt, uint64_t *d_out) {
+  int rc;
+  if ((rc = ensure(c, &c->d_term, &c->cap_term, std::max<size_t>(n_terms, 1024)))) return rc;
+  if ((rc = ensure(c, &c->d_pidx, &c->cap_pidx, std::max<size_t>(n_terms, 1024)))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(c->d_term, h_term, n_terms * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->d_pidx, h_pidx, n_terms * 4, cudaMemcpyHostToDevice, c->stream));
+  const unsigned th = (unsigned)std::min<size_t>(256, c->N_E / 2);
+  const unsigned gx = (unsigned)(c->N_E / 2 / th), gy = (unsigned)(c->L_R * c->L_E);
+  // split the term range so that the grid has >= ~4 blocks per SM; each split streams >= 8 terms
+  const unsigned base_blocks = gx * gy;
+  unsigned splits = std::max(1u, (148u * 8 + base_blocks - 1) / base_blocks);
+  splits = (unsigned)std::min<size_t>(splits, (n_terms + 7) / 8);
+  splits = std::max(1u, splits);
+  const unsigned tps = (unsigned)((n_terms + splits - 1) / splits);
+  splits = (unsigned)((n_terms + tps - 1) / tps);
+  uint64_t *d_partial = d_out;
+  if (splits > 1) {
+    if ((rc = ensure(c, &c->d_partial, &c->cap_partial, (size_t)splits * c->enc_words()))) return rc;
+    d_partial = c->d_partial;
+  }
+  {
+    LaunchScope ls(c, "k_crs_lincomb");
+    k_crs_lincomb<4><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, c->d_term, c->d_pidx, (uint32_t)n_terms, tps,
+                                                                 d_pntt, d_partial);
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (splits > 1) {
+    LaunchScope ls(c, "k_enc_sum");
+    const size_t pairs = c->enc_words() / 2;
+    k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_partial, splits, d_out);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return RSG_OK;
+}
+
+extern "C" int rsg_crs_lincomb(rsg_context *c, const uint64_t *d_crs, const uint32_t *h_term, const uint32_t *h_pidx, size_t n_terms,
+                               const uint64_t *d_pntt, uint64_t *d_out) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  if (!n_terms) return fail(RSG_ERR_ARG, "empty term list");
+  std::lock_guard<std::mutex> g(c->mu);
+  return launch_lincomb(c, d_crs, h_term, h_pidx, n_terms, d_pntt, d_out);
+}
+
+extern "C" int rsg_inner_product(rsg_context *c, const rsg_crs *crs, size_t crs_first, const rsg_ringvec *coeffs, size_t coeff_first,
+                                 size_t count, const uint8_t *h_tags, uint64_t *h_out, uint64_t *d_out, size_t *n_used) {
+  if (!c || !crs || !coeffs || !h_tags) return fail(RSG_ERR_ARG, "null argument");
+  if (crs_first + count > crs->n || coeff_first + count > coeffs->n) return fail(RSG_ERR_ARG, "range");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  std::vector<uint32_t> term, pidx, eidx;
+  for (size_t i = 0; i < count; i++) {
+    if (h_tags[i] == RSG_TERM_SKIP) continue;
+    term.push_back((uint32_t)(crs_first + i));
+    if (h_tags[i] == RSG_TERM_ONE) pidx.push_back(0xFFFFFFFFu);
+    else { pidx.push_back((uint32_t)eidx.size()); eidx.push_back((uint32_t)(coeff_first + i)); }
+  }
+  if (n_used) *n_used = term.size();
+  int rc;
+  uint64_t *out = d_out;
+  if (!out) {
+    if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, c->enc_words()))) return rc;
+    out = c->d_out_scratch;
+  }
+  if (term.empty()) {
+    CUDA_TRY(cudaMemsetAsync(out, 0, c->enc_words() * 8, c->stream));
+  } else {
+    const size_t G = eidx.size();
+    if (G) {
+      if ((rc = ensure(c, &c->d_plain, &c->cap_plain, G * c->L_R * c->N_E))) return rc;
+      if ((rc = ensure(c, &c->d_pntt, &c->cap_pntt, G * c->L_R * c->L_E * c->N_E))) return rc;
+      if ((rc = ensure(c, &c->d_eidx, &c->cap_eidx, std::max<size_t>(G, 1024)))) return rc;
+      CUDA_TRY(cudaMemcpyAsync(c->d_eidx, eidx.data(), G * 4, cudaMemcpyHostToDevice, c->stream));
+      if ((rc = launch_encode(c, coeffs->d, c->d_eidx, G, c->d_plain))) return rc;
+      if ((rc = launch_lift_ntt(c, c->d_plain, G, c->d_pntt))) return rc;
+    }
+    if ((rc = launch_lincomb(c, crs->d, term.data(), pidx.data(), term.size(), c->d_pntt, out))) return rc;
+  }
+  if (h_out) CUDA_TRY(cudaMemcpyAsync(h_out, out, c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));   // h_term/h_pidx staging vectors die with this frame
+  return RSG_OK;
+}
+
+extern "C" int rsg_enc_sum(rsg_context *c, const uint64_t *d_parts, size_t parts, uint64_t *d_out) {
+  if (!c || !d_parts || !d_out || !parts) return fail(RSG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  LaunchScope ls(c, "k_enc_sum");
+  const size_t pairs = c->enc_words() / 2;
+  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_parts, (uint32_t)parts, d_out);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+extern "C" int rsg_enc_add(rsg_context *c, uint64_t *d_acc, const uint64_t *d_other) {
+  if (!c || !d_acc || !d_other) return fail(RSG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  // two-part sum with parts not adjacent: stage through the partial buffer
+  int rc;
+  if ((rc = ensure(c, &c->d_partial, &c->cap_partial, 2 * c->enc_words()))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(c->d_partial, d_acc, c->enc_words() * 8, cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->d_partial + c->enc_words(), d_other, c->enc_words() * 8, cudaMemcpyDeviceToDevice, c->stream));
+  LaunchScope ls(c, "k_enc_sum");
+  const size_t pairs = c->enc_words() / 2;
+  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, c->d_partial, 2, d_acc);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// witness map
+// Per-prime constants for the domain {0..n-1}: Z, V^-1 (column j = coefficients of the j-th Lagrange basis
+// polynomial, i.e. what interpolate() accumulates for y = e_j, polynomials.tcc:26-41) and the Toeplitz matrix of
+// rev(Z)^-1 mod x^(n-1) that turns "top half of the dividend" into the quotient of the long division by Z.
+static int get_witness_tables(rsg_context *c, size_t n, WitnessTables **out) {
+  auto it = c->wit.find(n);
+  if (it != c->wit.end()) { *out = &it->second; return RSG_OK; }
+  if (n < 1) return fail(RSG_ERR_ARG, "n must be >= 1");
+  for (uint64_t p : c->q)
+    if (p <= 2 * n) return fail(RSG_ERR_ARG, "domain {0..n-1} is not an exceptional set for this modulus");
+  WitnessTables wt;
+  const size_t L_R = c->L_R, m = n > 0 ? n - 1 : 0;
+  std::vector<uint64_t> Vinv(L_R * n * n), T(L_R * std::max<size_t>(m * m, 1), 0);
+  wt.h_Z.assign(L_R * (n + 1), 0);
+  for (size_t j = 0; j < L_R; j++) {
+    const uint64_t p = c->q[j];
+    uint64_t *Z = wt.h_Z.data() + j * (n + 1);
+    Z[0] = 1;
+    for (size_t i = 0; i < n; i++) {   // multiply by (x - i)
+      const uint64_t neg = (p - i % p) % p;
+      for (size_t k = i + 2; k-- > 0;) {
+        const uint64_t lower = k ? Z[k - 1] : 0;
+        const uint64_t same = k <= i ? h_mulmod(Z[k], neg, p) : 0;
+        Z[k] = (same + lower) % p;
+      }
+    }
+    // phi_x = Z'(x) = prod_{i != x} (x - i) = x! (n-1-x)! (-1)^(n-1-x)
+    std::vector<uint64_t> fact(n + 1, 1);
+    for (size_t i = 1; i <= n; i++) fact[i] = h_mulmod(fact[i - 1], i % p, p);
+    uint64_t *V = Vinv.data() + j * n * n;
+    std::vector<uint64_t> b(n);
+    for (size_t x = 0; x < n; x++) {
+      uint64_t phi = h_mulmod(fact[x], fact[n - 1 - x], p);
+      if ((n - 1 - x) & 1) phi = (p - phi) % p;
+      const uint64_t iphi = h_inv(phi, p);
+      // synthetic division Z(x) / (x - x0): b[n-1] = 1, b[k-1] = Z[k] + x0 * b[k]
+      b[n - 1] = 1;
+      for (size_t k = n - 1; k > 0; k--) b[k - 1] = (Z[k] + h_mulmod(x % p, b[k], p)) % p;
+      for (size_t k = 0; k < n; k++) V[k * n + x] = h_mulmod(b[k], iphi, p);
+    }
+    if (m) {
+      // u = rev(Z)^-1 mod x^m, rev(Z)_i = Z[n - i] (rev(Z)_0 = 1)
+      std::vector<uint64_t> u(m, 0);
+      u[0] = 1;
+      for (size_t i = 1; i < m; i++) {
+        u128 acc = 0;
+        for (size_t t = 1; t <= i; t++) acc += (u128)h_mulmod(Z[n - t], u[i - t], p);
+        u[i] = (p - (uint64_t)(acc % p)) % p;
+      }
+      uint64_t *Tm = T.data() + j * m * m;
+      for (size_t k = 0; k < m; k++)
+        for (size_t col = k; col < m; col++) Tm[k * m + col] = u[col - k];
+    }
+  }
+  void *v = nullptr;
+  CUDA_TRY(cudaMalloc(&v, Vinv.size() * 8));
+  wt.d_Vinv = (uint64_t *)v;
+  CUDA_TRY(cudaMemcpy(wt.d_Vinv, Vinv.data(), Vinv.size() * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&v, T.size() * 8));
+  wt.d_T = (uint64_t *)v;
+  CUDA_TRY(cudaMemcpy(wt.d_T, T.data(), T.size() * 8, cudaMemcpyHostToDevice));
+  auto ins = c->wit.emplace(n, std::move(wt));
+  *out = &ins.first->second;
+  return RSG_OK;
+}
+
+static int launch_modmat(rsg_context *c, const uint64_t *d_M, size_t rows, size_t K, const uint64_t *d_Y, uint64_t *d_C, size_t batch,
+                         bool upper, const char *name) {
+  if (!rows || !batch) return RSG_OK;
+  dim3 grid((unsigned)((rows + MM_ROWS - 1) / MM_ROWS), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), (unsigned)(batch * c->L_R));
+  LaunchScope ls(c, name);
+  k_modmat<<<grid, MM_THREADS, 0, c->stream>>>(c->d_modq, d_M, (uint32_t)rows, (uint32_t)K, d_Y, d_C, (uint32_t)c->N_R, (uint32_t)c->L_R,
+                                               upper ? 1u : 0u, (uint32_t)K);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+
+extern "C" int rsg_interpolate(rsg_context *c, size_t n, size_t batch, const rsg_ringvec *y, size_t y_first, rsg_ringvec *out,
+                               size_t out_first) {
+  if (!c || !y || !out) return fail(RSG_ERR_ARG, "null argument");
+  if (y_first + batch * n > y->n || out_first + batch * n > out->n) return fail(RSG_ERR_ARG, "range");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  WitnessTables *wt;
+  int rc = get_witness_tables(c, n, &wt);
+  if (rc) return rc;
+  return launch_modmat(c, wt->d_Vinv, n, n, y->d + y_first * c->ring_words(), out->d + out_first * c->ring_words(), batch, false,
+                       "k_modmat_interp");
+}
+
+extern "C" int rsg_vanishing(rsg_context *c, size_t n, uint64_t *h_Z) {
+  if (!c || !h_Z) return fail(RSG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  WitnessTables *wt;
+  int rc = get_witness_tables(c, n, &wt);
+  if (rc) return rc;
+  memcpy(h_Z, wt->h_Z.data(), wt->h_Z.size() * 8);
+  return RSG_OK;
+}
+
+extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
+  if (!c || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
+  if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  WitnessTables *wt;
+  int rc = get_witness_tables(c, n, &wt);
+  if (rc) return rc;
+  const size_t W = c->ring_words();
+  // scratch: aA, aB (n each) + Ptop (n-1): reuse d_plain (words)
+  if ((rc = ensure(c, &c->d_plain, &c->cap_plain, (3 * n) * W))) return rc;
+  uint64_t *aA = c->d_plain, *aB = aA + n * W, *Ptop = aB + n * W;
+  // evals order: A_mid,B_mid,C_mid,A_io,B_io,C_io,A_full,B_full,C_full ; coeffs order: A_io,B_io,C_io,A_mid,B_mid,C_mid
+  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, evals->d + 3 * n * W, coeffs->d, 3, false, "k_modmat_interp"))) return rc;
+  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, evals->d, coeffs->d + 3 * n * W, 3, false, "k_modmat_interp"))) return rc;
+  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, evals->d + 6 * n * W, aA, 2, false, "k_modmat_interp"))) return rc;
+  CUDA_TRY(cudaMemsetAsync(H->d, 0, (n + 1) * W * 8, c->stream));
+  if (n >= 2) {
+    {
+      dim3 grid((unsigned)((n - 1 + MM_ROWS - 1) / MM_ROWS), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), (unsigned)c->L_R);
+      LaunchScope ls(c, "k_conv_top");
+      k_conv_top<<<grid, MM_THREADS, 0, c->stream>>>(c->d_modq, aA, aB, (uint32_t)n, (uint32_t)n, (uint32_t)n, Ptop, (uint32_t)c->N_R,
+                                                     (uint32_t)c->L_R);
+      CUDA_TRY(cudaGetLastError());
+    }
+    if ((rc = launch_modmat(c, wt->d_T, n - 1, n - 1, Ptop, H->d, 1, true, "k_modmat_divZ"))) return rc;
+  }
+  return RSG_OK;
+}

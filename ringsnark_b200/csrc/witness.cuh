@@ -1,0 +1,104 @@
+// Witness-map kernels (hot path (a)): slot-parallel restatement of
+//   interpolate            ringsnark/util/polynomials.tcc:9-43        (coeffs = V^-1 y on the domain {0..n-1})
+//   multiply / add / divide ringsnark/util/polynomials.tcc:61-81       (H = (A*B - C) / Z, Z monic)
+//   r1cs_to_qrp_witness_map ringsnark/reductions/r1cs_to_qrp/r1cs_to_qrp.tcc:148-259
+// The reference runs an O(n^2) scalar routine per ring element with every "scalar" a length-N_R*L_R vector.
+// Every slot of one ring prime sees the SAME domain, so V^-1 (Lagrange basis coefficients) and the power-series
+// inverse of rev(Z) are per-prime constants built once on the host; the device work is then
+//   (1) k_modmat   : C = M * Y over Z_p, M constant (n x n), Y = n ring elements x slots    [interpolation, division]
+//   (2) k_conv_top : top half of the per-slot product A*B (only coefficients n..2n-2 reach the quotient)
+// Exactly the residues the reference computes: all results are canonical and the quotient of the long division
+// by a monic Z depends only on the dividend's coefficients of degree >= n (Knuth 4.6.1 D).
+#pragma once
+#include "modarith.cuh"
+
+namespace rsg {
+
+constexpr int MM_ROWS = 8;      // output rows per thread
+constexpr int MM_THREADS = 128; // slots per block
+constexpr int MM_KTILE = 64;    // matrix columns staged per shared-memory tile
+
+// C[v][r][slot] = sum_c M[limb][r][c] * Y[v][c][slot]  mod q_limb
+//   Y element (v*K + c), C element (v*Mrows + r); element layout [L_R][N_R].
+//   c_lo[r] (nullable): first non-zero column of row r is >= c_lo_of_tile -- used for triangular matrices.
+// grid (ceil(Mrows/MM_ROWS), N_R/MM_THREADS, batch*L_R): row tiles vary fastest so co-resident blocks share Y in L2.
+__global__ void __launch_bounds__(MM_THREADS) k_modmat(const ModConst *__restrict__ mods, const uint64_t *__restrict__ M,
+                                                       uint32_t Mrows, uint32_t K, const uint64_t *__restrict__ Y,
+                                                       uint64_t *__restrict__ C, uint32_t N_R, uint32_t L_R,
+                                                       uint32_t upper_triangular, uint32_t K_valid) {
+  __shared__ uint64_t tile[MM_ROWS][MM_KTILE];
+  const uint32_t r0 = blockIdx.x * MM_ROWS;
+  const uint32_t slot = blockIdx.y * MM_THREADS + threadIdx.x;
+  const uint32_t v = blockIdx.z / L_R, limb = blockIdx.z - v * L_R;
+  const size_t W = (size_t)N_R * L_R;
+  const uint64_t *Mp = M + (size_t)limb * Mrows * K;
+  const uint64_t *Yp = Y + (size_t)v * K * W + (size_t)limb * N_R + slot;
+  Acc192 acc[MM_ROWS];
+#pragma unroll
+  for (int r = 0; r < MM_ROWS; r++) acc[r].clear();
+  // triangular: row r only has columns >= r, so this row tile starts at column r0 (rounded down to a tile)
+  const uint32_t c_begin = upper_triangular ? (r0 / MM_KTILE) * MM_KTILE : 0;
+  const uint32_t c_end = min(K, K_valid);
+  for (uint32_t c0 = c_begin; c0 < c_end; c0 += MM_KTILE) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < MM_ROWS * MM_KTILE; i += MM_THREADS) {
+      const uint32_t r = i / MM_KTILE, c = i % MM_KTILE;
+      tile[r][c] = (r0 + r < Mrows && c0 + c < c_end) ? Mp[(size_t)(r0 + r) * K + c0 + c] : 0;
+    }
+    __syncthreads();
+    const uint32_t cn = min((uint32_t)MM_KTILE, c_end - c0);
+    if (slot < N_R) {
+#pragma unroll 4
+      for (uint32_t c = 0; c < cn; c++) {
+        const uint64_t y = Yp[(size_t)(c0 + c) * W];
+#pragma unroll
+        for (int r = 0; r < MM_ROWS; r++) acc[r].mac(tile[r][c], y);
+      }
+    }
+  }
+  if (slot < N_R) {
+    const ModConst m = mods[limb];
+    uint64_t *Cp = C + (size_t)v * Mrows * W + (size_t)limb * N_R + slot;
+#pragma unroll
+    for (int r = 0; r < MM_ROWS; r++)
+      if (r0 + r < Mrows) Cp[(size_t)(r0 + r) * W] = acc[r].reduce(m);
+  }
+}
+
+// Ptop[i][slot] = sum_j A[j][slot] * B[n + i - j][slot],  i in [0, n-1), j in [i+1, n)  -- coefficient n+i of A*B.
+// Elements j >= lenA of A and >= lenB of B count as zero (Boost normalize() through RingElem::operator==).
+// grid (ceil((n-1)/MM_ROWS), N_R/MM_THREADS, L_R)
+__global__ void __launch_bounds__(MM_THREADS) k_conv_top(const ModConst *__restrict__ mods, const uint64_t *__restrict__ A,
+                                                         const uint64_t *__restrict__ B, uint32_t n, uint32_t lenA,
+                                                         uint32_t lenB, uint64_t *__restrict__ Ptop, uint32_t N_R,
+                                                         uint32_t L_R) {
+  const uint32_t i0 = blockIdx.x * MM_ROWS;
+  const uint32_t slot = blockIdx.y * MM_THREADS + threadIdx.x;
+  const uint32_t limb = blockIdx.z;
+  if (slot >= N_R) return;
+  const size_t W = (size_t)N_R * L_R;
+  const uint64_t *Ap = A + (size_t)limb * N_R + slot;
+  const uint64_t *Bp = B + (size_t)limb * N_R + slot;
+  Acc192 acc[MM_ROWS];
+  uint64_t win[MM_ROWS];   // win[r] = B[n + i0 + r - j]
+#pragma unroll
+  for (int r = 0; r < MM_ROWS; r++) { acc[r].clear(); win[r] = 0; }
+  // j runs from i0+1; at that point only r = 0 has an in-range B index (n-1)
+  for (uint32_t j = i0 + 1; j < n; j++) {
+    // shift the window: index for r at this j equals index for r-1 at j-1
+#pragma unroll
+    for (int r = MM_ROWS - 1; r > 0; r--) win[r] = win[r - 1];
+    const uint32_t bi = n + i0 - j;                     // index for r = 0
+    win[0] = bi < lenB ? Bp[(size_t)bi * W] : 0;
+    const uint64_t a = j < lenA ? Ap[(size_t)j * W] : 0;
+#pragma unroll
+    for (int r = 0; r < MM_ROWS; r++) acc[r].mac(a, win[r]);
+  }
+  const ModConst m = mods[limb];
+  uint64_t *Pp = Ptop + (size_t)limb * N_R + slot;
+#pragma unroll
+  for (int r = 0; r < MM_ROWS; r++)
+    if (i0 + r < n - 1) Pp[(size_t)(i0 + r) * W] = acc[r].reduce(m);
+}
+
+}  // namespace rsg

@@ -1,0 +1,212 @@
+"""GPU parity tests: every kernel of librsgpu.so, called through the C ABI, against
+  (1) the golden vectors produced by the unmodified reference (tests/golden/*.rsgv),
+  (2) the C oracle on seeded inputs,
+  (3) fresh dumps from oracle/_ref/ref_harness (prebuilt; travels to the GPU box) at the reference's own sizes.
+Bit-exact (integer path): np.array_equal everywhere."""
+import glob
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from rsgv import Case
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.rsgv")))
+IDS = [os.path.basename(g)[:-5] for g in GOLD]
+REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+
+def make_ctx(case):
+    import ringsnark_b200 as rs
+    return rs.Context(case.N_R, case.q, case.N_E, case.Q)
+
+
+@pytest.fixture(scope="module", params=GOLD, ids=IDS)
+def gold(request):
+    case = Case(request.param)
+    ctx = make_ctx(case)
+    yield case, ctx
+    ctx.close()
+
+
+def _torch_dev(arr):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).cuda()
+
+
+def _host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def test_raw_ntt(gold):
+    import ctypes as C
+    case, ctx = gold
+    d = case.d
+    x = _torch_dev(d["kat_ntt_in"])
+    assert ctx.lib.rsg_ntt(ctx.h, C.c_void_p(x.data_ptr()), 1, 0, 0, 0) == 0
+    ctx.sync()
+    assert np.array_equal(_host(x), d["kat_ntt_fwd_Q0"])
+    assert ctx.lib.rsg_ntt(ctx.h, C.c_void_p(x.data_ptr()), 1, 0, 0, 1) == 0
+    ctx.sync()
+    assert np.array_equal(_host(x), d["kat_ntt_in"])
+    y = _torch_dev(d["kat_intt_in"])
+    assert ctx.lib.rsg_ntt(ctx.h, C.c_void_p(y.data_ptr()), 1, 1, 0, 1) == 0
+    ctx.sync()
+    assert np.array_equal(_host(y), d["kat_intt_inv_q0"])
+
+
+def test_batch_encode_and_lift(gold):
+    import ctypes as C
+    import torch
+    case, ctx = gold
+    words, _, _ = case.ring("kat_elem")
+    ring = _torch_dev(words[0])
+    plain = torch.zeros(case.L_R * case.N_E, dtype=torch.int64, device="cuda")
+    pntt = torch.zeros(case.L_R * case.L_E * case.N_E, dtype=torch.int64, device="cuda")
+    assert ctx.lib.rsg_batch_encode(ctx.h, C.c_void_p(ring.data_ptr()), 1, C.c_void_p(plain.data_ptr())) == 0
+    assert ctx.lib.rsg_plain_to_ntt(ctx.h, C.c_void_p(plain.data_ptr()), 1, C.c_void_p(pntt.data_ptr())) == 0
+    ctx.sync()
+    assert np.array_equal(_host(plain), case.d["kat_plain_coeff"])
+    assert np.array_equal(_host(pntt), case.d["kat_plain_ntt"])
+
+
+def _ip(case, ctx, crs, name):
+    words, tag, scalar = case.ring(name)
+    vec = ctx.ringvec_from(words)
+    tags = ctx.term_tags(vec, tag, scalar)
+    assert np.array_equal(tags, O.term_tags(words, tag, scalar)), name   # host dispatch == reference dispatch
+    return ctx.inner_product(crs, vec, tags)
+
+
+def test_inner_products_and_proof(gold):
+    case, ctx = gold
+    s_pows = ctx.crs_from(case.enc("crs_s_pows")[0])
+    delta_ts = ctx.crs_from(case.enc("crs_delta_ts")[0])
+    delta_mid = ctx.crs_from(case.enc("crs_delta_mid")[0])
+    ip, ip_size = case.enc("ip")
+    order = [(s_pows, "wit_A_io"), (s_pows, "wit_A_mid"), (s_pows, "wit_B_io"), (s_pows, "wit_B_mid"),
+             (delta_ts, "wit_H"), (delta_mid, "auxiliary_input")]
+    mine = []
+    for k, (crs, name) in enumerate(order):
+        out, used = _ip(case, ctx, crs, name)
+        assert (used == 0) == (int(ip_size[k][0]) == 2 ** 64 - 1), name
+        if used:
+            assert np.array_equal(out, ip[k]), name
+        mine.append((out, used))
+    proof, _ = case.enc("proof")
+    alpha, _ = case.enc("crs_alpha")
+    beta, _ = case.enc("crs_beta")
+    import ctypes as C
+
+    def total(parts):
+        parts = [w for w, used in parts if used]
+        stack = _torch_dev(np.stack(parts))
+        out = _torch_dev(np.zeros(case.enc_words, dtype=np.uint64))
+        assert ctx.lib.rsg_enc_sum(ctx.h, C.c_void_p(stack.data_ptr()), len(parts), C.c_void_p(out.data_ptr())) == 0
+        ctx.sync()
+        return _host(out)
+
+    assert np.array_equal(total([mine[0], mine[1], (alpha[0], 1)]), proof[0])
+    assert np.array_equal(total([mine[2], mine[3], (beta[0], 1)]), proof[1])
+    assert np.array_equal(total([mine[4], mine[5]]), proof[2])
+
+
+def test_witness_map(gold):
+    case, ctx = gold
+    n = case.n
+    Z = ctx.vanishing(n)
+    zw, _, _ = case.ring("wit_Z")
+    for j in range(case.L_R):
+        assert np.array_equal(Z[j], zw[:, j * case.N_R])
+    order = ["A_mid", "B_mid", "C_mid", "A_io", "B_io", "C_io", "A_full", "B_full", "C_full"]
+    evals = np.concatenate([case.ring("eval_" + k)[0] for k in order])
+    ev = ctx.ringvec_from(evals)
+    coeffs, H = ctx.witness_map(n, ev)
+    got = coeffs.download()
+    for idx, k in enumerate(["A_io", "B_io", "C_io", "A_mid", "B_mid", "C_mid"]):
+        assert np.array_equal(got[idx * n:(idx + 1) * n], case.ring("wit_" + k)[0]), k
+    assert np.array_equal(H.download(), case.ring("wit_H")[0])
+
+
+def test_is_zero_prefix(gold):
+    case, ctx = gold
+    rng = np.random.default_rng(7)
+    W = case.W
+    elems = rng.integers(0, 1 << 20, size=(6, W), dtype=np.uint64)
+    elems[0] = 0
+    elems[1, :W // 8] = 0                     # bytes [0, W): still one partial word short of "zero"
+    elems[2, :W // 8 + 1] = 0                 # reference says zero although the tail is not
+    elems[3, :W // 8] = 0
+    elems[3, W // 8] = np.uint64(1) << np.uint64(56)  # only the byte outside the compared window is set
+    elems[4, 0] = 1
+    vec = ctx.ringvec_from(elems)
+    want = np.array([O.is_zero_quirk(e) for e in elems], dtype=np.uint8)
+    assert np.array_equal(vec.is_zero_prefix(), want)
+    assert list(want[:4]) == [1, 0, 1, 1]
+
+
+def test_lincomb_random_vs_oracle(gold):
+    """Seeded synthetic CRS + coefficients (incl. ONE and SKIP tags, > 1 split) against the C oracle."""
+    case, ctx = gold
+    T = 37
+    crs = ctx.crs(T)
+    crs.fill_uniform(123)
+    vec = ctx.ringvec(T)
+    vec.fill_uniform(456)
+    tags = np.full(T, 2, dtype=np.uint8)
+    tags[[3, 11]] = 0
+    tags[[0, 20, 36]] = 1
+    out, used = ctx.inner_product(crs, vec, tags)
+    want, used_o = O.inner_product(crs.download(), vec.download(), tags, case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)
+    assert used == used_o == T - 2
+    assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("name", ["c1", "c3p", "c4s"])
+def test_reference_sized_cases(name):
+    """Full-size parameter sets of the reference (N_E = 8192 / 16384, both plain-lift paths): fresh dump from the
+    compiled reference, then every prover inner product, the proof and the witness map must be bit-identical."""
+    if not os.path.exists(REF_HARNESS):
+        pytest.skip("oracle/_ref/ref_harness not built (needs /root/reference at build time)")
+    import ctypes as C
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, name + ".rsgv")
+        subprocess.check_call([REF_HARNESS, "dump", name, path, "77"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        case = Case(path)
+    ctx = make_ctx(case)
+    try:
+        n = case.n
+        order = ["A_mid", "B_mid", "C_mid", "A_io", "B_io", "C_io", "A_full", "B_full", "C_full"]
+        ev = ctx.ringvec_from(np.concatenate([case.ring("eval_" + k)[0] for k in order]))
+        coeffs, H = ctx.witness_map(n, ev)
+        got = coeffs.download()
+        for idx, k in enumerate(["A_io", "B_io", "C_io", "A_mid", "B_mid", "C_mid"]):
+            assert np.array_equal(got[idx * n:(idx + 1) * n], case.ring("wit_" + k)[0]), k
+        assert np.array_equal(H.download(), case.ring("wit_H")[0])
+        s_pows = ctx.crs_from(case.enc("crs_s_pows")[0])
+        delta_ts = ctx.crs_from(case.enc("crs_delta_ts")[0])
+        delta_mid = ctx.crs_from(case.enc("crs_delta_mid")[0])
+        ip, ip_size = case.enc("ip")
+        # the prover's five/six inner products straight from the GPU witness (device-resident coefficients)
+        tag_h = np.ones(n + 1, dtype=np.uint8)
+        tag_h[n - 1:] = 0
+        jobs = [(s_pows, coeffs, 0, n, None), (s_pows, coeffs, 3 * n, n, None), (s_pows, coeffs, n, n, None),
+                (s_pows, coeffs, 4 * n, n, None), (delta_ts, H, 0, n + 1, None)]
+        for k, (crs, vec, first, cnt, _) in enumerate(jobs):
+            tags = ctx.term_tags(vec, first=first, count=cnt)
+            out, used = ctx.inner_product(crs, vec, tags, coeff_first=first)
+            assert (used == 0) == (int(ip_size[k][0]) == 2 ** 64 - 1), k
+            if used:
+                assert np.array_equal(out, ip[k]), k
+        aux_w, aux_t, aux_s = case.ring("auxiliary_input")
+        aux = ctx.ringvec_from(aux_w)
+        out, used = ctx.inner_product(delta_mid, aux, ctx.term_tags(aux, aux_t, aux_s))
+        assert np.array_equal(out, ip[5])
+    finally:
+        ctx.close()
