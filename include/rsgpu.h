@@ -89,8 +89,9 @@ int rsg_inner_product(rsg_context *ctx, const rsg_crs *crs, size_t crs_first, co
                       size_t *n_used);
 /* EncodingElem::operator+= for non-empty operands (seal_ring.tcc:479-507 -> evaluator.cpp:217-231). */
 int rsg_enc_add(rsg_context *ctx, uint64_t *d_acc, const uint64_t *d_other);
-/* Sum of `parts` encodings stored back to back (the kernel that follows the NCCL all-gather). */
-int rsg_enc_sum(rsg_context *ctx, const uint64_t *d_parts, size_t parts, uint64_t *d_out);
+/* out = sum of `parts` blocks stored back to back, each block = n_enc encodings (n_enc = 3: a whole proof):
+ * the modular-add kernel that follows the NCCL all-gather (modular addition is not an NCCL reduction). */
+int rsg_enc_sum(rsg_context *ctx, const uint64_t *d_parts, size_t parts, size_t n_enc, uint64_t *d_out);
 
 /* ---- hot path (a): r1cs_to_qrp_witness_map (reductions/r1cs_to_qrp/r1cs_to_qrp.tcc:148-259) ----
  * evals: 9*n ring elements, order A_mid,B_mid,C_mid,A_io,B_io,C_io,A_full,B_full,C_full (the outputs of
@@ -105,6 +106,34 @@ int rsg_interpolate(rsg_context *ctx, size_t n, size_t batch, const rsg_ringvec 
                     size_t out_first);
 /* util/evaluation_domain.tcc:53-60: coefficients of Z(x) = prod_{i<n}(x-i) mod each ring prime: h_Z[L_R][n+1]. */
 int rsg_vanishing(rsg_context *ctx, size_t n, uint64_t *h_Z);
+
+/* ---- the step before the hot path: linear_combination::evaluate (relations/variable.tcc:246-254) ----
+ * R1CS in CSR form, rows r = m*n + i for matrix m in {A, B, C} and constraint i; col 0 is the constant wire,
+ * col v >= 1 is variable v (primary inputs first); coeff are the uint64 scalars of the linear terms
+ * (relations/variable.hpp:29: negative integers wrap through uint64, as in the reference). */
+typedef struct rsg_r1cs rsg_r1cs;
+int rsg_r1cs_create(rsg_context *ctx, size_t n, size_t n_io, size_t n_aux, const uint32_t *h_row_ptr /* 3n+1 */,
+                    const uint32_t *h_col, const uint64_t *h_coeff, rsg_r1cs **out);
+void rsg_r1cs_destroy(rsg_r1cs *r);
+/* assignment: n_io + n_aux ring elements; evals: 9n elements in rsg_witness_map's input order. */
+int rsg_r1cs_evaluate(rsg_context *ctx, const rsg_r1cs *r, const rsg_ringvec *assignment, rsg_ringvec *evals);
+
+/* ---- groth16::prover (zk_proof_systems/groth16/groth16.tcc:69-115), whole prover in one call ----
+ * The proving key's CRS vectors live in ONE arena; each vector may be a shard [lo, hi) of its terms (multi-GPU:
+ * the partial proofs of all ranks are all-gathered and summed with rsg_enc_sum). */
+typedef struct {
+  size_t s_pows_off, s_pows_lo, s_pows_hi;          /* s_pows[0..n]  (groth16.hpp:17); the prover uses [0, n) */
+  size_t delta_ts_off, delta_ts_lo, delta_ts_hi;    /* delta_ts[0..n] */
+  size_t delta_mid_off, delta_mid_lo, delta_mid_hi; /* delta_mid[0..n_aux) */
+  size_t alpha_idx, beta_idx;                       /* arena index, or (size_t)-1 if this shard does not add them */
+} rsg_groth16_layout;
+#define RSG_AUX_POLY 0xFF   /* h_aux_kind[i]: element is a polynomial -> SealPoly::is_zero prefix test decides */
+/* h_assignment (host, nullable): if given it is first copied into `assignment` (n_io + n_aux elements).
+ * h_aux_kind (nullable = all RSG_AUX_POLY): RSG_TERM_* for auxiliary inputs the caller holds as scalars.
+ * Outputs (either may be NULL): 3 encodings A, B, C.  n_used[3] (nullable): summed terms per proof element. */
+int rsg_groth16_prove(rsg_context *ctx, const rsg_r1cs *r1cs, const rsg_crs *crs, const rsg_groth16_layout *layout,
+                      rsg_ringvec *assignment, const uint64_t *h_assignment, const uint8_t *h_aux_kind,
+                      uint64_t *h_proof, uint64_t *d_proof, size_t *n_used);
 
 /* ---- low-level entry points used by tests and by the multi-GPU driver (device pointers) ---- */
 /* BatchEncoder::encode (batchencoder.cpp:110-149): count elements [L_R][N_R] -> plaintext coeffs [count][L_R][N_E] */

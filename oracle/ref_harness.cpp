@@ -198,6 +198,23 @@ static int cmd_dump(const std::string &name, const std::string &out, uint64_t se
       put_ring(w, std::string("eval_C_") + names[k], yc);
     }
   }
+  // (1b) the constraint system itself in CSR form (rows m*n + i, m in {A,B,C}; col 0 = constant wire)
+  {
+    vector<uint64_t> row_ptr{0}, col, coeff;
+    for (int m = 0; m < 3; m++)
+      for (size_t i = 0; i < n; i++) {
+        const auto &lc = m == 0 ? s.cs.constraints[i].a : (m == 1 ? s.cs.constraints[i].b : s.cs.constraints[i].c);
+        for (const auto &lt : lc.terms) {
+          if (!lt.coeff.is_scalar()) throw std::logic_error("non-scalar linear-term coefficient");
+          col.push_back(lt.index);
+          coeff.push_back(lt.coeff.get_scalar());
+        }
+        row_ptr.push_back(col.size());
+      }
+    w.put("r1cs_row_ptr", row_ptr);
+    w.put("r1cs_col", col);
+    w.put("r1cs_coeff", coeff);
+  }
   put_ring(w, "primary_input", s.primary);
   put_ring(w, "auxiliary_input", s.auxiliary);
 

@@ -6,4 +6,5 @@ This Python package is only the thin ctypes mirror used by tests/ and bench.py. 
 works anywhere, computing needs a CUDA device.
 """
 from .capi import RsgError, lib_path, load_library  # noqa: F401
-from .backend import Context, Crs, RingVec, TERM_GENERAL, TERM_ONE, TERM_SKIP  # noqa: F401
+from .backend import (AUX_POLY, Context, Crs, Groth16ProvingKey, R1cs, RingVec, TERM_GENERAL, TERM_ONE,  # noqa: F401
+                      TERM_SKIP)

@@ -102,6 +102,10 @@ class Context:
                                          _ptr(out) if to_host else None, C.c_void_p(d_out) if d_out else None, C.byref(used)))
         return out, int(used.value)
 
+    def enc_sum(self, d_parts, parts, n_enc, d_out):
+        """Modular sum of `parts` blocks of n_enc encodings (device pointers): runs after the NCCL all-gather."""
+        check(self.lib.rsg_enc_sum(self.h, C.c_void_p(d_parts), parts, n_enc, C.c_void_p(d_out)))
+
     # ---- hot path (a)
     def witness_map(self, n, evals, coeffs=None, H=None):
         coeffs = coeffs or RingVec(self, 6 * n)
@@ -118,6 +122,98 @@ class Context:
         Z = np.zeros((self.L_R, n + 1), dtype=np.uint64)
         check(self.lib.rsg_vanishing(self.h, n, _ptr(Z)))
         return Z
+
+
+class Groth16Layout(C.Structure):
+    """rsg_groth16_layout (include/rsgpu.h)."""
+    _fields_ = [(k, C.c_size_t) for k in (
+        "s_pows_off", "s_pows_lo", "s_pows_hi", "delta_ts_off", "delta_ts_lo", "delta_ts_hi",
+        "delta_mid_off", "delta_mid_lo", "delta_mid_hi", "alpha_idx", "beta_idx")]
+
+
+NONE = (1 << 64) - 1
+AUX_POLY = 0xFF
+
+
+class R1cs:
+    """Constraint system in CSR form on the device (relations/constraint_satisfaction_problems/r1cs/r1cs.hpp:118-162)."""
+
+    def __init__(self, ctx, n, n_io, n_aux, row_ptr, col, coeff):
+        self.ctx, self.n, self.n_io, self.n_aux = ctx, int(n), int(n_io), int(n_aux)
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        col = np.ascontiguousarray(col, dtype=np.uint32)
+        coeff = _u64(coeff)
+        assert row_ptr.size == 3 * self.n + 1
+        h = C.c_void_p()
+        check(ctx.lib.rsg_r1cs_create(ctx.h, self.n, self.n_io, self.n_aux, _ptr(row_ptr), _ptr(col), _ptr(coeff), C.byref(h)))
+        self.h = h
+
+    def evaluate(self, assignment, evals=None):
+        evals = evals or RingVec(self.ctx, 9 * self.n)
+        check(self.ctx.lib.rsg_r1cs_evaluate(self.ctx.h, self.h, assignment.h, evals.h))
+        return evals
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.rsg_r1cs_destroy(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+
+class Groth16ProvingKey:
+    """groth16::proving_key (zk_proof_systems/groth16/groth16.hpp:10-47) with every CRS vector in ONE arena:
+    [ s_pows[lo:hi) | delta_ts[lo:hi) | delta_mid[lo:hi) | alpha | beta ].  rank/world shard each vector by term."""
+
+    def __init__(self, ctx, r1cs, rank=0, world=1):
+        self.ctx, self.r1cs = ctx, r1cs
+        n, aux = r1cs.n, r1cs.n_aux
+
+        def shard(total):
+            per = (total + world - 1) // world
+            return min(total, rank * per), min(total, (rank + 1) * per)
+
+        s_lo, s_hi = shard(n + 1)
+        t_lo, t_hi = shard(n + 1)
+        m_lo, m_hi = shard(aux)
+        L = Groth16Layout()
+        L.s_pows_off, L.s_pows_lo, L.s_pows_hi = 0, s_lo, s_hi
+        L.delta_ts_off, L.delta_ts_lo, L.delta_ts_hi = s_hi - s_lo, t_lo, t_hi
+        L.delta_mid_off, L.delta_mid_lo, L.delta_mid_hi = L.delta_ts_off + (t_hi - t_lo), m_lo, m_hi
+        end = L.delta_mid_off + (m_hi - m_lo)
+        L.alpha_idx, L.beta_idx = (end, end + 1) if rank == 0 else (NONE, NONE)
+        self.layout = L
+        self.n_elems = end + 2
+        self.crs = Crs(ctx, self.n_elems)
+        self.assignment = RingVec(ctx, r1cs.n_io + r1cs.n_aux)
+
+    def load(self, s_pows, delta_ts, delta_mid, alpha, beta):
+        """Full (unsharded) CRS vectors as host words -> this rank's shard of the arena."""
+        L = self.layout
+        self.crs.upload(s_pows[L.s_pows_lo:L.s_pows_hi], L.s_pows_off)
+        self.crs.upload(delta_ts[L.delta_ts_lo:L.delta_ts_hi], L.delta_ts_off)
+        if L.delta_mid_hi > L.delta_mid_lo:
+            self.crs.upload(delta_mid[L.delta_mid_lo:L.delta_mid_hi], L.delta_mid_off)
+        if L.alpha_idx != NONE:
+            self.crs.upload(alpha, L.alpha_idx)
+            self.crs.upload(beta, L.beta_idx)
+
+    def prove(self, h_assignment=None, aux_kind=None, to_host=True, d_proof=None):
+        """groth16::prover (groth16.tcc:69-115). h_assignment: host words [n_io+n_aux][L_R*N_R] (None = use what is
+        already resident in self.assignment). Returns (proof words [3][enc_words] or None, n_used[3])."""
+        ctx = self.ctx
+        out = np.empty((3, ctx.enc_words), dtype=np.uint64) if to_host else None
+        used = (C.c_size_t * 3)()
+        if h_assignment is not None:
+            h_assignment = _u64(h_assignment)
+        if aux_kind is not None:
+            aux_kind = np.ascontiguousarray(aux_kind, dtype=np.uint8)
+        check(ctx.lib.rsg_groth16_prove(ctx.h, self.r1cs.h, self.crs.h, C.byref(self.layout), self.assignment.h,
+                                        _ptr(h_assignment) if h_assignment is not None else None,
+                                        _ptr(aux_kind) if aux_kind is not None else None,
+                                        _ptr(out) if to_host else None, C.c_void_p(d_proof) if d_proof else None, used))
+        return out, [int(u) for u in used]
 
 
 class _Arena:

@@ -43,10 +43,14 @@ SIGNATURES = {
     "rsg_ringvec_is_zero_prefix": (_int, [_vp, _sz, _sz, _vp]),
     "rsg_inner_product": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _vp, _vp, _vp, C.POINTER(_sz)]),
     "rsg_enc_add": (_int, [_vp, _vp, _vp]),
-    "rsg_enc_sum": (_int, [_vp, _vp, _sz, _vp]),
+    "rsg_enc_sum": (_int, [_vp, _vp, _sz, _sz, _vp]),
     "rsg_witness_map": (_int, [_vp, _sz, _vp, _vp, _vp]),
     "rsg_interpolate": (_int, [_vp, _sz, _sz, _vp, _sz, _vp, _sz]),
     "rsg_vanishing": (_int, [_vp, _sz, _vp]),
+    "rsg_r1cs_create": (_int, [_vp, _sz, _sz, _sz, _vp, _vp, _vp, _pp]),
+    "rsg_r1cs_destroy": (None, [_vp]),
+    "rsg_r1cs_evaluate": (_int, [_vp, _vp, _vp, _vp]),
+    "rsg_groth16_prove": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rsg_batch_encode": (_int, [_vp, _vp, _sz, _vp]),
     "rsg_plain_to_ntt": (_int, [_vp, _vp, _sz, _vp]),
     "rsg_ntt": (_int, [_vp, _vp, _sz, _int, _sz, _int]),

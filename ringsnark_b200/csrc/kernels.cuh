@@ -175,10 +175,11 @@ __global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict
 }
 
 // out[w] = sum_s parts[s][w] mod Q_l(w): the modular-add kernel (after split-K or after the NCCL all-gather).
+// `n_enc` encodings per part (a whole proof = 3), parts stored back to back.
 __global__ void __launch_bounds__(256) k_enc_sum(const DevParams *__restrict__ P, const uint64_t *__restrict__ parts,
-                                                 uint32_t n_parts, uint64_t *__restrict__ out) {
+                                                 uint32_t n_parts, uint32_t n_enc, uint64_t *__restrict__ out) {
   const uint32_t N_E = P->N_E, L_E = P->L_E;
-  const size_t enc_words = (size_t)P->L_R * 2 * L_E * N_E;
+  const size_t enc_words = (size_t)n_enc * P->L_R * 2 * L_E * N_E;
   const size_t w = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (w >= enc_words) return;
   const uint32_t l = (uint32_t)((w / N_E) % L_E);

@@ -160,6 +160,11 @@ struct rsg_context {
   size_t cap_term = 0, cap_pidx = 0, cap_eidx = 0;
   uint64_t *d_out_scratch = nullptr;
   size_t cap_out_scratch = 0;
+  uint64_t *d_chunk = nullptr;      // per-chunk partial encodings of lincomb_terms
+  size_t cap_chunk = 0;
+  uint64_t *d_evals = nullptr, *d_wit = nullptr;   // prover scratch: 9n evaluations; [6n coeffs | n+1 H]
+  size_t cap_evals = 0, cap_wit = 0;
+  size_t pntt_budget_words = (size_t)4 << 27;      // 4 GiB of NTT-domain plaintexts per chunk
   uint8_t *d_flags = nullptr;
   size_t cap_flags = 0;
   size_t enc_words() const { return L_R * 2 * L_E * N_E; }
@@ -311,6 +316,7 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
   for (auto &kv : c->wit) { cudaFree(kv.second.d_Vinv); cudaFree(kv.second.d_T); }
   cudaFree(c->d_plain); cudaFree(c->d_pntt); cudaFree(c->d_partial);
   cudaFree(c->d_term); cudaFree(c->d_pidx); cudaFree(c->d_eidx); cudaFree(c->d_flags); cudaFree(c->d_out_scratch);
+  cudaFree(c->d_chunk); cudaFree(c->d_evals); cudaFree(c->d_wit);
   for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -550,16 +556,13 @@ extern "C" int rsg_ntt(rsg_context *c, uint64_t *d, size_t batch, int which, siz
 
 // ------------------------------------------------------------------------------------------------------------
 // lincomb
-static int launch_lincomb(rsg_context *c, const uint64_t *d_crs, const uint32_t *h_term, const uint32_t *h_pidx, size_t n_terms,
+// d_term / d_pidx: device arrays of n_terms entries (already uploaded).
+static int launch_lincomb(rsg_context *c, const uint64_t *d_crs, const uint32_t *d_term, const uint32_t *d_pidx, size_t n_terms,
                           const uint64_t *d_pntt, uint64_t *d_out) {
   int rc;
-  if ((rc = ensure(c, &c->d_term, &c->cap_term, std::max<size_t>(n_terms, 1024)))) return rc;
-  if ((rc = ensure(c, &c->d_pidx, &c->cap_pidx, std::max<size_t>(n_terms, 1024)))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(c->d_term, h_term, n_terms * 4, cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->d_pidx, h_pidx, n_terms * 4, cudaMemcpyHostToDevice, c->stream));
   const unsigned th = (unsigned)std::min<size_t>(256, c->N_E / 2);
   const unsigned gx = (unsigned)(c->N_E / 2 / th), gy = (unsigned)(c->L_R * c->L_E);
-  // split the term range so that the grid has >= ~4 blocks per SM; each split streams >= 8 terms
+  // split the term range so that the grid has >= ~8 blocks per SM; each split streams >= 8 terms
   const unsigned base_blocks = gx * gy;
   unsigned splits = std::max(1u, (148u * 8 + base_blocks - 1) / base_blocks);
   splits = (unsigned)std::min<size_t>(splits, (n_terms + 7) / 8);
@@ -573,14 +576,14 @@ static int launch_lincomb(rsg_context *c, const uint64_t *d_crs, const uint32_t 
   }
   {
     LaunchScope ls(c, "k_crs_lincomb");
-    k_crs_lincomb<4><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, c->d_term, c->d_pidx, (uint32_t)n_terms, tps,
-                                                                 d_pntt, d_partial);
+    k_crs_lincomb<4><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, d_term, d_pidx, (uint32_t)n_terms, tps, d_pntt,
+                                                                 d_partial);
   }
   CUDA_TRY(cudaGetLastError());
   if (splits > 1) {
     LaunchScope ls(c, "k_enc_sum");
     const size_t pairs = c->enc_words() / 2;
-    k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_partial, splits, d_out);
+    k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_partial, splits, 1, d_out);
     CUDA_TRY(cudaGetLastError());
   }
   return RSG_OK;
@@ -591,7 +594,97 @@ extern "C" int rsg_crs_lincomb(rsg_context *c, const uint64_t *d_crs, const uint
   if (!c) return fail(RSG_ERR_STATE, "context not set");
   if (!n_terms) return fail(RSG_ERR_ARG, "empty term list");
   std::lock_guard<std::mutex> g(c->mu);
-  return launch_lincomb(c, d_crs, h_term, h_pidx, n_terms, d_pntt, d_out);
+  int rc;
+  if ((rc = ensure(c, &c->d_term, &c->cap_term, std::max<size_t>(n_terms, 1024)))) return rc;
+  if ((rc = ensure(c, &c->d_pidx, &c->cap_pidx, std::max<size_t>(n_terms, 1024)))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(c->d_term, h_term, n_terms * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->d_pidx, h_pidx, n_terms * 4, cudaMemcpyHostToDevice, c->stream));
+  return launch_lincomb(c, d_crs, c->d_term, c->d_pidx, n_terms, d_pntt, d_out);
+}
+
+// One linear combination over an arbitrary term list: the engine behind rsg_inner_product and rsg_groth16_prove.
+struct TermSpec {
+  uint32_t crs_idx;            // which encoding of the arena
+  const uint64_t *ring_base;   // vector the coefficient lives in (nullptr for RSG_TERM_ONE)
+  uint32_t elem;               // element index inside ring_base
+};
+static int lincomb_terms(rsg_context *c, const uint64_t *d_crs, const std::vector<TermSpec> &terms, uint64_t *d_out) {
+  int rc;
+  if (terms.empty()) {
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, c->enc_words() * 8, c->stream));
+    return RSG_OK;
+  }
+  const size_t per_general = c->L_R * c->L_E * c->N_E;
+  const size_t max_general = std::max<size_t>(1, c->pntt_budget_words / per_general);
+  // cut into chunks holding <= max_general GENERAL terms each
+  struct Chunk { size_t t0, t1, g0, g1; };
+  std::vector<Chunk> chunks;
+  std::vector<uint32_t> term(terms.size()), pidx(terms.size()), eidx;
+  {
+    size_t t0 = 0, g0 = 0, g = 0;
+    for (size_t t = 0; t < terms.size(); t++) {
+      term[t] = terms[t].crs_idx;
+      if (terms[t].ring_base) {
+        if (g - g0 == max_general) { chunks.push_back({t0, t, g0, g}); t0 = t; g0 = g; }
+        pidx[t] = (uint32_t)(g - g0);
+        eidx.push_back(terms[t].elem);
+        g++;
+      } else {
+        pidx[t] = 0xFFFFFFFFu;
+      }
+    }
+    chunks.push_back({t0, terms.size(), g0, g});
+  }
+  const size_t G = eidx.size();
+  if ((rc = ensure(c, &c->d_term, &c->cap_term, std::max<size_t>(terms.size(), 1024)))) return rc;
+  if ((rc = ensure(c, &c->d_pidx, &c->cap_pidx, std::max<size_t>(terms.size(), 1024)))) return rc;
+  if ((rc = ensure(c, &c->d_eidx, &c->cap_eidx, std::max<size_t>(G, 1024)))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(c->d_term, term.data(), term.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->d_pidx, pidx.data(), pidx.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  if (G) CUDA_TRY(cudaMemcpyAsync(c->d_eidx, eidx.data(), G * 4, cudaMemcpyHostToDevice, c->stream));
+  const size_t max_g = std::min(G, max_general);
+  if (max_g) {
+    if ((rc = ensure(c, &c->d_plain, &c->cap_plain, max_g * c->L_R * c->N_E))) return rc;
+    if ((rc = ensure(c, &c->d_pntt, &c->cap_pntt, max_g * per_general))) return rc;
+  }
+  uint64_t *chunk_out = d_out;
+  if (chunks.size() > 1) {
+    if ((rc = ensure(c, &c->d_chunk, &c->cap_chunk, chunks.size() * c->enc_words()))) return rc;
+    chunk_out = c->d_chunk;
+  }
+  // pageable host staging above is consumed synchronously by cudaMemcpyAsync, so the vectors may die with this frame
+  for (size_t k = 0; k < chunks.size(); k++) {
+    const Chunk &ch = chunks[k];
+    // encode runs of consecutive general terms that share a source vector
+    size_t g = ch.g0;
+    size_t t = ch.t0;
+    while (g < ch.g1) {
+      while (!terms[t].ring_base) t++;
+      const uint64_t *base = terms[t].ring_base;
+      size_t run = 0, tt = t;
+      while (tt < ch.t1 && g + run < ch.g1) {
+        if (terms[tt].ring_base) {
+          if (terms[tt].ring_base != base) break;
+          run++;
+        }
+        tt++;
+      }
+      if ((rc = launch_encode(c, base, c->d_eidx + g, run, c->d_plain + (g - ch.g0) * c->L_R * c->N_E))) return rc;
+      g += run;
+      t = tt;
+    }
+    if ((rc = launch_lift_ntt(c, c->d_plain, ch.g1 - ch.g0, c->d_pntt))) return rc;
+    if ((rc = launch_lincomb(c, d_crs, c->d_term + ch.t0, c->d_pidx + ch.t0, ch.t1 - ch.t0, c->d_pntt,
+                             chunk_out + (chunks.size() > 1 ? k * c->enc_words() : 0))))
+      return rc;
+  }
+  if (chunks.size() > 1) {
+    LaunchScope ls(c, "k_enc_sum");
+    const size_t pairs = c->enc_words() / 2;
+    k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, chunk_out, (uint32_t)chunks.size(), 1, d_out);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return RSG_OK;
 }
 
 extern "C" int rsg_inner_product(rsg_context *c, const rsg_crs *crs, size_t crs_first, const rsg_ringvec *coeffs, size_t coeff_first,
@@ -600,45 +693,30 @@ extern "C" int rsg_inner_product(rsg_context *c, const rsg_crs *crs, size_t crs_
   if (crs_first + count > crs->n || coeff_first + count > coeffs->n) return fail(RSG_ERR_ARG, "range");
   std::lock_guard<std::mutex> g(c->mu);
   CUDA_TRY(cudaSetDevice(c->device));
-  std::vector<uint32_t> term, pidx, eidx;
+  std::vector<TermSpec> terms;
   for (size_t i = 0; i < count; i++) {
     if (h_tags[i] == RSG_TERM_SKIP) continue;
-    term.push_back((uint32_t)(crs_first + i));
-    if (h_tags[i] == RSG_TERM_ONE) pidx.push_back(0xFFFFFFFFu);
-    else { pidx.push_back((uint32_t)eidx.size()); eidx.push_back((uint32_t)(coeff_first + i)); }
+    terms.push_back({(uint32_t)(crs_first + i), h_tags[i] == RSG_TERM_ONE ? nullptr : coeffs->d, (uint32_t)(coeff_first + i)});
   }
-  if (n_used) *n_used = term.size();
+  if (n_used) *n_used = terms.size();
   int rc;
   uint64_t *out = d_out;
   if (!out) {
-    if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, c->enc_words()))) return rc;
+    if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 3 * c->enc_words()))) return rc;
     out = c->d_out_scratch;
   }
-  if (term.empty()) {
-    CUDA_TRY(cudaMemsetAsync(out, 0, c->enc_words() * 8, c->stream));
-  } else {
-    const size_t G = eidx.size();
-    if (G) {
-      if ((rc = ensure(c, &c->d_plain, &c->cap_plain, G * c->L_R * c->N_E))) return rc;
-      if ((rc = ensure(c, &c->d_pntt, &c->cap_pntt, G * c->L_R * c->L_E * c->N_E))) return rc;
-      if ((rc = ensure(c, &c->d_eidx, &c->cap_eidx, std::max<size_t>(G, 1024)))) return rc;
-      CUDA_TRY(cudaMemcpyAsync(c->d_eidx, eidx.data(), G * 4, cudaMemcpyHostToDevice, c->stream));
-      if ((rc = launch_encode(c, coeffs->d, c->d_eidx, G, c->d_plain))) return rc;
-      if ((rc = launch_lift_ntt(c, c->d_plain, G, c->d_pntt))) return rc;
-    }
-    if ((rc = launch_lincomb(c, crs->d, term.data(), pidx.data(), term.size(), c->d_pntt, out))) return rc;
-  }
+  if ((rc = lincomb_terms(c, crs->d, terms, out))) return rc;
   if (h_out) CUDA_TRY(cudaMemcpyAsync(h_out, out, c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));   // h_term/h_pidx staging vectors die with this frame
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
 }
 
-extern "C" int rsg_enc_sum(rsg_context *c, const uint64_t *d_parts, size_t parts, uint64_t *d_out) {
-  if (!c || !d_parts || !d_out || !parts) return fail(RSG_ERR_ARG, "null argument");
+extern "C" int rsg_enc_sum(rsg_context *c, const uint64_t *d_parts, size_t parts, size_t n_enc, uint64_t *d_out) {
+  if (!c || !d_parts || !d_out || !parts || !n_enc) return fail(RSG_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> g(c->mu);
   LaunchScope ls(c, "k_enc_sum");
-  const size_t pairs = c->enc_words() / 2;
-  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_parts, (uint32_t)parts, d_out);
+  const size_t pairs = n_enc * c->enc_words() / 2;
+  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_parts, (uint32_t)parts, (uint32_t)n_enc, d_out);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -652,7 +730,7 @@ extern "C" int rsg_enc_add(rsg_context *c, uint64_t *d_acc, const uint64_t *d_ot
   CUDA_TRY(cudaMemcpyAsync(c->d_partial + c->enc_words(), d_other, c->enc_words() * 8, cudaMemcpyDeviceToDevice, c->stream));
   LaunchScope ls(c, "k_enc_sum");
   const size_t pairs = c->enc_words() / 2;
-  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, c->d_partial, 2, d_acc);
+  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, c->d_partial, 2, 1, d_acc);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -759,11 +837,7 @@ extern "C" int rsg_vanishing(rsg_context *c, size_t n, uint64_t *h_Z) {
   return RSG_OK;
 }
 
-extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
-  if (!c || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
-  if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
-  std::lock_guard<std::mutex> g(c->mu);
-  CUDA_TRY(cudaSetDevice(c->device));
+static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, uint64_t *d_coeffs, uint64_t *d_H) {
   WitnessTables *wt;
   int rc = get_witness_tables(c, n, &wt);
   if (rc) return rc;
@@ -772,10 +846,10 @@ extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *eval
   if ((rc = ensure(c, &c->d_plain, &c->cap_plain, (3 * n) * W))) return rc;
   uint64_t *aA = c->d_plain, *aB = aA + n * W, *Ptop = aB + n * W;
   // evals order: A_mid,B_mid,C_mid,A_io,B_io,C_io,A_full,B_full,C_full ; coeffs order: A_io,B_io,C_io,A_mid,B_mid,C_mid
-  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, evals->d + 3 * n * W, coeffs->d, 3, false, "k_modmat_interp"))) return rc;
-  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, evals->d, coeffs->d + 3 * n * W, 3, false, "k_modmat_interp"))) return rc;
-  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, evals->d + 6 * n * W, aA, 2, false, "k_modmat_interp"))) return rc;
-  CUDA_TRY(cudaMemsetAsync(H->d, 0, (n + 1) * W * 8, c->stream));
+  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 3 * n * W, d_coeffs, 3, false, "k_modmat_interp"))) return rc;
+  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals, d_coeffs + 3 * n * W, 3, false, "k_modmat_interp"))) return rc;
+  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 6 * n * W, aA, 2, false, "k_modmat_interp"))) return rc;
+  CUDA_TRY(cudaMemsetAsync(d_H, 0, (n + 1) * W * 8, c->stream));
   if (n >= 2) {
     {
       dim3 grid((unsigned)((n - 1 + MM_ROWS - 1) / MM_ROWS), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), (unsigned)c->L_R);
@@ -784,7 +858,142 @@ extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *eval
                                                      (uint32_t)c->L_R);
       CUDA_TRY(cudaGetLastError());
     }
-    if ((rc = launch_modmat(c, wt->d_T, n - 1, n - 1, Ptop, H->d, 1, true, "k_modmat_divZ"))) return rc;
+    if ((rc = launch_modmat(c, wt->d_T, n - 1, n - 1, Ptop, d_H, 1, true, "k_modmat_divZ"))) return rc;
   }
+  return RSG_OK;
+}
+
+extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
+  if (!c || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
+  if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  return witness_map_dev(c, n, evals->d, coeffs->d, H->d);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// R1CS evaluation (the step before the hot path)
+struct rsg_r1cs {
+  rsg_context *ctx;
+  size_t n, n_io, n_aux;
+  uint32_t *d_row_ptr = nullptr, *d_col = nullptr;
+  uint64_t *d_coeff = nullptr;
+};
+extern "C" int rsg_r1cs_create(rsg_context *c, size_t n, size_t n_io, size_t n_aux, const uint32_t *h_row_ptr, const uint32_t *h_col,
+                               const uint64_t *h_coeff, rsg_r1cs **out) {
+  if (!c || !h_row_ptr || !out || !n) return fail(RSG_ERR_ARG, "null argument");
+  const size_t nnz = h_row_ptr[3 * n];
+  for (size_t t = 0; t < nnz; t++)
+    if (h_col[t] > n_io + n_aux) return fail(RSG_ERR_ARG, "variable index out of range");
+  CUDA_TRY(cudaSetDevice(c->device));
+  rsg_r1cs *r = new rsg_r1cs{c, n, n_io, n_aux};
+  void *v;
+  CUDA_TRY(cudaMalloc(&v, (3 * n + 1) * 4)); r->d_row_ptr = (uint32_t *)v;
+  CUDA_TRY(cudaMalloc(&v, std::max<size_t>(nnz, 1) * 4)); r->d_col = (uint32_t *)v;
+  CUDA_TRY(cudaMalloc(&v, std::max<size_t>(nnz, 1) * 8)); r->d_coeff = (uint64_t *)v;
+  CUDA_TRY(cudaMemcpy(r->d_row_ptr, h_row_ptr, (3 * n + 1) * 4, cudaMemcpyHostToDevice));
+  if (nnz) {
+    CUDA_TRY(cudaMemcpy(r->d_col, h_col, nnz * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->d_coeff, h_coeff, nnz * 8, cudaMemcpyHostToDevice));
+  }
+  *out = r;
+  return RSG_OK;
+}
+extern "C" void rsg_r1cs_destroy(rsg_r1cs *r) {
+  if (!r) return;
+  cudaStreamSynchronize(r->ctx->stream);
+  cudaFree(r->d_row_ptr); cudaFree(r->d_col); cudaFree(r->d_coeff);
+  delete r;
+}
+static int r1cs_eval_dev(rsg_context *c, const rsg_r1cs *r, const uint64_t *d_assign, uint64_t *d_evals) {
+  const unsigned sblocks = (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS);
+  dim3 grid((unsigned)r->n, 3, (unsigned)(c->L_R * sblocks));
+  LaunchScope ls(c, "k_r1cs_eval");
+  k_r1cs_eval<<<grid, MM_THREADS, 0, c->stream>>>(c->d_modq, r->d_row_ptr, r->d_col, r->d_coeff, (uint32_t)r->n, (uint32_t)r->n_io, d_assign,
+                                                  d_evals, (uint32_t)c->N_R, (uint32_t)c->L_R);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+extern "C" int rsg_r1cs_evaluate(rsg_context *c, const rsg_r1cs *r, const rsg_ringvec *assignment, rsg_ringvec *evals) {
+  if (!c || !r || !assignment || !evals) return fail(RSG_ERR_ARG, "null argument");
+  if (assignment->n < r->n_io + r->n_aux || evals->n < 9 * r->n) return fail(RSG_ERR_ARG, "vector sizes");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  return r1cs_eval_dev(c, r, assignment->d, evals->d);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// groth16::prover (groth16.tcc:69-115) in one call.  A = <s_pows, A_io> + <s_pows, A_mid> + alpha etc. are each ONE
+// linear combination over the concatenated term lists: modular addition is associative and every result canonical,
+// so the words equal those of the reference's inner_product / operator+= sequence.
+extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg_crs *crs, const rsg_groth16_layout *L,
+                                 rsg_ringvec *assignment, const uint64_t *h_assignment, const uint8_t *h_aux_kind, uint64_t *h_proof,
+                                 uint64_t *d_proof, size_t *n_used) {
+  if (!c || !r1cs || !crs || !L || !assignment) return fail(RSG_ERR_ARG, "null argument");
+  const size_t n = r1cs->n, n_io = r1cs->n_io, n_aux = r1cs->n_aux, W = c->ring_words();
+  if (assignment->n < n_io + n_aux) return fail(RSG_ERR_ARG, "assignment too short");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc;
+  if (h_assignment)
+    CUDA_TRY(cudaMemcpyAsync(assignment->d, h_assignment, (n_io + n_aux) * W * 8, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = ensure(c, &c->d_evals, &c->cap_evals, 9 * n * W))) return rc;
+  if ((rc = ensure(c, &c->d_wit, &c->cap_wit, (7 * n + 1) * W))) return rc;
+  uint64_t *coeffs = c->d_wit, *H = c->d_wit + 6 * n * W;
+  if ((rc = r1cs_eval_dev(c, r1cs, assignment->d, c->d_evals))) return rc;
+  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H))) return rc;
+  // SealPoly::is_zero prefix flags of every coefficient the prover feeds to inner_product: [6n coeffs | n+1 H | aux]
+  const size_t n_flags = 7 * n + 1 + n_aux;
+  if ((rc = ensure(c, &c->d_flags, &c->cap_flags, n_flags))) return rc;
+  {
+    LaunchScope ls(c, "k_is_zero_prefix");
+    k_is_zero_prefix<<<(unsigned)(7 * n + 1), 256, 0, c->stream>>>(c->d_wit, (uint32_t)W, c->d_flags);
+  }
+  if (n_aux) {
+    LaunchScope ls(c, "k_is_zero_prefix");
+    k_is_zero_prefix<<<(unsigned)n_aux, 256, 0, c->stream>>>(assignment->d + n_io * W, (uint32_t)W, c->d_flags + 7 * n + 1);
+  }
+  CUDA_TRY(cudaGetLastError());
+  std::vector<uint8_t> flags(n_flags);
+  CUDA_TRY(cudaMemcpyAsync(flags.data(), c->d_flags, n_flags, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+
+  uint64_t *out = d_proof;
+  if (!out) {
+    if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 3 * c->enc_words()))) return rc;
+    out = c->d_out_scratch;
+  }
+  const size_t NONE = (size_t)-1;
+  auto add_vec = [&](std::vector<TermSpec> &terms, size_t off, size_t lo, size_t hi, size_t limit, const uint64_t *base, size_t elem0,
+                     const uint8_t *zero_flag) {
+    for (size_t i = lo; i < std::min(hi, limit); i++)
+      if (!zero_flag[i]) terms.push_back({(uint32_t)(off + i - lo), base, (uint32_t)(elem0 + i)});
+  };
+  // coeffs order: A_io, B_io, C_io, A_mid, B_mid, C_mid
+  std::vector<TermSpec> tA, tB, tC;
+  add_vec(tA, L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 0, flags.data());
+  add_vec(tA, L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 3 * n, flags.data() + 3 * n);
+  if (L->alpha_idx != NONE) tA.push_back({(uint32_t)L->alpha_idx, nullptr, 0});
+  add_vec(tB, L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, n, flags.data() + n);
+  add_vec(tB, L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 4 * n, flags.data() + 4 * n);
+  if (L->beta_idx != NONE) tB.push_back({(uint32_t)L->beta_idx, nullptr, 0});
+  add_vec(tC, L->delta_ts_off, L->delta_ts_lo, L->delta_ts_hi, n + 1, H, 0, flags.data() + 6 * n);
+  for (size_t i = L->delta_mid_lo; i < std::min(L->delta_mid_hi, n_aux); i++) {
+    const uint8_t kind = h_aux_kind ? h_aux_kind[i] : (uint8_t)RSG_AUX_POLY;
+    const uint32_t ci = (uint32_t)(L->delta_mid_off + i - L->delta_mid_lo);
+    if (kind == RSG_AUX_POLY) {
+      if (!flags[7 * n + 1 + i]) tC.push_back({ci, assignment->d, (uint32_t)(n_io + i)});
+    } else if (kind == RSG_TERM_ONE) {
+      tC.push_back({ci, nullptr, 0});
+    } else if (kind == RSG_TERM_GENERAL) {
+      tC.push_back({ci, assignment->d, (uint32_t)(n_io + i)});
+    }
+  }
+  if (n_used) { n_used[0] = tA.size(); n_used[1] = tB.size(); n_used[2] = tC.size(); }
+  if ((rc = lincomb_terms(c, crs->d, tA, out))) return rc;
+  if ((rc = lincomb_terms(c, crs->d, tB, out + c->enc_words()))) return rc;
+  if ((rc = lincomb_terms(c, crs->d, tC, out + 2 * c->enc_words()))) return rc;
+  if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 3 * c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
 }

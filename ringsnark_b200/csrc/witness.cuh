@@ -101,4 +101,43 @@ __global__ void __launch_bounds__(MM_THREADS) k_conv_top(const ModConst *__restr
     if (i0 + r < n - 1) Pp[(size_t)(i0 + r) * W] = acc[r].reduce(m);
 }
 
+
+// linear_combination::evaluate (ringsnark/relations/variable.tcc:246-254) for all 3n linear combinations and the
+// three assignments the witness map uses (r1cs_to_qrp.tcc:167-219): "mid" (primary inputs zeroed), "io" (auxiliary
+// inputs zeroed), "full".  The constant wire (index 0) contributes its coefficient under ALL three assignments, as
+// the reference does.  Coefficients are uint64 scalars reduced mod q_j
+// (multiply_poly_scalar_coeffmod semantics).  CSR rows r = m*n + i for matrix m in {A,B,C}.
+//   evals element ((variant*3 + m)*n + i), variant 0 = mid, 1 = io, 2 = full.
+// grid (n, 3, L_R * ceil(N_R/MM_THREADS))
+__global__ void __launch_bounds__(MM_THREADS) k_r1cs_eval(const ModConst *__restrict__ mods, const uint32_t *__restrict__ row_ptr,
+                                                          const uint32_t *__restrict__ col, const uint64_t *__restrict__ coeff,
+                                                          uint32_t n, uint32_t n_io, const uint64_t *__restrict__ assign,
+                                                          uint64_t *__restrict__ evals, uint32_t N_R, uint32_t L_R) {
+  const uint32_t i = blockIdx.x, m = blockIdx.y;
+  const uint32_t sblocks = (N_R + MM_THREADS - 1) / MM_THREADS;
+  const uint32_t limb = blockIdx.z / sblocks, slot = (blockIdx.z - limb * sblocks) * MM_THREADS + threadIdx.x;
+  if (slot >= N_R) return;
+  const size_t W = (size_t)N_R * L_R;
+  const ModConst mc = mods[limb];
+  const uint32_t r = m * n + i;
+  Acc192 a_mid, a_io, a_full;
+  a_mid.clear(); a_io.clear(); a_full.clear();
+  for (uint32_t t = row_ptr[r]; t < row_ptr[r + 1]; t++) {
+    const uint32_t idx = col[t];
+    const uint64_t c = reduce64(coeff[t], mc);
+    if (idx == 0) {
+      a_mid.add(c); a_io.add(c); a_full.add(c);
+    } else {
+      const uint64_t x = assign[(size_t)(idx - 1) * W + (size_t)limb * N_R + slot];
+      a_full.mac(c, x);
+      if (idx - 1 < n_io) a_io.mac(c, x);
+      else a_mid.mac(c, x);
+    }
+  }
+  const size_t o = (size_t)limb * N_R + slot;
+  evals[((size_t)(0 * 3 + m) * n + i) * W + o] = a_mid.reduce(mc);
+  evals[((size_t)(1 * 3 + m) * n + i) * W + o] = a_io.reduce(mc);
+  evals[((size_t)(2 * 3 + m) * n + i) * W + o] = a_full.reduce(mc);
+}
+
 }  // namespace rsg
