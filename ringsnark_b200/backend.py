@@ -162,29 +162,38 @@ class R1cs:
             pass
 
 
+def groth16_shard_layout(n, n_aux, rank=0, world=1):
+    """Term sharding of the ringGroth16 CRS across `world` ranks (pure host logic, no GPU needed).
+    s_pows[0..n], delta_ts[0..n] and delta_mid[0..n_aux) are each cut into `world` contiguous term ranges; rank r's
+    arena is [ s_pows[lo:hi) | delta_ts[lo:hi) | delta_mid[lo:hi) | alpha | beta ]; only rank 0 adds alpha and beta
+    (groth16.tcc:95,103).  Returns a dict with the rsg_groth16_layout fields plus n_elems."""
+    def shard(total):
+        per = (total + world - 1) // world
+        return min(total, rank * per), min(total, (rank + 1) * per)
+
+    s_lo, s_hi = shard(n + 1)
+    t_lo, t_hi = shard(n + 1)
+    m_lo, m_hi = shard(n_aux)
+    d = dict(s_pows_off=0, s_pows_lo=s_lo, s_pows_hi=s_hi)
+    d.update(delta_ts_off=s_hi - s_lo, delta_ts_lo=t_lo, delta_ts_hi=t_hi)
+    d.update(delta_mid_off=d["delta_ts_off"] + (t_hi - t_lo), delta_mid_lo=m_lo, delta_mid_hi=m_hi)
+    end = d["delta_mid_off"] + (m_hi - m_lo)
+    d.update(alpha_idx=end if rank == 0 else NONE, beta_idx=end + 1 if rank == 0 else NONE, n_elems=end + 2)
+    return d
+
+
 class Groth16ProvingKey:
     """groth16::proving_key (zk_proof_systems/groth16/groth16.hpp:10-47) with every CRS vector in ONE arena:
     [ s_pows[lo:hi) | delta_ts[lo:hi) | delta_mid[lo:hi) | alpha | beta ].  rank/world shard each vector by term."""
 
     def __init__(self, ctx, r1cs, rank=0, world=1):
         self.ctx, self.r1cs = ctx, r1cs
-        n, aux = r1cs.n, r1cs.n_aux
-
-        def shard(total):
-            per = (total + world - 1) // world
-            return min(total, rank * per), min(total, (rank + 1) * per)
-
-        s_lo, s_hi = shard(n + 1)
-        t_lo, t_hi = shard(n + 1)
-        m_lo, m_hi = shard(aux)
+        d = groth16_shard_layout(r1cs.n, r1cs.n_aux, rank, world)
         L = Groth16Layout()
-        L.s_pows_off, L.s_pows_lo, L.s_pows_hi = 0, s_lo, s_hi
-        L.delta_ts_off, L.delta_ts_lo, L.delta_ts_hi = s_hi - s_lo, t_lo, t_hi
-        L.delta_mid_off, L.delta_mid_lo, L.delta_mid_hi = L.delta_ts_off + (t_hi - t_lo), m_lo, m_hi
-        end = L.delta_mid_off + (m_hi - m_lo)
-        L.alpha_idx, L.beta_idx = (end, end + 1) if rank == 0 else (NONE, NONE)
+        for k, _ in Groth16Layout._fields_:
+            setattr(L, k, d[k])
         self.layout = L
-        self.n_elems = end + 2
+        self.n_elems = d["n_elems"]
         self.crs = Crs(ctx, self.n_elems)
         self.assignment = RingVec(ctx, r1cs.n_io + r1cs.n_aux)
 

@@ -1,0 +1,91 @@
+"""world_size-2 (and 3) host-side logic of the N-GPU path on CPU with the gloo backend: the term sharding of the
+proving key partitions every CRS vector exactly, and partial proofs (computed here by the C oracle, standing in for
+each rank's GPU) all-gathered and summed with modular addition equal the reference's proof."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, golden, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import oracle_lib as O
+    from rsgv import Case
+    from ringsnark_b200.backend import NONE, groth16_shard_layout
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = Case(golden)
+        n, aux = case.n, case.aux
+        L = groth16_shard_layout(n, aux, rank, world)
+        # (1) layouts of all ranks partition the term ranges
+        mine = torch.tensor([L["s_pows_lo"], L["s_pows_hi"], L["delta_ts_lo"], L["delta_ts_hi"], L["delta_mid_lo"],
+                             L["delta_mid_hi"], int(L["alpha_idx"] != NONE)], dtype=torch.int64)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        allv = torch.stack(allv).numpy()
+        for lo_c, hi_c, total in ((0, 1, n + 1), (2, 3, n + 1), (4, 5, aux)):
+            assert allv[0, lo_c] == 0 and allv[-1, hi_c] == total
+            assert all(allv[r, hi_c] == allv[r + 1, lo_c] for r in range(world - 1))
+        assert allv[:, 6].sum() == 1 and allv[0, 6] == 1
+        # (2) partial proofs from the rank's term ranges; all-gather; modular add == reference proof
+        s_pows, _ = case.enc("crs_s_pows")
+        delta_ts, _ = case.enc("crs_delta_ts")
+        delta_mid, _ = case.enc("crs_delta_mid")
+        alpha, _ = case.enc("crs_alpha")
+        beta, _ = case.enc("crs_beta")
+
+        def part(crs, name, lo, hi, limit):
+            words, tag, scalar = case.ring(name)
+            tags = O.term_tags(words, tag, scalar)
+            hi = min(hi, limit)
+            if hi <= lo:
+                return np.zeros(case.enc_words, dtype=np.uint64)
+            out, _ = O.inner_product(crs[lo:hi], words[lo:hi], tags[lo:hi], case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)
+            return out
+
+        def add(a, b):
+            return O.enc_add(a, b, case.L_R, case.N_E, case.L_E, case.Q)
+
+        A = add(part(s_pows, "wit_A_io", L["s_pows_lo"], L["s_pows_hi"], n), part(s_pows, "wit_A_mid", L["s_pows_lo"], L["s_pows_hi"], n))
+        B = add(part(s_pows, "wit_B_io", L["s_pows_lo"], L["s_pows_hi"], n), part(s_pows, "wit_B_mid", L["s_pows_lo"], L["s_pows_hi"], n))
+        Cc = add(part(delta_ts, "wit_H", L["delta_ts_lo"], L["delta_ts_hi"], n + 1),
+                 part(delta_mid, "auxiliary_input", L["delta_mid_lo"], L["delta_mid_hi"], aux))
+        if L["alpha_idx"] != NONE:
+            A, B = add(A, alpha[0]), add(B, beta[0])
+        mine = torch.from_numpy(np.stack([A, B, Cc]).view(np.int64))
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        total = None
+        for g in gathered:
+            g = g.numpy().view(np.uint64)
+            total = g if total is None else np.stack([add(total[e], g[e]) for e in range(3)])
+        ok = np.array_equal(total, case.enc("proof")[0])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_prover_gloo(world):
+    golden = os.path.join(HERE, "golden", "tiny_quirks.rsgv")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, golden, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(world))
+    assert res == [(r, True) for r in range(world)]
