@@ -87,8 +87,15 @@ int rsg_ringvec_is_zero_prefix(const rsg_ringvec *v, size_t first, size_t count,
 int rsg_inner_product(rsg_context *ctx, const rsg_crs *crs, size_t crs_first, const rsg_ringvec *coeffs,
                       size_t coeff_first, size_t count, const uint8_t *h_tags, uint64_t *h_out, uint64_t *d_out,
                       size_t *n_used);
-/* EncodingElem::operator+= for non-empty operands (seal_ring.tcc:479-507 -> evaluator.cpp:217-231). */
+/* Same with explicit term lists (iterator ranges that are not contiguous in their arenas): term i multiplies
+ * crs[h_crs_idx[i]] by coeffs[h_coeff_idx[i]]. */
+int rsg_inner_product_idx(rsg_context *ctx, const rsg_crs *crs, const uint32_t *h_crs_idx, const rsg_ringvec *coeffs,
+                          const uint32_t *h_coeff_idx, size_t count, const uint8_t *h_tags, uint64_t *h_out,
+                          uint64_t *d_out, size_t *n_used);
+/* EncodingElem::operator+= for non-empty operands (seal_ring.tcc:479-507 -> evaluator.cpp:217-231): acc += other. */
 int rsg_enc_add(rsg_context *ctx, uint64_t *d_acc, const uint64_t *d_other);
+/* Copy-construct encodings inside / between arenas (EncodingElem's value semantics, seal_ring.hpp:245-247). */
+int rsg_crs_copy(rsg_crs *dst, size_t dst_first, const rsg_crs *src, size_t src_first, size_t count);
 /* out = sum of `parts` blocks stored back to back, each block = n_enc encodings (n_enc = 3: a whole proof):
  * the modular-add kernel that follows the NCCL all-gather (modular addition is not an NCCL reduction). */
 int rsg_enc_sum(rsg_context *ctx, const uint64_t *d_parts, size_t parts, size_t n_enc, uint64_t *d_out);
@@ -101,6 +108,11 @@ int rsg_enc_sum(rsg_context *ctx, const uint64_t *d_parts, size_t parts, size_t 
  * Interpolation on the domain {0..n-1} (util/polynomials.tcc:9-43), product and exact division by the monic
  * Z (util/polynomials.tcc:61-81, util/evaluation_domain.tcc:53-84); all slot-parallel on the GPU. */
 int rsg_witness_map(rsg_context *ctx, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H);
+/* The zero-knowledge variant rinocchio::prover calls (rinocchio.tcc:88-93, r1cs_to_qrp.tcc:225-235):
+ * h_d = 3 ring elements d1, d2, d3 (host words, [3][L_R][N_R]); H[i] += d2*A[i] + d1*B[i] (i < n), H[0] -= d3,
+ * H[i] += d1*d2*Z[i] (i <= n) with A, B the interpolants of the FULL assignment.  h_d == NULL is rsg_witness_map. */
+int rsg_witness_map_zk(rsg_context *ctx, size_t n, const rsg_ringvec *evals, const uint64_t *h_d, rsg_ringvec *coeffs,
+                       rsg_ringvec *H);
 /* util/polynomials.tcc:9-43 on its own: vectors of n ring elements; `batch` vectors back to back. */
 int rsg_interpolate(rsg_context *ctx, size_t n, size_t batch, const rsg_ringvec *y, size_t y_first, rsg_ringvec *out,
                     size_t out_first);

@@ -1,0 +1,226 @@
+// Drop-in harness: instantiates the UNMODIFIED reference templates (ringsnark/zk_proof_systems, reductions, relations,
+// util under /root/reference) twice in one process --
+//   (1) over ringsnark::seal::{RingElem, EncodingElem}        (the reference's SEAL CPU backend), and
+//   (2) over ringsnark::seal_gpu::{RingElem, EncodingElem}    (ringsnark_b200/cpp, librsgpu.so on the B200)
+// on the same circuit, the same assignment, the same CRS and the same prover randomness, and compares the proofs
+// word for word; then lets the reference verifier judge both proofs (instantiated over (2) for the GPU proof, over (1)
+// for the reference's): the verdicts must agree.  The reference verifier is not always right about honest proofs
+// (circuits that touch the constant wire; tiny parameter sets can also run out of noise budget), which
+// is why "same verdict as the reference" is the criterion and acceptance is asserted per case in tests/.
+// Built by oracle/Makefile.ref into oracle/_ref/dropin_harness.  TEST INFRASTRUCTURE (it links the reference); it is
+// the evidence that the backend is a drop-in, not part of the product.
+//
+//   dropin_harness <case> [seed] [groth16|rinocchio|both]      -> one JSON line on stdout, exit 0 iff all checks pass
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+
+#include <ringsnark/seal/seal_ring.hpp>
+#include <ringsnark/seal/seal_util.hpp>
+#include <ringsnark/seal_gpu/seal_ring.hpp>
+#include <ringsnark/zk_proof_systems/groth16/groth16.hpp>
+#include <ringsnark/zk_proof_systems/rinocchio/rinocchio.hpp>
+
+#include "cases.hpp"
+#include "poly_arith.h"
+#include "seal/seal.h"
+
+typedef ringsnark::seal::RingElem R;
+typedef ringsnark::seal::EncodingElem E;
+typedef ringsnark::seal_gpu::RingElem GR;
+typedef ringsnark::seal_gpu::EncodingElem GE;
+using std::vector;
+
+struct RingAccess : R {
+  static void seed(uint64_t s) {
+    prng = seal::Blake2xbPRNGFactory(seal::prng_seed_type{s, 0x52494e47, 0, 0, 0, 0, 0, 0}).create();
+  }
+};
+struct EncAccess : E {
+  static const vector<seal::Ciphertext> &cts(const E &e) { return e.*(&EncAccess::ciphertexts); }
+};
+
+static seal::SEALContext *g_ring = nullptr;
+
+static R make_elem(int kind) {
+  R r = R::random_element();
+  if (kind == 1) {
+    auto &p = r.get_poly();
+    size_t L = p.get_coeff_modulus_count(), N = p.get_coeff_count();
+    vector<uint64_t> w(L * N);
+    for (size_t j = 0; j < L; j++) {
+      auto limb = p.get_limb(j);
+      for (size_t i = 0; i < N; i++) w[j * N + i] = limb[i];
+    }
+    for (size_t i = 0; i < L * N / 8 + 1; i++) w[i] = 0;
+    w[L * N - 1] |= 1;
+    r = R(polytools::SealPoly(*g_ring, w, &g_ring->first_parms_id()));
+  }
+  return r;
+}
+static GR make_elem_gpu(int kind) { return GR(make_elem(kind)); }
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// words of a reference encoding, [L_R][2][L_E][N_E]; empty / size-0 ciphertexts give zeros
+static vector<uint64_t> flatten(const E &e, size_t L_R, size_t L_E, size_t N_E) {
+  const size_t per = 2 * L_E * N_E;
+  vector<uint64_t> w(L_R * per, 0);
+  if (e.is_empty()) return w;
+  const auto &cts = EncAccess::cts(e);
+  for (size_t j = 0; j < L_R; j++)
+    if (cts[j].size() == 2) memcpy(w.data() + j * per, cts[j].data(), per * 8);
+  return w;
+}
+static vector<E> to_ref(const vector<GE> &v) {
+  vector<E> out;
+  out.reserve(v.size());
+  for (const auto &e : v) out.push_back(e.to_seal());
+  return out;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    std::cerr << "usage: dropin_harness <case> [seed] [groth16|rinocchio|both]\n";
+    return 2;
+  }
+  try {
+    const std::string name = argv[1];
+    const uint64_t seed = argc >= 3 ? std::stoull(argv[2]) : 0xB200;
+    const std::string which = argc >= 4 ? argv[3] : "both";
+    std::streambuf *cout_buf = std::cout.rdbuf(std::cerr.rdbuf());   // the provers chat on stdout
+
+    const cases::CaseSpec spec = cases::get_case(name);
+    g_ring = new seal::SEALContext(cases::make_ring_context(spec));
+    if (!g_ring->parameters_set()) throw std::invalid_argument(std::string("ring context: ") + g_ring->parameter_error_message());
+    R::set_context(*g_ring);
+    E::set_contexts(cases::make_enc_contexts(spec, *g_ring, seed));
+    GR::set_context(*g_ring);             // shares the ring context
+    GE::set_contexts(E::get_contexts());  // shares the seeded encoding contexts, creates the GPU context
+
+    // the same circuit and assignment for both ring types (same wiring seed, same element stream)
+    ringsnark::r1cs_constraint_system<R> cs;
+    ringsnark::r1cs_constraint_system<GR> gcs;
+    vector<R> assignment;
+    vector<GR> gassignment;
+    RingAccess::seed(seed);
+    cases::build_circuit<R, ringsnark::r1cs_constraint_system<R>, ringsnark::r1cs_constraint<R>, ringsnark::linear_combination<R>,
+                         ringsnark::variable<R>>(spec, seed, cs, assignment, &make_elem);
+    RingAccess::seed(seed);
+    cases::build_circuit<GR, ringsnark::r1cs_constraint_system<GR>, ringsnark::r1cs_constraint<GR>, ringsnark::linear_combination<GR>,
+                         ringsnark::variable<GR>>(spec, seed, gcs, gassignment, &make_elem_gpu);
+    vector<R> primary(assignment.begin(), assignment.begin() + spec.io), auxiliary(assignment.begin() + spec.io, assignment.end());
+    vector<GR> gprimary(gassignment.begin(), gassignment.begin() + spec.io), gauxiliary(gassignment.begin() + spec.io, gassignment.end());
+    const bool sat = cs.is_satisfied(primary, auxiliary);
+
+    auto ep = E::get_contexts()[0].first_context_data()->parms();
+    const size_t L_R = g_ring->first_context_data()->parms().coeff_modulus().size();
+    const size_t L_E = ep.coeff_modulus().size(), N_E = ep.poly_modulus_degree();
+
+    std::ostringstream js;
+    js << "{\"case\":\"" << name << "\",\"seed\":" << seed << ",\"n\":" << spec.n << ",\"r1cs_satisfied\":" << (sat ? "true" : "false");
+    bool all_ok = true;
+
+    if (which == "groth16" || which == "both") {
+      namespace G = ringsnark::groth16;
+      RingAccess::seed(seed + 1);
+      double t0 = now_s();
+      const auto kp = G::generator<GR, GE>(gcs);   // SEAL keygen/encode, ciphertexts land in HBM arenas
+      const double t_gen = now_s() - t0;
+      // the same CRS for the reference prover
+      G::proving_key<R, E> pk_ref(cs, kp.pk.alpha.to_seal(), kp.pk.beta.to_seal(), to_ref(kp.pk.s_pows), to_ref(kp.pk.gamma_io),
+                                  to_ref(kp.pk.delta_mid), to_ref(kp.pk.delta_ts), nullptr);
+      t0 = now_s();
+      const auto proof_ref = G::prover<R, E>(pk_ref, primary, auxiliary);
+      const double t_ref = now_s() - t0;
+      (void)G::prover<GR, GE>(kp.pk, gprimary, gauxiliary);   // warm-up: per-n witness tables, scratch allocations
+      t0 = now_s();
+      const auto proof_gpu = G::prover<GR, GE>(kp.pk, gprimary, gauxiliary);
+      const double t_gpu = now_s() - t0;
+      const bool eqA = flatten(proof_ref.A, L_R, L_E, N_E) == proof_gpu.A.words();
+      const bool eqB = flatten(proof_ref.B, L_R, L_E, N_E) == proof_gpu.B.words();
+      const bool eqC = flatten(proof_ref.C, L_R, L_E, N_E) == proof_gpu.C.words();
+      bool verified = false;
+      try {
+        verified = G::verifier<GR, GE>(kp.vk, gprimary, proof_gpu);
+      } catch (const std::exception &ex) {
+        std::cerr << "verifier threw: " << ex.what() << std::endl;
+      }
+      // the reference's own verdict on the reference's own proof (same key material): the GPU path must get the same one
+      bool verified_ref = false;
+      try {
+        G::verification_key<R, E> vk_ref(pk_ref, kp.vk.s.host(), kp.vk.alpha.host(), kp.vk.beta.host(), kp.vk.gamma.host(),
+                                         kp.vk.delta.host(), kp.vk.sk_enc);
+        verified_ref = G::verifier<R, E>(vk_ref, primary, proof_ref);
+      } catch (const std::exception &ex) {
+        std::cerr << "reference verifier threw: " << ex.what() << std::endl;
+      }
+      const bool ok = eqA && eqB && eqC && verified == verified_ref;
+      all_ok = all_ok && ok;
+      js << ",\"groth16\":{\"bit_exact\":[" << eqA << "," << eqB << "," << eqC << "],\"verified\":" << (verified ? "true" : "false")
+         << ",\"verified_ref\":" << (verified_ref ? "true" : "false") << ",\"generator_s\":" << t_gen << ",\"prover_ref_s\":" << t_ref
+         << ",\"prover_gpu_s\":" << t_gpu << ",\"ok\":" << (ok ? "true" : "false") << "}";
+    }
+
+    if (which == "rinocchio" || which == "both") {
+      namespace P = ringsnark::rinocchio;
+      RingAccess::seed(seed + 2);
+      double t0 = now_s();
+      const auto kp = P::generator<GR, GE>(gcs);
+      const double t_gen = now_s() - t0;
+      const auto &k = kp.pk;
+      P::proving_key<R, E> pk_ref(cs, to_ref(k.s_pows), to_ref(k.alpha_s_pows), to_ref(k.beta_prods), k.beta_rv_ts.to_seal(),
+                                  k.beta_rw_ts.to_seal(), k.beta_ry_ts.to_seal(), k.alpha_rv_ts.to_seal(), k.alpha_rw_ts.to_seal(),
+                                  k.alpha_ry_ts.to_seal(), to_ref(k.rv_vs), to_ref(k.rw_ws), to_ref(k.ry_ys), nullptr);
+      // identical zero-knowledge randomness d1, d2, d3 for both provers: same PRNG seed before each run
+      RingAccess::seed(seed + 3);
+      t0 = now_s();
+      const auto proof_ref = P::prover<R, E>(pk_ref, primary, auxiliary);
+      const double t_ref = now_s() - t0;
+      RingAccess::seed(seed + 3);
+      (void)P::prover<GR, GE>(kp.pk, gprimary, gauxiliary);
+      RingAccess::seed(seed + 3);
+      t0 = now_s();
+      const auto proof_gpu = P::prover<GR, GE>(kp.pk, gprimary, gauxiliary);
+      const double t_gpu = now_s() - t0;
+      const E *re[9] = {&proof_ref.A, &proof_ref.A_prime, &proof_ref.B, &proof_ref.B_prime, &proof_ref.C,
+                        &proof_ref.C_prime, &proof_ref.D, &proof_ref.D_prime, &proof_ref.F};
+      const GE *ge[9] = {&proof_gpu.A, &proof_gpu.A_prime, &proof_gpu.B, &proof_gpu.B_prime, &proof_gpu.C,
+                         &proof_gpu.C_prime, &proof_gpu.D, &proof_gpu.D_prime, &proof_gpu.F};
+      bool eq_all = true;
+      js << ",\"rinocchio\":{\"bit_exact\":[";
+      for (int i = 0; i < 9; i++) {
+        const bool eq = flatten(*re[i], L_R, L_E, N_E) == ge[i]->words() && re[i]->is_empty() == ge[i]->is_empty();
+        eq_all = eq_all && eq;
+        js << (i ? "," : "") << eq;
+      }
+      bool verified = false;
+      try {
+        verified = P::verifier<GR, GE>(kp.vk, gprimary, proof_gpu);
+      } catch (const std::exception &ex) {
+        std::cerr << "verifier threw: " << ex.what() << std::endl;
+      }
+      bool verified_ref = false;
+      try {
+        P::verification_key<R, E> vk_ref(pk_ref, kp.vk.s.host(), kp.vk.alpha.host(), kp.vk.beta.host(), kp.vk.r_v.host(),
+                                         kp.vk.r_w.host(), kp.vk.r_y.host(), kp.vk.sk_enc);
+        verified_ref = P::verifier<R, E>(vk_ref, primary, proof_ref);
+      } catch (const std::exception &ex) {
+        std::cerr << "reference verifier threw: " << ex.what() << std::endl;
+      }
+      const bool ok = eq_all && verified == verified_ref;
+      all_ok = all_ok && ok;
+      js << "],\"verified\":" << (verified ? "true" : "false") << ",\"verified_ref\":" << (verified_ref ? "true" : "false")
+         << ",\"generator_s\":" << t_gen << ",\"prover_ref_s\":" << t_ref << ",\"prover_gpu_s\":" << t_gpu << ",\"ok\":" << (ok ? "true" : "false")
+         << "}";
+    }
+    js << ",\"ok\":" << (all_ok ? "true" : "false") << "}";
+    std::cout.rdbuf(cout_buf);
+    std::cout << js.str() << std::endl;
+    return all_ok ? 0 : 1;
+  } catch (const std::exception &ex) {
+    std::cerr << "dropin_harness: " << ex.what() << std::endl;
+    return 3;
+  }
+}

@@ -188,6 +188,16 @@ int ro_is_equal_quirk(const uint64_t *a, const uint64_t *b, size_t size) { retur
  * Per general term and ring limb j: batch-encode limb j mod q_j (a11), lift + NTT (a12/a13), dyadic product with
  * both ciphertext polynomials (a14, util/polyarithsmallmod.cpp:226-284), modular add (a15, evaluator.cpp:217-231).
  */
+/* SEAL refuses "transparent" results (c1 identically zero, ciphertext.h:451-456; evaluator.cpp:233-239) and
+ * EncodingElem::operator+= answers by replacing that ring limb with an empty zero ciphertext (seal_ring.tcc:493-504):
+ * on flat words, the limb's c0 is dropped as well.  Returns 1 if the limb was transparent. */
+static int drop_if_transparent(uint64_t *ct, size_t N_E, size_t L_E) {
+  for (size_t w = L_E * N_E; w < 2 * L_E * N_E; w++)
+    if (ct[w]) return 0;
+  memset(ct, 0, 2 * L_E * N_E * 8);
+  return 1;
+}
+
 size_t ro_inner_product(const uint64_t *crs, const uint64_t *coeff, const uint8_t *tag, size_t T, size_t N_R, size_t L_R,
                         const uint64_t *q, size_t N_E, size_t L_E, const uint64_t *Q, uint64_t *out) {
   size_t per_ct = 2 * L_E * N_E, per_enc = L_R * per_ct, used = 0;
@@ -212,6 +222,8 @@ size_t ro_inner_product(const uint64_t *crs, const uint64_t *coeff, const uint8_
             a[x] = addmod(a[x], term, Q[l]);
           }
         }
+      /* the first summed term is a copy (seal_ring.tcc:485-488); every later one goes through add_inplace */
+      if (used > 1) drop_if_transparent(acc, N_E, L_E);
     }
   }
   free(plain); free(pntt);
@@ -226,6 +238,7 @@ void ro_enc_add(uint64_t *acc, const uint64_t *other, size_t L_R, size_t N_E, si
         size_t off = ((j * 2 + k) * L_E + l) * N_E;
         for (size_t x = 0; x < N_E; x++) acc[off + x] = addmod(acc[off + x], other[off + x], Q[l]);
       }
+  for (size_t j = 0; j < L_R; j++) drop_if_transparent(acc + j * 2 * L_E * N_E, N_E, L_E);
 }
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -42,9 +42,12 @@ SIGNATURES = {
     "rsg_ringvec_destroy": (None, [_vp]),
     "rsg_ringvec_is_zero_prefix": (_int, [_vp, _sz, _sz, _vp]),
     "rsg_inner_product": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _vp, _vp, _vp, C.POINTER(_sz)]),
+    "rsg_inner_product_idx": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(_sz)]),
     "rsg_enc_add": (_int, [_vp, _vp, _vp]),
+    "rsg_crs_copy": (_int, [_vp, _sz, _vp, _sz, _sz]),
     "rsg_enc_sum": (_int, [_vp, _vp, _sz, _sz, _vp]),
     "rsg_witness_map": (_int, [_vp, _sz, _vp, _vp, _vp]),
+    "rsg_witness_map_zk": (_int, [_vp, _sz, _vp, _vp, _vp, _vp]),
     "rsg_interpolate": (_int, [_vp, _sz, _sz, _vp, _sz, _vp, _sz]),
     "rsg_vanishing": (_int, [_vp, _sz, _vp]),
     "rsg_r1cs_create": (_int, [_vp, _sz, _sz, _sz, _vp, _vp, _vp, _pp]),

@@ -193,6 +193,87 @@ __global__ void __launch_bounds__(256) k_enc_sum(const DevParams *__restrict__ P
   *reinterpret_cast<ulonglong2 *>(out + w) = acc;
 }
 
+// out = a + b mod Q_l over one encoding (EncodingElem::operator+=, evaluator.cpp:217-231); out may alias a.
+__global__ void __launch_bounds__(256) k_enc_add(const DevParams *__restrict__ P, const uint64_t *a, const uint64_t *__restrict__ b,
+                                                 uint64_t *out) {
+  const uint32_t N_E = P->N_E, L_E = P->L_E;
+  const size_t enc_words = (size_t)P->L_R * 2 * L_E * N_E;
+  const size_t w = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (w >= enc_words) return;
+  const uint64_t p = P->Q[(uint32_t)((w / N_E) % L_E)].p;
+  const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(a + w), y = *reinterpret_cast<const ulonglong2 *>(b + w);
+  *reinterpret_cast<ulonglong2 *>(out + w) = make_ulonglong2(add_mod(x.x, y.x, p), add_mod(x.y, y.y, p));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// "Transparent ciphertext" semantics.  SEAL throws when an addition yields a ciphertext whose c1 is identically zero
+// (evaluator.cpp:233-239) and EncodingElem::operator+= answers by replacing that limb with an empty zero ciphertext
+// (seal_ring.tcc:493-504): the running sum of an inner product is DROPPED whenever a prefix of it is transparent.
+// k_probe makes that observable at negligible cost: per ring limb j it forms the running sum of the c1 contributions
+// at one fixed slot (k = 1, l = 0, x = 0) over the term list and flags the terms where it is zero -- a necessary
+// condition for the prefix to be transparent.  The host resolves flagged prefixes exactly (rsgpu.cu).
+// grid (L_R), 256 threads; carry[j] holds the running sum across chunks of the term list.
+__global__ void __launch_bounds__(256) k_probe(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
+                                               const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
+                                               uint32_t n_terms, const uint64_t *__restrict__ pntt, uint64_t *__restrict__ carry,
+                                               uint8_t *__restrict__ flags, uint32_t flag_stride) {
+  __shared__ uint64_t warp_tot[8];
+  __shared__ uint64_t run;
+  const uint32_t j = blockIdx.x, N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
+  const ModConst m = P->Q[0];
+  const size_t ct_words = 2 * (size_t)L_E * N_E, enc_words = (size_t)L_R * ct_words;
+  const size_t c_off = (size_t)j * ct_words + (size_t)L_E * N_E;   // k = 1, l = 0, x = 0
+  const size_t p_off = (size_t)j * L_E * N_E, p_stride = (size_t)L_R * L_E * N_E;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) run = carry[j];
+  __syncthreads();
+  for (uint32_t base = 0; base < n_terms; base += 256) {
+    const uint32_t t = base + threadIdx.x;
+    uint64_t v = 0;
+    if (t < n_terms) {
+      const uint64_t cw = crs[(size_t)term[t] * enc_words + c_off];
+      const uint32_t pi = pidx[t];
+      v = pi != 0xFFFFFFFFu ? mul_mod(cw, pntt[(size_t)pi * p_stride + p_off], m) : cw;
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, v, off);
+      if (lane >= off) v = add_mod(v, o, m.p);
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    uint64_t pre = run;
+    for (uint32_t w = 0; w < warp; w++) pre = add_mod(pre, warp_tot[w], m.p);
+    v = add_mod(v, pre, m.p);
+    if (t < n_terms) flags[(size_t)j * flag_stride + t] = v == 0;
+    __syncthreads();
+    if (threadIdx.x == 255) run = v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) carry[j] = run;
+}
+
+// nz[j] |= 1 iff the c1 polynomial (all L_E limbs) of ring limb j of one encoding has a non-zero word.
+// grid (blocks, L_R); nz must be zeroed by the caller.
+__global__ void __launch_bounds__(256) k_c1_nonzero(const DevParams *__restrict__ P, const uint64_t *__restrict__ enc,
+                                                    uint32_t *__restrict__ nz) {
+  const uint32_t j = blockIdx.y;
+  const size_t half = (size_t)P->L_E * P->N_E;
+  const uint64_t *c1 = enc + (size_t)j * 2 * half + half;
+  uint32_t any = 0;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < half; w += (size_t)gridDim.x * blockDim.x) any |= c1[w] != 0;
+  if (__syncthreads_or((int)any) && threadIdx.x == 0) atomicOr(nz + j, 1u);
+}
+// Ring limbs whose c1 is identically zero become all-zero words (the reference's empty zero ciphertext). grid (blocks, L_R)
+__global__ void __launch_bounds__(256) k_zero_transparent(const DevParams *__restrict__ P, uint64_t *__restrict__ enc,
+                                                          const uint32_t *__restrict__ nz) {
+  const uint32_t j = blockIdx.y;
+  if (nz[j]) return;
+  const size_t ct_words = 2 * (size_t)P->L_E * P->N_E;
+  uint64_t *ct = enc + (size_t)j * ct_words;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < ct_words; w += (size_t)gridDim.x * blockDim.x) ct[w] = 0;
+}
+
 // flags[e] = 1 iff bytes [0, W + 7) of element e are zero (W = words per element); one block per element.
 __global__ void __launch_bounds__(256) k_is_zero_prefix(const uint64_t *__restrict__ ring, uint32_t W,
                                                         uint8_t *__restrict__ flags) {

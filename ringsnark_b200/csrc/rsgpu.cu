@@ -134,6 +134,7 @@ struct TimingRec {
 struct WitnessTables {   // per constraint count n
   uint64_t *d_Vinv = nullptr;   // [L_R][n][n]
   uint64_t *d_T = nullptr;      // [L_R][n-1][n-1] upper-triangular Toeplitz of rev(Z)^-1
+  uint64_t *d_Z = nullptr;      // [L_R][n+1]
   std::vector<uint64_t> h_Z;    // [L_R][n+1]
 };
 
@@ -167,6 +168,18 @@ struct rsg_context {
   size_t pntt_budget_words = (size_t)4 << 27;      // 4 GiB of NTT-domain plaintexts per chunk
   uint8_t *d_flags = nullptr;
   size_t cap_flags = 0;
+  uint64_t *d_zk = nullptr;         // d1, d2, d3 of the zero-knowledge witness map
+  size_t cap_zk = 0;
+  // transparent-ciphertext emulation (kernels.cuh: k_probe): per-term candidate flags [slot][L_R][T], running sums, nz words
+  uint8_t *d_probe = nullptr;
+  size_t cap_probe = 0;
+  uint64_t *d_probe_carry = nullptr;
+  uint32_t *d_nz = nullptr;
+  uint64_t *d_exact = nullptr;      // scratch encodings of the exact (slow) path
+  size_t cap_exact = 0;
+  uint64_t *d_ip = nullptr;         // the separate inner products of rsg_groth16_prove
+  size_t cap_ip = 0;
+  uint64_t exact_fallbacks = 0;     // how often a flagged prefix had to be resolved exactly
   size_t enc_words() const { return L_R * 2 * L_E * N_E; }
   size_t ring_words() const { return L_R * N_R; }
 };
@@ -304,6 +317,8 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
     if ((rc = upload_vec(c, mq, &c->d_modq))) return rc;
     if ((rc = upload_vec(c, mQ, &c->d_modQ))) return rc;
   }
+  if ((rc = dev_alloc(c, &c->d_probe_carry, MAX_LR, false))) return rc;
+  if ((rc = dev_alloc(c, &c->d_nz, MAX_LR, false))) return rc;
   *out = c;
   return RSG_OK;
 }
@@ -313,10 +328,11 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (void *p : c->owned) cudaFree(p);
-  for (auto &kv : c->wit) { cudaFree(kv.second.d_Vinv); cudaFree(kv.second.d_T); }
+  for (auto &kv : c->wit) { cudaFree(kv.second.d_Vinv); cudaFree(kv.second.d_T); cudaFree(kv.second.d_Z); }
   cudaFree(c->d_plain); cudaFree(c->d_pntt); cudaFree(c->d_partial);
   cudaFree(c->d_term); cudaFree(c->d_pidx); cudaFree(c->d_eidx); cudaFree(c->d_flags); cudaFree(c->d_out_scratch);
-  cudaFree(c->d_chunk); cudaFree(c->d_evals); cudaFree(c->d_wit);
+  cudaFree(c->d_chunk); cudaFree(c->d_evals); cudaFree(c->d_wit); cudaFree(c->d_zk);
+  cudaFree(c->d_probe); cudaFree(c->d_probe_carry); cudaFree(c->d_nz); cudaFree(c->d_exact); cudaFree(c->d_ip);
   for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -608,8 +624,11 @@ struct TermSpec {
   const uint64_t *ring_base;   // vector the coefficient lives in (nullptr for RSG_TERM_ONE)
   uint32_t elem;               // element index inside ring_base
 };
-static int lincomb_terms(rsg_context *c, const uint64_t *d_crs, const std::vector<TermSpec> &terms, uint64_t *d_out) {
+// d_probe_flags (nullable): receives the k_probe candidate flags, layout [L_R][terms.size()].
+static int lincomb_terms(rsg_context *c, const uint64_t *d_crs, const std::vector<TermSpec> &terms, uint64_t *d_out,
+                         uint8_t *d_probe_flags = nullptr) {
   int rc;
+  if (d_probe_flags && !terms.empty()) CUDA_TRY(cudaMemsetAsync(c->d_probe_carry, 0, MAX_LR * 8, c->stream));
   if (terms.empty()) {
     CUDA_TRY(cudaMemsetAsync(d_out, 0, c->enc_words() * 8, c->stream));
     return RSG_OK;
@@ -677,6 +696,12 @@ static int lincomb_terms(rsg_context *c, const uint64_t *d_crs, const std::vecto
     if ((rc = launch_lincomb(c, d_crs, c->d_term + ch.t0, c->d_pidx + ch.t0, ch.t1 - ch.t0, c->d_pntt,
                              chunk_out + (chunks.size() > 1 ? k * c->enc_words() : 0))))
       return rc;
+    if (d_probe_flags) {
+      LaunchScope ls(c, "k_probe");
+      k_probe<<<(unsigned)c->L_R, 256, 0, c->stream>>>(c->d_params, d_crs, c->d_term + ch.t0, c->d_pidx + ch.t0, (uint32_t)(ch.t1 - ch.t0),
+                                                        c->d_pntt, c->d_probe_carry, d_probe_flags + ch.t0, (uint32_t)terms.size());
+      CUDA_TRY(cudaGetLastError());
+    }
   }
   if (chunks.size() > 1) {
     LaunchScope ls(c, "k_enc_sum");
@@ -687,16 +712,98 @@ static int lincomb_terms(rsg_context *c, const uint64_t *d_crs, const std::vecto
   return RSG_OK;
 }
 
-extern "C" int rsg_inner_product(rsg_context *c, const rsg_crs *crs, size_t crs_first, const rsg_ringvec *coeffs, size_t coeff_first,
-                                 size_t count, const uint8_t *h_tags, uint64_t *h_out, uint64_t *d_out, size_t *n_used) {
+// acc += other with the reference's transparent-result rule (seal_ring.tcc:493-504): a ring limb whose c1 sums to zero
+// becomes the empty zero ciphertext (all-zero words).  Entirely on the device, no host round trip.
+static int enc_add_fix(rsg_context *c, uint64_t *d_acc, const uint64_t *d_other) {
+  const size_t pairs = c->enc_words() / 2;
+  {
+    LaunchScope ls(c, "k_enc_add");
+    k_enc_add<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_acc, d_other, d_acc);
+  }
+  CUDA_TRY(cudaMemsetAsync(c->d_nz, 0, MAX_LR * 4, c->stream));
+  const dim3 grid((unsigned)std::min<size_t>(64, (c->L_E * c->N_E + 255) / 256), (unsigned)c->L_R);
+  {
+    LaunchScope ls(c, "k_c1_nonzero");
+    k_c1_nonzero<<<grid, 256, 0, c->stream>>>(c->d_params, d_acc, c->d_nz);
+  }
+  {
+    LaunchScope ls(c, "k_zero_transparent");
+    k_zero_transparent<<<grid, 256, 0, c->stream>>>(c->d_params, d_acc, c->d_nz);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+
+// Exact resolution of flagged prefixes for ONE inner product (rare: needs a structured CRS, e.g. the seeded test CRS in
+// which every ciphertext shares its uniform polynomial).  flags: host copy of the probe flags [L_R][T].
+// Reference sequence per ring limb (seal_ring.tcc:415-431,479-507): res = tmp_0; then res += tmp_t and, if the sum's c1 is
+// identically zero, res = empty zero ciphertext, from which the next += restarts.  The probe's running sum is zero at a
+// restart, so the candidate set stays valid after it.
+static int inner_product_exact(rsg_context *c, const uint64_t *d_crs, const std::vector<TermSpec> &terms, const uint8_t *flags,
+                               uint64_t *d_out) {
+  int rc;
+  const size_t T = terms.size(), L_R = c->L_R, ct_words = 2 * c->L_E * c->N_E;
+  c->exact_fallbacks++;
+  if ((rc = ensure(c, &c->d_exact, &c->cap_exact, c->enc_words()))) return rc;
+  std::vector<size_t> start(L_R, 0);
+  const dim3 grid((unsigned)std::min<size_t>(64, (c->L_E * c->N_E + 255) / 256), (unsigned)L_R);
+  for (size_t j = 0; j < L_R; j++)
+    for (size_t t = 0; t < T; t++) {
+      if (!flags[j * T + t] || t < start[j]) continue;
+      std::vector<TermSpec> sub(terms.begin() + start[j], terms.begin() + t + 1);
+      if ((rc = lincomb_terms(c, d_crs, sub, c->d_exact))) return rc;
+      CUDA_TRY(cudaMemsetAsync(c->d_nz, 0, MAX_LR * 4, c->stream));
+      k_c1_nonzero<<<grid, 256, 0, c->stream>>>(c->d_params, c->d_exact, c->d_nz);
+      c->launches++;
+      uint32_t nz[MAX_LR];
+      CUDA_TRY(cudaMemcpyAsync(nz, c->d_nz, L_R * 4, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (!nz[j]) start[j] = t + 1;   // transparent prefix: the reference drops it
+    }
+  for (size_t j = 0; j < L_R; j++) {
+    if (start[j] == 0) continue;      // untouched limb: d_out already holds the plain sum
+    uint64_t *dst = d_out + j * ct_words;
+    if (start[j] >= T) {
+      CUDA_TRY(cudaMemsetAsync(dst, 0, ct_words * 8, c->stream));
+    } else {
+      std::vector<TermSpec> sub(terms.begin() + start[j], terms.end());
+      if ((rc = lincomb_terms(c, d_crs, sub, c->d_exact))) return rc;
+      CUDA_TRY(cudaMemcpyAsync(dst, c->d_exact + j * ct_words, ct_words * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
+  return RSG_OK;
+}
+
+// One EncodingElem::inner_product with the reference's exact semantics; synchronises the stream.
+static int inner_product_terms(rsg_context *c, const uint64_t *d_crs, const std::vector<TermSpec> &terms, uint64_t *d_out) {
+  int rc;
+  const size_t T = terms.size(), L_R = c->L_R;
+  if (T) {
+    if ((rc = ensure(c, &c->d_probe, &c->cap_probe, std::max<size_t>(L_R * T, 4096)))) return rc;
+  }
+  if ((rc = lincomb_terms(c, d_crs, terms, d_out, T ? c->d_probe : nullptr))) return rc;
+  if (!T) return RSG_OK;
+  std::vector<uint8_t> flags(L_R * T);
+  CUDA_TRY(cudaMemcpyAsync(flags.data(), c->d_probe, L_R * T, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  bool any = false;
+  for (uint8_t f : flags) any |= f != 0;
+  if (any && (rc = inner_product_exact(c, d_crs, terms, flags.data(), d_out))) return rc;
+  return RSG_OK;
+}
+
+static int inner_product_impl(rsg_context *c, const rsg_crs *crs, size_t crs_first, const uint32_t *h_crs_idx,
+                              const rsg_ringvec *coeffs, size_t coeff_first, const uint32_t *h_coeff_idx, size_t count,
+                              const uint8_t *h_tags, uint64_t *h_out, uint64_t *d_out, size_t *n_used) {
   if (!c || !crs || !coeffs || !h_tags) return fail(RSG_ERR_ARG, "null argument");
-  if (crs_first + count > crs->n || coeff_first + count > coeffs->n) return fail(RSG_ERR_ARG, "range");
   std::lock_guard<std::mutex> g(c->mu);
   CUDA_TRY(cudaSetDevice(c->device));
   std::vector<TermSpec> terms;
   for (size_t i = 0; i < count; i++) {
     if (h_tags[i] == RSG_TERM_SKIP) continue;
-    terms.push_back({(uint32_t)(crs_first + i), h_tags[i] == RSG_TERM_ONE ? nullptr : coeffs->d, (uint32_t)(coeff_first + i)});
+    const size_t ci = h_crs_idx ? h_crs_idx[i] : crs_first + i, ri = h_coeff_idx ? h_coeff_idx[i] : coeff_first + i;
+    if (ci >= crs->n || (h_tags[i] != RSG_TERM_ONE && ri >= coeffs->n)) return fail(RSG_ERR_ARG, "term index out of range");
+    terms.push_back({(uint32_t)ci, h_tags[i] == RSG_TERM_ONE ? nullptr : coeffs->d, (uint32_t)ri});
   }
   if (n_used) *n_used = terms.size();
   int rc;
@@ -705,10 +812,22 @@ extern "C" int rsg_inner_product(rsg_context *c, const rsg_crs *crs, size_t crs_
     if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 3 * c->enc_words()))) return rc;
     out = c->d_out_scratch;
   }
-  if ((rc = lincomb_terms(c, crs->d, terms, out))) return rc;
+  if ((rc = inner_product_terms(c, crs->d, terms, out))) return rc;
   if (h_out) CUDA_TRY(cudaMemcpyAsync(h_out, out, c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
+}
+extern "C" int rsg_inner_product(rsg_context *c, const rsg_crs *crs, size_t crs_first, const rsg_ringvec *coeffs, size_t coeff_first,
+                                 size_t count, const uint8_t *h_tags, uint64_t *h_out, uint64_t *d_out, size_t *n_used) {
+  if (!crs || !coeffs) return fail(RSG_ERR_ARG, "null argument");
+  if (crs_first + count > crs->n || coeff_first + count > coeffs->n) return fail(RSG_ERR_ARG, "range");
+  return inner_product_impl(c, crs, crs_first, nullptr, coeffs, coeff_first, nullptr, count, h_tags, h_out, d_out, n_used);
+}
+extern "C" int rsg_inner_product_idx(rsg_context *c, const rsg_crs *crs, const uint32_t *h_crs_idx, const rsg_ringvec *coeffs,
+                                     const uint32_t *h_coeff_idx, size_t count, const uint8_t *h_tags, uint64_t *h_out,
+                                     uint64_t *d_out, size_t *n_used) {
+  if (!h_crs_idx || !h_coeff_idx) return fail(RSG_ERR_ARG, "null index list");
+  return inner_product_impl(c, crs, 0, h_crs_idx, coeffs, 0, h_coeff_idx, count, h_tags, h_out, d_out, n_used);
 }
 
 extern "C" int rsg_enc_sum(rsg_context *c, const uint64_t *d_parts, size_t parts, size_t n_enc, uint64_t *d_out) {
@@ -723,15 +842,17 @@ extern "C" int rsg_enc_sum(rsg_context *c, const uint64_t *d_parts, size_t parts
 extern "C" int rsg_enc_add(rsg_context *c, uint64_t *d_acc, const uint64_t *d_other) {
   if (!c || !d_acc || !d_other) return fail(RSG_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> g(c->mu);
-  // two-part sum with parts not adjacent: stage through the partial buffer
-  int rc;
-  if ((rc = ensure(c, &c->d_partial, &c->cap_partial, 2 * c->enc_words()))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(c->d_partial, d_acc, c->enc_words() * 8, cudaMemcpyDeviceToDevice, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->d_partial + c->enc_words(), d_other, c->enc_words() * 8, cudaMemcpyDeviceToDevice, c->stream));
-  LaunchScope ls(c, "k_enc_sum");
-  const size_t pairs = c->enc_words() / 2;
-  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, c->d_partial, 2, 1, d_acc);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaSetDevice(c->device));
+  return enc_add_fix(c, d_acc, d_other);
+}
+extern "C" int rsg_crs_copy(rsg_crs *dst, size_t dst_first, const rsg_crs *src, size_t src_first, size_t count) {
+  if (!dst || !src || dst->ctx != src->ctx) return fail(RSG_ERR_ARG, "null or foreign arena");
+  if (dst_first + count > dst->n || src_first + count > src->n) return fail(RSG_ERR_ARG, "CRS range");
+  rsg_context *c = dst->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(dst->d + dst_first * c->enc_words(), src->d + src_first * c->enc_words(), count * c->enc_words() * 8,
+                           cudaMemcpyDeviceToDevice, c->stream));
   return RSG_OK;
 }
 
@@ -797,6 +918,9 @@ static int get_witness_tables(rsg_context *c, size_t n, WitnessTables **out) {
   CUDA_TRY(cudaMalloc(&v, T.size() * 8));
   wt.d_T = (uint64_t *)v;
   CUDA_TRY(cudaMemcpy(wt.d_T, T.data(), T.size() * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&v, wt.h_Z.size() * 8));
+  wt.d_Z = (uint64_t *)v;
+  CUDA_TRY(cudaMemcpy(wt.d_Z, wt.h_Z.data(), wt.h_Z.size() * 8, cudaMemcpyHostToDevice));
   auto ins = c->wit.emplace(n, std::move(wt));
   *out = &ins.first->second;
   return RSG_OK;
@@ -837,7 +961,8 @@ extern "C" int rsg_vanishing(rsg_context *c, size_t n, uint64_t *h_Z) {
   return RSG_OK;
 }
 
-static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, uint64_t *d_coeffs, uint64_t *d_H) {
+static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, uint64_t *d_coeffs, uint64_t *d_H,
+                           const uint64_t *d_zk = nullptr) {
   WitnessTables *wt;
   int rc = get_witness_tables(c, n, &wt);
   if (rc) return rc;
@@ -860,15 +985,32 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
     }
     if ((rc = launch_modmat(c, wt->d_T, n - 1, n - 1, Ptop, d_H, 1, true, "k_modmat_divZ"))) return rc;
   }
+  if (d_zk) {
+    LaunchScope ls(c, "k_h_patch");
+    k_h_patch<<<dim3((unsigned)(n + 1), (unsigned)((W + 255) / 256)), 256, 0, c->stream>>>(c->d_modq, d_H, aA, aB, d_zk, wt->d_Z, (uint32_t)n,
+                                                                                         (uint32_t)c->N_R, (uint32_t)c->L_R);
+    CUDA_TRY(cudaGetLastError());
+  }
   return RSG_OK;
 }
 
-extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
+extern "C" int rsg_witness_map_zk(rsg_context *c, size_t n, const rsg_ringvec *evals, const uint64_t *h_d, rsg_ringvec *coeffs,
+                                  rsg_ringvec *H) {
   if (!c || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
   if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
   std::lock_guard<std::mutex> g(c->mu);
   CUDA_TRY(cudaSetDevice(c->device));
-  return witness_map_dev(c, n, evals->d, coeffs->d, H->d);
+  const uint64_t *d_zk = nullptr;
+  if (h_d) {
+    int rc = ensure(c, &c->d_zk, &c->cap_zk, 3 * c->ring_words());
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->d_zk, h_d, 3 * c->ring_words() * 8, cudaMemcpyHostToDevice, c->stream));
+    d_zk = c->d_zk;
+  }
+  return witness_map_dev(c, n, evals->d, coeffs->d, H->d, d_zk);
+}
+extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
+  return rsg_witness_map_zk(c, n, evals, nullptr, coeffs, H);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -969,30 +1111,79 @@ extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg
     for (size_t i = lo; i < std::min(hi, limit); i++)
       if (!zero_flag[i]) terms.push_back({(uint32_t)(off + i - lo), base, (uint32_t)(elem0 + i)});
   };
-  // coeffs order: A_io, B_io, C_io, A_mid, B_mid, C_mid
-  std::vector<TermSpec> tA, tB, tC;
-  add_vec(tA, L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 0, flags.data());
-  add_vec(tA, L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 3 * n, flags.data() + 3 * n);
-  if (L->alpha_idx != NONE) tA.push_back({(uint32_t)L->alpha_idx, nullptr, 0});
-  add_vec(tB, L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, n, flags.data() + n);
-  add_vec(tB, L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 4 * n, flags.data() + 4 * n);
-  if (L->beta_idx != NONE) tB.push_back({(uint32_t)L->beta_idx, nullptr, 0});
-  add_vec(tC, L->delta_ts_off, L->delta_ts_lo, L->delta_ts_hi, n + 1, H, 0, flags.data() + 6 * n);
+  // The reference's sequence (groth16.tcc:89-112): six separate inner products, combined with operator+=.
+  //   A = <s_pows, A_io> + <s_pows, A_mid> + alpha;  B likewise with beta;  C = <delta_ts, H> [+ <delta_mid, aux>]
+  // coeffs order in HBM: A_io, B_io, C_io, A_mid, B_mid, C_mid
+  std::vector<TermSpec> ip[6];
+  add_vec(ip[0], L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 0, flags.data());
+  add_vec(ip[1], L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 3 * n, flags.data() + 3 * n);
+  add_vec(ip[2], L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, n, flags.data() + n);
+  add_vec(ip[3], L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 4 * n, flags.data() + 4 * n);
+  add_vec(ip[4], L->delta_ts_off, L->delta_ts_lo, L->delta_ts_hi, n + 1, H, 0, flags.data() + 6 * n);
   for (size_t i = L->delta_mid_lo; i < std::min(L->delta_mid_hi, n_aux); i++) {
     const uint8_t kind = h_aux_kind ? h_aux_kind[i] : (uint8_t)RSG_AUX_POLY;
     const uint32_t ci = (uint32_t)(L->delta_mid_off + i - L->delta_mid_lo);
     if (kind == RSG_AUX_POLY) {
-      if (!flags[7 * n + 1 + i]) tC.push_back({ci, assignment->d, (uint32_t)(n_io + i)});
+      if (!flags[7 * n + 1 + i]) ip[5].push_back({ci, assignment->d, (uint32_t)(n_io + i)});
     } else if (kind == RSG_TERM_ONE) {
-      tC.push_back({ci, nullptr, 0});
+      ip[5].push_back({ci, nullptr, 0});
     } else if (kind == RSG_TERM_GENERAL) {
-      tC.push_back({ci, assignment->d, (uint32_t)(n_io + i)});
+      ip[5].push_back({ci, assignment->d, (uint32_t)(n_io + i)});
     }
   }
-  if (n_used) { n_used[0] = tA.size(); n_used[1] = tB.size(); n_used[2] = tC.size(); }
-  if ((rc = lincomb_terms(c, crs->d, tA, out))) return rc;
-  if ((rc = lincomb_terms(c, crs->d, tB, out + c->enc_words()))) return rc;
-  if ((rc = lincomb_terms(c, crs->d, tC, out + 2 * c->enc_words()))) return rc;
+  const size_t E = c->enc_words();
+  if (n_used) {
+    n_used[0] = ip[0].size() + ip[1].size() + (L->alpha_idx != NONE);
+    n_used[1] = ip[2].size() + ip[3].size() + (L->beta_idx != NONE);
+    n_used[2] = ip[4].size() + ip[5].size();
+  }
+  size_t probe_off[7] = {0};
+  for (int k = 0; k < 6; k++) probe_off[k + 1] = probe_off[k] + c->L_R * ip[k].size();
+  if ((rc = ensure(c, &c->d_ip, &c->cap_ip, 6 * E))) return rc;
+  if ((rc = ensure(c, &c->d_probe, &c->cap_probe, std::max<size_t>(probe_off[6], 4096)))) return rc;
+  for (int k = 0; k < 6; k++)
+    if (!ip[k].empty() && (rc = lincomb_terms(c, crs->d, ip[k], c->d_ip + k * E, c->d_probe + probe_off[k]))) return rc;
+  // EncodingElem::operator+= chain of one proof element: copy the first non-empty operand, then add with the
+  // transparent-result rule (an empty inner product is the additive identity, seal_ring.tcc:482-488)
+  auto combine = [&](int e) -> int {
+    const uint64_t *src[3] = {nullptr, nullptr, nullptr};
+    const int a = e == 2 ? 4 : 2 * e, b = a + 1;
+    if (!ip[a].empty()) src[0] = c->d_ip + a * E;
+    if (!ip[b].empty()) src[1] = c->d_ip + b * E;
+    const size_t extra = e == 0 ? L->alpha_idx : (e == 1 ? L->beta_idx : NONE);
+    if (extra != NONE) src[2] = crs->d + extra * E;
+    uint64_t *acc = out + e * E;
+    bool have = false;
+    for (int k = 0; k < 3; k++) {
+      if (!src[k]) continue;
+      if (!have) {
+        CUDA_TRY(cudaMemcpyAsync(acc, src[k], E * 8, cudaMemcpyDeviceToDevice, c->stream));
+        have = true;
+      } else {
+        int r = enc_add_fix(c, acc, src[k]);
+        if (r) return r;
+      }
+    }
+    if (!have) CUDA_TRY(cudaMemsetAsync(acc, 0, E * 8, c->stream));
+    return RSG_OK;
+  };
+  for (int e = 0; e < 3; e++)
+    if ((rc = combine(e))) return rc;
+  if (probe_off[6]) {
+    std::vector<uint8_t> pf(probe_off[6]);
+    CUDA_TRY(cudaMemcpyAsync(pf.data(), c->d_probe, probe_off[6], cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    bool redo[3] = {false, false, false};
+    for (int k = 0; k < 6; k++) {
+      bool any = false;
+      for (size_t i = probe_off[k]; i < probe_off[k + 1]; i++) any |= pf[i] != 0;
+      if (!any) continue;
+      if ((rc = inner_product_exact(c, crs->d, ip[k], pf.data() + probe_off[k], c->d_ip + k * E))) return rc;
+      redo[k == 4 || k == 5 ? 2 : k / 2] = true;
+    }
+    for (int e = 0; e < 3; e++)
+      if (redo[e] && (rc = combine(e))) return rc;
+  }
   if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 3 * c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;

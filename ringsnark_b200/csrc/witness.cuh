@@ -101,6 +101,32 @@ __global__ void __launch_bounds__(MM_THREADS) k_conv_top(const ModConst *__restr
     if (i0 + r < n - 1) Pp[(size_t)(i0 + r) * W] = acc[r].reduce(m);
 }
 
+// Zero-knowledge patch of H (r1cs_to_qrp.tcc:225-235, evaluation_domain.tcc:62-76):
+//   H[i] += d2*A[i] + d1*B[i]  (i < n);   H[0] -= d3;   H[i] += (d1*d2) * Z[i]  (i <= n)
+// d = 3 ring elements d1,d2,d3; Z = per-prime constants [L_R][n+1].  grid (n+1, ceil(W/256)).
+__global__ void __launch_bounds__(256) k_h_patch(const ModConst *__restrict__ mods, uint64_t *__restrict__ H,
+                                                 const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                 const uint64_t *__restrict__ d, const uint64_t *__restrict__ Z, uint32_t n,
+                                                 uint32_t N_R, uint32_t L_R) {
+  const uint32_t i = blockIdx.x;
+  const uint32_t w = blockIdx.y * blockDim.x + threadIdx.x;
+  const uint32_t W = N_R * L_R;
+  if (w >= W) return;
+  const uint32_t limb = w / N_R;
+  const ModConst m = mods[limb];
+  const uint64_t d1 = d[w], d2 = d[(size_t)W + w], d3 = d[2 * (size_t)W + w];
+  Acc192 acc;
+  acc.clear();
+  acc.add(H[(size_t)i * W + w]);
+  if (i < n) {
+    acc.mac(d2, A[(size_t)i * W + w]);
+    acc.mac(d1, B[(size_t)i * W + w]);
+  }
+  acc.mac(mul_mod(d1, d2, m), Z[(size_t)limb * (n + 1) + i]);
+  uint64_t r = acc.reduce(m);
+  if (i == 0) r = sub_mod(r, d3, m.p);
+  H[(size_t)i * W + w] = r;
+}
 
 // linear_combination::evaluate (ringsnark/relations/variable.tcc:246-254) for all 3n linear combinations and the
 // three assignments the witness map uses (r1cs_to_qrp.tcc:167-219): "mid" (primary inputs zeroed), "io" (auxiliary

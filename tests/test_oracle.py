@@ -102,7 +102,12 @@ def test_inner_products_and_proof(case):
     B = total([mine[2], mine[3], (beta[0], 1)])
     Cc = total([mine[4], mine[5]])
     assert np.array_equal(A, proof[0]) and np.array_equal(B, proof[1]) and np.array_equal(Cc, proof[2])
-    assert int(case.d["verified"][0]) == 1
+    # the reference verifier accepted these words -- except where the circuit touches the constant wire in a constraint
+    # the io/mid split counts twice; tiny_transp (seed 11 of tiny_quirks) is such a circuit
+    assert int(case.d["verified"][0]) == (0 if int(case.seed) == 11 else 1)
+    if int(case.seed) == 11:
+        # ... and its <s_pows, A_io> is transparent in ring limb 0: the reference leaves an empty zero ciphertext there
+        assert [int(x) for x in ip_size[0]] == [0, 2] and not ip[0][:case.enc_words // case.L_R].any()
 
 
 def test_witness_map(case):
