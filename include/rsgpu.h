@@ -113,6 +113,12 @@ int rsg_witness_map(rsg_context *ctx, size_t n, const rsg_ringvec *evals, rsg_ri
  * H[i] += d1*d2*Z[i] (i <= n) with A, B the interpolants of the FULL assignment.  h_d == NULL is rsg_witness_map. */
 int rsg_witness_map_zk(rsg_context *ctx, size_t n, const rsg_ringvec *evals, const uint64_t *h_d, rsg_ringvec *coeffs,
                        rsg_ringvec *H);
+/* The same when `evals` IS the output of rsg_r1cs_evaluate(r1cs, .): then full = mid + io - (constant wire), interpolation
+ * is linear, and the interpolants of the full assignment are formed from the other six instead of being computed
+ * (6 instead of 8 matrix products per proof; identical residues). */
+typedef struct rsg_r1cs rsg_r1cs;
+int rsg_witness_map_r1cs(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *evals, const uint64_t *h_d,
+                         rsg_ringvec *coeffs, rsg_ringvec *H);
 /* util/polynomials.tcc:9-43 on its own: vectors of n ring elements; `batch` vectors back to back. */
 int rsg_interpolate(rsg_context *ctx, size_t n, size_t batch, const rsg_ringvec *y, size_t y_first, rsg_ringvec *out,
                     size_t out_first);
@@ -123,7 +129,6 @@ int rsg_vanishing(rsg_context *ctx, size_t n, uint64_t *h_Z);
  * R1CS in CSR form, rows r = m*n + i for matrix m in {A, B, C} and constraint i; col 0 is the constant wire,
  * col v >= 1 is variable v (primary inputs first); coeff are the uint64 scalars of the linear terms
  * (relations/variable.hpp:29: negative integers wrap through uint64, as in the reference). */
-typedef struct rsg_r1cs rsg_r1cs;
 int rsg_r1cs_create(rsg_context *ctx, size_t n, size_t n_io, size_t n_aux, const uint32_t *h_row_ptr /* 3n+1 */,
                     const uint32_t *h_col, const uint64_t *h_coeff, rsg_r1cs **out);
 void rsg_r1cs_destroy(rsg_r1cs *r);

@@ -559,6 +559,11 @@ inline qrp_witness<seal_gpu::RingElem> r1cs_to_qrp_witness_map<seal_gpu::RingEle
       }
       row_ptr.push_back((uint32_t)col.size());
     }
+  rsg_r1cs *r1cs = nullptr;   // non-null: the evaluations were produced on the device from this CSR system
+  struct R1csGuard {
+    rsg_r1cs *&r;
+    ~R1csGuard() { rsg_r1cs_destroy(r); }
+  } guard{r1cs};
   if (scalar_coeffs) {
     // integer coefficients (every reference driver except the NTT demo): sparse evaluate on the device
     std::vector<uint64_t> w;
@@ -567,11 +572,8 @@ inline qrp_witness<seal_gpu::RingElem> r1cs_to_qrp_witness_map<seal_gpu::RingEle
     for (const auto &r : auxiliary_input) r.append_words(w);
     auto assignment = make_vec(n_io + n_aux);
     if (n_io + n_aux) D::check(rsg_ringvec_upload(assignment->v, 0, n_io + n_aux, w.data()));
-    rsg_r1cs *r1cs = nullptr;
     D::check(rsg_r1cs_create(b.ctx, n, n_io, n_aux, row_ptr.data(), col.data(), coeff.data(), &r1cs));
-    const int rc = rsg_r1cs_evaluate(b.ctx, r1cs, assignment->v, evals->v);
-    rsg_r1cs_destroy(r1cs);
-    D::check(rc);
+    D::check(rsg_r1cs_evaluate(b.ctx, r1cs, assignment->v, evals->v));
   } else {
     // ring-element coefficients: linear_combination::evaluate as written (relations/variable.tcc:246-254), then upload
     r1cs_variable_assignment<R> mid(n_io, R::zero()), io(primary_input), full(primary_input);
@@ -599,7 +601,8 @@ inline qrp_witness<seal_gpu::RingElem> r1cs_to_qrp_witness_map<seal_gpu::RingEle
     d2.append_words(dw);
     d3.append_words(dw);
   }
-  D::check(rsg_witness_map_zk(b.ctx, n, evals->v, zk ? dw.data() : nullptr, coeffs->v, H->v));
+  if (r1cs) D::check(rsg_witness_map_r1cs(b.ctx, r1cs, evals->v, zk ? dw.data() : nullptr, coeffs->v, H->v));
+  else D::check(rsg_witness_map_zk(b.ctx, n, evals->v, zk ? dw.data() : nullptr, coeffs->v, H->v));
   coeffs->zero.resize(6 * n);
   H->zero.resize(n + 1);
   D::check(rsg_ringvec_is_zero_prefix(coeffs->v, 0, 6 * n, coeffs->zero.data()));

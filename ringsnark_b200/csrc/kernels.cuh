@@ -61,14 +61,16 @@ __global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Centred lift into Q_l + forward NTT.  grid (count, L_R, L_E).
-template <int LOGN>
+// Centred lift into Q_l + forward NTT.  grid (count * L_E, L_R): the L_E limbs of one plaintext are neighbours in launch
+// order, so the eight CTAs that read the same coefficient vector run together and seven of the reads hit L2.
+// LAZY (every Q_l < 2^58): correction-free butterflies, one Barrett reduction per word at the store.
+template <int LOGN, bool LAZY>
 __global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
                                                       uint64_t *__restrict__ out) {
   extern __shared__ uint64_t sm[];
   constexpr uint32_t n = 1u << LOGN;
-  const uint32_t e = blockIdx.x, j = blockIdx.y, l = blockIdx.z;
   const uint32_t L_R = P->L_R, L_E = P->L_E;
+  const uint32_t e = blockIdx.x / L_E, l = blockIdx.x - e * L_E, j = blockIdx.y;
   const ModConst m = P->Q[l];
   const uint64_t thr = P->thr[j], tm = P->tmodQ[j][l];
   const uint64_t *src = plain + ((size_t)e * L_R + j) * n;
@@ -79,9 +81,10 @@ __global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restric
     sm[pad_idx(i)] = r;
   }
   __syncthreads();
-  ntt_forward_smem<LOGN>(sm, P->fwdQ[l], m.p, 0, 0);
+  ntt_forward_smem<LOGN, LAZY>(sm, P->fwdQ[l], m.p, 0, 0);
   uint64_t *dst = out + (((size_t)e * L_R + j) * L_E + l) * n;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = canon4(sm[pad_idx(i)], m.p);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    dst[i] = LAZY ? reduce64(sm[pad_idx(i)], m) : canon4(sm[pad_idx(i)], m.p);
 }
 
 // Raw NTT of `batch` polynomials in place; grid (batch).

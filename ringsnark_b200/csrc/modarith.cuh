@@ -88,6 +88,13 @@ struct Acc192 {
         : "+l"(lo), "+l"(hi), "+r"(top)
         : "l"(a));
   }
+  __device__ __forceinline__ void add128(uint64_t a_lo, uint64_t a_hi) {
+    asm("add.cc.u64 %0, %0, %3;\n\t"
+        "addc.cc.u64 %1, %1, %4;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+l"(lo), "+l"(hi), "+r"(top)
+        : "l"(a_lo), "l"(a_hi));
+  }
   __device__ __forceinline__ uint64_t reduce(const ModConst &m) const {
     uint64_t r = reduce128(lo, hi, m);
     if (top) {

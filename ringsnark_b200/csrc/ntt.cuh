@@ -40,41 +40,62 @@ __device__ __forceinline__ void bfly_inv(uint64_t &x, uint64_t &y, const Twiddle
   y = mul_shoup_lazy(d, t, p);
 }
 
-// One pass = RL consecutive levels [s, s+RL) done in registers on 2^RL elements spaced g = n >> (s+RL) apart.
+// Lazy forward butterfly for primes below 2^58: no range correction at all.  The Shoup quotient is taken from three of
+// the four 32x32 partial products (one IMAD.WIDE + two IMAD.HI instead of a full 64x64 high product), which
+// under-estimates it by at most 2, so y*w - q*p lies in [0, 4p) for ANY 64-bit y; with the constant 4p added to the
+// difference every level raises the bound of the values by 4p: p -> (4*levels + 1) p <= 61 p < 2^64 for 15 levels.
+// The caller canonicalises once at the end (reduce64).  Same residues as SEAL's schedule.
+__device__ __forceinline__ uint64_t mul_shoup_approx(uint64_t y, const Twiddle &t, uint64_t p) {
+  const uint32_t y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32), q0 = (uint32_t)t.wq, q1 = (uint32_t)(t.wq >> 32);
+  const uint64_t q = (uint64_t)y1 * q1 + __umulhi(y1, q0) + __umulhi(y0, q1);
+  return y * t.w - q * p;
+}
+__device__ __forceinline__ void bfly_fwd_lazy(uint64_t &x, uint64_t &y, const Twiddle &t, uint64_t p, uint64_t four_p) {
+  const uint64_t v = mul_shoup_approx(y, t, p);
+  y = x - v + four_p;
+  x = x + v;
+}
+
+// One pass = RL consecutive levels [S, S+RL) done in registers on 2^RL elements spaced g = n >> (S+RL) apart.
 // n = local transform size (1 << LOGN); `lvl0` = levels already applied outside (0 unless the polynomial was
 // pre-split in global memory), `blk` = index of this local block among the 1 << lvl0 blocks.
-template <int LOGN, int RL, bool INVERSE>
-__device__ __forceinline__ void ntt_pass(uint64_t *sm, int s, const Twiddle *tab, uint64_t p, uint32_t lvl0,
-                                         uint32_t blk) {
+// Padded addresses: pad_idx(base + k*g) == pad_idx(base) + k*g + ((k*g) >> 4) for every pass shape used here (the low
+// four bits of base and of k*g never carry), so the 2^RL offsets are compile-time constants.
+template <int LOGN, int RL, int S, bool INVERSE, bool LAZY>
+__device__ __forceinline__ void ntt_pass(uint64_t *sm, const Twiddle *tab, uint64_t p, uint32_t lvl0, uint32_t blk) {
   constexpr uint32_t n = 1u << LOGN;
   constexpr int R = 1 << RL;
-  const uint64_t two_p = p << 1;
-  const uint32_t g = n >> (s + RL);                 // element stride inside an item
-  const uint32_t items = n >> RL;
+  constexpr uint32_t g = n >> (S + RL);             // element stride inside an item
+  constexpr uint32_t items = n >> RL;
+  const uint64_t two_p = p << 1, four_p = p << 2;
   for (uint32_t item = threadIdx.x; item < items; item += blockDim.x) {
     const uint32_t o = item & (g - 1);
-    const uint32_t b = item / g;                    // block index at level s (g is a power of two)
-    const uint32_t base = b * (n >> s) + o;
+    const uint32_t b = item / g;                    // block index at level S (g is a power of two)
+    const uint32_t base = b * (n >> S) + o;
+    uint64_t *ptr = sm + pad_idx(base);
     uint64_t v[R];
 #pragma unroll
-    for (int k = 0; k < R; k++) v[k] = sm[pad_idx(base + k * g)];
+    for (int k = 0; k < R; k++) v[k] = ptr[k * g + ((k * g) >> 4)];
     if (!INVERSE) {
 #pragma unroll
       for (int u = 0; u < RL; u++) {
         const int half = R >> (u + 1);
-        const uint32_t tbase = (1u << (lvl0 + s + u)) + (blk << (s + u)) + (b << u);
+        const uint32_t tbase = (1u << (lvl0 + S + u)) + (blk << (S + u)) + (b << u);
 #pragma unroll
         for (int grp = 0; grp < (1 << u); grp++) {
           const Twiddle t = load_tw(tab, tbase + grp);
 #pragma unroll
-          for (int k = 0; k < half; k++) bfly_fwd(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, two_p);
+          for (int k = 0; k < half; k++) {
+            if (LAZY) bfly_fwd_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, four_p);
+            else bfly_fwd(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, two_p);
+          }
         }
       }
     } else {
 #pragma unroll
       for (int u = RL - 1; u >= 0; u--) {
         const int half = R >> (u + 1);
-        const uint32_t tbase = (1u << (lvl0 + s + u)) + (blk << (s + u)) + (b << u);
+        const uint32_t tbase = (1u << (lvl0 + S + u)) + (blk << (S + u)) + (b << u);
 #pragma unroll
         for (int grp = 0; grp < (1 << u); grp++) {
           const Twiddle t = load_tw(tab, tbase + grp);
@@ -84,45 +105,46 @@ __device__ __forceinline__ void ntt_pass(uint64_t *sm, int s, const Twiddle *tab
       }
     }
 #pragma unroll
-    for (int k = 0; k < R; k++) sm[pad_idx(base + k * g)] = v[k];
+    for (int k = 0; k < R; k++) ptr[k * g + ((k * g) >> 4)] = v[k];
   }
 }
 
-// All LOGN levels of the local block, forward.  Input in [0, 4p) (canonical is fine), output lazy in [0, 4p).
-template <int LOGN>
+template <int LOGN, int S, bool INVERSE, bool LAZY>
+struct PassChain {   // levels [S, LOGN): radix-16 passes while four levels remain, then one pass for the rest
+  static __device__ __forceinline__ void fwd(uint64_t *sm, const Twiddle *tab, uint64_t p, uint32_t lvl0, uint32_t blk) {
+    constexpr int REMAIN = LOGN - S;
+    if constexpr (REMAIN > 0) {
+      constexpr int RL = REMAIN >= 4 ? 4 : REMAIN;
+      ntt_pass<LOGN, RL, S, false, LAZY>(sm, tab, p, lvl0, blk);
+      __syncthreads();
+      PassChain<LOGN, S + RL, INVERSE, LAZY>::fwd(sm, tab, p, lvl0, blk);
+    }
+  }
+  // inverse: levels run LOGN-1 .. 0; the odd-sized pass comes first (at the top levels)
+  static __device__ __forceinline__ void inv(uint64_t *sm, const Twiddle *tab, uint64_t p, uint32_t lvl0, uint32_t blk) {
+    constexpr int REMAIN = LOGN - S;   // here S counts the levels already undone from the top
+    if constexpr (REMAIN > 0) {
+      constexpr int RL = (REMAIN % 4) ? (REMAIN % 4) : 4;
+      ntt_pass<LOGN, RL, REMAIN - RL, true, false>(sm, tab, p, lvl0, blk);
+      __syncthreads();
+      PassChain<LOGN, S + RL, INVERSE, LAZY>::inv(sm, tab, p, lvl0, blk);
+    }
+  }
+};
+
+// All LOGN levels of the local block, forward.  Input canonical (or < 4p when !LAZY); output lazy: < 4p (!LAZY) or
+// < (4*LOGN + 1) p (LAZY, primes below 2^58 only).
+template <int LOGN, bool LAZY = false>
 __device__ __forceinline__ void ntt_forward_smem(uint64_t *sm, const Twiddle *tab, uint64_t p, uint32_t lvl0,
                                                  uint32_t blk) {
-  constexpr int FULL = LOGN / 4, REM = LOGN % 4;
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < FULL; i++) {
-    ntt_pass<LOGN, 4, false>(sm, s, tab, p, lvl0, blk);
-    s += 4;
-    __syncthreads();
-  }
-  if (REM == 3) ntt_pass<LOGN, 3, false>(sm, s, tab, p, lvl0, blk);
-  if (REM == 2) ntt_pass<LOGN, 2, false>(sm, s, tab, p, lvl0, blk);
-  if (REM == 1) ntt_pass<LOGN, 1, false>(sm, s, tab, p, lvl0, blk);
-  if (REM) __syncthreads();
+  PassChain<LOGN, 0, false, LAZY>::fwd(sm, tab, p, lvl0, blk);
 }
 
 // All LOGN levels, inverse (levels run LOGN-1 .. 0).  Input in [0, 2p), output lazy in [0, 2p), NOT yet scaled.
 template <int LOGN>
 __device__ __forceinline__ void ntt_inverse_smem(uint64_t *sm, const Twiddle *tab, uint64_t p, uint32_t lvl0,
                                                  uint32_t blk) {
-  constexpr int FULL = LOGN / 4, REM = LOGN % 4;
-  int s = LOGN;
-  if (REM == 3) ntt_pass<LOGN, 3, true>(sm, s - 3, tab, p, lvl0, blk);
-  if (REM == 2) ntt_pass<LOGN, 2, true>(sm, s - 2, tab, p, lvl0, blk);
-  if (REM == 1) ntt_pass<LOGN, 1, true>(sm, s - 1, tab, p, lvl0, blk);
-  if (REM) __syncthreads();
-  s -= REM;
-#pragma unroll
-  for (int i = 0; i < FULL; i++) {
-    s -= 4;
-    ntt_pass<LOGN, 4, true>(sm, s, tab, p, lvl0, blk);
-    __syncthreads();
-  }
+  PassChain<LOGN, 0, true, false>::inv(sm, tab, p, lvl0, blk);
 }
 
 }  // namespace rsg

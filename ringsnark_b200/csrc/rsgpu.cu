@@ -194,6 +194,15 @@ struct rsg_ringvec {
   uint64_t *d;
 };
 
+struct rsg_r1cs {
+  rsg_context *ctx;
+  size_t n, n_io, n_aux;
+  uint32_t *d_row_ptr = nullptr, *d_col = nullptr;
+  uint64_t *d_coeff = nullptr;
+  std::vector<uint64_t> h_const;   // [2][L_R][n]: constant-wire coefficient of A_i, B_i mod q_j
+  uint64_t *d_cc = nullptr;        // [2][L_R][n]: its interpolant V^-1 * const, built on first use
+};
+
 struct LaunchScope {   // counts launches and optionally brackets them with events
   rsg_context *c;
   const char *name;
@@ -496,7 +505,8 @@ static int set_smem_attrs() {
   if (done[dev]) return RSG_OK;
   const int bytes = (int)ntt_smem(LOGN);
   CUDA_TRY(cudaFuncSetAttribute(k_encode_intt<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done[dev] = true;
@@ -530,11 +540,14 @@ static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count
   if (!count) return RSG_OK;
   const unsigned th = ntt_threads(c->logN);
   const size_t sm = ntt_smem(c->logN);
-  // grid.x is the term index: up to 2^31-1
-  dim3 grid((unsigned)count, (unsigned)c->L_R, (unsigned)c->L_E);
+  // grid.x = term * L_E + limb: up to 2^31-1
+  dim3 grid((unsigned)(count * c->L_E), (unsigned)c->L_R);
+  bool lazy = true;   // correction-free butterflies need (4 * log2 N + 1) * Q_l < 2^64
+  for (uint64_t p : c->Q) lazy = lazy && p < (1ull << 58);
   LaunchScope ls(c, "k_lift_fwd_ntt");
   DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG>(); if (rc) return rc;
-                           k_lift_fwd_ntt<LG><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
+                           if (lazy) k_lift_fwd_ntt<LG, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
+                           else k_lift_fwd_ntt<LG, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -929,10 +942,19 @@ static int get_witness_tables(rsg_context *c, size_t n, WitnessTables **out) {
 static int launch_modmat(rsg_context *c, const uint64_t *d_M, size_t rows, size_t K, const uint64_t *d_Y, uint64_t *d_C, size_t batch,
                          bool upper, const char *name) {
   if (!rows || !batch) return RSG_OK;
-  dim3 grid((unsigned)((rows + MM_ROWS - 1) / MM_ROWS), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), (unsigned)(batch * c->L_R));
   LaunchScope ls(c, name);
-  k_modmat<<<grid, MM_THREADS, 0, c->stream>>>(c->d_modq, d_M, (uint32_t)rows, (uint32_t)K, d_Y, d_C, (uint32_t)c->N_R, (uint32_t)c->L_R,
-                                               upper ? 1u : 0u, (uint32_t)K);
+  bool small = true;   // every ring prime < 2^54: the FP64-pipe kernel (exact; see witness.cuh)
+  for (uint64_t p : c->q) small = small && p < (1ull << 54);
+  dim3 grid((unsigned)((rows + MM_ROWS - 1) / MM_ROWS), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), (unsigned)(batch * c->L_R));
+  if (small) {
+    // 8 rows x 1 slot per thread, 2 columns of Y prefetched, 3 CTAs/SM: best of the shapes measured on B200
+    dim3 gridf((unsigned)((rows + 7) / 8), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), grid.z);
+    k_modmat_f64<8, 1, 2, 3><<<gridf, MM_THREADS, 0, c->stream>>>(c->d_modq, d_M, (uint32_t)rows, (uint32_t)K, d_Y, d_C, (uint32_t)c->N_R,
+                                                                  (uint32_t)c->L_R, upper ? 1u : 0u);
+  }
+  else
+    k_modmat<<<grid, MM_THREADS, 0, c->stream>>>(c->d_modq, d_M, (uint32_t)rows, (uint32_t)K, d_Y, d_C, (uint32_t)c->N_R, (uint32_t)c->L_R,
+                                                 upper ? 1u : 0u, (uint32_t)K);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -961,8 +983,12 @@ extern "C" int rsg_vanishing(rsg_context *c, size_t n, uint64_t *h_Z) {
   return RSG_OK;
 }
 
+static int launch_modmat(rsg_context *c, const uint64_t *d_M, size_t rows, size_t K, const uint64_t *d_Y, uint64_t *d_C, size_t batch,
+                         bool upper, const char *name);
+// r1cs (nullable): the evaluations come from rsg_r1cs_evaluate on this system, so full = mid + io - constant wire and the
+// two interpolants of the full assignment follow by linearity (6 matrix products per proof instead of 8).
 static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, uint64_t *d_coeffs, uint64_t *d_H,
-                           const uint64_t *d_zk = nullptr) {
+                           const uint64_t *d_zk = nullptr, rsg_r1cs *r1cs = nullptr) {
   WitnessTables *wt;
   int rc = get_witness_tables(c, n, &wt);
   if (rc) return rc;
@@ -973,7 +999,31 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
   // evals order: A_mid,B_mid,C_mid,A_io,B_io,C_io,A_full,B_full,C_full ; coeffs order: A_io,B_io,C_io,A_mid,B_mid,C_mid
   if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 3 * n * W, d_coeffs, 3, false, "k_modmat_interp"))) return rc;
   if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals, d_coeffs + 3 * n * W, 3, false, "k_modmat_interp"))) return rc;
-  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 6 * n * W, aA, 2, false, "k_modmat_interp"))) return rc;
+  if (r1cs && r1cs->n == n) {
+    if (!r1cs->d_cc) {
+      uint64_t *d_const = nullptr;
+      void *v = nullptr;
+      CUDA_TRY(cudaMalloc(&v, r1cs->h_const.size() * 8));
+      d_const = (uint64_t *)v;
+      CUDA_TRY(cudaMalloc(&v, r1cs->h_const.size() * 8));
+      r1cs->d_cc = (uint64_t *)v;
+      CUDA_TRY(cudaMemcpyAsync(d_const, r1cs->h_const.data(), r1cs->h_const.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      for (int m = 0; m < 2; m++) {
+        LaunchScope ls(c, "k_matvec");
+        k_matvec<<<dim3((unsigned)((n + 127) / 128), (unsigned)c->L_R), 128, 0, c->stream>>>(
+            c->d_modq, wt->d_Vinv, (uint32_t)n, d_const + m * c->L_R * n, r1cs->d_cc + m * c->L_R * n);
+      }
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      cudaFree(d_const);
+    }
+    LaunchScope ls(c, "k_full_from_parts");
+    k_full_from_parts<<<dim3((unsigned)n, (unsigned)((W + 255) / 256), 2), 256, 0, c->stream>>>(c->d_modq, d_coeffs, r1cs->d_cc, aA, (uint32_t)n,
+                                                                                               (uint32_t)c->N_R, (uint32_t)c->L_R);
+    CUDA_TRY(cudaGetLastError());
+  } else if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 6 * n * W, aA, 2, false, "k_modmat_interp"))) {
+    return rc;
+  }
   CUDA_TRY(cudaMemsetAsync(d_H, 0, (n + 1) * W * 8, c->stream));
   if (n >= 2) {
     {
@@ -1009,18 +1059,29 @@ extern "C" int rsg_witness_map_zk(rsg_context *c, size_t n, const rsg_ringvec *e
   }
   return witness_map_dev(c, n, evals->d, coeffs->d, H->d, d_zk);
 }
+extern "C" int rsg_witness_map_r1cs(rsg_context *c, rsg_r1cs *r1cs, const rsg_ringvec *evals, const uint64_t *h_d, rsg_ringvec *coeffs,
+                                    rsg_ringvec *H) {
+  if (!c || !r1cs || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
+  const size_t n = r1cs->n;
+  if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t *d_zk = nullptr;
+  if (h_d) {
+    int rc = ensure(c, &c->d_zk, &c->cap_zk, 3 * c->ring_words());
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->d_zk, h_d, 3 * c->ring_words() * 8, cudaMemcpyHostToDevice, c->stream));
+    d_zk = c->d_zk;
+  }
+  return witness_map_dev(c, n, evals->d, coeffs->d, H->d, d_zk, r1cs);
+}
 extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
   return rsg_witness_map_zk(c, n, evals, nullptr, coeffs, H);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // R1CS evaluation (the step before the hot path)
-struct rsg_r1cs {
-  rsg_context *ctx;
-  size_t n, n_io, n_aux;
-  uint32_t *d_row_ptr = nullptr, *d_col = nullptr;
-  uint64_t *d_coeff = nullptr;
-};
+
 extern "C" int rsg_r1cs_create(rsg_context *c, size_t n, size_t n_io, size_t n_aux, const uint32_t *h_row_ptr, const uint32_t *h_col,
                                const uint64_t *h_coeff, rsg_r1cs **out) {
   if (!c || !h_row_ptr || !out || !n) return fail(RSG_ERR_ARG, "null argument");
@@ -1029,6 +1090,15 @@ extern "C" int rsg_r1cs_create(rsg_context *c, size_t n, size_t n_io, size_t n_a
     if (h_col[t] > n_io + n_aux) return fail(RSG_ERR_ARG, "variable index out of range");
   CUDA_TRY(cudaSetDevice(c->device));
   rsg_r1cs *r = new rsg_r1cs{c, n, n_io, n_aux};
+  r->h_const.assign(2 * c->L_R * n, 0);
+  for (size_t m = 0; m < 2; m++)
+    for (size_t i = 0; i < n; i++)
+      for (size_t t = h_row_ptr[m * n + i]; t < h_row_ptr[m * n + i + 1]; t++)
+        if (h_col[t] == 0)
+          for (size_t j = 0; j < c->L_R; j++) {
+            uint64_t &acc = r->h_const[(m * c->L_R + j) * n + i];
+            acc = (uint64_t)(((u128)acc + h_coeff[t] % c->q[j]) % c->q[j]);
+          }
   void *v;
   CUDA_TRY(cudaMalloc(&v, (3 * n + 1) * 4)); r->d_row_ptr = (uint32_t *)v;
   CUDA_TRY(cudaMalloc(&v, std::max<size_t>(nnz, 1) * 4)); r->d_col = (uint32_t *)v;
@@ -1044,7 +1114,7 @@ extern "C" int rsg_r1cs_create(rsg_context *c, size_t n, size_t n_io, size_t n_a
 extern "C" void rsg_r1cs_destroy(rsg_r1cs *r) {
   if (!r) return;
   cudaStreamSynchronize(r->ctx->stream);
-  cudaFree(r->d_row_ptr); cudaFree(r->d_col); cudaFree(r->d_coeff);
+  cudaFree(r->d_row_ptr); cudaFree(r->d_col); cudaFree(r->d_coeff); cudaFree(r->d_cc);
   delete r;
 }
 static int r1cs_eval_dev(rsg_context *c, const rsg_r1cs *r, const uint64_t *d_assign, uint64_t *d_evals) {
@@ -1083,7 +1153,7 @@ extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg
   if ((rc = ensure(c, &c->d_wit, &c->cap_wit, (7 * n + 1) * W))) return rc;
   uint64_t *coeffs = c->d_wit, *H = c->d_wit + 6 * n * W;
   if ((rc = r1cs_eval_dev(c, r1cs, assignment->d, c->d_evals))) return rc;
-  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H))) return rc;
+  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H, nullptr, const_cast<rsg_r1cs *>(r1cs)))) return rc;
   // SealPoly::is_zero prefix flags of every coefficient the prover feeds to inner_product: [6n coeffs | n+1 H | aux]
   const size_t n_flags = 7 * n + 1 + n_aux;
   if ((rc = ensure(c, &c->d_flags, &c->cap_flags, n_flags))) return rc;

@@ -65,6 +65,129 @@ __global__ void __launch_bounds__(MM_THREADS) k_modmat(const ModConst *__restric
   }
 }
 
+// The same product for primes below 2^54 (every ring prime of the reference's configs: 36..54 bit) on the FP64 pipe.
+// Measured on B200 (scratch/ubench2.cu): DFMA issues at 64 lanes/clk/SM, the same as a 32-bit IMAD, whereas a 32x32->64
+// IMAD.WIDE costs ~3 IMAD slots and a 64x64 high product ~9 -- so the cheapest exact wide multiply-accumulate on this
+// part is the double-precision FMA.  The constant matrix entry is cut into two 27-bit halves and the variable operand
+// into three 18-bit thirds: every partial product is < 2^45 and a double accumulates 128 of them exactly (< 2^52).
+// Six DFMA per 54x54-bit MAC, no carries, no reductions in the inner loop; the six sums (weights 2^0, 2^18, 2^27, 2^36,
+// 2^45, 2^63) are folded into a running canonical residue once per tile of 128 columns.  Integer in, integer out: the
+// doubles hold exact integers throughout, so the result is the same canonical residue as the integer kernel's.
+// Each thread owns one slot x MM_ROWS rows; the matrix tile is staged in shared memory as doubles, [column][row].
+constexpr int MMF_KTILE = 128;
+__device__ __forceinline__ double u32_to_double_exact(uint32_t v) {   // v as a double via the 2^52 mantissa trick
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+__device__ __forceinline__ uint64_t double_to_u64_exact(double d) {   // exact integer 0 <= d < 2^52
+  return (uint64_t)__double_as_longlong(d + 4503599627370496.0) & 0x000FFFFFFFFFFFFFull;
+}
+// Register tile: MM_ROWS rows x MMF_SLOTS slots per thread (96 double accumulators).  Shared-memory return bandwidth is
+// the second limit after the FP64 pipe -- every lane of a warp needs the same matrix entry, and a broadcast LDS.128 still
+// returns 512 B -- so each fetched entry must feed two slots (LDS at ~2/3 of the DFMA time instead of 4/3).
+template <int ROWS, int MMF_SLOTS, int MMF_PF, int MINB>
+__global__ void __launch_bounds__(MM_THREADS, MINB) k_modmat_f64(const ModConst *__restrict__ mods, const uint64_t *__restrict__ M,
+                                                              uint32_t Mrows, uint32_t K, const uint64_t *__restrict__ Y,
+                                                              uint64_t *__restrict__ C, uint32_t N_R, uint32_t L_R,
+                                                              uint32_t upper_triangular) {
+  __shared__ __align__(16) double2 tile[MMF_KTILE][ROWS];   // (low 27 bits, high 27 bits) of M[r0 + r][c0 + c]
+  const uint32_t r0 = blockIdx.x * ROWS;
+  const uint32_t slot0 = blockIdx.y * (MM_THREADS * MMF_SLOTS) + threadIdx.x;
+  const uint32_t v = blockIdx.z / L_R, limb = blockIdx.z - v * L_R;
+  const size_t W = (size_t)N_R * L_R;
+  const uint64_t *Mp = M + (size_t)limb * Mrows * K;
+  const uint64_t *Yp[MMF_SLOTS];
+  bool live[MMF_SLOTS];
+#pragma unroll
+  for (int s = 0; s < MMF_SLOTS; s++) {
+    live[s] = slot0 + s * MM_THREADS < N_R;
+    Yp[s] = Y + (size_t)v * K * W + (size_t)limb * N_R + (live[s] ? slot0 + s * MM_THREADS : 0);   // dead lanes re-read slot 0
+  }
+  const ModConst m = mods[limb];
+  uint64_t *Cp = C + (size_t)v * Mrows * W + (size_t)limb * N_R + slot0;
+  const uint32_t c_begin = upper_triangular ? (r0 / MMF_KTILE) * MMF_KTILE : 0;
+  for (uint32_t c0 = c_begin; c0 < K; c0 += MMF_KTILE) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ROWS * MMF_KTILE; i += MM_THREADS) {
+      const uint32_t r = i / MMF_KTILE, c = i % MMF_KTILE;   // coalesced along a matrix row
+      const uint64_t mv = (r0 + r < Mrows && c0 + c < K) ? Mp[(size_t)(r0 + r) * K + c0 + c] : 0;
+      tile[c][r] = make_double2(u32_to_double_exact((uint32_t)mv & 0x7FFFFFFu), u32_to_double_exact((uint32_t)(mv >> 27)));
+    }
+    __syncthreads();
+    const uint32_t cn = min((uint32_t)MMF_KTILE, K - c0);
+    double acc[MMF_SLOTS][ROWS][6];
+#pragma unroll
+    for (int s = 0; s < MMF_SLOTS; s++)
+#pragma unroll
+      for (int r = 0; r < ROWS; r++)
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[s][r][k] = 0.0;
+    // columns in groups of MMF_PF, the next group's Y words already in flight; columns past K meet zero tile entries
+    uint64_t ynext[MMF_SLOTS][MMF_PF];
+#pragma unroll
+    for (int s = 0; s < MMF_SLOTS; s++)
+#pragma unroll
+      for (int k = 0; k < MMF_PF; k++) ynext[s][k] = Yp[s][(size_t)min(c0 + k, K - 1) * W];
+    for (uint32_t c = 0; c < cn; c += MMF_PF) {
+      uint64_t ycur[MMF_SLOTS][MMF_PF];
+#pragma unroll
+      for (int s = 0; s < MMF_SLOTS; s++)
+#pragma unroll
+        for (int k = 0; k < MMF_PF; k++) ycur[s][k] = ynext[s][k];
+      if (c + MMF_PF < cn) {
+#pragma unroll
+        for (int s = 0; s < MMF_SLOTS; s++)
+#pragma unroll
+          for (int k = 0; k < MMF_PF; k++) ynext[s][k] = Yp[s][(size_t)min(c0 + c + MMF_PF + k, K - 1) * W];
+      }
+#pragma unroll
+      for (int k = 0; k < MMF_PF; k++) {
+        double y0[MMF_SLOTS], y1[MMF_SLOTS], y2[MMF_SLOTS];
+#pragma unroll
+        for (int s = 0; s < MMF_SLOTS; s++) {
+          y0[s] = u32_to_double_exact((uint32_t)ycur[s][k] & 0x3FFFFu);
+          y1[s] = u32_to_double_exact((uint32_t)(ycur[s][k] >> 18) & 0x3FFFFu);
+          y2[s] = u32_to_double_exact((uint32_t)(ycur[s][k] >> 36));
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+          const double2 mm = tile[c + k][r];
+#pragma unroll
+          for (int s = 0; s < MMF_SLOTS; s++) {
+            acc[s][r][0] = fma(mm.x, y0[s], acc[s][r][0]);
+            acc[s][r][1] = fma(mm.x, y1[s], acc[s][r][1]);
+            acc[s][r][2] = fma(mm.x, y2[s], acc[s][r][2]);
+            acc[s][r][3] = fma(mm.y, y0[s], acc[s][r][3]);
+            acc[s][r][4] = fma(mm.y, y1[s], acc[s][r][4]);
+            acc[s][r][5] = fma(mm.y, y2[s], acc[s][r][5]);
+          }
+        }
+      }
+    }
+    // fold: sum_k acc_k * 2^w_k, w = {0, 18, 36, 27, 45, 63} (< 2^116): one Barrett reduction per output per tile, added to
+    // the running canonical residue kept in C itself (this thread is the only writer of its outputs)
+#pragma unroll
+    for (int s = 0; s < MMF_SLOTS; s++) {
+      if (!live[s]) continue;
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        if (r0 + r >= Mrows) continue;
+        uint64_t lo = double_to_u64_exact(acc[s][r][0]), hi = 0;
+        const int wsh[5] = {18, 36, 27, 45, 63};
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          const uint64_t x = double_to_u64_exact(acc[s][r][k + 1]);
+          const uint64_t t = x << wsh[k];
+          lo += t;
+          hi += (lo < t) + (x >> (64 - wsh[k]));
+        }
+        uint64_t *o = Cp + (size_t)(r0 + r) * W + s * MM_THREADS;
+        const uint64_t part = reduce128(lo, hi, m);
+        *o = c0 == c_begin ? part : add_mod(*o, part, m.p);
+      }
+    }
+  }
+}
+
 // Ptop[i][slot] = sum_j A[j][slot] * B[n + i - j][slot],  i in [0, n-1), j in [i+1, n)  -- coefficient n+i of A*B.
 // Elements j >= lenA of A and >= lenB of B count as zero (Boost normalize() through RingElem::operator==).
 // grid (ceil((n-1)/MM_ROWS), N_R/MM_THREADS, L_R)
@@ -99,6 +222,35 @@ __global__ void __launch_bounds__(MM_THREADS) k_conv_top(const ModConst *__restr
 #pragma unroll
   for (int r = 0; r < MM_ROWS; r++)
     if (i0 + r < n - 1) Pp[(size_t)(i0 + r) * W] = acc[r].reduce(m);
+}
+
+// out[limb][r] = sum_c M[limb][r][c] * x[limb][c] mod q_limb: the interpolant of a per-constraint CONSTANT (the same in
+// every slot), i.e. of the constant wire's contribution.  grid (ceil(n/128), L_R), tiny.
+__global__ void __launch_bounds__(128) k_matvec(const ModConst *__restrict__ mods, const uint64_t *__restrict__ M, uint32_t n,
+                                                const uint64_t *__restrict__ x, uint64_t *__restrict__ out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x, limb = blockIdx.y;
+  if (r >= n) return;
+  const uint64_t *row = M + ((size_t)limb * n + r) * n, *xv = x + (size_t)limb * n;
+  Acc192 acc;
+  acc.clear();
+  for (uint32_t c = 0; c < n; c++) acc.mac(row[c], xv[c]);
+  out[(size_t)limb * n + r] = acc.reduce(mods[limb]);
+}
+// Interpolation is linear and full = mid + io - constant (the constant wire is counted under both partial assignments,
+// r1cs_to_qrp.tcc:167-201 with variable.tcc:246-254), so the interpolants of the FULL assignment need no product of their own:
+//   aA[k] = A_io[k] + A_mid[k] - cc[0][limb][k],  aB likewise with cc[1].   coeffs order: A_io,B_io,C_io,A_mid,B_mid,C_mid.
+// grid (n, ceil(W/256), 2)
+__global__ void __launch_bounds__(256) k_full_from_parts(const ModConst *__restrict__ mods, const uint64_t *__restrict__ coeffs,
+                                                         const uint64_t *__restrict__ cc, uint64_t *__restrict__ aAB, uint32_t n,
+                                                         uint32_t N_R, uint32_t L_R) {
+  const uint32_t k = blockIdx.x, w = blockIdx.y * blockDim.x + threadIdx.x, m = blockIdx.z;
+  const uint32_t W = N_R * L_R;
+  if (w >= W) return;
+  const uint32_t limb = w / N_R;
+  const uint64_t p = mods[limb].p;
+  const uint64_t io = coeffs[((size_t)m * n + k) * W + w], mid = coeffs[((size_t)(3 + m) * n + k) * W + w];
+  const uint64_t c = cc[((size_t)m * L_R + limb) * n + k];
+  aAB[((size_t)m * n + k) * W + w] = sub_mod(add_mod(io, mid, p), c, p);
 }
 
 // Zero-knowledge patch of H (r1cs_to_qrp.tcc:225-235, evaluation_domain.tcc:62-76):
