@@ -10,8 +10,9 @@ N_E = 2^14, 8 RNS limbs of 48/49 bit, n = 1031 constraints, 517 primary + 1538 a
   value : ms per proof, CRS + assignment resident in HBM, timed with CUDA events on the launching stream
   e2e   : ms per proof through the C-ABI call rsg_groth16_prove with HOST buffers (pinned): H2D of the assignment and
           D2H of the proof inside the timed region
-  N > 1 : strong scaling of ONE proof: every CRS vector is sharded by term across the ranks, each rank produces a partial
-          proof, one NCCL all-gather + the modular-add kernel combine them (the witness map is replicated per rank)
+  N > 1 : strong scaling of ONE proof (ringsnark_b200/distributed.py): witness map sharded by slot, one NCCL all-to-all
+          (slots <-> terms), every CRS vector sharded by term, one NCCL all-gather of the partial proofs + the modular-add
+          kernel
   --impl reference : the reference's own CPU prover (oracle/_ref/ref_harness = unmodified ringSNARK + SEAL 4.1.1),
           bounded sample, extrapolated to the workload as stated in `sample`
 """
@@ -74,7 +75,7 @@ def run_reference_arm(args, cfg_name, cfg):
     for _ in range(max(1, min(args.steps, 2))):      # each "step" is a fresh bounded sample
         last = cpu_reference_sample(cfg_name, cfg, budget="small")
         if last is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness not built (needs /root/reference at build time)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/ref_harness not built (needs /root/reference at build time)"})
             return
         vals.append(last["value"])
     v = statistics.median(vals)
@@ -87,13 +88,13 @@ def run_reference_arm(args, cfg_name, cfg):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(cfg_name, cfg, gpus):
     return {"workload": f"{cfg_name}: ringGroth16 prover, N_R={cfg['N_R']}, L_R={len(cfg['q'])}, N_E={cfg['N_E']}, "
                         f"L_E={len(cfg['Q'])}, n={cfg['n']} constraints, io={cfg['io']}, aux={cfg['aux']}",
-            "crs": "synthetic uniform residues", "sharding": f"terms/{gpus}" if gpus > 1 else "none",
+            "crs": "synthetic uniform residues", "sharding": f"witness map by slot/{gpus}, all-to-all, lincombs by term/{gpus}, all-gather + modular add" if gpus > 1 else "none",
             "l2": "inputs larger than L2 (CRS streamed per proof >> 126 MB)"}
 
 
@@ -176,42 +177,66 @@ def run_gpu_arm(args, cfg_name, cfg):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, io, aux = cfg["n"], cfg["io"], cfg["aux"]
-    ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"], device=local)
     stream = torch.cuda.Stream()
-    ctx.set_stream(stream.cuda_stream)
     row_ptr, col, coeff = synthetic_r1cs(n, io, aux, seed=1)
-    r1cs = rs.R1cs(ctx, n, io, aux, row_ptr, col, coeff)
-    pk = rs.Groth16ProvingKey(ctx, r1cs, rank, world)
-    pk.crs.fill_uniform(0xB200 + rank)
     h_assign_np = make_assignment(cfg, row_ptr, col, coeff, seed=0xB200)
-    h_assign = torch.from_numpy(h_assign_np.view(np.int64)).pin_memory()
-    h_proof = torch.empty(3 * ctx.enc_words, dtype=torch.int64).pin_memory()
-    pk.assignment.upload(h_assign_np)
-    d_part = torch.zeros(3 * ctx.enc_words, dtype=torch.int64, device="cuda")
-    d_all = torch.zeros(world * 3 * ctx.enc_words, dtype=torch.int64, device="cuda") if world > 1 else None
-    d_final = torch.zeros(3 * ctx.enc_words, dtype=torch.int64, device="cuda")
-    h_assign_ptr = h_assign.numpy().view(np.uint64)
-    h_proof_np = h_proof.numpy().view(np.uint64)
-
     import ctypes as C
     from ringsnark_b200.capi import check
+    single = world == 1
+    if single:
+        ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"], device=local)
+        ctx.set_stream(stream.cuda_stream)
+        ctxs = [ctx]
+        r1cs = rs.R1cs(ctx, n, io, aux, row_ptr, col, coeff)
+        pk = rs.Groth16ProvingKey(ctx, r1cs, 0, 1)
+        pk.crs.fill_uniform(0xB200)
+        layout = pk.layout
+        h_assign = torch.from_numpy(h_assign_np.view(np.int64)).pin_memory()
+        h_proof = torch.empty(3 * ctx.enc_words, dtype=torch.int64).pin_memory()
+        pk.assignment.upload(h_assign_np)
+        d_final = torch.zeros(3 * ctx.enc_words, dtype=torch.int64, device="cuda")
+        h_assign_ptr = h_assign.numpy().view(np.uint64)
+        h_proof_np = h_proof.numpy().view(np.uint64)
+        h2d_bytes = int(h_assign.numel() * 8)
 
-    def prove(host_io):
-        """one step; returns nothing, leaves the (combined) proof in d_final / h_proof"""
-        with torch.cuda.stream(stream):
-            used = (C.c_size_t * 3)()
-            single = world == 1
-            check(ctx.lib.rsg_groth16_prove(
-                ctx.h, r1cs.h, pk.crs.h, C.byref(pk.layout), pk.assignment.h,
-                C.c_void_p(h_assign_ptr.ctypes.data) if host_io else None, None,
-                C.c_void_p(h_proof_np.ctypes.data) if (host_io and single) else None,
-                C.c_void_p(d_part.data_ptr()), used))
-            if not single:
-                dist.all_gather_into_tensor(d_all, d_part)
-                ctx.enc_sum(d_all.data_ptr(), world, 3, d_final.data_ptr())
+        def prove(host_io):
+            """one step; leaves the proof in d_final / h_proof"""
+            with torch.cuda.stream(stream):
+                used = (C.c_size_t * 3)()
+                check(ctx.lib.rsg_groth16_prove(
+                    ctx.h, r1cs.h, pk.crs.h, C.byref(pk.layout), pk.assignment.h,
+                    C.c_void_p(h_assign_ptr.ctypes.data) if host_io else None, None,
+                    C.c_void_p(h_proof_np.ctypes.data) if host_io else None,
+                    C.c_void_p(d_final.data_ptr()), used))
+                return [int(u) for u in used]
+    else:
+        # slot-sharded witness map -> all-to-all -> term-sharded lincombs -> all-gather + modular add (distributed.py)
+        from ringsnark_b200.distributed import ShardedGroth16Prover, slot_shard
+        sp = ShardedGroth16Prover(cfg, (row_ptr, col, coeff), rank, world, device=local, stream=stream.cuda_stream)
+        ctx = sp.ctxP
+        ctxs = [sp.ctxP, sp.ctxW]
+        sp.crs.fill_uniform(0xB200 + rank)
+        layout = sp.layout
+        h_shard = torch.from_numpy(slot_shard(h_assign_np, sp.L_R, sp.N_R, rank, world).view(np.int64)).pin_memory()
+        h_aux = torch.from_numpy(np.ascontiguousarray(h_assign_np[io + sp.m_lo:io + sp.m_hi]).view(np.int64)).pin_memory()
+        h_proof = torch.empty(3 * ctx.enc_words, dtype=torch.int64).pin_memory()
+        sp.load_assignment_shards(h_shard, h_aux, non_blocking=False)
+        d_all = torch.zeros(world * 3 * ctx.enc_words, dtype=torch.int64, device="cuda")
+        h2d_bytes = int((h_shard.numel() + h_aux.numel()) * 8)
+
+        def prove(host_io):
+            with torch.cuda.stream(stream):
                 if host_io:
-                    h_proof.copy_(d_final, non_blocking=True)
-            return [int(u) for u in used]
+                    sp.load_assignment_shards(h_shard, h_aux)
+                send = sp.witness_phase()
+                recv = torch.empty_like(send)
+                dist.all_to_all_single(recv, send)
+                used = sp.lincomb_phase(recv)
+                dist.all_gather_into_tensor(d_all, sp.t_part)
+                sp.combine(d_all)
+                if host_io:
+                    h_proof.copy_(sp.t_final, non_blocking=True)
+                return used
 
     def barrier():
         torch.cuda.synchronize()
@@ -235,8 +260,9 @@ def run_gpu_arm(args, cfg_name, cfg):
     # ---- timed region 1: device-resident inputs ("value"), with per-kernel event timing for the roofline
     sampler = ClockSampler(local)
     sampler.start()
-    ctx.enable_timing(True)
-    l0 = ctx.launch_count()
+    for cx in ctxs:
+        cx.enable_timing(True)
+    l0 = sum(cx.launch_count() for cx in ctxs)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -245,13 +271,17 @@ def run_gpu_arm(args, cfg_name, cfg):
     ev1.record(stream)
     barrier()
     ms_dev = reduce_max(ev0.elapsed_time(ev1) / args.steps)
-    launches = ctx.launch_count() - l0
+    launches = sum(cx.launch_count() for cx in ctxs) - l0
     kern = {}
     for name in ("k_crs_lincomb", "k_lift_fwd_ntt", "k_encode_intt", "k_modmat_interp", "k_modmat_divZ", "k_conv_top",
-                 "k_r1cs_eval", "k_enc_sum", "k_is_zero_prefix"):
-        ms, cnt = ctx.timing(name)
+                 "k_r1cs_eval", "k_enc_sum", "k_enc_add", "k_is_zero_prefix", "k_probe", "k_full_from_parts"):
+        ms = cnt = 0
+        for cx in ctxs:
+            m_, c_ = cx.timing(name)
+            ms, cnt = ms + m_, cnt + c_
         kern[name] = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps}
-    ctx.enable_timing(False)
+    for cx in ctxs:
+        cx.enable_timing(False)
 
     # ---- timed region 2: through the C ABI with host buffers ("e2e")
     barrier()
@@ -266,8 +296,11 @@ def run_gpu_arm(args, cfg_name, cfg):
     # ---- roofline of the dominant kernel (k_crs_lincomb): algorithmic bytes per step / its device time per step
     L_R, L_E, N_E = len(cfg["q"]), len(cfg["Q"]), cfg["N_E"]
     row = L_R * L_E * N_E * 8
-    ones = [1 if pk.layout.alpha_idx != rs.backend.NONE else 0, 1 if pk.layout.beta_idx != rs.backend.NONE else 0, 0]
-    alg_bytes = sum(row * (3 * (u - o) + 2 * o + 2) for u, o in zip(used, ones))
+    ones = [1 if layout.alpha_idx != rs.backend.NONE else 0, 1 if layout.beta_idx != rs.backend.NONE else 0, 0]
+    # alpha / beta are added by k_enc_add, every other term is streamed by k_crs_lincomb: 3 words per slot per term
+    # (2 CRS + 1 NTT-domain plaintext) + one 2-word output per launch
+    lin_launches = kern["k_crs_lincomb"]["launches_per_step"]
+    alg_bytes = row * (3 * sum(u - o for u, o in zip(used, ones)) + 2 * lin_launches)
     lin_ms = kern["k_crs_lincomb"]["ms_per_step"]
     peaks = {}
     try:
@@ -289,7 +322,7 @@ def run_gpu_arm(args, cfg_name, cfg):
             "metric": METRIC, "value": ms_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(cfg_name, cfg, world),
-            "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h_assign.numel() * 8),
+            "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(h_proof.numel() * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -306,13 +339,34 @@ def run_gpu_arm(args, cfg_name, cfg):
                 line["cpu_baseline"] = cpu_reference_sample(cfg_name, cfg)
             except Exception as ex:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"error": str(ex)[:200]}
-        print(json.dumps(line))
-    ctx.close()
+        emit(line)
+    if single:
+        ctx.close()
+    else:
+        sp.close()
     if dist:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else a library prints on fd 1 during the
+    run (e.g. NCCL's version banner) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -152,6 +152,18 @@ int rsg_groth16_prove(rsg_context *ctx, const rsg_r1cs *r1cs, const rsg_crs *crs
                       rsg_ringvec *assignment, const uint64_t *h_assignment, const uint8_t *h_aux_kind,
                       uint64_t *h_proof, uint64_t *d_proof, size_t *n_used);
 
+/* The second half of rsg_groth16_prove on its own (the multi-GPU driver runs the witness map sharded by SLOT, exchanges
+ * the coefficients with one all-to-all, and then calls this on every rank's TERM shard): the six inner products and the
+ * operator+= chain of groth16.tcc:89-112 from device-resident coefficient vectors.  d_vec[k], k = A_io, A_mid, B_io, B_mid
+ * (terms [s_pows_lo, min(s_pows_hi, n))), H (terms [delta_ts_lo, min(delta_ts_hi, n+1))), aux (terms [delta_mid_lo,
+ * min(delta_mid_hi, n_aux))), each points at the ring element of the FIRST term of its range. h_aux_kind is indexed by the
+ * absolute auxiliary index as in rsg_groth16_prove. */
+int rsg_groth16_lincombs(rsg_context *ctx, const rsg_crs *crs, const rsg_groth16_layout *layout, size_t n, size_t n_aux,
+                         const uint64_t *const d_vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
+                         size_t *n_used);
+/* A non-owning rsg_ringvec over caller-owned device memory (e.g. a torch tensor): n_elems ring elements at d_words. */
+int rsg_ringvec_wrap(rsg_context *ctx, uint64_t *d_words, size_t n_elems, rsg_ringvec **out);
+
 /* ---- low-level entry points used by tests and by the multi-GPU driver (device pointers) ---- */
 /* BatchEncoder::encode (batchencoder.cpp:110-149): count elements [L_R][N_R] -> plaintext coeffs [count][L_R][N_E] */
 int rsg_batch_encode(rsg_context *ctx, const uint64_t *d_ring, size_t count, uint64_t *d_plain);

@@ -192,6 +192,7 @@ struct rsg_ringvec {
   rsg_context *ctx;
   size_t n;
   uint64_t *d;
+  bool owned = true;
 };
 
 struct rsg_r1cs {
@@ -471,8 +472,15 @@ extern "C" size_t rsg_ringvec_size(const rsg_ringvec *r) { return r ? r->n : 0; 
 extern "C" void rsg_ringvec_destroy(rsg_ringvec *r) {
   if (!r) return;
   cudaStreamSynchronize(r->ctx->stream);
-  cudaFree(r->d);
+  if (r->owned) cudaFree(r->d);
   delete r;
+}
+extern "C" int rsg_ringvec_wrap(rsg_context *c, uint64_t *d_words, size_t n, rsg_ringvec **out) {
+  if (!c || !d_words || !out) return fail(RSG_ERR_ARG, "null argument");
+  rsg_ringvec *r = new rsg_ringvec{c, n, d_words};
+  r->owned = false;
+  *out = r;
+  return RSG_OK;
 }
 
 extern "C" int rsg_ringvec_is_zero_prefix(const rsg_ringvec *r, size_t first, size_t count, uint8_t *h_flags) {
@@ -1135,39 +1143,33 @@ extern "C" int rsg_r1cs_evaluate(rsg_context *c, const rsg_r1cs *r, const rsg_ri
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// groth16::prover (groth16.tcc:69-115) in one call.  A = <s_pows, A_io> + <s_pows, A_mid> + alpha etc. are each ONE
-// linear combination over the concatenated term lists: modular addition is associative and every result canonical,
-// so the words equal those of the reference's inner_product / operator+= sequence.
-extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg_crs *crs, const rsg_groth16_layout *L,
-                                 rsg_ringvec *assignment, const uint64_t *h_assignment, const uint8_t *h_aux_kind, uint64_t *h_proof,
-                                 uint64_t *d_proof, size_t *n_used) {
-  if (!c || !r1cs || !crs || !L || !assignment) return fail(RSG_ERR_ARG, "null argument");
-  const size_t n = r1cs->n, n_io = r1cs->n_io, n_aux = r1cs->n_aux, W = c->ring_words();
-  if (assignment->n < n_io + n_aux) return fail(RSG_ERR_ARG, "assignment too short");
-  std::lock_guard<std::mutex> g(c->mu);
-  CUDA_TRY(cudaSetDevice(c->device));
+// groth16::prover (groth16.tcc:69-115): the witness map, then the reference's own sequence of six inner products combined
+// with operator+= (kept separate, not fused into three, because the transparent-ciphertext rule is order-dependent).
+// The six inner products + operator+= chain of groth16.tcc:89-112 over this shard's term ranges.  vec[k] (k = A_io, A_mid,
+// B_io, B_mid, H, aux) is the address element 0 of that coefficient vector WOULD have: only the elements of the shard's
+// ranges ([s_lo, min(s_hi, n)) for the first four, [t_lo, min(t_hi, n+1)) for H, [m_lo, min(m_hi, n_aux)) for aux) are read.
+static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
+                                const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
+                                size_t *n_used) {
   int rc;
-  if (h_assignment)
-    CUDA_TRY(cudaMemcpyAsync(assignment->d, h_assignment, (n_io + n_aux) * W * 8, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = ensure(c, &c->d_evals, &c->cap_evals, 9 * n * W))) return rc;
-  if ((rc = ensure(c, &c->d_wit, &c->cap_wit, (7 * n + 1) * W))) return rc;
-  uint64_t *coeffs = c->d_wit, *H = c->d_wit + 6 * n * W;
-  if ((rc = r1cs_eval_dev(c, r1cs, assignment->d, c->d_evals))) return rc;
-  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H, nullptr, const_cast<rsg_r1cs *>(r1cs)))) return rc;
-  // SealPoly::is_zero prefix flags of every coefficient the prover feeds to inner_product: [6n coeffs | n+1 H | aux]
-  const size_t n_flags = 7 * n + 1 + n_aux;
-  if ((rc = ensure(c, &c->d_flags, &c->cap_flags, n_flags))) return rc;
-  {
-    LaunchScope ls(c, "k_is_zero_prefix");
-    k_is_zero_prefix<<<(unsigned)(7 * n + 1), 256, 0, c->stream>>>(c->d_wit, (uint32_t)W, c->d_flags);
-  }
-  if (n_aux) {
-    LaunchScope ls(c, "k_is_zero_prefix");
-    k_is_zero_prefix<<<(unsigned)n_aux, 256, 0, c->stream>>>(assignment->d + n_io * W, (uint32_t)W, c->d_flags + 7 * n + 1);
-  }
+  const size_t W = c->ring_words();
+  const size_t NONE = (size_t)-1;
+  // SealPoly::is_zero prefix flags of every coefficient fed to inner_product (one launch per vector range, one copy)
+  struct Range { size_t lo, hi; };
+  const Range rg[6] = {{L->s_pows_lo, std::min(L->s_pows_hi, n)}, {L->s_pows_lo, std::min(L->s_pows_hi, n)},
+                       {L->s_pows_lo, std::min(L->s_pows_hi, n)}, {L->s_pows_lo, std::min(L->s_pows_hi, n)},
+                       {L->delta_ts_lo, std::min(L->delta_ts_hi, n + 1)}, {L->delta_mid_lo, std::min(L->delta_mid_hi, n_aux)}};
+  size_t foff[7] = {0};
+  for (int k = 0; k < 6; k++) foff[k + 1] = foff[k] + (rg[k].hi > rg[k].lo ? rg[k].hi - rg[k].lo : 0);
+  if ((rc = ensure(c, &c->d_flags, &c->cap_flags, std::max<size_t>(foff[6], 1)))) return rc;
+  for (int k = 0; k < 6; k++)
+    if (foff[k + 1] > foff[k]) {
+      LaunchScope ls(c, "k_is_zero_prefix");
+      k_is_zero_prefix<<<(unsigned)(foff[k + 1] - foff[k]), 256, 0, c->stream>>>(vec[k] + rg[k].lo * W, (uint32_t)W, c->d_flags + foff[k]);
+    }
   CUDA_TRY(cudaGetLastError());
-  std::vector<uint8_t> flags(n_flags);
-  CUDA_TRY(cudaMemcpyAsync(flags.data(), c->d_flags, n_flags, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<uint8_t> flags(std::max<size_t>(foff[6], 1));
+  if (foff[6]) CUDA_TRY(cudaMemcpyAsync(flags.data(), c->d_flags, foff[6], cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
 
   uint64_t *out = d_proof;
@@ -1175,30 +1177,20 @@ extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg
     if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 3 * c->enc_words()))) return rc;
     out = c->d_out_scratch;
   }
-  const size_t NONE = (size_t)-1;
-  auto add_vec = [&](std::vector<TermSpec> &terms, size_t off, size_t lo, size_t hi, size_t limit, const uint64_t *base, size_t elem0,
-                     const uint8_t *zero_flag) {
-    for (size_t i = lo; i < std::min(hi, limit); i++)
-      if (!zero_flag[i]) terms.push_back({(uint32_t)(off + i - lo), base, (uint32_t)(elem0 + i)});
-  };
-  // The reference's sequence (groth16.tcc:89-112): six separate inner products, combined with operator+=.
-  //   A = <s_pows, A_io> + <s_pows, A_mid> + alpha;  B likewise with beta;  C = <delta_ts, H> [+ <delta_mid, aux>]
-  // coeffs order in HBM: A_io, B_io, C_io, A_mid, B_mid, C_mid
   std::vector<TermSpec> ip[6];
-  add_vec(ip[0], L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 0, flags.data());
-  add_vec(ip[1], L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 3 * n, flags.data() + 3 * n);
-  add_vec(ip[2], L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, n, flags.data() + n);
-  add_vec(ip[3], L->s_pows_off, L->s_pows_lo, L->s_pows_hi, n, coeffs, 4 * n, flags.data() + 4 * n);
-  add_vec(ip[4], L->delta_ts_off, L->delta_ts_lo, L->delta_ts_hi, n + 1, H, 0, flags.data() + 6 * n);
-  for (size_t i = L->delta_mid_lo; i < std::min(L->delta_mid_hi, n_aux); i++) {
+  const size_t crs_off[6] = {L->s_pows_off, L->s_pows_off, L->s_pows_off, L->s_pows_off, L->delta_ts_off, L->delta_mid_off};
+  for (int k = 0; k < 5; k++)
+    for (size_t i = rg[k].lo; i < rg[k].hi; i++)
+      if (!flags[foff[k] + i - rg[k].lo]) ip[k].push_back({(uint32_t)(crs_off[k] + i - rg[k].lo), vec[k], (uint32_t)i});
+  for (size_t i = rg[5].lo; i < rg[5].hi; i++) {
     const uint8_t kind = h_aux_kind ? h_aux_kind[i] : (uint8_t)RSG_AUX_POLY;
-    const uint32_t ci = (uint32_t)(L->delta_mid_off + i - L->delta_mid_lo);
+    const uint32_t ci = (uint32_t)(crs_off[5] + i - rg[5].lo);
     if (kind == RSG_AUX_POLY) {
-      if (!flags[7 * n + 1 + i]) ip[5].push_back({ci, assignment->d, (uint32_t)(n_io + i)});
+      if (!flags[foff[5] + i - rg[5].lo]) ip[5].push_back({ci, vec[5], (uint32_t)i});
     } else if (kind == RSG_TERM_ONE) {
       ip[5].push_back({ci, nullptr, 0});
     } else if (kind == RSG_TERM_GENERAL) {
-      ip[5].push_back({ci, assignment->d, (uint32_t)(n_io + i)});
+      ip[5].push_back({ci, vec[5], (uint32_t)i});
     }
   }
   const size_t E = c->enc_words();
@@ -1257,4 +1249,39 @@ extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg
   if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 3 * c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
+}
+
+extern "C" int rsg_groth16_lincombs(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
+                                    const uint64_t *const d_vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
+                                    size_t *n_used) {
+  if (!c || !crs || !L || !d_vec) return fail(RSG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  // shard pointers address the FIRST element of each range; rebase them to element 0 (never dereferenced below the range)
+  const size_t W = c->ring_words();
+  const uint64_t *vec[6];
+  const size_t lo[6] = {L->s_pows_lo, L->s_pows_lo, L->s_pows_lo, L->s_pows_lo, L->delta_ts_lo, L->delta_mid_lo};
+  for (int k = 0; k < 6; k++) vec[k] = d_vec[k] ? d_vec[k] - lo[k] * W : nullptr;
+  return groth16_lincombs_dev(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, d_proof, n_used);
+}
+
+extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg_crs *crs, const rsg_groth16_layout *L,
+                                 rsg_ringvec *assignment, const uint64_t *h_assignment, const uint8_t *h_aux_kind, uint64_t *h_proof,
+                                 uint64_t *d_proof, size_t *n_used) {
+  if (!c || !r1cs || !crs || !L || !assignment) return fail(RSG_ERR_ARG, "null argument");
+  const size_t n = r1cs->n, n_io = r1cs->n_io, n_aux = r1cs->n_aux, W = c->ring_words();
+  if (assignment->n < n_io + n_aux) return fail(RSG_ERR_ARG, "assignment too short");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc;
+  if (h_assignment)
+    CUDA_TRY(cudaMemcpyAsync(assignment->d, h_assignment, (n_io + n_aux) * W * 8, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = ensure(c, &c->d_evals, &c->cap_evals, 9 * n * W))) return rc;
+  if ((rc = ensure(c, &c->d_wit, &c->cap_wit, (7 * n + 1) * W))) return rc;
+  uint64_t *coeffs = c->d_wit, *H = c->d_wit + 6 * n * W;
+  if ((rc = r1cs_eval_dev(c, r1cs, assignment->d, c->d_evals))) return rc;
+  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H, nullptr, const_cast<rsg_r1cs *>(r1cs)))) return rc;
+  // coeffs order in HBM: A_io, B_io, C_io, A_mid, B_mid, C_mid
+  const uint64_t *vec[6] = {coeffs, coeffs + 3 * n * W, coeffs + n * W, coeffs + 4 * n * W, H, assignment->d + n_io * W};
+  return groth16_lincombs_dev(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, d_proof, n_used);
 }

@@ -1,0 +1,151 @@
+"""Multi-GPU ringGroth16 prover: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
+
+SURVEY.md section 8(e): the witness map shards by SLOT (every slot of Z_q^N is an independent copy of the computation),
+the CRS linear combinations shard by TERM.  Between the two sits the path's one real exchange step: after the witness map
+rank r holds slots [r*S, (r+1)*S) of EVERY coefficient, for the lincombs it needs ALL slots of the coefficients of ITS
+terms -- an all-to-all (about 10 MB per rank at C4).  Each rank then produces a partial proof (3 encodings) over its term
+range; one all-gather of the partials and the modular-add kernel (modular addition is not an NCCL reduction) finish.
+
+    phase 1  rsg_r1cs_evaluate + rsg_witness_map_r1cs   on a context with N_R/G slots      (sharded by slot)
+    phase 2  all_to_all_single                                                             (slots <-> terms)
+    phase 3  rsg_groth16_lincombs                        on the full context, term shard of the CRS
+    phase 4  all_gather_into_tensor + rsg_enc_sum
+
+The index bookkeeping (`send_rows`, `unpack`) is pure host logic and is exercised on CPU with gloo in
+tests/test_multi_rank_cpu.py; tests/test_gpu_parity.py runs all phases for G simulated ranks on one GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .backend import Context, Groth16Layout, NONE, R1cs, groth16_shard_layout
+from .capi import check
+
+VEC_ROWS = ("A_io", "A_mid", "B_io", "B_mid", "H")
+
+
+def rows_per_rank(n, world):
+    """Terms of s_pows[0..n] / delta_ts[0..n] per rank (the last rank may hold fewer)."""
+    return (n + 1 + world - 1) // world
+
+
+def send_rows(n, world):
+    """Row indices into the rank-local witness tensor [7n+2 rows] = [A_io|B_io|C_io|A_mid|B_mid|C_mid (n each) | H (n+1) |
+    one zero row], in the order the all-to-all ships them: for every destination d, for every vector of VEC_ROWS, the
+    `per` coefficients of d's term range (indices past the end of a vector point at the zero row)."""
+    per = rows_per_rank(n, world)
+    base = {"A_io": 0, "A_mid": 3 * n, "B_io": n, "B_mid": 4 * n, "H": 6 * n}
+    length = {"A_io": n, "A_mid": n, "B_io": n, "B_mid": n, "H": n + 1}
+    zero_row = 7 * n + 1
+    idx = np.empty((world, len(VEC_ROWS), per), dtype=np.int64)
+    for d in range(world):
+        for v, name in enumerate(VEC_ROWS):
+            for i in range(per):
+                k = d * per + i
+                idx[d, v, i] = base[name] + k if k < length[name] else zero_row
+    return idx.reshape(-1), per
+
+
+def unpack(recv, world, per, L_R, S):
+    """recv: [world (source rank = slot block), 5, per, L_R, S] -> [5, per, L_R, world*S]: full ring elements of this
+    rank's terms (element layout [L_R][N_R], poly_arith.h:81-102)."""
+    return recv.reshape(world, len(VEC_ROWS), per, L_R, S).permute(1, 2, 3, 0, 4).reshape(len(VEC_ROWS), per, L_R * world * S)
+
+
+def slot_shard(words, L_R, N_R, rank, world):
+    """[k][L_R*N_R] host words -> the rank's slot block [k][L_R*S]."""
+    S = N_R // world
+    w = np.asarray(words).reshape(-1, L_R, N_R)
+    return np.ascontiguousarray(w[:, :, rank * S:(rank + 1) * S]).reshape(w.shape[0], L_R * S)
+
+
+class ShardedGroth16Prover:
+    """One rank of the G-GPU prover.  `exchange(send) -> recv` and `gather(part) -> all_parts` are injected so that the
+    same code runs under NCCL (bench.py), and rank-by-rank on one GPU in the tests."""
+
+    def __init__(self, cfg, r1cs_csr, rank, world, device=0, stream=None):
+        import torch
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.n, self.io, self.aux = cfg["n"], cfg["io"], cfg["aux"]
+        self.N_R, self.L_R = cfg["N_R"], len(cfg["q"])
+        assert self.N_R % world == 0, "slot sharding needs N_R divisible by the number of ranks"
+        self.S = self.N_R // world
+        n = self.n
+        self.ctxP = Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"], device=device)      # lincombs: full ring elements
+        self.ctxW = Context(self.S, cfg["q"], cfg["N_E"], cfg["Q"], device=device)          # witness map: this rank's slots
+        if stream is not None:
+            self.ctxP.set_stream(stream)
+            self.ctxW.set_stream(stream)
+        row_ptr, col, coeff = r1cs_csr
+        self.r1csW = R1cs(self.ctxW, n, self.io, self.aux, row_ptr, col, coeff)
+        d = groth16_shard_layout(n, self.aux, rank, world)
+        self.layout = Groth16Layout()
+        for k, _ in Groth16Layout._fields_:
+            setattr(self.layout, k, d[k])
+        self.crs = self.ctxP.crs(d["n_elems"])
+        dev = torch.device("cuda", device)
+        Ws = self.L_R * self.S
+        # witness tensor of this slot block: [6n coefficients | n+1 H | zero row]; the library writes into it through wraps
+        self.t_wit = torch.zeros(7 * n + 2, Ws, dtype=torch.int64, device=dev)
+        self.t_assign = torch.zeros(self.io + self.aux, Ws, dtype=torch.int64, device=dev)
+        self.t_evals = torch.zeros(9 * n, Ws, dtype=torch.int64, device=dev)
+        idx, self.per = send_rows(n, world)
+        self.idx = torch.from_numpy(idx).to(dev)
+        self.m_lo, self.m_hi = d["delta_mid_lo"], d["delta_mid_hi"]
+        self.t_aux = torch.zeros(max(self.m_hi - self.m_lo, 1), self.L_R * self.N_R, dtype=torch.int64, device=dev)
+        self.t_part = torch.zeros(3 * self.ctxP.enc_words, dtype=torch.int64, device=dev)
+        self.t_final = torch.zeros(3 * self.ctxP.enc_words, dtype=torch.int64, device=dev)
+        self._wraps = []
+        self.rv_assign = self._wrap(self.ctxW, self.t_assign, self.io + self.aux)
+        self.rv_evals = self._wrap(self.ctxW, self.t_evals, 9 * n)
+        self.rv_coeffs = self._wrap(self.ctxW, self.t_wit, 6 * n)
+        self.rv_H = self._wrap(self.ctxW, self.t_wit[6 * n:], n + 1)
+
+    def _wrap(self, ctx, tensor, n_elems):
+        h = C.c_void_p()
+        check(ctx.lib.rsg_ringvec_wrap(ctx.h, C.c_void_p(tensor.data_ptr()), n_elems, C.byref(h)))
+        self._wraps.append((ctx, h))
+        return h
+
+    def load_assignment(self, words, non_blocking=False):
+        """Host words of the FULL assignment [io+aux][L_R*N_R] (numpy, or pre-sharded pinned torch tensors via
+        load_assignment_shards)."""
+        torch = self.torch
+        shard = torch.from_numpy(slot_shard(words, self.L_R, self.N_R, self.rank, self.world).view(np.int64))
+        aux = torch.from_numpy(np.ascontiguousarray(np.asarray(words)[self.io + self.m_lo:self.io + self.m_hi]).view(np.int64))
+        self.load_assignment_shards(shard, aux, non_blocking)
+
+    def load_assignment_shards(self, shard, aux, non_blocking=True):
+        self.t_assign.copy_(shard, non_blocking=non_blocking)
+        if self.m_hi > self.m_lo:
+            self.t_aux[:self.m_hi - self.m_lo].copy_(aux, non_blocking=non_blocking)
+
+    def witness_phase(self):
+        """Phase 1 + the pack of phase 2: returns the send buffer [world * 5 * per, L_R*S]."""
+        lib, ctx = self.ctxW.lib, self.ctxW
+        check(lib.rsg_r1cs_evaluate(ctx.h, self.r1csW.h, self.rv_assign, self.rv_evals))
+        check(lib.rsg_witness_map_r1cs(ctx.h, self.r1csW.h, self.rv_evals, None, self.rv_coeffs, self.rv_H))
+        return self.t_wit.index_select(0, self.idx)
+
+    def lincomb_phase(self, recv, h_proof_ptr=None):
+        """Phase 3 from the received buffer [world, 5, per, L_R, S]; leaves the partial proof in t_part."""
+        full = unpack(recv, self.world, self.per, self.L_R, self.S).contiguous()
+        self._full = full   # keep alive until the kernels have run
+        ptrs = (C.c_void_p * 6)(*[full[v].data_ptr() for v in range(5)], self.t_aux.data_ptr())
+        used = (C.c_size_t * 3)()
+        check(self.ctxP.lib.rsg_groth16_lincombs(self.ctxP.h, self.crs.h, C.byref(self.layout), self.n, self.aux, ptrs, None,
+                                                 C.c_void_p(h_proof_ptr) if h_proof_ptr else None,
+                                                 C.c_void_p(self.t_part.data_ptr()), used))
+        return [int(u) for u in used]
+
+    def combine(self, all_parts):
+        """Phase 4 after the all-gather: modular sum of the `world` partial proofs."""
+        self.ctxP.enc_sum(all_parts.data_ptr(), self.world, 3, self.t_final.data_ptr())
+
+    def close(self):
+        for ctx, h in self._wraps:
+            ctx.lib.rsg_ringvec_destroy(h)
+        self._wraps = []
+        self.ctxW.close()
+        self.ctxP.close()

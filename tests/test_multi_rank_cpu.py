@@ -89,3 +89,57 @@ def test_sharded_prover_gloo(world):
         assert p.exitcode == 0
     res = sorted(q.get(timeout=10) for _ in range(world))
     assert res == [(r, True) for r in range(world)]
+
+
+def _exchange_worker(rank, world, port, golden, q):
+    """The slots<->terms exchange of ringsnark_b200/distributed.py on CPU: every rank starts from its SLOT block of the
+    reference's witness (all coefficients) and must end with ALL slots of the coefficients of ITS term range."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    from rsgv import Case
+    from ringsnark_b200.distributed import VEC_ROWS, send_rows, slot_shard, unpack
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = Case(golden)
+        n, L_R, N_R = case.n, case.L_R, case.N_R
+        S = N_R // world
+        order = ["A_io", "B_io", "C_io", "A_mid", "B_mid", "C_mid"]
+        full = np.concatenate([case.ring("wit_" + k)[0] for k in order] + [case.ring("wit_H")[0]])   # [7n+1][L_R*N_R]
+        wit = np.concatenate([slot_shard(full, L_R, N_R, rank, world), np.zeros((1, L_R * S), dtype=np.uint64)])
+        idx, per = send_rows(n, world)
+        send = torch.from_numpy(wit[idx].view(np.int64))
+        # gloo has no all_to_all: gather everything, keep the blocks addressed to this rank
+        allsend = [torch.zeros_like(send) for _ in range(world)]
+        dist.all_gather(allsend, send)
+        blk = 5 * per
+        recv = torch.stack([s[rank * blk:(rank + 1) * blk] for s in allsend])
+        got = unpack(recv, world, per, L_R, S).numpy().view(np.uint64)                    # [5][per][L_R*N_R]
+        ok = True
+        for v, name in enumerate(VEC_ROWS):
+            ref = case.ring("wit_" + name)[0]
+            for i in range(per):
+                k = rank * per + i
+                want = ref[k] if k < ref.shape[0] else np.zeros(L_R * N_R, dtype=np.uint64)
+                ok = ok and np.array_equal(got[v, i], want)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slot_to_term_exchange_gloo(world):
+    golden = os.path.join(HERE, "golden", "tiny_fast.rsgv")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, golden, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(world))
+    assert res == [(r, True) for r in range(world)]
