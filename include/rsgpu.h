@@ -80,6 +80,22 @@ void rsg_ringvec_destroy(rsg_ringvec *v);
  * [0, L_R*N_R + 7) of element first+i are zero.  One kernel + one small copy for the whole range. */
 int rsg_ringvec_is_zero_prefix(const rsg_ringvec *v, size_t first, size_t count, uint8_t *h_flags);
 
+/* ---- RingElem operators on device-resident vectors: the element-wise fall-backs of the RingT concept (seal_ring.tcc:
+ * 105-263 over poly_arith.cpp:164-350).  `count` elements starting at the given indices; out may alias a. ---- */
+#define RSG_OP_ADD 0
+#define RSG_OP_SUB 1
+#define RSG_OP_MUL 2
+int rsg_ring_binop(rsg_context *ctx, int op, const rsg_ringvec *a, size_t a_first, const rsg_ringvec *b, size_t b_first,
+                   rsg_ringvec *out, size_t out_first, size_t count);
+/* poly (op) scalar with SEAL's scalar semantics: add/sub take the scalar as is (one correction), mul reduces it first. */
+int rsg_ring_scalar_op(rsg_context *ctx, int op, const rsg_ringvec *a, size_t a_first, uint64_t scalar, rsg_ringvec *out,
+                       size_t out_first, size_t count);
+int rsg_ring_negate(rsg_context *ctx, const rsg_ringvec *a, size_t a_first, rsg_ringvec *out, size_t out_first, size_t count);
+/* Per-slot inverses; RSG_ERR_NOTINV if some element has a zero slot ("element is not invertible in ring",
+ * seal_ring.tcc:87-103); h_ok (nullable) receives 1 per invertible element. */
+int rsg_ring_invert(rsg_context *ctx, const rsg_ringvec *a, size_t a_first, rsg_ringvec *out, size_t out_first, size_t count,
+                    uint8_t *h_ok);
+
 /* ---- hot path (b): EncodingElem::inner_product (seal_ring.tcc:361-433) ----
  * out = sum over i in [0, count) with tag[i] != SKIP of crs[crs_first+i] (*) coeffs[coeff_first+i].
  * h_out (host, may be NULL) and/or d_out (device, may be NULL) receive one encoding.  *n_used = number of summed

@@ -41,6 +41,10 @@ SIGNATURES = {
     "rsg_ringvec_size": (_sz, [_vp]),
     "rsg_ringvec_destroy": (None, [_vp]),
     "rsg_ringvec_is_zero_prefix": (_int, [_vp, _sz, _sz, _vp]),
+    "rsg_ring_binop": (_int, [_vp, _int, _vp, _sz, _vp, _sz, _vp, _sz, _sz]),
+    "rsg_ring_scalar_op": (_int, [_vp, _int, _vp, _sz, _u64, _vp, _sz, _sz]),
+    "rsg_ring_negate": (_int, [_vp, _vp, _sz, _vp, _sz, _sz]),
+    "rsg_ring_invert": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _vp]),
     "rsg_inner_product": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _vp, _vp, _vp, C.POINTER(_sz)]),
     "rsg_inner_product_idx": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(_sz)]),
     "rsg_enc_add": (_int, [_vp, _vp, _vp]),

@@ -14,6 +14,7 @@
 #include "../../include/rsgpu.h"
 #include "kernels.cuh"
 #include "witness.cuh"
+#include "ringops.cuh"
 
 using namespace rsg;
 typedef unsigned __int128 u128;
@@ -498,6 +499,88 @@ extern "C" int rsg_ringvec_is_zero_prefix(const rsg_ringvec *r, size_t first, si
   CUDA_TRY(cudaMemcpyAsync(h_flags, c->d_flags, count, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// element-wise RingElem operators
+static int ring_range(const rsg_ringvec *v, size_t first, size_t count) { return v && first + count <= v->n; }
+static dim3 ring_grid(const rsg_context *c, size_t count) {
+  return dim3((unsigned)((c->N_R + 255) / 256), (unsigned)c->L_R, (unsigned)count);
+}
+extern "C" int rsg_ring_binop(rsg_context *c, int op, const rsg_ringvec *a, size_t a_first, const rsg_ringvec *b, size_t b_first,
+                              rsg_ringvec *out, size_t out_first, size_t count) {
+  if (!c || op < 0 || op > 2) return fail(RSG_ERR_ARG, "bad operator");
+  if (!ring_range(a, a_first, count) || !ring_range(b, b_first, count) || !ring_range(out, out_first, count)) return fail(RSG_ERR_ARG, "ringvec range");
+  if (!count) return RSG_OK;
+  if (count > 65535) return fail(RSG_ERR_UNSUPPORTED, "at most 65535 elements per call");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t W = c->ring_words();
+  LaunchScope ls(c, "k_ring_binop");
+  k_ring_binop<<<ring_grid(c, count), 256, 0, c->stream>>>(c->d_modq, op, a->d + a_first * W, b->d + b_first * W, out->d + out_first * W,
+                                                           (uint32_t)c->N_R, (uint32_t)c->L_R);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+extern "C" int rsg_ring_scalar_op(rsg_context *c, int op, const rsg_ringvec *a, size_t a_first, uint64_t scalar, rsg_ringvec *out,
+                                  size_t out_first, size_t count) {
+  if (!c || op < 0 || op > 2) return fail(RSG_ERR_ARG, "bad operator");
+  if (!ring_range(a, a_first, count) || !ring_range(out, out_first, count)) return fail(RSG_ERR_ARG, "ringvec range");
+  if (!count) return RSG_OK;
+  if (count > 65535) return fail(RSG_ERR_UNSUPPORTED, "at most 65535 elements per call");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t W = c->ring_words();
+  LaunchScope ls(c, "k_ring_scalar");
+  k_ring_scalar<<<ring_grid(c, count), 256, 0, c->stream>>>(c->d_modq, op, a->d + a_first * W, scalar, out->d + out_first * W,
+                                                            (uint32_t)c->N_R, (uint32_t)c->L_R);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+extern "C" int rsg_ring_negate(rsg_context *c, const rsg_ringvec *a, size_t a_first, rsg_ringvec *out, size_t out_first, size_t count) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  if (!ring_range(a, a_first, count) || !ring_range(out, out_first, count)) return fail(RSG_ERR_ARG, "ringvec range");
+  if (!count) return RSG_OK;
+  if (count > 65535) return fail(RSG_ERR_UNSUPPORTED, "at most 65535 elements per call");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t W = c->ring_words();
+  LaunchScope ls(c, "k_ring_negate");
+  k_ring_negate<<<ring_grid(c, count), 256, 0, c->stream>>>(c->d_modq, a->d + a_first * W, out->d + out_first * W, (uint32_t)c->N_R,
+                                                            (uint32_t)c->L_R);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+extern "C" int rsg_ring_invert(rsg_context *c, const rsg_ringvec *a, size_t a_first, rsg_ringvec *out, size_t out_first, size_t count,
+                               uint8_t *h_ok) {
+  if (!c) return fail(RSG_ERR_STATE, "context not set");
+  if (!ring_range(a, a_first, count) || !ring_range(out, out_first, count)) return fail(RSG_ERR_ARG, "ringvec range");
+  if (!count) return RSG_OK;
+  if (count > 65535) return fail(RSG_ERR_UNSUPPORTED, "at most 65535 elements per call");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t W = c->ring_words();
+  uint32_t *d_bad = nullptr;
+  void *v = nullptr;
+  CUDA_TRY(cudaMalloc(&v, count * 4));
+  d_bad = (uint32_t *)v;
+  CUDA_TRY(cudaMemsetAsync(d_bad, 0, count * 4, c->stream));
+  {
+    LaunchScope ls(c, "k_ring_invert");
+    k_ring_invert<<<ring_grid(c, count), 256, 0, c->stream>>>(c->d_modq, a->d + a_first * W, out->d + out_first * W, (uint32_t)c->N_R,
+                                                              (uint32_t)c->L_R, d_bad);
+  }
+  std::vector<uint32_t> bad(count);
+  cudaError_t e = cudaMemcpyAsync(bad.data(), d_bad, count * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return fail(RSG_ERR_CUDA, cudaGetErrorString(e));
+  bool any = false;
+  for (size_t i = 0; i < count; i++) {
+    if (h_ok) h_ok[i] = bad[i] ? 0 : 1;
+    any |= bad[i] != 0;
+  }
+  return any ? fail(RSG_ERR_NOTINV, "element is not invertible in ring") : RSG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------

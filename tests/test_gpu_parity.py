@@ -369,3 +369,47 @@ def test_slot_and_term_sharded_prover(gold, world):
     finally:
         for p in provers:
             p.close()
+
+
+def test_ring_elementwise_ops(gold):
+    """RingElem operators on the device (seal_ring.tcc:105-263 over poly_arith.cpp:164-350) against exact integer
+    arithmetic, including SEAL's unreduced-scalar add/sub and the not-invertible error."""
+    import ctypes as C
+    import ringsnark_b200 as rs
+    case, ctx = gold
+    N_R, L_R = case.N_R, case.L_R
+    q = [int(x) for x in case.q]
+    a, b, out = ctx.ringvec(5), ctx.ringvec(5), ctx.ringvec(5)
+    a.fill_uniform(11)
+    b.fill_uniform(12)
+    A = a.download().reshape(5, L_R, N_R).astype(object)
+    B = b.download().reshape(5, L_R, N_R).astype(object)
+    lib = ctx.lib
+
+    def want(fn):
+        return np.stack([np.stack([fn(A[e, j], B[e, j], q[j]) for j in range(L_R)]) for e in range(5)]).astype(np.uint64).reshape(5, -1)
+
+    for op, fn in ((0, lambda x, y, p: (x + y) % p), (1, lambda x, y, p: (x - y) % p), (2, lambda x, y, p: (x * y) % p)):
+        assert lib.rsg_ring_binop(ctx.h, op, a.h, 0, b.h, 0, out.h, 0, 5) == 0
+        assert np.array_equal(out.download(), want(fn)), op
+    s = 12345
+    for op, fn in ((0, lambda x, y, p: (x + s) % p), (1, lambda x, y, p: (x - s) % p), (2, lambda x, y, p: (x * s) % p)):
+        assert lib.rsg_ring_scalar_op(ctx.h, op, a.h, 1, s, out.h, 1, 3) == 0
+        assert np.array_equal(out.download(1, 3), want(fn)[1:4]), op
+    big = max(q) + 5       # SEAL's add_uint_mod takes the scalar as is: ONE conditional subtraction, not a reduction
+    assert lib.rsg_ring_scalar_op(ctx.h, 0, a.h, 0, big, out.h, 0, 5) == 0
+    assert np.array_equal(out.download(), want(lambda x, y, p: np.where(x + big >= p, x + big - p, x + big)))
+    assert lib.rsg_ring_scalar_op(ctx.h, 2, a.h, 0, big, out.h, 0, 5) == 0     # multiply reduces it first
+    assert np.array_equal(out.download(), want(lambda x, y, p: (x * big) % p))
+    assert lib.rsg_ring_negate(ctx.h, a.h, 0, out.h, 0, 5) == 0
+    assert np.array_equal(out.download(), want(lambda x, y, p: (-x) % p))
+    ok = np.zeros(5, dtype=np.uint8)
+    assert lib.rsg_ring_invert(ctx.h, a.h, 0, out.h, 0, 5, ok.ctypes.data_as(C.c_void_p)) == 0 and ok.all()
+    inv = out.download().reshape(5, L_R, N_R).astype(object)
+    for j in range(L_R):
+        assert ((inv[:, j] * A[:, j]) % q[j] == 1).all()
+    z = a.download()
+    z[2, 7] = 0                                   # one zero slot: the element is not a unit of the ring
+    a.upload(z)
+    rc = lib.rsg_ring_invert(ctx.h, a.h, 0, out.h, 0, 5, ok.ctypes.data_as(C.c_void_p))
+    assert rc == -4 and list(ok) == [1, 1, 0, 1, 1] and b"not invertible" in lib.rsg_last_error()
