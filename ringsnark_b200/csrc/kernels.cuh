@@ -24,6 +24,8 @@ struct DevParams {
   const Twiddle *invq[MAX_LR];   // inverse tables mod q_j (batch encoder)
   Twiddle invN_q[MAX_LR];        // N_E^-1 mod q_j
   Twiddle invN_Q[MAX_LE];        // N_E^-1 mod Q_l
+  Twiddle invNw_q[MAX_LR];       // N_E^-1 * psi^-(N/2) mod q_j: last inverse stage of the split transform (N_E = 2^15)
+  Twiddle invNw_Q[MAX_LE];
   uint64_t thr[MAX_LR];          // ceil(q_j / 2): plain_upper_half_threshold (context.cpp:329)
   uint64_t tmodQ[MAX_LR][MAX_LE];  // q_j mod Q_l
   const uint32_t *index_map;     // matrix_reps_index_map_ (batchencoder.cpp:64-88), N_E entries
@@ -37,14 +39,18 @@ __device__ __forceinline__ uint64_t canon4(uint64_t x, uint64_t p) {  // [0,4p) 
 
 // ---------------------------------------------------------------------------------------------------------
 // Batch encode: ring limb (N_R slot values) -> plaintext polynomial coefficients mod t = q_j (N_E words).
-// grid (count, L_R); elem_idx (nullable) selects which ring element each block encodes.
-template <int LOGN>
+// grid (count << LVL0, L_R); elem_idx (nullable) selects which ring element each block encodes.
+// N_E = 2^(LOGN + LVL0).  A 2^15-point polynomial does not fit one SM's shared memory (256 KiB + padding > 227 KiB), so for
+// LVL0 = 1 each CTA owns one HALF: the inverse transform's levels LOGN..1 stay inside a half (they are the independent
+// sub-transforms of the bit-reversed input), the CTA leaves its lazy values in `plain`, and k_intt_finish applies the
+// last level (pairs i, i + N/2) together with the N^-1 scaling SEAL merges into it (util/dwthandler.h:60-73).
+template <int LOGN, int LVL0>
 __global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict__ P, const uint64_t *__restrict__ ring,
                                                      const uint32_t *__restrict__ elem_idx,
                                                      uint64_t *__restrict__ plain) {
   extern __shared__ uint64_t sm[];
   constexpr uint32_t n = 1u << LOGN;
-  const uint32_t j = blockIdx.y, e = blockIdx.x;
+  const uint32_t j = blockIdx.y, e = blockIdx.x >> LVL0, h = blockIdx.x & ((1u << LVL0) - 1);
   const uint32_t N_R = P->N_R, L_R = P->L_R;
   const uint32_t src_e = elem_idx ? elem_idx[e] : e;
   const uint64_t *src = ring + ((size_t)src_e * L_R + j) * N_R;
@@ -52,55 +58,114 @@ __global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict
   for (uint32_t i = threadIdx.x; i < padded_words(n); i += blockDim.x) sm[i] = 0;
   __syncthreads();
   const uint32_t *map = P->index_map;
-  for (uint32_t k = threadIdx.x; k < N_R; k += blockDim.x) sm[pad_idx(__ldg(map + k))] = src[k];
+  for (uint32_t k = threadIdx.x; k < N_R; k += blockDim.x) {
+    const uint32_t pos = __ldg(map + k);
+    if ((pos >> LOGN) == h) sm[pad_idx(pos & (n - 1))] = src[k];
+  }
   __syncthreads();
-  ntt_inverse_smem<LOGN>(sm, P->invq[j], p, 0, 0);
-  const Twiddle invn = P->invN_q[j];
-  uint64_t *dst = plain + ((size_t)e * L_R + j) * n;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = mul_shoup(sm[pad_idx(i)], invn, p);
+  ntt_inverse_smem<LOGN>(sm, P->invq[j], p, LVL0, h);
+  uint64_t *dst = plain + (((size_t)e * L_R + j) << (LOGN + LVL0)) + (size_t)h * n;
+  if (LVL0 == 0) {
+    const Twiddle invn = P->invN_q[j];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = mul_shoup(sm[pad_idx(i)], invn, p);
+  } else {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = sm[pad_idx(i)];   // lazy, < 2p
+  }
+}
+
+// Last Gentleman-Sande level of a split inverse transform + scaling: (x, y) -> ((x + y) N^-1, (x - y) w N^-1), canonical.
+// data: `polys` polynomials of 2*half words, values < 2p.  which_q: per-polynomial modulus index = poly % n_mod.
+__global__ void __launch_bounds__(256) k_intt_finish(uint64_t *__restrict__ data, uint32_t half, size_t polys,
+                                                     const ModConst *__restrict__ mods, const Twiddle *__restrict__ invn,
+                                                     const Twiddle *__restrict__ invnw, uint32_t n_mod, uint32_t fixed_mod) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= polys * half) return;
+  const size_t poly = t / half;
+  const uint32_t i = (uint32_t)(t - poly * half);
+  const uint32_t mi = fixed_mod != 0xFFFFFFFFu ? fixed_mod : (uint32_t)(poly % n_mod);
+  const uint64_t p = mods[mi].p, two_p = p << 1;
+  uint64_t *d = data + poly * 2 * half;
+  const uint64_t x = d[i], y = d[i + half];
+  uint64_t s2 = x + y;
+  s2 = s2 >= two_p ? s2 - two_p : s2;
+  d[i] = mul_shoup(s2, invn[mi], p);
+  d[i + half] = mul_shoup(x - y + two_p, invnw[mi], p);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Centred lift into Q_l + forward NTT.  grid (count * L_E, L_R): the L_E limbs of one plaintext are neighbours in launch
-// order, so the eight CTAs that read the same coefficient vector run together and seven of the reads hit L2.
+// Centred lift into Q_l + forward NTT.  grid ((count * L_E) << LVL0, L_R): the L_E limbs of one plaintext are neighbours in
+// launch order, so the CTAs that read the same coefficient vector run together and all but one of the reads hit L2.
 // LAZY (every Q_l < 2^58): correction-free butterflies, one Barrett reduction per word at the store.
-template <int LOGN, bool LAZY>
+// LVL0 = 1 (N_E = 2^15): the first Cooley-Tukey level pairs i with i + N/2 and is applied while loading (each of the two
+// CTAs lifts both words and keeps its own half); the remaining levels are two independent 2^14-point transforms.
+template <int LOGN, int LVL0, bool LAZY>
 __global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
                                                       uint64_t *__restrict__ out) {
   extern __shared__ uint64_t sm[];
   constexpr uint32_t n = 1u << LOGN;
   const uint32_t L_R = P->L_R, L_E = P->L_E;
-  const uint32_t e = blockIdx.x / L_E, l = blockIdx.x - e * L_E, j = blockIdx.y;
+  const uint32_t h = blockIdx.x & ((1u << LVL0) - 1), el = blockIdx.x >> LVL0;
+  const uint32_t e = el / L_E, l = el - e * L_E, j = blockIdx.y;
   const ModConst m = P->Q[l];
   const uint64_t thr = P->thr[j], tm = P->tmodQ[j][l];
-  const uint64_t *src = plain + ((size_t)e * L_R + j) * n;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const uint64_t v = src[i];
+  const uint64_t *src = plain + (((size_t)e * L_R + j) << (LOGN + LVL0));
+  auto lift = [&](uint64_t v) {
     uint64_t r = reduce64(v, m);
     if (v >= thr) r = sub_mod(r, tm, m.p);   // v + (Q - t)  ==  v - t  (mod Q_l)
-    sm[pad_idx(i)] = r;
+    return r;
+  };
+  if (LVL0 == 0) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[pad_idx(i)] = lift(src[i]);
+  } else {
+    const Twiddle t0 = load_tw(P->fwdQ[l], 1);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      uint64_t x = lift(src[i]), y = lift(src[i + n]);
+      if (LAZY) bfly_fwd_lazy(x, y, t0, m.p, m.p << 2);
+      else bfly_fwd(x, y, t0, m.p, m.p << 1);
+      sm[pad_idx(i)] = h ? y : x;
+    }
   }
   __syncthreads();
-  ntt_forward_smem<LOGN, LAZY>(sm, P->fwdQ[l], m.p, 0, 0);
-  uint64_t *dst = out + (((size_t)e * L_R + j) * L_E + l) * n;
+  ntt_forward_smem<LOGN, LAZY>(sm, P->fwdQ[l], m.p, LVL0, h);
+  uint64_t *dst = out + (((((size_t)e * L_R + j) * L_E + l)) << (LOGN + LVL0)) + (size_t)h * n;
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
     dst[i] = LAZY ? reduce64(sm[pad_idx(i)], m) : canon4(sm[pad_idx(i)], m.p);
 }
 
-// Raw NTT of `batch` polynomials in place; grid (batch).
-template <int LOGN, bool INVERSE>
-__global__ void __launch_bounds__(512) k_ntt(uint64_t *__restrict__ data, const Twiddle *__restrict__ tab, uint64_t p,
-                                             Twiddle invn) {
+// Raw NTT of `batch` polynomials; grid (batch << LVL0).  In place for LVL0 = 0.  For LVL0 = 1 the forward transform reads
+// `src` and writes `dst` (they must differ: both CTAs of a polynomial read both halves), the inverse works in place on its
+// own half and is completed by k_intt_finish.
+template <int LOGN, int LVL0, bool INVERSE>
+__global__ void __launch_bounds__(512) k_ntt(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
+                                             const Twiddle *__restrict__ tab, uint64_t p, Twiddle invn) {
   extern __shared__ uint64_t sm[];
   constexpr uint32_t n = 1u << LOGN;
-  uint64_t *d = data + (size_t)blockIdx.x * n;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[pad_idx(i)] = d[i];
-  __syncthreads();
+  const uint32_t h = blockIdx.x & ((1u << LVL0) - 1);
+  const size_t poly = (size_t)(blockIdx.x >> LVL0) << (LOGN + LVL0);
+  const uint64_t *s = src + poly;
+  uint64_t *d = dst + poly + (size_t)h * n;
   if (INVERSE) {
-    ntt_inverse_smem<LOGN>(sm, tab, p, 0, 0);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = mul_shoup(sm[pad_idx(i)], invn, p);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[pad_idx(i)] = s[(size_t)h * n + i];
+    __syncthreads();
+    ntt_inverse_smem<LOGN>(sm, tab, p, LVL0, h);
+    if (LVL0 == 0) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = mul_shoup(sm[pad_idx(i)], invn, p);
+    } else {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = sm[pad_idx(i)];
+    }
   } else {
-    ntt_forward_smem<LOGN>(sm, tab, p, 0, 0);
+    if (LVL0 == 0) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[pad_idx(i)] = s[i];
+    } else {
+      const Twiddle t0 = load_tw(tab, 1);
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint64_t x = s[i], y = s[i + n];
+        bfly_fwd(x, y, t0, p, p << 1);
+        sm[pad_idx(i)] = h ? y : x;
+      }
+    }
+    __syncthreads();
+    ntt_forward_smem<LOGN>(sm, tab, p, LVL0, h);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = canon4(sm[pad_idx(i)], p);
   }
 }

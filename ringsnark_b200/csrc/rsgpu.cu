@@ -147,6 +147,7 @@ struct rsg_context {
   DevParams hp;                 // host copy
   DevParams *d_params = nullptr;
   ModConst *d_modq = nullptr, *d_modQ = nullptr;
+  Twiddle *d_invN_q = nullptr, *d_invNw_q = nullptr, *d_invN_Q = nullptr, *d_invNw_Q = nullptr;
   std::vector<void *> owned;    // device allocations freed at destroy
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -259,7 +260,7 @@ static int upload_vec(rsg_context *c, const std::vector<T> &h, T **d) {
 extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, const uint64_t *q, size_t N_E, size_t L_E,
                                   const uint64_t *Q, int device) {
   if (!out || !q || !Q) return fail(RSG_ERR_ARG, "null argument");
-  if (N_E < 256 || N_E > 16384 || (N_E & (N_E - 1))) return fail(RSG_ERR_UNSUPPORTED, "N_E must be a power of two in [256, 16384]");
+  if (N_E < 256 || N_E > 32768 || (N_E & (N_E - 1))) return fail(RSG_ERR_UNSUPPORTED, "N_E must be a power of two in [256, 32768]");
   if (N_R == 0 || N_R > N_E || (N_R & (N_R - 1))) return fail(RSG_ERR_ARG, "N_R must be a power of two <= N_E");
   if (L_R == 0 || L_R > (size_t)MAX_LR || L_E == 0 || L_E > (size_t)MAX_LE) return fail(RSG_ERR_ARG, "limb count out of range");
   for (size_t i = 0; i < L_R + L_E; i++) {
@@ -295,6 +296,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
     if ((rc = upload_vec(c, inv, &d))) return rc;
     hp.invQ[l] = d;
     hp.invN_Q[l] = h_twiddle(h_inv(N_E % Q[l], Q[l]), Q[l]);
+    hp.invNw_Q[l] = h_twiddle(h_mulmod(hp.invN_Q[l].w, inv[1].w, Q[l]), Q[l]);
   }
   for (size_t j = 0; j < L_R; j++) {
     hp.q[j] = h_modconst(q[j]);
@@ -305,6 +307,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
     if ((rc = upload_vec(c, inv, &d))) return rc;
     hp.invq[j] = d;
     hp.invN_q[j] = h_twiddle(h_inv(N_E % q[j], q[j]), q[j]);
+    hp.invNw_q[j] = h_twiddle(h_mulmod(hp.invN_q[j].w, inv[1].w, q[j]), q[j]);
     hp.thr[j] = (q[j] + 1) >> 1;
     for (size_t l = 0; l < L_E; l++) hp.tmodQ[j][l] = q[j] % Q[l];
   }
@@ -327,6 +330,11 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
     std::vector<ModConst> mq(hp.q, hp.q + L_R), mQ(hp.Q, hp.Q + L_E);
     if ((rc = upload_vec(c, mq, &c->d_modq))) return rc;
     if ((rc = upload_vec(c, mQ, &c->d_modQ))) return rc;
+    std::vector<Twiddle> a(hp.invN_q, hp.invN_q + L_R), b(hp.invNw_q, hp.invNw_q + L_R), a2(hp.invN_Q, hp.invN_Q + L_E),
+        b2(hp.invNw_Q, hp.invNw_Q + L_E);
+    if ((rc = upload_vec(c, a, &c->d_invN_q)) || (rc = upload_vec(c, b, &c->d_invNw_q)) || (rc = upload_vec(c, a2, &c->d_invN_Q)) ||
+        (rc = upload_vec(c, b2, &c->d_invNw_Q)))
+      return rc;
   }
   if ((rc = dev_alloc(c, &c->d_probe_carry, MAX_LR, false))) return rc;
   if ((rc = dev_alloc(c, &c->d_nz, MAX_LR, false))) return rc;
@@ -584,61 +592,79 @@ extern "C" int rsg_ring_invert(rsg_context *c, const rsg_ringvec *a, size_t a_fi
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// NTT launch helpers
-static unsigned ntt_threads(int logn) { return (unsigned)std::max(32, std::min(512, (1 << logn) / 16)); }
-static size_t ntt_smem(int logn) { return (size_t)padded_words(1u << logn) * 8; }
+// NTT launch helpers.  N_E = 2^15 runs as two 2^14-point halves per polynomial (LV = 1, see kernels.cuh).
+static int local_logn(int logN) { return logN > 14 ? 14 : logN; }
+static unsigned ntt_threads(int logN) { return (unsigned)std::max(32, std::min(512, (1 << local_logn(logN)) / 16)); }
+static size_t ntt_smem(int logN) { return (size_t)padded_words(1u << local_logn(logN)) * 8; }
 
-template <int LOGN>
+template <int LOGN, int LV>
 static int set_smem_attrs() {
   static bool done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (done[dev]) return RSG_OK;
-  const int bytes = (int)ntt_smem(LOGN);
-  CUDA_TRY(cudaFuncSetAttribute(k_encode_intt<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int bytes = (int)padded_words(1u << LOGN) * 8;
+  CUDA_TRY(cudaFuncSetAttribute(k_encode_intt<LOGN, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done[dev] = true;
   return RSG_OK;
 }
 
 #define DISPATCH_LOGN(logn, ...)                  \
   switch (logn) {                                 \
-    case 8: { constexpr int LG = 8; __VA_ARGS__; } break;   \
-    case 9: { constexpr int LG = 9; __VA_ARGS__; } break;   \
-    case 10: { constexpr int LG = 10; __VA_ARGS__; } break; \
-    case 11: { constexpr int LG = 11; __VA_ARGS__; } break; \
-    case 12: { constexpr int LG = 12; __VA_ARGS__; } break; \
-    case 13: { constexpr int LG = 13; __VA_ARGS__; } break; \
-    case 14: { constexpr int LG = 14; __VA_ARGS__; } break; \
+    case 8: { constexpr int LG = 8, LV = 0; __VA_ARGS__; } break;   \
+    case 9: { constexpr int LG = 9, LV = 0; __VA_ARGS__; } break;   \
+    case 10: { constexpr int LG = 10, LV = 0; __VA_ARGS__; } break; \
+    case 11: { constexpr int LG = 11, LV = 0; __VA_ARGS__; } break; \
+    case 12: { constexpr int LG = 12, LV = 0; __VA_ARGS__; } break; \
+    case 13: { constexpr int LG = 13, LV = 0; __VA_ARGS__; } break; \
+    case 14: { constexpr int LG = 14, LV = 0; __VA_ARGS__; } break; \
+    case 15: { constexpr int LG = 14, LV = 1; __VA_ARGS__; } break; \
     default: return fail(RSG_ERR_UNSUPPORTED, "unsupported N_E"); \
   }
+
+// split inverse transforms leave the last level to this kernel; fixed_mod = 0xFFFFFFFF: modulus = polynomial index % n_mod
+static int launch_intt_finish(rsg_context *c, uint64_t *d, size_t polys, const ModConst *mods, const Twiddle *invn,
+                              const Twiddle *invnw, uint32_t n_mod, uint32_t fixed_mod) {
+  const uint32_t half = (uint32_t)(c->N_E / 2);
+  LaunchScope ls(c, "k_intt_finish");
+  k_intt_finish<<<(unsigned)((polys * half + 255) / 256), 256, 0, c->stream>>>(d, half, polys, mods, invn, invnw, n_mod, fixed_mod);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
 
 static int launch_encode(rsg_context *c, const uint64_t *d_ring, const uint32_t *d_eidx, size_t count, uint64_t *d_plain) {
   if (!count) return RSG_OK;
   const unsigned th = ntt_threads(c->logN);
   const size_t sm = ntt_smem(c->logN);
-  dim3 grid((unsigned)count, (unsigned)c->L_R);
-  LaunchScope ls(c, "k_encode_intt");
-  DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG>(); if (rc) return rc;
-                           k_encode_intt<LG><<<grid, th, sm, c->stream>>>(c->d_params, d_ring, d_eidx, d_plain); });
+  const unsigned split = c->logN > 14 ? 2 : 1;
+  dim3 grid((unsigned)count * split, (unsigned)c->L_R);
+  {
+    LaunchScope ls(c, "k_encode_intt");
+    DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
+                             k_encode_intt<LG, LV><<<grid, th, sm, c->stream>>>(c->d_params, d_ring, d_eidx, d_plain); });
+  }
   CUDA_TRY(cudaGetLastError());
+  if (split > 1)   // plaintexts are [count][L_R] polynomials: modulus index = polynomial index % L_R
+    return launch_intt_finish(c, d_plain, count * c->L_R, c->d_modq, c->d_invN_q, c->d_invNw_q, (uint32_t)c->L_R, 0xFFFFFFFFu);
   return RSG_OK;
 }
 static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count, uint64_t *d_pntt) {
   if (!count) return RSG_OK;
   const unsigned th = ntt_threads(c->logN);
   const size_t sm = ntt_smem(c->logN);
-  // grid.x = term * L_E + limb: up to 2^31-1
-  dim3 grid((unsigned)(count * c->L_E), (unsigned)c->L_R);
+  const unsigned split = c->logN > 14 ? 2 : 1;
+  // grid.x = (term * L_E + limb) * split: up to 2^31-1
+  dim3 grid((unsigned)(count * c->L_E * split), (unsigned)c->L_R);
   bool lazy = true;   // correction-free butterflies need (4 * log2 N + 1) * Q_l < 2^64
   for (uint64_t p : c->Q) lazy = lazy && p < (1ull << 58);
   LaunchScope ls(c, "k_lift_fwd_ntt");
-  DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG>(); if (rc) return rc;
-                           if (lazy) k_lift_fwd_ntt<LG, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
-                           else k_lift_fwd_ntt<LG, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
+  DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
+                           if (lazy) k_lift_fwd_ntt<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
+                           else k_lift_fwd_ntt<LG, LV, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -663,14 +689,27 @@ extern "C" int rsg_ntt(rsg_context *c, uint64_t *d, size_t batch, int which, siz
   const Twiddle invn = which == 0 ? c->hp.invN_Q[idx] : c->hp.invN_q[idx];
   const unsigned th = ntt_threads(c->logN);
   const size_t sm = ntt_smem(c->logN);
-  LaunchScope ls(c, inverse ? "k_ntt_inv" : "k_ntt_fwd");
-  DISPATCH_LOGN(c->logN, {
-    int rc = set_smem_attrs<LG>();
+  const unsigned split = c->logN > 14 ? 2 : 1;
+  const uint64_t *src = d;
+  if (split > 1 && !inverse) {   // the split forward transform is out of place: stage the input
+    int rc = ensure(c, &c->d_plain, &c->cap_plain, batch * c->N_E);
     if (rc) return rc;
-    if (inverse) k_ntt<LG, true><<<(unsigned)batch, th, sm, c->stream>>>(d, tab, p, invn);
-    else k_ntt<LG, false><<<(unsigned)batch, th, sm, c->stream>>>(d, tab, p, invn);
-  });
+    CUDA_TRY(cudaMemcpyAsync(c->d_plain, d, batch * c->N_E * 8, cudaMemcpyDeviceToDevice, c->stream));
+    src = c->d_plain;
+  }
+  {
+    LaunchScope ls(c, inverse ? "k_ntt_inv" : "k_ntt_fwd");
+    DISPATCH_LOGN(c->logN, {
+      int rc = set_smem_attrs<LG, LV>();
+      if (rc) return rc;
+      if (inverse) k_ntt<LG, LV, true><<<(unsigned)batch * split, th, sm, c->stream>>>(src, d, tab, p, invn);
+      else k_ntt<LG, LV, false><<<(unsigned)batch * split, th, sm, c->stream>>>(src, d, tab, p, invn);
+    });
+  }
   CUDA_TRY(cudaGetLastError());
+  if (split > 1 && inverse)
+    return launch_intt_finish(c, d, batch, which == 0 ? c->d_modQ : c->d_modq, which == 0 ? c->d_invN_Q : c->d_invN_q,
+                              which == 0 ? c->d_invNw_Q : c->d_invNw_q, 1, (uint32_t)idx);
   return RSG_OK;
 }
 

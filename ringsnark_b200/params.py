@@ -9,6 +9,10 @@ Q_8192 = [8796092858369, 8796092792833, 17592186028033, 17592185438209]
 Q_16384 = [281474976546817, 281474976317441, 281474975662081, 562949952798721, 562949952700417, 562949952274433,
            562949951979521, 562949951881217]
 
+# first 8 primes of BFVDefault(32768) (55 bit): SURVEY.md 8(d) config C5 uses 8 data-level limbs at N_E = 2^15
+Q_32768_8 = [0x7fffffffe90001, 0x7fffffffbf0001, 0x7fffffffbd0001, 0x7fffffffba0001, 0x7fffffffaa0001, 0x7fffffffa50001,
+             0x7fffffff9f0001, 0x7fffffff7e0001]
+
 CONFIGS = {
     # examples/example_SEAL.cpp: N_R = 4096, default_double_batching_modulus(4096, 8192) first level
     "c1": dict(N_R=4096, q=[68718428161, 68719230977], N_E=8192, Q=Q_8192, n=2, io=5, aux=1),
@@ -18,6 +22,9 @@ CONFIGS = {
     # benchmarks/bench_logistic_regression_inference.cpp:20-27,72-126 (shape): one 54-bit ring prime
     "c4": dict(N_R=2048, q=[18014398508400641], N_E=16384, Q=Q_16384, n=1031, io=517, aux=1538),
     "c4m": dict(N_R=2048, q=[18014398508400641], N_E=16384, Q=Q_16384, n=129, io=65, aux=192),
+    # SURVEY.md 8(d) C5 parameters (N_R = N_E = 2^15, one 54-bit ring prime = 1 mod 2^16, 8 x 55-bit limbs) with a circuit
+    # small enough for the O(n^2) witness map; the n = 2^16 circuit itself needs the fast interpolation that is not built yet
+    "c5s": dict(N_R=32768, q=[18014398506729473], N_E=32768, Q=Q_32768_8, n=257, io=129, aux=384),
     "c4s": dict(N_R=2048, q=[18014398508400641], N_E=16384, Q=Q_16384, n=33, io=17, aux=48),
 }
 

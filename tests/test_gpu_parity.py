@@ -413,3 +413,51 @@ def test_ring_elementwise_ops(gold):
     a.upload(z)
     rc = lib.rsg_ring_invert(ctx.h, a.h, 0, out.h, 0, 5, ok.ctypes.data_as(C.c_void_p))
     assert rc == -4 and list(ok) == [1, 1, 0, 1, 1] and b"not invertible" in lib.rsg_last_error()
+
+
+def test_n32768_against_oracle():
+    """N_E = 2^15 (SURVEY.md 8(d) C5 parameters: 8 x 55-bit limbs, 54-bit ring prime): a 2^15-point polynomial does not fit
+    one SM's shared memory, so every NTT runs as two 2^14-point halves (kernels.cuh).  Raw transforms, batch encode, lift
+    and a 12-term inner product against the C oracle."""
+    import ctypes as C
+    import torch
+    import ringsnark_b200 as rs
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c5s"]
+    ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"])
+    try:
+        N, q0, Q0 = cfg["N_E"], int(cfg["q"][0]), int(cfg["Q"][0])
+        rng = np.random.default_rng(5)
+        x = rng.integers(0, Q0, size=N, dtype=np.uint64)
+        d = _torch_dev(x)
+        assert ctx.lib.rsg_ntt(ctx.h, C.c_void_p(d.data_ptr()), 1, 0, 0, 0) == 0
+        ctx.sync()
+        assert np.array_equal(_host(d), O.ntt_forward(x, Q0))
+        assert ctx.lib.rsg_ntt(ctx.h, C.c_void_p(d.data_ptr()), 1, 0, 0, 1) == 0
+        ctx.sync()
+        assert np.array_equal(_host(d), x)
+        y = rng.integers(0, q0, size=N, dtype=np.uint64)
+        d = _torch_dev(y)
+        assert ctx.lib.rsg_ntt(ctx.h, C.c_void_p(d.data_ptr()), 1, 1, 0, 1) == 0
+        ctx.sync()
+        assert np.array_equal(_host(d), O.ntt_inverse(y, q0))
+        T = 12
+        crs = ctx.crs(T); crs.fill_uniform(3)
+        vec = ctx.ringvec(T); vec.fill_uniform(4)
+        w = vec.download()
+        ring = _torch_dev(w[0])
+        plain = torch.zeros(N, dtype=torch.int64, device="cuda")
+        pntt = torch.zeros(ctx.L_E * N, dtype=torch.int64, device="cuda")
+        assert ctx.lib.rsg_batch_encode(ctx.h, C.c_void_p(ring.data_ptr()), 1, C.c_void_p(plain.data_ptr())) == 0
+        assert ctx.lib.rsg_plain_to_ntt(ctx.h, C.c_void_p(plain.data_ptr()), 1, C.c_void_p(pntt.data_ptr())) == 0
+        ctx.sync()
+        enc = O.batch_encode(w[0], N, q0)
+        assert np.array_equal(_host(plain), enc)
+        assert np.array_equal(_host(pntt).reshape(ctx.L_E, N), O.plain_lift_ntt(enc, q0, ctx.Q))
+        tags = np.full(T, 2, dtype=np.uint8)
+        tags[5] = 1
+        out, used = ctx.inner_product(crs, vec, tags)
+        want, _ = O.inner_product(crs.download(), w, tags, ctx.N_R, ctx.L_R, ctx.q, ctx.N_E, ctx.L_E, ctx.Q)
+        assert used == T and np.array_equal(out, want)
+    finally:
+        ctx.close()
