@@ -135,6 +135,10 @@ int rsg_witness_map_zk(rsg_context *ctx, size_t n, const rsg_ringvec *evals, con
 typedef struct rsg_r1cs rsg_r1cs;
 int rsg_witness_map_r1cs(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *evals, const uint64_t *h_d,
                          rsg_ringvec *coeffs, rsg_ringvec *H);
+/* The witness map as groth16::prover consumes it (groth16.tcc:82-112, non-ZK): coefficients_for_C_io / C_mid are never
+ * read by that prover and C does not reach the quotient H (deg C < n = deg Z), so only A and B are interpolated
+ * (4 matrix products).  The C_io / C_mid blocks of `coeffs` are left untouched. */
+int rsg_witness_map_groth16(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H);
 /* util/polynomials.tcc:9-43 on its own: vectors of n ring elements; `batch` vectors back to back. */
 int rsg_interpolate(rsg_context *ctx, size_t n, size_t batch, const rsg_ringvec *y, size_t y_first, rsg_ringvec *out,
                     size_t out_first);

@@ -182,6 +182,8 @@ struct rsg_context {
   uint64_t *d_ip = nullptr;         // the separate inner products of rsg_groth16_prove
   size_t cap_ip = 0;
   uint64_t exact_fallbacks = 0;     // how often a flagged prefix had to be resolved exactly
+  bool f64_ntt = false;             // every Q_l < 2^49: forward NTTs of the plaintext pipeline run on the FP64 pipe
+  int ntt_mode = 0;                 // 0 = auto; RSG_NTT=int forces the integer kernel, f64r4 the radix-16 FP64 chain
   size_t enc_words() const { return L_R * 2 * L_E * N_E; }
   size_t ring_words() const { return L_R * N_R; }
 };
@@ -281,6 +283,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   c->Q.assign(Q, Q + L_E);
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
+  if (const char *m = getenv("RSG_NTT")) c->ntt_mode = !strcmp(m, "int") ? 1 : (!strcmp(m, "f64r4") ? 2 : 0);
 
   DevParams &hp = c->hp;
   memset(&hp, 0, sizeof(hp));
@@ -298,6 +301,22 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
     hp.invN_Q[l] = h_twiddle(h_inv(N_E % Q[l], Q[l]), Q[l]);
     hp.invNw_Q[l] = h_twiddle(h_mulmod(hp.invN_Q[l].w, inv[1].w, Q[l]), Q[l]);
   }
+  // FP64-pipe forward tables (ntt_f64.cuh) when every data-level prime is below 2^49
+  c->f64_ntt = true;
+  for (size_t l = 0; l < L_E; l++) c->f64_ntt = c->f64_ntt && Q[l] < (1ull << 49);
+  if (c->f64_ntt)
+    for (size_t l = 0; l < L_E; l++) {
+      h_tables(c->logN, Q[l], fwd, inv);
+      std::vector<TwiddleF> tf(fwd.size());
+      for (size_t i = 0; i < fwd.size(); i++) {
+        tf[i].w = (double)fwd[i].w;                                       // exact: w < 2^49
+        tf[i].wp = (double)((long double)fwd[i].w / (long double)Q[l]);   // RN(w / p) up to a 2^-64 relative pre-rounding
+      }
+      TwiddleF *d;
+      if ((rc = upload_vec(c, tf, &d))) return rc;
+      hp.fwdQ_f64[l] = d;
+      hp.Qinv_f64[l] = (double)(1.0L / (long double)Q[l]);
+    }
   for (size_t j = 0; j < L_R; j++) {
     hp.q[j] = h_modconst(q[j]);
     h_tables(c->logN, q[j], fwd, inv);
@@ -607,6 +626,8 @@ static int set_smem_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(k_encode_intt<LOGN, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done[dev] = true;
@@ -662,6 +683,14 @@ static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count
   bool lazy = true;   // correction-free butterflies need (4 * log2 N + 1) * Q_l < 2^64
   for (uint64_t p : c->Q) lazy = lazy && p < (1ull << 58);
   LaunchScope ls(c, "k_lift_fwd_ntt");
+  if (c->f64_ntt && c->ntt_mode != 1) {
+    const bool r4 = c->ntt_mode == 2;
+    DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
+                             if (r4) k_lift_fwd_ntt_f64<LG, LV, 4><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
+                             else k_lift_fwd_ntt_f64<LG, LV, 5><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
                            if (lazy) k_lift_fwd_ntt<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
                            else k_lift_fwd_ntt<LG, LV, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
@@ -1118,7 +1147,7 @@ static int launch_modmat(rsg_context *c, const uint64_t *d_M, size_t rows, size_
 // r1cs (nullable): the evaluations come from rsg_r1cs_evaluate on this system, so full = mid + io - constant wire and the
 // two interpolants of the full assignment follow by linearity (6 matrix products per proof instead of 8).
 static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, uint64_t *d_coeffs, uint64_t *d_H,
-                           const uint64_t *d_zk = nullptr, rsg_r1cs *r1cs = nullptr) {
+                           const uint64_t *d_zk = nullptr, rsg_r1cs *r1cs = nullptr, bool need_C = true) {
   WitnessTables *wt;
   int rc = get_witness_tables(c, n, &wt);
   if (rc) return rc;
@@ -1127,8 +1156,11 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
   if ((rc = ensure(c, &c->d_plain, &c->cap_plain, (3 * n) * W))) return rc;
   uint64_t *aA = c->d_plain, *aB = aA + n * W, *Ptop = aB + n * W;
   // evals order: A_mid,B_mid,C_mid,A_io,B_io,C_io,A_full,B_full,C_full ; coeffs order: A_io,B_io,C_io,A_mid,B_mid,C_mid
-  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 3 * n * W, d_coeffs, 3, false, "k_modmat_interp"))) return rc;
-  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals, d_coeffs + 3 * n * W, 3, false, "k_modmat_interp"))) return rc;
+  // need_C = false (ringGroth16, groth16.tcc:89-112): C_io / C_mid are never read by the prover and C does not reach the
+  // quotient (deg C < n), so only A and B are interpolated
+  const size_t nb = need_C ? 3 : 2;
+  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 3 * n * W, d_coeffs, nb, false, "k_modmat_interp"))) return rc;
+  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals, d_coeffs + 3 * n * W, nb, false, "k_modmat_interp"))) return rc;
   if (r1cs && r1cs->n == n) {
     if (!r1cs->d_cc) {
       uint64_t *d_const = nullptr;
@@ -1204,6 +1236,14 @@ extern "C" int rsg_witness_map_r1cs(rsg_context *c, rsg_r1cs *r1cs, const rsg_ri
     d_zk = c->d_zk;
   }
   return witness_map_dev(c, n, evals->d, coeffs->d, H->d, d_zk, r1cs);
+}
+extern "C" int rsg_witness_map_groth16(rsg_context *c, rsg_r1cs *r1cs, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
+  if (!c || !r1cs || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
+  const size_t n = r1cs->n;
+  if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  return witness_map_dev(c, n, evals->d, coeffs->d, H->d, nullptr, r1cs, /*need_C=*/false);
 }
 extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
   return rsg_witness_map_zk(c, n, evals, nullptr, coeffs, H);
@@ -1402,7 +1442,7 @@ extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg
   if ((rc = ensure(c, &c->d_wit, &c->cap_wit, (7 * n + 1) * W))) return rc;
   uint64_t *coeffs = c->d_wit, *H = c->d_wit + 6 * n * W;
   if ((rc = r1cs_eval_dev(c, r1cs, assignment->d, c->d_evals))) return rc;
-  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H, nullptr, const_cast<rsg_r1cs *>(r1cs)))) return rc;
+  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H, nullptr, const_cast<rsg_r1cs *>(r1cs), /*need_C=*/false))) return rc;
   // coeffs order in HBM: A_io, B_io, C_io, A_mid, B_mid, C_mid
   const uint64_t *vec[6] = {coeffs, coeffs + 3 * n * W, coeffs + n * W, coeffs + 4 * n * W, H, assignment->d + n_io * W};
   return groth16_lincombs_dev(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, d_proof, n_used);

@@ -6,7 +6,7 @@ rank r holds slots [r*S, (r+1)*S) of EVERY coefficient, for the lincombs it need
 terms -- an all-to-all (about 10 MB per rank at C4).  Each rank then produces a partial proof (3 encodings) over its term
 range; one all-gather of the partials and the modular-add kernel (modular addition is not an NCCL reduction) finish.
 
-    phase 1  rsg_r1cs_evaluate + rsg_witness_map_r1cs   on a context with N_R/G slots      (sharded by slot)
+    phase 1  rsg_r1cs_evaluate + rsg_witness_map_groth16  on a context with N_R/G slots      (sharded by slot)
     phase 2  all_to_all_single                                                             (slots <-> terms)
     phase 3  rsg_groth16_lincombs                        on the full context, term shard of the CRS
     phase 4  all_gather_into_tensor + rsg_enc_sum
@@ -125,7 +125,7 @@ class ShardedGroth16Prover:
         """Phase 1 + the pack of phase 2: returns the send buffer [world * 5 * per, L_R*S]."""
         lib, ctx = self.ctxW.lib, self.ctxW
         check(lib.rsg_r1cs_evaluate(ctx.h, self.r1csW.h, self.rv_assign, self.rv_evals))
-        check(lib.rsg_witness_map_r1cs(ctx.h, self.r1csW.h, self.rv_evals, None, self.rv_coeffs, self.rv_H))
+        check(lib.rsg_witness_map_groth16(ctx.h, self.r1csW.h, self.rv_evals, self.rv_coeffs, self.rv_H))
         return self.t_wit.index_select(0, self.idx)
 
     def lincomb_phase(self, recv, h_proof_ptr=None):

@@ -461,3 +461,44 @@ def test_n32768_against_oracle():
         assert used == T and np.array_equal(out, want)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name", ["c4", "c1", "c3p"])
+def test_fp64_forward_ntt_edge_values(name, monkeypatch):
+    """The plaintext pipeline's forward NTTs run on the FP64 pipe when every Q_l < 2^49 (csrc/ntt_f64.cuh): exact integers
+    in doubles, re-centred every pass.  Random and adversarial coefficient patterns (extremes of the lift, +-p/2 boundaries,
+    constant / alternating vectors that maximise growth) against the C oracle, and against the integer kernel (RSG_NTT=int)."""
+    import ctypes as C
+    import torch
+    import ringsnark_b200 as rs
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS[name]
+    N, t, Q = cfg["N_E"], int(cfg["q"][0]), [int(x) for x in cfg["Q"]]
+    rng = np.random.default_rng(11)
+    thr = (t + 1) // 2
+    pats = [rng.integers(0, t, size=N, dtype=np.uint64),
+            np.full(N, t - 1, dtype=np.uint64), np.full(N, thr, dtype=np.uint64), np.full(N, thr - 1, dtype=np.uint64),
+            np.zeros(N, dtype=np.uint64), np.ones(N, dtype=np.uint64)]
+    for p in (Q[0], Q[-1]):   # lifted value = +-floor(p/2): the centring boundary, constant and with alternating sign
+        half = p // 2
+        pats.append(np.full(N, half % t, dtype=np.uint64))
+        pats.append(np.full(N, (half + 1) % t, dtype=np.uint64))
+        alt = np.where(np.arange(N) % 2 == 0, half % t, (t - half) % t).astype(np.uint64)
+        pats.append(alt)
+    pats.append(np.where(rng.integers(0, 2, size=N) == 0, 0, t - 1).astype(np.uint64))
+    plain_h = np.stack(pats)
+    want = np.stack([O.plain_lift_ntt(p, t, Q) for p in pats])
+    outs = {}
+    for mode in ("f64", "f64r4", "int"):
+        monkeypatch.setenv("RSG_NTT", mode)
+        ctx = rs.Context(cfg["N_R"], cfg["q"][:1], N, cfg["Q"])
+        try:
+            plain = _torch_dev(plain_h)
+            pntt = torch.zeros(len(pats) * len(Q) * N, dtype=torch.int64, device="cuda")
+            assert ctx.lib.rsg_plain_to_ntt(ctx.h, C.c_void_p(plain.data_ptr()), len(pats), C.c_void_p(pntt.data_ptr())) == 0
+            ctx.sync()
+            outs[mode] = _host(pntt).reshape(len(pats), len(Q), N)
+        finally:
+            ctx.close()
+    for mode, got in outs.items():
+        assert np.array_equal(got, want), f"{mode} forward NTT differs from the oracle"
