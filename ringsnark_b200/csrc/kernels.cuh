@@ -30,7 +30,7 @@ struct DevParams {
   uint64_t thr[MAX_LR];          // ceil(q_j / 2): plain_upper_half_threshold (context.cpp:329)
   uint64_t tmodQ[MAX_LR][MAX_LE];  // q_j mod Q_l
   const uint32_t *index_map;     // matrix_reps_index_map_ (batchencoder.cpp:64-88), N_E entries
-  const TwiddleF *fwdQ_f64[MAX_LE];  // forward tables mod Q_l as doubles (null unless every Q_l < 2^49; ntt_f64.cuh)
+  const double *fwdQ_f64[MAX_LE];    // forward tables mod Q_l as doubles (null unless every Q_l < 2^49; ntt_f64.cuh)
   double Qinv_f64[MAX_LE];       // RN(1 / Q_l)
 };
 
@@ -136,8 +136,31 @@ __global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restric
 }
 
 // The same kernel on the FP64 pipe (every Q_l < 2^49; ntt_f64.cuh): the lift stays integer (one Barrett reduction per word),
-// the residue is centred and converted once, all LOGN levels run on exact doubles, and the store canonicalises.
-template <int LOGN, int LVL0, int MAXRL>
+// the residue is centred and converted once, all LOGN levels run on exact doubles, and the store canonicalises.  For
+// LVL0 = 0 the first pass reads the coefficients straight from global memory and the last pass writes the result straight
+// to global memory (no separate load / store phases).
+struct LiftIoF64 {
+  const uint64_t *src;
+  uint64_t *dst;
+  ModConst m;
+  uint64_t thr, tm;
+  double pd, pinv;
+  __device__ __forceinline__ uint64_t load_raw(uint32_t i) const { return __ldg(src + i); }
+  __device__ __forceinline__ double lift(uint64_t v) const {
+    uint64_t r = reduce64(v, m);
+    if (v >= thr) r = sub_mod(r, tm, m.p);   // v + (Q - t)  ==  v - t  (mod Q_l)
+    return centre_to_f64(r, m.p);
+  }
+  template <int R>
+  __device__ __forceinline__ void store(uint32_t base, const double (&v)[R]) const {
+    static_assert(R % 2 == 0, "pairs");
+#pragma unroll
+    for (int k = 0; k < R; k += 2)
+      *reinterpret_cast<ulonglong2 *>(dst + base + k) = make_ulonglong2(canon_f64(v[k], pd, pinv, m.p), canon_f64(v[k + 1], pd, pinv, m.p));
+  }
+};
+
+template <int LOGN, int LVL0>
 __global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
                                                           uint64_t *__restrict__ out) {
   extern __shared__ double smf[];
@@ -145,30 +168,27 @@ __global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__res
   const uint32_t L_R = P->L_R, L_E = P->L_E;
   const uint32_t h = blockIdx.x & ((1u << LVL0) - 1), el = blockIdx.x >> LVL0;
   const uint32_t e = el / L_E, l = el - e * L_E, j = blockIdx.y;
-  const ModConst m = P->Q[l];
-  const double pd = (double)m.p, pinv = P->Qinv_f64[l];
-  const uint64_t thr = P->thr[j], tm = P->tmodQ[j][l];
-  const uint64_t *src = plain + (((size_t)e * L_R + j) << (LOGN + LVL0));
-  const TwiddleF *tab = P->fwdQ_f64[l];
-  auto lift = [&](uint64_t v) {
-    uint64_t r = reduce64(v, m);
-    if (v >= thr) r = sub_mod(r, tm, m.p);   // v + (Q - t)  ==  v - t  (mod Q_l)
-    return centre_to_f64(r, m.p);
-  };
-  if (LVL0 == 0) {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) smf[pad_idx(i)] = lift(src[i]);
-  } else {
-    const TwiddleF t0 = load_twf(tab, 1);
+  LiftIoF64 io;
+  io.m = P->Q[l];
+  io.pd = (double)io.m.p;
+  io.pinv = P->Qinv_f64[l];
+  io.thr = P->thr[j];
+  io.tm = P->tmodQ[j][l];
+  io.src = plain + (((size_t)e * L_R + j) << (LOGN + LVL0));
+  io.dst = out + (((((size_t)e * L_R + j) * L_E + l)) << (LOGN + LVL0)) + (size_t)h * n;
+  const double *tab = P->fwdQ_f64[l];
+  typename PassChainF<LOGN, 0, LVL0 == 0>::Tw tw0;
+  tw0.load(tab, LVL0, h, threadIdx.x);
+  if (LVL0 != 0) {
+    const double w0 = __ldg(tab + 1), w0p = __dmul_rn(w0, io.pinv);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      double x = lift(src[i]), y = lift(src[i + n]);
-      bfly_fwd_f64(x, y, t0, pd);
-      smf[pad_idx(i)] = recentre_f64(h ? y : x, pd, pinv);
+      double x = io.lift(io.src[i]), y = io.lift(io.src[i + n]);
+      bfly_fwd_f64(x, y, w0, w0p, io.pd);
+      smf[pad_idx(i)] = recentre_f64(h ? y : x, io.pd, io.pinv);
     }
+    __syncthreads();
   }
-  __syncthreads();
-  ntt_forward_smem_f64<LOGN, MAXRL>(smf, tab, pd, pinv, LVL0, h);
-  uint64_t *dst = out + (((((size_t)e * L_R + j) * L_E + l)) << (LOGN + LVL0)) + (size_t)h * n;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = canon_f64(smf[pad_idx(i)], pd, pinv, m.p);
+  PassChainF<LOGN, 0, LVL0 == 0>::fwd(smf, tab, io.pd, io.pinv, LVL0, h, tw0, io);
 }
 
 // Raw NTT of `batch` polynomials; grid (batch << LVL0).  In place for LVL0 = 0.  For LVL0 = 1 the forward transform reads

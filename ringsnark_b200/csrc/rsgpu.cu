@@ -183,7 +183,7 @@ struct rsg_context {
   size_t cap_ip = 0;
   uint64_t exact_fallbacks = 0;     // how often a flagged prefix had to be resolved exactly
   bool f64_ntt = false;             // every Q_l < 2^49: forward NTTs of the plaintext pipeline run on the FP64 pipe
-  int ntt_mode = 0;                 // 0 = auto; RSG_NTT=int forces the integer kernel, f64r4 the radix-16 FP64 chain
+  int ntt_mode = 0;                 // 0 = auto; RSG_NTT=int forces the integer kernel
   size_t enc_words() const { return L_R * 2 * L_E * N_E; }
   size_t ring_words() const { return L_R * N_R; }
 };
@@ -283,7 +283,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   c->Q.assign(Q, Q + L_E);
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
-  if (const char *m = getenv("RSG_NTT")) c->ntt_mode = !strcmp(m, "int") ? 1 : (!strcmp(m, "f64r4") ? 2 : 0);
+  if (const char *m = getenv("RSG_NTT")) c->ntt_mode = !strcmp(m, "int") ? 1 : (!strcmp(m, "f64s") ? 2 : 0);
 
   DevParams &hp = c->hp;
   memset(&hp, 0, sizeof(hp));
@@ -307,12 +307,9 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (c->f64_ntt)
     for (size_t l = 0; l < L_E; l++) {
       h_tables(c->logN, Q[l], fwd, inv);
-      std::vector<TwiddleF> tf(fwd.size());
-      for (size_t i = 0; i < fwd.size(); i++) {
-        tf[i].w = (double)fwd[i].w;                                       // exact: w < 2^49
-        tf[i].wp = (double)((long double)fwd[i].w / (long double)Q[l]);   // RN(w / p) up to a 2^-64 relative pre-rounding
-      }
-      TwiddleF *d;
+      std::vector<double> tf(fwd.size());
+      for (size_t i = 0; i < fwd.size(); i++) tf[i] = (double)fwd[i].w;   // exact: w < 2^49
+      double *d;
       if ((rc = upload_vec(c, tf, &d))) return rc;
       hp.fwdQ_f64[l] = d;
       hp.Qinv_f64[l] = (double)(1.0L / (long double)Q[l]);
@@ -626,8 +623,7 @@ static int set_smem_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(k_encode_intt<LOGN, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done[dev] = true;
@@ -683,11 +679,17 @@ static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count
   bool lazy = true;   // correction-free butterflies need (4 * log2 N + 1) * Q_l < 2^64
   for (uint64_t p : c->Q) lazy = lazy && p < (1ull << 58);
   LaunchScope ls(c, "k_lift_fwd_ntt");
+  if (c->f64_ntt && c->ntt_mode == 2 && c->logN == 14) {   // experiment: two decoupled 2^13-point CTAs per polynomial
+    static bool attr_done = false;
+    const int bytes = (int)padded_words(1u << 13) * 8;
+    if (!attr_done) { CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<13, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); attr_done = true; }
+    k_lift_fwd_ntt_f64<13, 1><<<dim3((unsigned)(count * c->L_E * 2), (unsigned)c->L_R), 256, bytes, c->stream>>>(c->d_params, d_plain, d_pntt);
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   if (c->f64_ntt && c->ntt_mode != 1) {
-    const bool r4 = c->ntt_mode == 2;
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
-                             if (r4) k_lift_fwd_ntt_f64<LG, LV, 4><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
-                             else k_lift_fwd_ntt_f64<LG, LV, 5><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
+                             k_lift_fwd_ntt_f64<LG, LV><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
     CUDA_TRY(cudaGetLastError());
     return RSG_OK;
   }

@@ -489,7 +489,7 @@ def test_fp64_forward_ntt_edge_values(name, monkeypatch):
     plain_h = np.stack(pats)
     want = np.stack([O.plain_lift_ntt(p, t, Q) for p in pats])
     outs = {}
-    for mode in ("f64", "f64r4", "int"):
+    for mode in ("f64", "f64s", "int"):
         monkeypatch.setenv("RSG_NTT", mode)
         ctx = rs.Context(cfg["N_R"], cfg["q"][:1], N, cfg["Q"])
         try:
