@@ -263,6 +263,9 @@ def run_gpu_arm(args, cfg_name, cfg):
     for cx in ctxs:
         cx.enable_timing(True)
     l0 = sum(cx.launch_count() for cx in ctxs)
+    stat_names = ("lincomb_terms", "lincomb_plain_terms", "lincomb_launches", "ntt_forward_polys", "ntt_inverse_polys",
+                  "merged_lincombs", "exact_fallbacks")
+    st0 = {k: sum(cx.stat(k) for cx in ctxs) for k in stat_names}
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -272,9 +275,11 @@ def run_gpu_arm(args, cfg_name, cfg):
     barrier()
     ms_dev = reduce_max(ev0.elapsed_time(ev1) / args.steps)
     launches = sum(cx.launch_count() for cx in ctxs) - l0
+    stats = {k: (sum(cx.stat(k) for cx in ctxs) - st0[k]) / args.steps for k in stat_names}   # per proof, this rank
     kern = {}
     for name in ("k_crs_lincomb", "k_lift_fwd_ntt", "k_encode_intt", "k_modmat_interp", "k_modmat_divZ", "k_conv_top",
-                 "k_r1cs_eval", "k_enc_sum", "k_enc_add", "k_is_zero_prefix", "k_probe", "k_full_from_parts"):
+                 "k_r1cs_eval", "k_enc_sum", "k_enc_add", "k_is_zero_prefix", "k_probe", "k_probe_eval", "k_full_from_parts",
+                 "k_c1_nonzero", "k_zero_transparent"):
         ms = cnt = 0
         for cx in ctxs:
             m_, c_ = cx.timing(name)
@@ -299,8 +304,9 @@ def run_gpu_arm(args, cfg_name, cfg):
     ones = [1 if layout.alpha_idx != rs.backend.NONE else 0, 1 if layout.beta_idx != rs.backend.NONE else 0, 0]
     # alpha / beta are added by k_enc_add, every other term is streamed by k_crs_lincomb: 3 words per slot per term
     # (2 CRS + 1 NTT-domain plaintext) + one 2-word output per launch
-    lin_launches = kern["k_crs_lincomb"]["launches_per_step"]
-    alg_bytes = row * (3 * sum(u - o for u, o in zip(used, ones)) + 2 * lin_launches)
+    # counted by the library (rsg_context_stat): the merged A / B passes stream each s_pows element ONCE for io + mid
+    lin_launches = stats["lincomb_launches"]
+    alg_bytes = row * (2 * stats["lincomb_terms"] + stats["lincomb_plain_terms"] + 2 * lin_launches)
     lin_ms = kern["k_crs_lincomb"]["ms_per_step"]
     peaks = {}
     try:
@@ -314,7 +320,7 @@ def run_gpu_arm(args, cfg_name, cfg):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "lincomb_traffic.json"))).get("dram_bytes_per_step")
     except Exception:
         pass
-    ntt_butterflies = sum(u - o for u, o in zip(used, ones)) * L_R * (1 + L_E) * (N_E // 2) * (N_E.bit_length() - 1)
+    ntt_butterflies = (stats["ntt_forward_polys"] + stats["ntt_inverse_polys"]) * (N_E // 2) * (N_E.bit_length() - 1)
     ntt_ms = kern["k_lift_fwd_ntt"]["ms_per_step"] + kern["k_encode_intt"]["ms_per_step"]
 
     if rank == 0:
@@ -333,6 +339,7 @@ def run_gpu_arm(args, cfg_name, cfg):
             "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()},
             "ntt": {"butterflies_per_step": ntt_butterflies, "gbutterflies_per_s": ntt_butterflies / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None},
             "terms_per_step": used,
+            "work_per_step": stats,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -59,6 +59,11 @@ int rsg_context_sync(rsg_context *ctx);
 int rsg_context_set_stream(rsg_context *ctx, void *cuda_stream);
 /* Kernels launched by this context since creation (the bench's "gpu_launches" claim). */
 uint64_t rsg_context_launch_count(const rsg_context *ctx);
+/* Work counters since context creation (measurement only; bench.py derives the algorithmic bytes of k_crs_lincomb from
+ * them): "lincomb_terms" (CRS elements streamed), "lincomb_plain_terms" (of which multiplied by a plaintext),
+ * "lincomb_launches", "ntt_forward_polys", "ntt_inverse_polys" (N_E-point transforms), "merged_lincombs",
+ * "exact_fallbacks" (transparent-prefix resolutions, seal_ring.tcc:493-504).  Unknown name: 0. */
+uint64_t rsg_context_stat(const rsg_context *ctx, const char *name);
 
 /* ---- CRS: vector<EncodingElem> produced by EncodingElem::encode (seal_ring.tcc:324-359) ---- */
 int rsg_crs_create(rsg_context *ctx, size_t n_elems, rsg_crs **out);                         /* uninitialised arena */

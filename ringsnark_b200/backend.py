@@ -52,6 +52,9 @@ class Context:
     def launch_count(self):
         return int(self.lib.rsg_context_launch_count(self.h))
 
+    def stat(self, name):
+        return int(self.lib.rsg_context_stat(self.h, name.encode()))
+
     def enable_timing(self, on=True):
         check(self.lib.rsg_context_enable_timing(self.h, 1 if on else 0))
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     "rsg_context_sync": (_int, [_vp]),
     "rsg_context_set_stream": (_int, [_vp, _vp]),
     "rsg_context_launch_count": (_u64, [_vp]),
+    "rsg_context_stat": (_u64, [_vp, C.c_char_p]),
     "rsg_crs_create": (_int, [_vp, _sz, _pp]),
     "rsg_crs_upload": (_int, [_vp, _sz, _sz, _vp]),
     "rsg_crs_download": (_int, [_vp, _sz, _sz, _vp]),

@@ -6,6 +6,7 @@
 //   k_is_zero_prefix  SealPoly::is_zero (with its bug) poly_arith.cpp:147-153
 //   k_ntt             raw forward / inverse NTT        util/ntt.cpp:407-474
 #pragma once
+#include <type_traits>
 #include "ntt.cuh"
 #include "ntt_f64.cuh"
 
@@ -101,9 +102,11 @@ __global__ void __launch_bounds__(256) k_intt_finish(uint64_t *__restrict__ data
 // LAZY (every Q_l < 2^58): correction-free butterflies, one Barrett reduction per word at the store.
 // LVL0 = 1 (N_E = 2^15): the first Cooley-Tukey level pairs i with i + N/2 and is applied while loading (each of the two
 // CTAs lifts both words and keeps its own half); the remaining levels are two independent 2^14-point transforms.
+// is_signed: `plain` holds the SUM of two centred plaintexts as int64 words (k_centre_add) instead of residues mod t --
+// NTT_Q is linear, so two inner products over the same CRS range share one transform and one CRS pass.
 template <int LOGN, int LVL0, bool LAZY>
 __global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
-                                                      uint64_t *__restrict__ out) {
+                                                      uint32_t is_signed, uint64_t *__restrict__ out) {
   extern __shared__ uint64_t sm[];
   constexpr uint32_t n = 1u << LOGN;
   const uint32_t L_R = P->L_R, L_E = P->L_E;
@@ -112,17 +115,23 @@ __global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restric
   const ModConst m = P->Q[l];
   const uint64_t thr = P->thr[j], tm = P->tmodQ[j][l];
   const uint64_t *src = plain + (((size_t)e * L_R + j) << (LOGN + LVL0));
-  auto lift = [&](uint64_t v) {
+  auto lift = [&](uint32_t i) {
+    const uint64_t v = src[i];
+    if (is_signed) {
+      const long long sv = (long long)v;
+      const uint64_t r = reduce64((uint64_t)(sv < 0 ? -sv : sv), m);
+      return sv < 0 ? neg_mod(r, m.p) : r;
+    }
     uint64_t r = reduce64(v, m);
     if (v >= thr) r = sub_mod(r, tm, m.p);   // v + (Q - t)  ==  v - t  (mod Q_l)
     return r;
   };
   if (LVL0 == 0) {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[pad_idx(i)] = lift(src[i]);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[pad_idx(i)] = lift(i);
   } else {
     const Twiddle t0 = load_tw(P->fwdQ[l], 1);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      uint64_t x = lift(src[i]), y = lift(src[i + n]);
+      uint64_t x = lift(i), y = lift(i + n);
       if (LAZY) bfly_fwd_lazy(x, y, t0, m.p, m.p << 2);
       else bfly_fwd(x, y, t0, m.p, m.p << 1);
       sm[pad_idx(i)] = h ? y : x;
@@ -139,17 +148,25 @@ __global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restric
 // the residue is centred and converted once, all LOGN levels run on exact doubles, and the store canonicalises.  For
 // LVL0 = 0 the first pass reads the coefficients straight from global memory and the last pass writes the result straight
 // to global memory (no separate load / store phases).
+template <bool SIGNED>
 struct LiftIoF64 {
+  using Raw = uint64_t;
   const uint64_t *src;
   uint64_t *dst;
   ModConst m;
   uint64_t thr, tm;
   double pd, pinv;
-  __device__ __forceinline__ uint64_t load_raw(uint32_t i) const { return __ldg(src + i); }
-  __device__ __forceinline__ double lift(uint64_t v) const {
-    uint64_t r = reduce64(v, m);
-    if (v >= thr) r = sub_mod(r, tm, m.p);   // v + (Q - t)  ==  v - t  (mod Q_l)
-    return centre_to_f64(r, m.p);
+  __device__ __forceinline__ Raw load_raw(uint32_t i) const { return __ldg(src + i); }
+  __device__ __forceinline__ double lift(Raw v) const {
+    if constexpr (SIGNED) {   // sum of two centred plaintexts (k_centre_add), |v| < 2^61
+      const long long sv = (long long)v;
+      const uint64_t r = reduce64((uint64_t)(sv < 0 ? -sv : sv), m);
+      return centre_to_f64(sv < 0 ? neg_mod(r, m.p) : r, m.p);
+    } else {
+      uint64_t r = reduce64(v, m);
+      if (v >= thr) r = sub_mod(r, tm, m.p);   // v + (Q - t)  ==  v - t  (mod Q_l)
+      return centre_to_f64(r, m.p);
+    }
   }
   template <int R>
   __device__ __forceinline__ void store(uint32_t base, const double (&v)[R]) const {
@@ -160,7 +177,7 @@ struct LiftIoF64 {
   }
 };
 
-template <int LOGN, int LVL0>
+template <int LOGN, int LVL0, bool SIGNED>
 __global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
                                                           uint64_t *__restrict__ out) {
   extern __shared__ double smf[];
@@ -168,7 +185,7 @@ __global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__res
   const uint32_t L_R = P->L_R, L_E = P->L_E;
   const uint32_t h = blockIdx.x & ((1u << LVL0) - 1), el = blockIdx.x >> LVL0;
   const uint32_t e = el / L_E, l = el - e * L_E, j = blockIdx.y;
-  LiftIoF64 io;
+  LiftIoF64<SIGNED> io;
   io.m = P->Q[l];
   io.pd = (double)io.m.p;
   io.pinv = P->Qinv_f64[l];
@@ -182,7 +199,7 @@ __global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__res
   if (LVL0 != 0) {
     const double w0 = __ldg(tab + 1), w0p = __dmul_rn(w0, io.pinv);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      double x = io.lift(io.src[i]), y = io.lift(io.src[i + n]);
+      double x = io.lift(io.load_raw(i)), y = io.lift(io.load_raw(i + n));
       bfly_fwd_f64(x, y, w0, w0p, io.pd);
       smf[pad_idx(i)] = recentre_f64(h ? y : x, io.pd, io.pinv);
     }
@@ -332,6 +349,60 @@ __global__ void __launch_bounds__(256) k_enc_add(const DevParams *__restrict__ P
   *reinterpret_cast<ulonglong2 *>(out + w) = make_ulonglong2(add_mod(x.x, y.x, p), add_mod(x.y, y.y, p));
 }
 
+// comb[m][j][i] = centred(plain[pair[2m]][j][i]) + centred(plain[pair[2m+1]][j][i]) as int64 (second index 0xFFFFFFFF =
+// none), centred(v) = v - t for v >= ceil(t/2) (evaluator.cpp:2220-2259 lifts exactly these representatives into Q).
+// The sum of the lifts is the lift of the sum for EVERY Q_l, so the merged term needs one forward transform per limb.
+// grid (M, L_R), 256 threads, two words per access.
+__global__ void __launch_bounds__(256) k_centre_add(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
+                                                    const uint32_t *__restrict__ pair, uint64_t *__restrict__ comb) {
+  const uint32_t mi = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_R = P->L_R;
+  const uint64_t t = P->q[j].p, thr = P->thr[j];
+  const uint32_t ia = pair[2 * mi], ib = pair[2 * mi + 1];
+  const ulonglong2 *a = reinterpret_cast<const ulonglong2 *>(plain + ((size_t)ia * L_R + j) * N_E);
+  const ulonglong2 *b = ib != 0xFFFFFFFFu ? reinterpret_cast<const ulonglong2 *>(plain + ((size_t)ib * L_R + j) * N_E) : nullptr;
+  ulonglong2 *o = reinterpret_cast<ulonglong2 *>(comb + ((size_t)mi * L_R + j) * N_E);
+  auto centre = [&](uint64_t v) { return v >= thr ? v - t : v; };   // two's complement
+  for (uint32_t i = threadIdx.x; i < N_E / 2; i += blockDim.x) {
+    ulonglong2 x = a[i];
+    x.x = centre(x.x); x.y = centre(x.y);
+    if (b) {
+      const ulonglong2 y = b[i];
+      x.x += centre(y.x); x.y += centre(y.y);
+    }
+    o[i] = x;
+  }
+}
+
+// pval[g][j] = NTT_{Q_0}(lift(plain[g][j]))[0] = sum_i lift(plain[g][j][i]) * psi^i mod Q_0: the one NTT-domain word k_probe
+// needs per term, evaluated directly (an N_E-term dot product) for the parts of a merged lincomb, whose separate
+// transforms are never formed.  psi_pow[i] = psi^i mod Q_0 (psi = SEAL's minimal primitive 2N-th root).  grid (G, L_R).
+__global__ void __launch_bounds__(256) k_probe_eval(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
+                                                    const uint64_t *__restrict__ psi_pow, uint64_t *__restrict__ pval) {
+  __shared__ uint64_t part[8];
+  const uint32_t g = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_R = P->L_R;
+  const ModConst m = P->Q[0];
+  const uint64_t thr = P->thr[j], tm = P->tmodQ[j][0];
+  const uint64_t *src = plain + ((size_t)g * L_R + j) * N_E;
+  Acc192 acc;
+  acc.clear();
+  for (uint32_t i = threadIdx.x; i < N_E; i += blockDim.x) {
+    const uint64_t v = src[i];
+    uint64_t r = reduce64(v, m);
+    if (v >= thr) r = sub_mod(r, tm, m.p);
+    acc.mac(r, __ldg(psi_pow + i));
+  }
+  uint64_t s = acc.reduce(m);
+#pragma unroll
+  for (int off = 16; off; off >>= 1) s = add_mod(s, __shfl_xor_sync(0xFFFFFFFFu, s, off), m.p);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = part[0];
+    for (int w = 1; w < 8; w++) t = add_mod(t, part[w], m.p);
+    pval[(size_t)g * L_R + j] = t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // "Transparent ciphertext" semantics.  SEAL throws when an addition yields a ciphertext whose c1 is identically zero
 // (evaluator.cpp:233-239) and EncodingElem::operator+= answers by replacing that limb with an empty zero ciphertext
@@ -340,17 +411,19 @@ __global__ void __launch_bounds__(256) k_enc_add(const DevParams *__restrict__ P
 // at one fixed slot (k = 1, l = 0, x = 0) over the term list and flags the terms where it is zero -- a necessary
 // condition for the prefix to be transparent.  The host resolves flagged prefixes exactly (rsgpu.cu).
 // grid (L_R), 256 threads; carry[j] holds the running sum across chunks of the term list.
+// pv_stride != 0: the NTT-domain plaintext value of term t at the probe slot is pv[pidx[t] * pv_stride + j] (k_probe_eval
+// output of a merged lincomb) instead of being read from pntt.
 __global__ void __launch_bounds__(256) k_probe(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
                                                const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
                                                uint32_t n_terms, const uint64_t *__restrict__ pntt, uint64_t *__restrict__ carry,
-                                               uint8_t *__restrict__ flags, uint32_t flag_stride) {
+                                               uint8_t *__restrict__ flags, uint32_t flag_stride, uint32_t pv_stride) {
   __shared__ uint64_t warp_tot[8];
   __shared__ uint64_t run;
   const uint32_t j = blockIdx.x, N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
   const ModConst m = P->Q[0];
   const size_t ct_words = 2 * (size_t)L_E * N_E, enc_words = (size_t)L_R * ct_words;
   const size_t c_off = (size_t)j * ct_words + (size_t)L_E * N_E;   // k = 1, l = 0, x = 0
-  const size_t p_off = (size_t)j * L_E * N_E, p_stride = (size_t)L_R * L_E * N_E;
+  const size_t p_off = pv_stride ? j : (size_t)j * L_E * N_E, p_stride = pv_stride ? pv_stride : (size_t)L_R * L_E * N_E;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) run = carry[j];
   __syncthreads();

@@ -118,7 +118,7 @@ __device__ __forceinline__ void ntt_pass_f64(double *sm, const double *tab, doub
     double *ptr = sm + pad_idx(base);
     double v[R];
     if (IN_GLOBAL) {
-      uint64_t raw[R];
+      typename Io::Raw raw[R];
 #pragma unroll
       for (int k = 0; k < R; k++) raw[k] = io.load_raw(base + k * g);
 #pragma unroll

@@ -175,13 +175,20 @@ struct rsg_context {
   // transparent-ciphertext emulation (kernels.cuh: k_probe): per-term candidate flags [slot][L_R][T], running sums, nz words
   uint8_t *d_probe = nullptr;
   size_t cap_probe = 0;
-  uint64_t *d_probe_carry = nullptr;
+  uint64_t *d_probe_carry = nullptr;   // [2][MAX_LR]: second row for the second part of a merged lincomb
   uint32_t *d_nz = nullptr;
+  uint64_t *d_psi_pow = nullptr;    // psi^i mod Q_0, i < N_E (k_probe_eval)
+  uint32_t *d_mrg = nullptr;        // index lists of a merged lincomb
+  size_t cap_mrg = 0;
+  uint64_t *d_pval = nullptr;       // k_probe_eval output [plain slot][L_R]
+  size_t cap_pval = 0;
+  int merge_mode = 1;               // RSG_MERGE=0: never merge inner products over the same CRS range
   uint64_t *d_exact = nullptr;      // scratch encodings of the exact (slow) path
   size_t cap_exact = 0;
   uint64_t *d_ip = nullptr;         // the separate inner products of rsg_groth16_prove
   size_t cap_ip = 0;
   uint64_t exact_fallbacks = 0;     // how often a flagged prefix had to be resolved exactly
+  uint64_t st_lin_terms = 0, st_lin_plain = 0, st_lin_launches = 0, st_fwd_polys = 0, st_inv_polys = 0, st_merged = 0;
   bool f64_ntt = false;             // every Q_l < 2^49: forward NTTs of the plaintext pipeline run on the FP64 pipe
   int ntt_mode = 0;                 // 0 = auto; RSG_NTT=int forces the integer kernel
   size_t enc_words() const { return L_R * 2 * L_E * N_E; }
@@ -352,7 +359,16 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
         (rc = upload_vec(c, b2, &c->d_invNw_Q)))
       return rc;
   }
-  if ((rc = dev_alloc(c, &c->d_probe_carry, MAX_LR, false))) return rc;
+  if ((rc = dev_alloc(c, &c->d_probe_carry, 2 * MAX_LR, false))) return rc;
+  {
+    std::vector<uint64_t> pw(N_E);
+    const uint64_t psi = h_minimal_primitive_root(2 * N_E, Q[0]);
+    pw[0] = 1;
+    for (size_t i = 1; i < N_E; i++) pw[i] = h_mulmod(pw[i - 1], psi, Q[0]);
+    if ((rc = upload_vec(c, pw, &c->d_psi_pow))) return rc;
+  }
+  if (const char *m = getenv("RSG_MERGE")) c->merge_mode = atoi(m);
+  if (const char *m = getenv("RSG_PNTT_BUDGET_WORDS")) c->pntt_budget_words = std::max<size_t>(1, strtoull(m, nullptr, 10));   // tests: force chunking
   if ((rc = dev_alloc(c, &c->d_nz, MAX_LR, false))) return rc;
   *out = c;
   return RSG_OK;
@@ -386,6 +402,18 @@ extern "C" int rsg_context_set_stream(rsg_context *c, void *s) {
   return RSG_OK;
 }
 extern "C" uint64_t rsg_context_launch_count(const rsg_context *c) { return c ? c->launches : 0; }
+extern "C" uint64_t rsg_context_stat(const rsg_context *c, const char *name) {
+  if (!c || !name) return 0;
+  const std::string n(name);
+  if (n == "lincomb_terms") return c->st_lin_terms;       // CRS elements streamed by k_crs_lincomb
+  if (n == "lincomb_plain_terms") return c->st_lin_plain; // of which multiplied by an NTT-domain plaintext
+  if (n == "lincomb_launches") return c->st_lin_launches;
+  if (n == "ntt_forward_polys") return c->st_fwd_polys;   // N_E-point forward transforms (k_lift_fwd_ntt)
+  if (n == "ntt_inverse_polys") return c->st_inv_polys;   // N_E-point inverse transforms (k_encode_intt)
+  if (n == "merged_lincombs") return c->st_merged;
+  if (n == "exact_fallbacks") return c->exact_fallbacks;
+  return 0;
+}
 extern "C" int rsg_context_enable_timing(rsg_context *c, int on) {
   if (!c) return fail(RSG_ERR_STATE, "context not set");
   std::lock_guard<std::mutex> g(c->mu);
@@ -623,7 +651,8 @@ static int set_smem_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(k_encode_intt<LOGN, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done[dev] = true;
@@ -655,6 +684,7 @@ static int launch_intt_finish(rsg_context *c, uint64_t *d, size_t polys, const M
 
 static int launch_encode(rsg_context *c, const uint64_t *d_ring, const uint32_t *d_eidx, size_t count, uint64_t *d_plain) {
   if (!count) return RSG_OK;
+  c->st_inv_polys += count * c->L_R;
   const unsigned th = ntt_threads(c->logN);
   const size_t sm = ntt_smem(c->logN);
   const unsigned split = c->logN > 14 ? 2 : 1;
@@ -669,33 +699,28 @@ static int launch_encode(rsg_context *c, const uint64_t *d_ring, const uint32_t 
     return launch_intt_finish(c, d_plain, count * c->L_R, c->d_modq, c->d_invN_q, c->d_invNw_q, (uint32_t)c->L_R, 0xFFFFFFFFu);
   return RSG_OK;
 }
-static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count, uint64_t *d_pntt) {
+// is_signed: d_plain holds int64 sums of centred plaintexts (k_centre_add) instead of residues mod t
+static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count, uint64_t *d_pntt, bool is_signed = false) {
   if (!count) return RSG_OK;
   const unsigned th = ntt_threads(c->logN);
   const size_t sm = ntt_smem(c->logN);
   const unsigned split = c->logN > 14 ? 2 : 1;
+  c->st_fwd_polys += count * c->L_R * c->L_E;
   // grid.x = (term * L_E + limb) * split: up to 2^31-1
   dim3 grid((unsigned)(count * c->L_E * split), (unsigned)c->L_R);
   bool lazy = true;   // correction-free butterflies need (4 * log2 N + 1) * Q_l < 2^64
   for (uint64_t p : c->Q) lazy = lazy && p < (1ull << 58);
   LaunchScope ls(c, "k_lift_fwd_ntt");
-  if (c->f64_ntt && c->ntt_mode == 2 && c->logN == 14) {   // experiment: two decoupled 2^13-point CTAs per polynomial
-    static bool attr_done = false;
-    const int bytes = (int)padded_words(1u << 13) * 8;
-    if (!attr_done) { CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<13, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); attr_done = true; }
-    k_lift_fwd_ntt_f64<13, 1><<<dim3((unsigned)(count * c->L_E * 2), (unsigned)c->L_R), 256, bytes, c->stream>>>(c->d_params, d_plain, d_pntt);
-    CUDA_TRY(cudaGetLastError());
-    return RSG_OK;
-  }
   if (c->f64_ntt && c->ntt_mode != 1) {
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
-                             k_lift_fwd_ntt_f64<LG, LV><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
+                             if (is_signed) k_lift_fwd_ntt_f64<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
+                             else k_lift_fwd_ntt_f64<LG, LV, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
     CUDA_TRY(cudaGetLastError());
     return RSG_OK;
   }
   DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
-                           if (lazy) k_lift_fwd_ntt<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
-                           else k_lift_fwd_ntt<LG, LV, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
+                           if (lazy) k_lift_fwd_ntt<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, is_signed, d_pntt);
+                           else k_lift_fwd_ntt<LG, LV, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, is_signed, d_pntt); });
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -764,6 +789,8 @@ static int launch_lincomb(rsg_context *c, const uint64_t *d_crs, const uint32_t 
     if ((rc = ensure(c, &c->d_partial, &c->cap_partial, (size_t)splits * c->enc_words()))) return rc;
     d_partial = c->d_partial;
   }
+  c->st_lin_terms += n_terms;
+  c->st_lin_launches++;
   {
     LaunchScope ls(c, "k_crs_lincomb");
     k_crs_lincomb<4><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, d_term, d_pidx, (uint32_t)n_terms, tps, d_pntt,
@@ -829,6 +856,7 @@ static int lincomb_terms(rsg_context *c, const uint64_t *d_crs, const std::vecto
     chunks.push_back({t0, terms.size(), g0, g});
   }
   const size_t G = eidx.size();
+  c->st_lin_plain += G;
   if ((rc = ensure(c, &c->d_term, &c->cap_term, std::max<size_t>(terms.size(), 1024)))) return rc;
   if ((rc = ensure(c, &c->d_pidx, &c->cap_pidx, std::max<size_t>(terms.size(), 1024)))) return rc;
   if ((rc = ensure(c, &c->d_eidx, &c->cap_eidx, std::max<size_t>(G, 1024)))) return rc;
@@ -873,7 +901,7 @@ static int lincomb_terms(rsg_context *c, const uint64_t *d_crs, const std::vecto
     if (d_probe_flags) {
       LaunchScope ls(c, "k_probe");
       k_probe<<<(unsigned)c->L_R, 256, 0, c->stream>>>(c->d_params, d_crs, c->d_term + ch.t0, c->d_pidx + ch.t0, (uint32_t)(ch.t1 - ch.t0),
-                                                        c->d_pntt, c->d_probe_carry, d_probe_flags + ch.t0, (uint32_t)terms.size());
+                                                        c->d_pntt, c->d_probe_carry, d_probe_flags + ch.t0, (uint32_t)terms.size(), 0u);
       CUDA_TRY(cudaGetLastError());
     }
   }
@@ -886,14 +914,131 @@ static int lincomb_terms(rsg_context *c, const uint64_t *d_crs, const std::vecto
   return RSG_OK;
 }
 
+// Two inner products over the SAME CRS vector in one pass (groth16.tcc:89-103: <s_pows, a_io> + <s_pows, a_mid>):
+//   sum_i ct_i (.) NTT(lift(x_i)) + sum_i ct_i (.) NTT(lift(y_i)) = sum_i ct_i (.) NTT(lift(x_i) + lift(y_i))   (mod Q_l, exactly),
+// so each CRS element is streamed once and transformed once instead of twice.  The two batch encodings stay separate
+// (the centred lift is not additive).  d_out receives X + Y.  The transparent-prefix probes of the two parts are kept apart:
+// their NTT-domain probe words come from k_probe_eval, the flags go to d_flagsX / d_flagsY ([L_R][|X|] and [L_R][|Y|]).
+// Returns 1 (nothing launched) when the lists do not qualify: a non-general term, mixed source vectors, unsorted CRS indices.
+static int lincomb_merged(rsg_context *c, const uint64_t *d_crs, const std::vector<TermSpec> &X, const std::vector<TermSpec> &Y,
+                          uint64_t *d_out, uint8_t *d_flagsX, uint8_t *d_flagsY) {
+  int rc;
+  if (X.empty() || Y.empty()) return 1;
+  for (const std::vector<TermSpec> *v : {&X, &Y})
+    for (size_t i = 0; i < v->size(); i++) {
+      if (!(*v)[i].ring_base || (*v)[i].ring_base != (*v)[0].ring_base) return 1;
+      if (i && (*v)[i].crs_idx <= (*v)[i - 1].crs_idx) return 1;
+    }
+  struct M { uint32_t crs, x, y; };
+  const uint32_t NONE = 0xFFFFFFFFu;
+  std::vector<M> mt;
+  mt.reserve(X.size() + Y.size());
+  for (size_t a = 0, b = 0; a < X.size() || b < Y.size();) {
+    if (b >= Y.size() || (a < X.size() && X[a].crs_idx < Y[b].crs_idx)) { mt.push_back({X[a].crs_idx, (uint32_t)a, NONE}); a++; }
+    else if (a >= X.size() || Y[b].crs_idx < X[a].crs_idx) { mt.push_back({Y[b].crs_idx, NONE, (uint32_t)b}); b++; }
+    else { mt.push_back({X[a].crs_idx, (uint32_t)a, (uint32_t)b}); a++; b++; }
+  }
+  const size_t per_general = c->L_R * c->L_E * c->N_E, poly = c->L_R * c->N_E;
+  const size_t max_m = std::max<size_t>(1, c->pntt_budget_words / per_general);
+  const size_t n_chunks = (mt.size() + max_m - 1) / max_m, cm = std::min(mt.size(), max_m);
+  if ((rc = ensure(c, &c->d_plain, &c->cap_plain, 3 * cm * poly))) return rc;   // [X parts | Y parts | centred sums]
+  if ((rc = ensure(c, &c->d_pntt, &c->cap_pntt, cm * per_general))) return rc;
+  if ((rc = ensure(c, &c->d_pval, &c->cap_pval, std::max<size_t>(2 * cm * c->L_R, 1024)))) return rc;
+  // one upload: per chunk [term M | pidx M | pair 2M | eidxX | eidxY | crsX | slotX | crsY | slotY]
+  std::vector<uint32_t> buf;
+  struct Off { size_t term, pidx, pair, ex, ey, cx, sx, cy, sy, nx, ny, m, x0, y0; };
+  std::vector<Off> offs;
+  for (size_t k = 0; k < n_chunks; k++) {
+    const size_t m0 = k * max_m, m1 = std::min(mt.size(), m0 + max_m), Mk = m1 - m0;
+    std::vector<uint32_t> ex, ey, cx, cy, sx, sy, pair(2 * Mk);
+    size_t x0 = X.size(), y0 = Y.size();
+    for (size_t m = m0; m < m1; m++) {
+      if (mt[m].x != NONE) { x0 = std::min<size_t>(x0, mt[m].x); ex.push_back(X[mt[m].x].elem); cx.push_back(mt[m].crs); }
+      if (mt[m].y != NONE) { y0 = std::min<size_t>(y0, mt[m].y); ey.push_back(Y[mt[m].y].elem); cy.push_back(mt[m].crs); }
+    }
+    size_t ax = 0, ay = 0;
+    for (size_t m = m0; m < m1; m++) {
+      uint32_t s0 = NONE, s1 = NONE;
+      if (mt[m].x != NONE) { s0 = (uint32_t)ax; sx.push_back(s0); ax++; }
+      if (mt[m].y != NONE) { s1 = (uint32_t)(ex.size() + ay); sy.push_back(s1); ay++; }
+      if (s0 == NONE) std::swap(s0, s1);
+      pair[2 * (m - m0)] = s0;
+      pair[2 * (m - m0) + 1] = s1;
+    }
+    Off o;
+    o.m = Mk; o.nx = ex.size(); o.ny = ey.size(); o.x0 = x0; o.y0 = y0;
+    o.term = buf.size(); for (size_t m = m0; m < m1; m++) buf.push_back(mt[m].crs);
+    o.pidx = buf.size(); for (size_t m = 0; m < Mk; m++) buf.push_back((uint32_t)m);
+    o.pair = buf.size(); buf.insert(buf.end(), pair.begin(), pair.end());
+    o.ex = buf.size(); buf.insert(buf.end(), ex.begin(), ex.end());
+    o.ey = buf.size(); buf.insert(buf.end(), ey.begin(), ey.end());
+    o.cx = buf.size(); buf.insert(buf.end(), cx.begin(), cx.end());
+    o.sx = buf.size(); buf.insert(buf.end(), sx.begin(), sx.end());
+    o.cy = buf.size(); buf.insert(buf.end(), cy.begin(), cy.end());
+    o.sy = buf.size(); buf.insert(buf.end(), sy.begin(), sy.end());
+    offs.push_back(o);
+  }
+  c->st_merged++;
+  c->st_lin_plain += mt.size();
+  if ((rc = ensure(c, &c->d_mrg, &c->cap_mrg, std::max<size_t>(buf.size(), 4096)))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(c->d_mrg, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->d_probe_carry, 0, 2 * MAX_LR * 8, c->stream));
+  uint64_t *chunk_out = d_out;
+  if (n_chunks > 1) {
+    if ((rc = ensure(c, &c->d_chunk, &c->cap_chunk, n_chunks * c->enc_words()))) return rc;
+    chunk_out = c->d_chunk;
+  }
+  for (size_t k = 0; k < n_chunks; k++) {
+    const Off &o = offs[k];
+    const uint32_t *d = c->d_mrg;
+    if ((rc = launch_encode(c, X[0].ring_base, d + o.ex, o.nx, c->d_plain))) return rc;
+    if ((rc = launch_encode(c, Y[0].ring_base, d + o.ey, o.ny, c->d_plain + o.nx * poly))) return rc;
+    uint64_t *comb = c->d_plain + (o.nx + o.ny) * poly;
+    {
+      LaunchScope ls(c, "k_centre_add");
+      k_centre_add<<<dim3((unsigned)o.m, (unsigned)c->L_R), 256, 0, c->stream>>>(c->d_params, c->d_plain, d + o.pair, comb);
+    }
+    if ((rc = launch_lift_ntt(c, comb, o.m, c->d_pntt, true))) return rc;
+    if ((rc = launch_lincomb(c, d_crs, d + o.term, d + o.pidx, o.m, c->d_pntt, chunk_out + (n_chunks > 1 ? k * c->enc_words() : 0))))
+      return rc;
+    {
+      LaunchScope ls(c, "k_probe_eval");
+      k_probe_eval<<<dim3((unsigned)(o.nx + o.ny), (unsigned)c->L_R), 256, 0, c->stream>>>(c->d_params, c->d_plain, c->d_psi_pow, c->d_pval);
+    }
+    if (o.nx) {
+      LaunchScope ls(c, "k_probe");
+      k_probe<<<(unsigned)c->L_R, 256, 0, c->stream>>>(c->d_params, d_crs, d + o.cx, d + o.sx, (uint32_t)o.nx, c->d_pval, c->d_probe_carry,
+                                                        d_flagsX + o.x0, (uint32_t)X.size(), (uint32_t)c->L_R);
+    }
+    if (o.ny) {
+      LaunchScope ls(c, "k_probe");
+      k_probe<<<(unsigned)c->L_R, 256, 0, c->stream>>>(c->d_params, d_crs, d + o.cy, d + o.sy, (uint32_t)o.ny, c->d_pval,
+                                                        c->d_probe_carry + MAX_LR, d_flagsY + o.y0, (uint32_t)Y.size(), (uint32_t)c->L_R);
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (n_chunks > 1) {
+    LaunchScope ls(c, "k_enc_sum");
+    const size_t pairs = c->enc_words() / 2;
+    k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, chunk_out, (uint32_t)n_chunks, 1, d_out);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return RSG_OK;
+}
+
 // acc += other with the reference's transparent-result rule (seal_ring.tcc:493-504): a ring limb whose c1 sums to zero
 // becomes the empty zero ciphertext (all-zero words).  Entirely on the device, no host round trip.
+static int transparent_fix(rsg_context *c, uint64_t *d_acc);
 static int enc_add_fix(rsg_context *c, uint64_t *d_acc, const uint64_t *d_other) {
   const size_t pairs = c->enc_words() / 2;
   {
     LaunchScope ls(c, "k_enc_add");
     k_enc_add<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_acc, d_other, d_acc);
   }
+  return transparent_fix(c, d_acc);
+}
+// the rule alone, applied to a sum that is already formed
+static int transparent_fix(rsg_context *c, uint64_t *d_acc) {
   CUDA_TRY(cudaMemsetAsync(c->d_nz, 0, MAX_LR * 4, c->stream));
   const dim3 grid((unsigned)std::min<size_t>(64, (c->L_E * c->N_E + 255) / 256), (unsigned)c->L_R);
   {
@@ -1367,15 +1512,25 @@ static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_gr
   for (int k = 0; k < 6; k++) probe_off[k + 1] = probe_off[k] + c->L_R * ip[k].size();
   if ((rc = ensure(c, &c->d_ip, &c->cap_ip, 6 * E))) return rc;
   if ((rc = ensure(c, &c->d_probe, &c->cap_probe, std::max<size_t>(probe_off[6], 4096)))) return rc;
+  // A and B: <s_pows, x_io> + <s_pows, x_mid> share their CRS range -> one merged pass each (lincomb_merged)
+  bool merged[3] = {false, false, false};
+  for (int e = 0; e < 2 && c->merge_mode; e++) {
+    rc = lincomb_merged(c, crs->d, ip[2 * e], ip[2 * e + 1], c->d_ip + 2 * e * E, c->d_probe + probe_off[2 * e],
+                        c->d_probe + probe_off[2 * e + 1]);
+    if (rc < 0) return rc;
+    merged[e] = rc == 0;
+  }
   for (int k = 0; k < 6; k++)
-    if (!ip[k].empty() && (rc = lincomb_terms(c, crs->d, ip[k], c->d_ip + k * E, c->d_probe + probe_off[k]))) return rc;
+    if (!(k < 4 && merged[k / 2]) && !ip[k].empty() &&
+        (rc = lincomb_terms(c, crs->d, ip[k], c->d_ip + k * E, c->d_probe + probe_off[k])))
+      return rc;
   // EncodingElem::operator+= chain of one proof element: copy the first non-empty operand, then add with the
   // transparent-result rule (an empty inner product is the additive identity, seal_ring.tcc:482-488)
   auto combine = [&](int e) -> int {
     const uint64_t *src[3] = {nullptr, nullptr, nullptr};
     const int a = e == 2 ? 4 : 2 * e, b = a + 1;
     if (!ip[a].empty()) src[0] = c->d_ip + a * E;
-    if (!ip[b].empty()) src[1] = c->d_ip + b * E;
+    if (!ip[b].empty() && !merged[e]) src[1] = c->d_ip + b * E;   // merged: d_ip[a] already holds ip[a] + ip[b]
     const size_t extra = e == 0 ? L->alpha_idx : (e == 1 ? L->beta_idx : NONE);
     if (extra != NONE) src[2] = crs->d + extra * E;
     uint64_t *acc = out + e * E;
@@ -1385,6 +1540,10 @@ static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_gr
       if (!have) {
         CUDA_TRY(cudaMemcpyAsync(acc, src[k], E * 8, cudaMemcpyDeviceToDevice, c->stream));
         have = true;
+        if (k == 0 && merged[e]) {
+          int r = transparent_fix(c, acc);
+          if (r) return r;
+        }
       } else {
         int r = enc_add_fix(c, acc, src[k]);
         if (r) return r;
@@ -1400,6 +1559,20 @@ static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_gr
     CUDA_TRY(cudaMemcpyAsync(pf.data(), c->d_probe, probe_off[6], cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     bool redo[3] = {false, false, false};
+    // a flagged prefix inside a merged pair: form the two inner products separately after all, then resolve as usual
+    for (int e = 0; e < 2; e++) {
+      if (!merged[e]) continue;
+      bool any = false;
+      for (size_t i = probe_off[2 * e]; i < probe_off[2 * e + 2]; i++) any |= pf[i] != 0;
+      if (!any) continue;
+      merged[e] = false;
+      redo[e] = true;
+      for (int k = 2 * e; k < 2 * e + 2; k++)
+        if ((rc = lincomb_terms(c, crs->d, ip[k], c->d_ip + k * E, c->d_probe + probe_off[k]))) return rc;
+      CUDA_TRY(cudaMemcpyAsync(pf.data() + probe_off[2 * e], c->d_probe + probe_off[2 * e], probe_off[2 * e + 2] - probe_off[2 * e],
+                               cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
     for (int k = 0; k < 6; k++) {
       bool any = false;
       for (size_t i = probe_off[k]; i < probe_off[k + 1]; i++) any |= pf[i] != 0;

@@ -502,3 +502,31 @@ def test_fp64_forward_ntt_edge_values(name, monkeypatch):
             ctx.close()
     for mode, got in outs.items():
         assert np.array_equal(got, want), f"{mode} forward NTT differs from the oracle"
+
+
+@pytest.mark.parametrize("budget", [None, "1"])
+def test_merged_inner_products(gold, budget, monkeypatch):
+    """groth16.tcc:89-103 adds two inner products over the same s_pows range; the library streams that range once
+    (lincomb_merged).  The proof must equal the reference's and the unmerged path's, also when the NTT-domain scratch
+    budget forces one merged term per chunk."""
+    case, _ = gold
+    if budget:
+        monkeypatch.setenv("RSG_PNTT_BUDGET_WORDS", budget)
+    proofs, stats = [], []
+    for merge in ("1", "0"):
+        monkeypatch.setenv("RSG_MERGE", merge)
+        ctx = make_ctx(case)
+        try:
+            pk = _pk(case, ctx)
+            proof, _ = pk.prove(_assignment(case), _aux_kind(case))
+            proofs.append(proof)
+            stats.append((ctx.stat("merged_lincombs"), ctx.stat("lincomb_terms"), ctx.stat("exact_fallbacks")))
+        finally:
+            ctx.close()
+    assert np.array_equal(proofs[0], case.enc("proof")[0])
+    assert np.array_equal(proofs[1], case.enc("proof")[0])
+    assert stats[1][0] == 0
+    if int(case.seed) != 11:                       # tiny_transp un-merges after the probe flags a transparent prefix
+        assert stats[0][0] >= 1 and stats[0][1] < stats[1][1]
+    else:
+        assert stats[0][2] > 0
