@@ -277,7 +277,8 @@ def run_gpu_arm(args, cfg_name, cfg):
     launches = sum(cx.launch_count() for cx in ctxs) - l0
     stats = {k: (sum(cx.stat(k) for cx in ctxs) - st0[k]) / args.steps for k in stat_names}   # per proof, this rank
     kern = {}
-    for name in ("k_crs_lincomb", "k_lift_fwd_ntt", "k_encode_intt", "k_modmat_interp", "k_modmat_divZ", "k_conv_top",
+    for name in ("k_crs_lincomb", "k_lift_fwd_ntt", "k_encode_intt", "k_interp_fast", "k_quotient_fast", "k_modmat_interp",
+                 "k_modmat_divZ", "k_conv_top",
                  "k_r1cs_eval", "k_enc_sum", "k_enc_add", "k_is_zero_prefix", "k_probe", "k_probe_eval", "k_full_from_parts",
                  "k_c1_nonzero", "k_zero_transparent"):
         ms = cnt = 0

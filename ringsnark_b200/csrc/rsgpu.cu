@@ -14,6 +14,7 @@
 #include "../../include/rsgpu.h"
 #include "kernels.cuh"
 #include "witness.cuh"
+#include "witness_fast.cuh"
 #include "ringops.cuh"
 
 using namespace rsg;
@@ -133,10 +134,13 @@ struct TimingRec {
 };
 
 struct WitnessTables {   // per constraint count n
-  uint64_t *d_Vinv = nullptr;   // [L_R][n][n]
-  uint64_t *d_T = nullptr;      // [L_R][n-1][n-1] upper-triangular Toeplitz of rev(Z)^-1
+  uint64_t *d_Vinv = nullptr;   // [L_R][n][n]            dense path only (built on first use)
+  uint64_t *d_T = nullptr;      // [L_R][n-1][n-1] upper-triangular Toeplitz of rev(Z)^-1 (dense path only)
   uint64_t *d_Z = nullptr;      // [L_R][n+1]
   std::vector<uint64_t> h_Z;    // [L_R][n+1]
+  std::vector<uint64_t> h_u;    // [L_R][max(n-1,1)]  rev(Z)^-1 mod x^(n-1)
+  bool fast_ready = false;      // quasi-linear path (witness_fast.cuh)
+  FastTables ft;
 };
 
 struct rsg_context {
@@ -156,6 +160,9 @@ struct rsg_context {
   bool timing = false;
   std::vector<TimingRec> recs;
   std::map<size_t, WitnessTables> wit;
+  std::vector<std::vector<uint64_t>> h_fwdq;   // host copy of the forward twiddles mod q_j (witness_fast tables)
+  int witness_mode = 0;             // 0 = auto, 1 = dense (RSG_WITNESS=dense), 2 = quasi-linear wherever it applies (RSG_WITNESS=fast)
+  int wf_sl = 0;                    // RSG_WF_SL: slots per CTA of the quasi-linear kernels (0 = auto)
   // scratch (grown on demand)
   uint64_t *d_plain = nullptr, *d_pntt = nullptr, *d_partial = nullptr;
   size_t cap_plain = 0, cap_pntt = 0, cap_partial = 0;
@@ -188,6 +195,7 @@ struct rsg_context {
   uint64_t *d_ip = nullptr;         // the separate inner products of rsg_groth16_prove
   size_t cap_ip = 0;
   uint64_t exact_fallbacks = 0;     // how often a flagged prefix had to be resolved exactly
+  uint64_t st_wf = 0, st_wd = 0;
   uint64_t st_lin_terms = 0, st_lin_plain = 0, st_lin_launches = 0, st_fwd_polys = 0, st_inv_polys = 0, st_merged = 0;
   bool f64_ntt = false;             // every Q_l < 2^49: forward NTTs of the plaintext pipeline run on the FP64 pipe
   int ntt_mode = 0;                 // 0 = auto; RSG_NTT=int forces the integer kernel
@@ -324,6 +332,8 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   for (size_t j = 0; j < L_R; j++) {
     hp.q[j] = h_modconst(q[j]);
     h_tables(c->logN, q[j], fwd, inv);
+    c->h_fwdq.emplace_back(fwd.size());
+    for (size_t i = 0; i < fwd.size(); i++) c->h_fwdq.back()[i] = fwd[i].w;
     Twiddle *d;
     if ((rc = upload_vec(c, fwd, &d))) return rc;
     hp.fwdq[j] = d;
@@ -368,6 +378,8 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
     if ((rc = upload_vec(c, pw, &c->d_psi_pow))) return rc;
   }
   if (const char *m = getenv("RSG_MERGE")) c->merge_mode = atoi(m);
+  if (const char *m = getenv("RSG_WITNESS")) c->witness_mode = !strcmp(m, "dense") ? 1 : (!strcmp(m, "fast") ? 2 : 0);
+  if (const char *m = getenv("RSG_WF_SL")) c->wf_sl = atoi(m);
   if (const char *m = getenv("RSG_PNTT_BUDGET_WORDS")) c->pntt_budget_words = std::max<size_t>(1, strtoull(m, nullptr, 10));   // tests: force chunking
   if ((rc = dev_alloc(c, &c->d_nz, MAX_LR, false))) return rc;
   *out = c;
@@ -412,6 +424,8 @@ extern "C" uint64_t rsg_context_stat(const rsg_context *c, const char *name) {
   if (n == "ntt_inverse_polys") return c->st_inv_polys;   // N_E-point inverse transforms (k_encode_intt)
   if (n == "merged_lincombs") return c->st_merged;
   if (n == "exact_fallbacks") return c->exact_fallbacks;
+  if (n == "witness_fast_launches") return c->st_wf;      // k_interp_fast / k_quotient_fast launches
+  if (n == "witness_dense_launches") return c->st_wd;     // k_modmat* / k_conv_top launches
   return 0;
 }
 extern "C" int rsg_context_enable_timing(rsg_context *c, int on) {
@@ -1188,8 +1202,8 @@ static int get_witness_tables(rsg_context *c, size_t n, WitnessTables **out) {
     if (p <= 2 * n) return fail(RSG_ERR_ARG, "domain {0..n-1} is not an exceptional set for this modulus");
   WitnessTables wt;
   const size_t L_R = c->L_R, m = n > 0 ? n - 1 : 0;
-  std::vector<uint64_t> Vinv(L_R * n * n), T(L_R * std::max<size_t>(m * m, 1), 0);
   wt.h_Z.assign(L_R * (n + 1), 0);
+  wt.h_u.assign(L_R * std::max<size_t>(m, 1), 0);
   for (size_t j = 0; j < L_R; j++) {
     const uint64_t p = c->q[j];
     uint64_t *Z = wt.h_Z.data() + j * (n + 1);
@@ -1202,6 +1216,34 @@ static int get_witness_tables(rsg_context *c, size_t n, WitnessTables **out) {
         Z[k] = (same + lower) % p;
       }
     }
+    if (m) {
+      // u = rev(Z)^-1 mod x^m, rev(Z)_i = Z[n - i] (rev(Z)_0 = 1)
+      uint64_t *u = wt.h_u.data() + j * m;
+      u[0] = 1;
+      for (size_t i = 1; i < m; i++) {
+        u128 acc = 0;
+        for (size_t t = 1; t <= i; t++) acc += (u128)h_mulmod(Z[n - t], u[i - t], p);
+        u[i] = (p - (uint64_t)(acc % p)) % p;
+      }
+    }
+  }
+  void *v = nullptr;
+  CUDA_TRY(cudaMalloc(&v, wt.h_Z.size() * 8));
+  wt.d_Z = (uint64_t *)v;
+  CUDA_TRY(cudaMemcpy(wt.d_Z, wt.h_Z.data(), wt.h_Z.size() * 8, cudaMemcpyHostToDevice));
+  auto ins = c->wit.emplace(n, std::move(wt));
+  *out = &ins.first->second;
+  return RSG_OK;
+}
+
+// Dense-path constants: V^-1 and the Toeplitz matrix of rev(Z)^-1 (O(n^2) words each; small n, or RSG_WITNESS=dense).
+static int ensure_dense_tables(rsg_context *c, size_t n, WitnessTables *wt) {
+  if (wt->d_Vinv) return RSG_OK;
+  const size_t L_R = c->L_R, m = n - 1;
+  std::vector<uint64_t> Vinv(L_R * n * n), T(L_R * std::max<size_t>(m * m, 1), 0);
+  for (size_t j = 0; j < L_R; j++) {
+    const uint64_t p = c->q[j];
+    const uint64_t *Z = wt->h_Z.data() + j * (n + 1);
     // phi_x = Z'(x) = prod_{i != x} (x - i) = x! (n-1-x)! (-1)^(n-1-x)
     std::vector<uint64_t> fact(n + 1, 1);
     for (size_t i = 1; i <= n; i++) fact[i] = h_mulmod(fact[i - 1], i % p, p);
@@ -1217,38 +1259,215 @@ static int get_witness_tables(rsg_context *c, size_t n, WitnessTables **out) {
       for (size_t k = 0; k < n; k++) V[k * n + x] = h_mulmod(b[k], iphi, p);
     }
     if (m) {
-      // u = rev(Z)^-1 mod x^m, rev(Z)_i = Z[n - i] (rev(Z)_0 = 1)
-      std::vector<uint64_t> u(m, 0);
-      u[0] = 1;
-      for (size_t i = 1; i < m; i++) {
-        u128 acc = 0;
-        for (size_t t = 1; t <= i; t++) acc += (u128)h_mulmod(Z[n - t], u[i - t], p);
-        u[i] = (p - (uint64_t)(acc % p)) % p;
-      }
+      const uint64_t *u = wt->h_u.data() + j * m;
       uint64_t *Tm = T.data() + j * m * m;
       for (size_t k = 0; k < m; k++)
         for (size_t col = k; col < m; col++) Tm[k * m + col] = u[col - k];
     }
   }
   void *v = nullptr;
-  CUDA_TRY(cudaMalloc(&v, Vinv.size() * 8));
-  wt.d_Vinv = (uint64_t *)v;
-  CUDA_TRY(cudaMemcpy(wt.d_Vinv, Vinv.data(), Vinv.size() * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&v, T.size() * 8));
-  wt.d_T = (uint64_t *)v;
-  CUDA_TRY(cudaMemcpy(wt.d_T, T.data(), T.size() * 8, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&v, wt.h_Z.size() * 8));
-  wt.d_Z = (uint64_t *)v;
-  CUDA_TRY(cudaMemcpy(wt.d_Z, wt.h_Z.data(), wt.h_Z.size() * 8, cudaMemcpyHostToDevice));
-  auto ins = c->wit.emplace(n, std::move(wt));
-  *out = &ins.first->second;
+  wt->d_T = (uint64_t *)v;
+  CUDA_TRY(cudaMemcpy(wt->d_T, T.data(), T.size() * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&v, Vinv.size() * 8));
+  CUDA_TRY(cudaMemcpy(v, Vinv.data(), Vinv.size() * 8, cudaMemcpyHostToDevice));
+  wt->d_Vinv = (uint64_t *)v;
   return RSG_OK;
+}
+
+// ---- quasi-linear path (witness_fast.cuh) ---------------------------------------------------------------------
+// Transform size for n nodes: the power of two S >= n, doubled when more than WF_WC_MAX coefficients of a length-(2n-1)
+// product would wrap around modulo x^S + 1.
+static void wf_shape(size_t n, uint32_t *S, uint32_t *logS, uint32_t *wc) {
+  uint32_t lg = 5;
+  while (((size_t)1 << lg) < n) lg++;
+  size_t s = (size_t)1 << lg;
+  if (2 * n - 1 > s + WF_WC_MAX) { lg++; s <<= 1; }
+  *S = (uint32_t)s;
+  *logS = lg;
+  *wc = 2 * n - 1 > s ? (uint32_t)(2 * n - 1 - s) : 0;
+}
+static bool wf_supported(const rsg_context *c, size_t n) {
+  if (n < 2) return false;
+  uint32_t S, logS, wc;
+  wf_shape(n, &S, &logS, &wc);
+  if (S > c->N_E) return false;                                // no 2S-th root of unity guaranteed beyond N_E
+  if (wf_smem_bytes(S, 1) > 227 * 1024) return false;
+  for (uint64_t p : c->q)
+    if (p >= (1ull << 61)) return false;
+  return true;
+}
+static bool wf_use(const rsg_context *c, size_t n) {
+  if (c->witness_mode == 1 || !wf_supported(c, n)) return false;
+  return c->witness_mode == 2 || n >= 64;                      // below that the dense products are a handful of launches of nothing
+}
+// forward negacyclic transform on the host, the device's table order (h_tables): natural in, bit-reversed out
+static void h_ntt_fwd(std::vector<uint64_t> &a, int lg, uint64_t p, const std::vector<uint64_t> &tw) {
+  const size_t n = (size_t)1 << lg;
+  for (int s = 0; s < lg; s++) {
+    const size_t gap = n >> (s + 1);
+    for (size_t blk = 0; blk < ((size_t)1 << s); blk++) {
+      const uint64_t w = tw[((size_t)1 << s) + blk];
+      for (size_t o = 0; o < gap; o++) {
+        const size_t i = blk * 2 * gap + o;
+        const uint64_t x = a[i], y = h_mulmod(a[i + gap], w, p);
+        a[i] = (x + y) % p;
+        a[i + gap] = (x + p - y) % p;
+      }
+    }
+  }
+}
+static std::vector<uint64_t> h_polymul(const std::vector<uint64_t> &a, const std::vector<uint64_t> &b, uint64_t p) {
+  std::vector<uint64_t> r(a.size() + b.size() - 1, 0);
+  for (size_t i = 0; i < a.size(); i++) {
+    if (!a[i]) continue;
+    for (size_t k = 0; k < b.size(); k++) r[i + k] = (uint64_t)(((u128)a[i] * b[k] + r[i + k]) % p);
+  }
+  return r;
+}
+static int ensure_fast_tables(rsg_context *c, size_t n, WitnessTables *wt) {
+  if (wt->fast_ready) return RSG_OK;
+  FastTables &ft = wt->ft;
+  memset(&ft, 0, sizeof(ft));
+  uint32_t S, logS, wc;
+  wf_shape(n, &S, &logS, &wc);
+  ft.n = (uint32_t)n; ft.S = S; ft.logS = logS; ft.wc = wc;
+  uint32_t levels = 0;
+  for (size_t m = WF_B; m < n; m <<= 1) levels++;
+  ft.levels = std::max<uint32_t>(levels, 1);
+  const size_t L_R = c->L_R, npad = (n + WF_B - 1) / WF_B * WF_B, lu = n - 1;
+  std::vector<Twiddle> invfact(L_R * n), pts(L_R * npad), Ghat(L_R * S), Phat(L_R * ft.levels * S, Twiddle{0, 0}), Vhat(L_R * S);
+  std::vector<uint64_t> g_nat(L_R * n), Pnat(L_R * ft.levels * (S / 2 + 1), 0), v_nat(L_R * n, 0);
+  for (size_t j = 0; j < L_R; j++) {
+    const uint64_t p = c->q[j];
+    const std::vector<uint64_t> &tw = c->h_fwdq[j];
+    std::vector<uint64_t> fact(n + 1, 1), ifact(n + 1);
+    for (size_t i = 1; i <= n; i++) fact[i] = h_mulmod(fact[i - 1], i % p, p);
+    ifact[n] = h_inv(fact[n], p);
+    for (size_t i = n; i > 0; i--) ifact[i - 1] = h_mulmod(ifact[i], i % p, p);
+    for (size_t i = 0; i < n; i++) {
+      invfact[j * n + i] = h_twiddle(ifact[i], p);
+      g_nat[j * n + i] = (i & 1) ? (p - ifact[i]) % p : ifact[i];
+    }
+    for (size_t i = 0; i < npad; i++) pts[j * npad + i] = h_twiddle(i % p, p);
+    const uint64_t invS = h_inv(S % p, p);
+    ft.invS[j] = h_twiddle(invS, p);
+    {
+      std::vector<uint64_t> a(S, 0);
+      for (size_t i = 0; i < n; i++) a[i] = g_nat[j * n + i];
+      h_ntt_fwd(a, (int)logS, p, tw);
+      for (size_t i = 0; i < S; i++) Ghat[j * S + i] = h_twiddle(h_mulmod(a[i], invS, p), p);
+    }
+    {
+      std::vector<uint64_t> a(S, 0);
+      for (size_t i = 0; i < lu; i++) a[i] = v_nat[j * n + i] = wt->h_u[j * std::max<size_t>(lu, 1) + i];
+      h_ntt_fwd(a, (int)logS, p, tw);
+      for (size_t i = 0; i < S; i++) Vhat[j * S + i] = h_twiddle(h_mulmod(a[i], invS, p), p);
+    }
+    // subproduct tree over aligned node ranges: tree[r] = prod_{x in [r*size, (r+1)*size)} (X - x)
+    std::vector<std::vector<uint64_t>> tree(npad / WF_B);
+    for (size_t r = 0; r < tree.size(); r++) {
+      std::vector<uint64_t> f{1};
+      for (size_t x = r * WF_B; x < (r + 1) * WF_B; x++) f = h_polymul(f, {(p - x % p) % p, 1}, p);
+      tree[r] = std::move(f);
+    }
+    size_t lvl = 0;
+    for (size_t m = WF_B; m < n; m <<= 1, lvl++) {
+      // tree holds the products over ranges of m nodes; block b of this level needs tree[2b]
+      const size_t two_m = 2 * m, nb_active = (n - m + two_m - 1) / two_m;
+      int lg = 0;
+      while (((size_t)1 << lg) < two_m) lg++;
+      const uint64_t inv2m = h_inv(two_m % p, p);
+      for (size_t b = 0; b < nb_active; b++) {
+        std::vector<uint64_t> a(two_m, 0);
+        const std::vector<uint64_t> &P = tree[2 * b];
+        for (size_t i = 0; i <= m; i++) a[i] = P[i];
+        h_ntt_fwd(a, lg, p, tw);
+        Twiddle *dst = Phat.data() + (j * ft.levels + lvl) * S + b * two_m;
+        for (size_t i = 0; i < two_m; i++) dst[i] = h_twiddle(h_mulmod(a[i], inv2m, p), p);
+      }
+      const std::vector<uint64_t> &Pl = tree[2 * (nb_active - 1)];
+      std::copy(Pl.begin(), Pl.end(), Pnat.begin() + (j * ft.levels + lvl) * (S / 2 + 1));
+      std::vector<std::vector<uint64_t>> next;
+      for (size_t r = 0; 2 * r + 1 < tree.size(); r++) next.push_back(h_polymul(tree[2 * r], tree[2 * r + 1], p));
+      tree.swap(next);
+    }
+  }
+  int rc;
+  Twiddle *dt;
+  uint64_t *du;
+  if ((rc = upload_vec(c, invfact, &dt))) return rc;
+  ft.invfact = dt;
+  if ((rc = upload_vec(c, pts, &dt))) return rc;
+  ft.pts = dt;
+  if ((rc = upload_vec(c, Ghat, &dt))) return rc;
+  ft.Ghat = dt;
+  if ((rc = upload_vec(c, Phat, &dt))) return rc;
+  ft.Phat = dt;
+  if ((rc = upload_vec(c, Vhat, &dt))) return rc;
+  ft.Vhat = dt;
+  if ((rc = upload_vec(c, g_nat, &du))) return rc;
+  ft.g_nat = du;
+  if ((rc = upload_vec(c, Pnat, &du))) return rc;
+  ft.Pnat = du;
+  if ((rc = upload_vec(c, v_nat, &du))) return rc;
+  ft.v_nat = du;
+  wt->fast_ready = true;
+  return RSG_OK;
+}
+// slots per CTA: the largest power of two dividing the slot count whose two polynomial buffers stay below ~144 KiB
+static uint32_t wf_pick_sl(const rsg_context *c, uint32_t S, size_t nslots) {
+  uint32_t sl = 8;
+  if (c->wf_sl > 0) sl = (uint32_t)c->wf_sl;
+  while (sl > 1 && (nslots % sl || wf_smem_bytes(S, sl) > (c->wf_sl > 0 ? 227 : 144) * 1024)) sl >>= 1;
+  return sl;
+}
+template <int SL>
+static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
+                            size_t coef_stride, size_t limb_stride, size_t vec_stride) {
+  const size_t smem = wf_smem_bytes(ft.S, SL);
+  CUDA_TRY(cudaFuncSetAttribute(k_interp_fast<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_interp_fast<SL><<<dim3((unsigned)(nslots / SL), (unsigned)(batch * c->L_R)), 512, smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride,
+                                                                                                     limb_stride, vec_stride);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+static int launch_interp_fast(rsg_context *c, WitnessTables *wt, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
+                              size_t coef_stride, size_t limb_stride, size_t vec_stride, const char *name = "k_interp_fast") {
+  if (!batch) return RSG_OK;
+  LaunchScope ls(c, name);
+  c->st_wf++;
+  switch (wf_pick_sl(c, wt->ft.S, nslots)) {
+    case 8: return wf_launch_interp<8>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
+    case 4: return wf_launch_interp<4>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
+    case 2: return wf_launch_interp<2>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
+    default: return wf_launch_interp<1>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
+  }
+}
+template <int SL>
+static int wf_launch_quotient(rsg_context *c, const FastTables &ft, const uint64_t *A, const uint64_t *B, uint64_t *H) {
+  const size_t smem = wf_smem_bytes(ft.S, SL);
+  CUDA_TRY(cudaFuncSetAttribute(k_quotient_fast<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_quotient_fast<SL><<<dim3((unsigned)(c->N_R / SL), (unsigned)c->L_R), 512, smem, c->stream>>>(c->d_params, ft, A, B, H);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+static int launch_quotient_fast(rsg_context *c, WitnessTables *wt, const uint64_t *A, const uint64_t *B, uint64_t *H) {
+  LaunchScope ls(c, "k_quotient_fast");
+  c->st_wf++;
+  switch (wf_pick_sl(c, wt->ft.S, c->N_R)) {
+    case 8: return wf_launch_quotient<8>(c, wt->ft, A, B, H);
+    case 4: return wf_launch_quotient<4>(c, wt->ft, A, B, H);
+    case 2: return wf_launch_quotient<2>(c, wt->ft, A, B, H);
+    default: return wf_launch_quotient<1>(c, wt->ft, A, B, H);
+  }
 }
 
 static int launch_modmat(rsg_context *c, const uint64_t *d_M, size_t rows, size_t K, const uint64_t *d_Y, uint64_t *d_C, size_t batch,
                          bool upper, const char *name) {
   if (!rows || !batch) return RSG_OK;
   LaunchScope ls(c, name);
+  c->st_wd++;
   bool small = true;   // every ring prime < 2^54: the FP64-pipe kernel (exact; see witness.cuh)
   for (uint64_t p : c->q) small = small && p < (1ull << 54);
   dim3 grid((unsigned)((rows + MM_ROWS - 1) / MM_ROWS), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), (unsigned)(batch * c->L_R));
@@ -1265,6 +1484,18 @@ static int launch_modmat(rsg_context *c, const uint64_t *d_M, size_t rows, size_
   return RSG_OK;
 }
 
+// `batch` vectors of n ring elements: evaluations on {0..n-1} -> monomial coefficients, by whichever path applies
+static int interpolate_dev(rsg_context *c, size_t n, WitnessTables *wt, const uint64_t *d_Y, uint64_t *d_C, size_t batch) {
+  int rc;
+  const size_t W = c->ring_words();
+  if (wf_use(c, n)) {
+    if ((rc = ensure_fast_tables(c, n, wt))) return rc;
+    return launch_interp_fast(c, wt, d_Y, d_C, batch, c->N_R, W, c->N_R, n * W);
+  }
+  if ((rc = ensure_dense_tables(c, n, wt))) return rc;
+  return launch_modmat(c, wt->d_Vinv, n, n, d_Y, d_C, batch, false, "k_modmat_interp");
+}
+
 extern "C" int rsg_interpolate(rsg_context *c, size_t n, size_t batch, const rsg_ringvec *y, size_t y_first, rsg_ringvec *out,
                                size_t out_first) {
   if (!c || !y || !out) return fail(RSG_ERR_ARG, "null argument");
@@ -1274,8 +1505,7 @@ extern "C" int rsg_interpolate(rsg_context *c, size_t n, size_t batch, const rsg
   WitnessTables *wt;
   int rc = get_witness_tables(c, n, &wt);
   if (rc) return rc;
-  return launch_modmat(c, wt->d_Vinv, n, n, y->d + y_first * c->ring_words(), out->d + out_first * c->ring_words(), batch, false,
-                       "k_modmat_interp");
+  return interpolate_dev(c, n, wt, y->d + y_first * c->ring_words(), out->d + out_first * c->ring_words(), batch);
 }
 
 extern "C" int rsg_vanishing(rsg_context *c, size_t n, uint64_t *h_Z) {
@@ -1289,15 +1519,15 @@ extern "C" int rsg_vanishing(rsg_context *c, size_t n, uint64_t *h_Z) {
   return RSG_OK;
 }
 
-static int launch_modmat(rsg_context *c, const uint64_t *d_M, size_t rows, size_t K, const uint64_t *d_Y, uint64_t *d_C, size_t batch,
-                         bool upper, const char *name);
 // r1cs (nullable): the evaluations come from rsg_r1cs_evaluate on this system, so full = mid + io - constant wire and the
-// two interpolants of the full assignment follow by linearity (6 matrix products per proof instead of 8).
+// two interpolants of the full assignment follow by linearity (6 interpolations per proof instead of 8).
 static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, uint64_t *d_coeffs, uint64_t *d_H,
                            const uint64_t *d_zk = nullptr, rsg_r1cs *r1cs = nullptr, bool need_C = true) {
   WitnessTables *wt;
   int rc = get_witness_tables(c, n, &wt);
   if (rc) return rc;
+  const bool fast = wf_use(c, n);
+  if (fast ? (rc = ensure_fast_tables(c, n, wt)) : (rc = ensure_dense_tables(c, n, wt))) return rc;
   const size_t W = c->ring_words();
   // scratch: aA, aB (n each) + Ptop (n-1): reuse d_plain (words)
   if ((rc = ensure(c, &c->d_plain, &c->cap_plain, (3 * n) * W))) return rc;
@@ -1306,8 +1536,8 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
   // need_C = false (ringGroth16, groth16.tcc:89-112): C_io / C_mid are never read by the prover and C does not reach the
   // quotient (deg C < n), so only A and B are interpolated
   const size_t nb = need_C ? 3 : 2;
-  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 3 * n * W, d_coeffs, nb, false, "k_modmat_interp"))) return rc;
-  if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals, d_coeffs + 3 * n * W, nb, false, "k_modmat_interp"))) return rc;
+  if ((rc = interpolate_dev(c, n, wt, d_evals + 3 * n * W, d_coeffs, nb))) return rc;
+  if ((rc = interpolate_dev(c, n, wt, d_evals, d_coeffs + 3 * n * W, nb))) return rc;
   if (r1cs && r1cs->n == n) {
     if (!r1cs->d_cc) {
       uint64_t *d_const = nullptr;
@@ -1317,10 +1547,14 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
       CUDA_TRY(cudaMalloc(&v, r1cs->h_const.size() * 8));
       r1cs->d_cc = (uint64_t *)v;
       CUDA_TRY(cudaMemcpyAsync(d_const, r1cs->h_const.data(), r1cs->h_const.size() * 8, cudaMemcpyHostToDevice, c->stream));
-      for (int m = 0; m < 2; m++) {
-        LaunchScope ls(c, "k_matvec");
-        k_matvec<<<dim3((unsigned)((n + 127) / 128), (unsigned)c->L_R), 128, 0, c->stream>>>(
-            c->d_modq, wt->d_Vinv, (uint32_t)n, d_const + m * c->L_R * n, r1cs->d_cc + m * c->L_R * n);
+      if (fast) {   // the constants are [vector][L_R][n] words: one "slot" per limb
+        if ((rc = launch_interp_fast(c, wt, d_const, r1cs->d_cc, 2, 1, 1, n, c->L_R * n, "k_interp_fast_const"))) return rc;
+      } else {
+        for (int m = 0; m < 2; m++) {
+          LaunchScope ls(c, "k_matvec");
+          k_matvec<<<dim3((unsigned)((n + 127) / 128), (unsigned)c->L_R), 128, 0, c->stream>>>(
+              c->d_modq, wt->d_Vinv, (uint32_t)n, d_const + m * c->L_R * n, r1cs->d_cc + m * c->L_R * n);
+        }
       }
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1330,19 +1564,23 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
     k_full_from_parts<<<dim3((unsigned)n, (unsigned)((W + 255) / 256), 2), 256, 0, c->stream>>>(c->d_modq, d_coeffs, r1cs->d_cc, aA, (uint32_t)n,
                                                                                                (uint32_t)c->N_R, (uint32_t)c->L_R);
     CUDA_TRY(cudaGetLastError());
-  } else if ((rc = launch_modmat(c, wt->d_Vinv, n, n, d_evals + 6 * n * W, aA, 2, false, "k_modmat_interp"))) {
+  } else if ((rc = interpolate_dev(c, n, wt, d_evals + 6 * n * W, aA, 2))) {
     return rc;
   }
   CUDA_TRY(cudaMemsetAsync(d_H, 0, (n + 1) * W * 8, c->stream));
   if (n >= 2) {
-    {
-      dim3 grid((unsigned)((n - 1 + MM_ROWS - 1) / MM_ROWS), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), (unsigned)c->L_R);
-      LaunchScope ls(c, "k_conv_top");
-      k_conv_top<<<grid, MM_THREADS, 0, c->stream>>>(c->d_modq, aA, aB, (uint32_t)n, (uint32_t)n, (uint32_t)n, Ptop, (uint32_t)c->N_R,
-                                                     (uint32_t)c->L_R);
-      CUDA_TRY(cudaGetLastError());
+    if (fast) {
+      if ((rc = launch_quotient_fast(c, wt, aA, aB, d_H))) return rc;
+    } else {
+      {
+        dim3 grid((unsigned)((n - 1 + MM_ROWS - 1) / MM_ROWS), (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS), (unsigned)c->L_R);
+        LaunchScope ls(c, "k_conv_top");
+        k_conv_top<<<grid, MM_THREADS, 0, c->stream>>>(c->d_modq, aA, aB, (uint32_t)n, (uint32_t)n, (uint32_t)n, Ptop, (uint32_t)c->N_R,
+                                                       (uint32_t)c->L_R);
+        CUDA_TRY(cudaGetLastError());
+      }
+      if ((rc = launch_modmat(c, wt->d_T, n - 1, n - 1, Ptop, d_H, 1, true, "k_modmat_divZ"))) return rc;
     }
-    if ((rc = launch_modmat(c, wt->d_T, n - 1, n - 1, Ptop, d_H, 1, true, "k_modmat_divZ"))) return rc;
   }
   if (d_zk) {
     LaunchScope ls(c, "k_h_patch");

@@ -530,3 +530,80 @@ def test_merged_inner_products(gold, budget, monkeypatch):
         assert stats[0][0] >= 1 and stats[0][1] < stats[1][1]
     else:
         assert stats[0][2] > 0
+
+
+def _witness_both_modes(monkeypatch, N_R, q, N_E, Q, n, seed, with_r1cs=False):
+    """Witness map of random evaluations through the dense (RSG_WITNESS=dense) and the quasi-linear (RSG_WITNESS=fast)
+    kernels; returns {mode: (coeffs, H)}."""
+    import ringsnark_b200 as rs
+    out = {}
+    for mode in ("dense", "fast"):
+        monkeypatch.setenv("RSG_WITNESS", mode)
+        ctx = rs.Context(N_R, q, N_E, Q)
+        try:
+            ev = ctx.ringvec(9 * n)
+            ev.fill_uniform(seed)
+            coeffs, H = ctx.witness_map(n, ev)
+            out[mode] = (coeffs.download(), H.download(), ev.download())
+            fast, dense = ctx.stat("witness_fast_launches"), ctx.stat("witness_dense_launches")
+            assert (fast > 0 and dense == 0) if mode == "fast" else (fast == 0 and dense > 0)
+        finally:
+            ctx.close()
+    return out
+
+
+@pytest.mark.parametrize("n", [2, 3, 16, 17, 31, 32, 33, 48, 49, 64, 65, 129, 257, 300, 512, 1031])
+def test_fast_witness_map_equals_dense(n, monkeypatch):
+    """witness_fast.cuh (Newton coefficients by one product, Newton -> monomial on the subproduct tree, quotient by two
+    products, wrapped coefficients fixed up directly) must give the canonical residues of the dense V^-1 / Toeplitz products
+    at every shape: leaf only, one level, wrap counts 0 / 1 / 29 / 31, short trailing block, doubled transform size."""
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c3p"]          # four ring limbs, 43/44-bit primes
+    N_R = 64
+    res = _witness_both_modes(monkeypatch, N_R, cfg["q"], cfg["N_E"], cfg["Q"], n, seed=100 + n)
+    assert np.array_equal(res["dense"][2], res["fast"][2])
+    assert np.array_equal(res["dense"][0], res["fast"][0]), "interpolants differ"
+    assert np.array_equal(res["dense"][1], res["fast"][1]), "quotient differs"
+
+
+@pytest.mark.parametrize("n", [40, 129])
+def test_fast_witness_map_against_oracle(n, monkeypatch):
+    """The quasi-linear path against the C oracle's restatement of interpolate / multiply / divide (polynomials.tcc), 54-bit
+    ring prime (C4)."""
+    import ringsnark_b200 as rs
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c4"]
+    N_R, L_R, q = 32, 1, cfg["q"][:1]
+    monkeypatch.setenv("RSG_WITNESS", "fast")
+    ctx = rs.Context(N_R, q, cfg["N_E"], cfg["Q"])
+    try:
+        ev = ctx.ringvec(9 * n)
+        ev.fill_uniform(9)
+        coeffs, H = ctx.witness_map(n, ev)
+        e = ev.download()
+        got = coeffs.download()
+        want = {}
+        for idx, src in enumerate([3, 4, 5, 0, 1, 2]):     # coeffs order A_io,B_io,C_io,A_mid,B_mid,C_mid
+            want[idx] = O.interpolate(e[src * n:(src + 1) * n], N_R, L_R, q)
+            assert np.array_equal(got[idx * n:(idx + 1) * n], want[idx]), idx
+        aA, aB, aC = (O.interpolate(e[(6 + k) * n:(7 + k) * n], N_R, L_R, q) for k in range(3))
+        Hw, hl = O.witness_H(aA, aB, aC, N_R, L_R, q)
+        Hg = H.download()
+        assert hl == n - 1 and np.array_equal(Hg[:n - 1], Hw) and not Hg[n - 1:].any()
+    finally:
+        ctx.close()
+
+
+def test_fast_witness_proofs_match_reference(gold, monkeypatch):
+    """Whole proofs with the quasi-linear witness map forced on (the golden circuits have n = 2..5: leaf-only shapes, the
+    constant-wire interpolant through the one-slot launch): bit-identical to the reference's proof."""
+    case, _ = gold
+    monkeypatch.setenv("RSG_WITNESS", "fast")
+    ctx = make_ctx(case)
+    try:
+        pk = _pk(case, ctx)
+        proof, _ = pk.prove(_assignment(case), _aux_kind(case))
+        assert np.array_equal(proof, case.enc("proof")[0])
+        assert ctx.stat("witness_fast_launches") > 0 or case.n < 2
+    finally:
+        ctx.close()
