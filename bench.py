@@ -333,8 +333,13 @@ def run_gpu_arm(args, cfg_name, cfg):
                     "d2h_bytes_per_step": int(h_proof.numel() * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            # per launch: algorithmic bytes / average launch duration (the per-step sums divided by the launches per step);
+            # traffic = DRAM bytes per launch from the committed ncu --set full capture (profiles/lincomb_traffic.json)
             "roofline": {"kernel": "k_crs_lincomb", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "frac": achieved / peak if peak else None,
+                         "traffic": traffic / lin_launches if traffic and lin_launches else None,
+                         "algorithmic_bytes_per_launch": alg_bytes / lin_launches if lin_launches else None,
+                         "launch_ms": lin_ms / lin_launches if lin_launches else None, "launches_per_step": lin_launches,
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": lin_ms,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"},
             "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()},

@@ -163,6 +163,7 @@ struct rsg_context {
   std::vector<std::vector<uint64_t>> h_fwdq;   // host copy of the forward twiddles mod q_j (witness_fast tables)
   int witness_mode = 0;             // 0 = auto, 1 = dense (RSG_WITNESS=dense), 2 = quasi-linear wherever it applies (RSG_WITNESS=fast)
   int wf_sl = 0;                    // RSG_WF_SL: slots per CTA of the quasi-linear kernels (0 = auto)
+  int wf_threads = 0;               // RSG_WF_THREADS: threads per CTA of the quasi-linear kernels (0 = auto)
   // scratch (grown on demand)
   uint64_t *d_plain = nullptr, *d_pntt = nullptr, *d_partial = nullptr;
   size_t cap_plain = 0, cap_pntt = 0, cap_partial = 0;
@@ -380,6 +381,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (const char *m = getenv("RSG_MERGE")) c->merge_mode = atoi(m);
   if (const char *m = getenv("RSG_WITNESS")) c->witness_mode = !strcmp(m, "dense") ? 1 : (!strcmp(m, "fast") ? 2 : 0);
   if (const char *m = getenv("RSG_WF_SL")) c->wf_sl = atoi(m);
+  if (const char *m = getenv("RSG_WF_THREADS")) c->wf_threads = atoi(m);
   if (const char *m = getenv("RSG_PNTT_BUDGET_WORDS")) c->pntt_budget_words = std::max<size_t>(1, strtoull(m, nullptr, 10));   // tests: force chunking
   if ((rc = dev_alloc(c, &c->d_nz, MAX_LR, false))) return rc;
   *out = c;
@@ -1415,19 +1417,32 @@ static int ensure_fast_tables(rsg_context *c, size_t n, WitnessTables *wt) {
   wt->fast_ready = true;
   return RSG_OK;
 }
-// slots per CTA: the largest power of two dividing the slot count whose two polynomial buffers stay below ~144 KiB
+// slots per CTA: a power of two dividing the slot count; both polynomial buffers of a CTA stay below ~100 KiB (2 CTAs/SM)
 static uint32_t wf_pick_sl(const rsg_context *c, uint32_t S, size_t nslots) {
-  uint32_t sl = 8;
+  // measured on B200 at C4 (n = 1031, S = 2048): 2 slots x 256 threads, two CTAs per SM, beats 4 x 512 by 12 %
+  uint32_t sl = 2;
   if (c->wf_sl > 0) sl = (uint32_t)c->wf_sl;
-  while (sl > 1 && (nslots % sl || wf_smem_bytes(S, sl) > (c->wf_sl > 0 ? 227 : 144) * 1024)) sl >>= 1;
+  while (sl > 1 && (nslots % sl || wf_smem_bytes(S, sl) > (c->wf_sl > 0 ? 227 : 100) * 1024)) sl >>= 1;
   return sl;
+}
+// correction-free butterflies (witness_fast.cuh) need every ring prime below 2^57; RSG_WF_LAZY=0 forces the corrected ones
+static bool wf_lazy(const rsg_context *c) {
+  if (const char *m = getenv("RSG_WF_LAZY")) if (!atoi(m)) return false;
+  for (uint64_t p : c->q)
+    if (p >= (1ull << 57)) return false;
+  return true;
+}
+static unsigned wf_threads(const rsg_context *c, int sl) {
+  if (c->wf_threads >= 32 && c->wf_threads <= 512) return (unsigned)c->wf_threads & ~31u;
+  return sl >= 4 ? 512u : (sl == 2 ? 256u : 128u);
 }
 template <int SL>
 static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
                             size_t coef_stride, size_t limb_stride, size_t vec_stride) {
   const size_t smem = wf_smem_bytes(ft.S, SL);
-  CUDA_TRY(cudaFuncSetAttribute(k_interp_fast<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_interp_fast<SL><<<dim3((unsigned)(nslots / SL), (unsigned)(batch * c->L_R)), 512, smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride,
+  auto kern = wf_lazy(c) ? k_interp_fast<SL, true> : k_interp_fast<SL, false>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3((unsigned)(nslots / SL), (unsigned)(batch * c->L_R)), wf_threads(c, SL), smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride,
                                                                                                      limb_stride, vec_stride);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
@@ -1447,8 +1462,9 @@ static int launch_interp_fast(rsg_context *c, WitnessTables *wt, const uint64_t 
 template <int SL>
 static int wf_launch_quotient(rsg_context *c, const FastTables &ft, const uint64_t *A, const uint64_t *B, uint64_t *H) {
   const size_t smem = wf_smem_bytes(ft.S, SL);
-  CUDA_TRY(cudaFuncSetAttribute(k_quotient_fast<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_quotient_fast<SL><<<dim3((unsigned)(c->N_R / SL), (unsigned)c->L_R), 512, smem, c->stream>>>(c->d_params, ft, A, B, H);
+  auto kern = wf_lazy(c) ? k_quotient_fast<SL, true> : k_quotient_fast<SL, false>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3((unsigned)(c->N_R / SL), (unsigned)c->L_R), wf_threads(c, SL), smem, c->stream>>>(c->d_params, ft, A, B, H);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }

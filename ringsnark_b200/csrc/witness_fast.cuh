@@ -50,13 +50,16 @@ struct FastTables {              // device pointers; [L_R] major
 // negacyclic transforms of size 2^lg: per slot, transform b < nb occupies words [b << lg, (b+1) << lg) of the slot's
 // padded buffer.  Same butterflies, table order and laziness as ntt.cuh; sizes are run-time values here because one
 // kernel walks all levels of the divide and conquer.
-template <int RL, bool INVERSE>
+// LAZY (every ring prime below 2^57): butterflies without range corrections where the bound allows it -- forward values grow
+// by 4p per level from a canonical input (at most 13 levels here: < 53p < 2^64) and any 64-bit value is a valid operand of
+// the next Shoup multiplication; the inverse keeps its values in [0, 4p) with the three-product Shoup quotient.
+template <int RL, bool INVERSE, bool LAZY>
 __device__ __forceinline__ void wf_pass(uint64_t *buf, uint32_t slot_stride, uint32_t nslots, uint32_t nb, uint32_t lg,
                                         uint32_t s, const Twiddle *__restrict__ tab, uint64_t p) {
   constexpr int R = 1 << RL;
   const uint32_t lgi = lg - RL, lgg = lg - s - RL, g = 1u << lgg;
   const uint32_t per_slot = nb << lgi, total = per_slot * nslots;
-  const uint64_t two_p = p << 1;
+  const uint64_t two_p = p << 1, four_p = p << 2;
   for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
     const uint32_t slot = t / per_slot, r = t - slot * per_slot;
     const uint32_t b = r >> lgi, li = r & ((1u << lgi) - 1);
@@ -75,7 +78,10 @@ __device__ __forceinline__ void wf_pass(uint64_t *buf, uint32_t slot_stride, uin
         for (int grp = 0; grp < (1 << u); grp++) {
           const Twiddle tw = load_tw(tab, tbase + grp);
 #pragma unroll
-          for (int k = 0; k < half; k++) bfly_fwd(v[grp * 2 * half + k], v[grp * 2 * half + k + half], tw, p, two_p);
+          for (int k = 0; k < half; k++) {
+            if (LAZY) bfly_fwd_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], tw, p, four_p);
+            else bfly_fwd(v[grp * 2 * half + k], v[grp * 2 * half + k + half], tw, p, two_p);
+          }
         }
       }
     } else {
@@ -87,7 +93,10 @@ __device__ __forceinline__ void wf_pass(uint64_t *buf, uint32_t slot_stride, uin
         for (int grp = 0; grp < (1 << u); grp++) {
           const Twiddle tw = load_tw(tab, tbase + grp);
 #pragma unroll
-          for (int k = 0; k < half; k++) bfly_inv(v[grp * 2 * half + k], v[grp * 2 * half + k + half], tw, p, two_p);
+          for (int k = 0; k < half; k++) {
+            if (LAZY) bfly_inv_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], tw, p, four_p);
+            else bfly_inv(v[grp * 2 * half + k], v[grp * 2 * half + k + half], tw, p, two_p);
+          }
         }
       }
     }
@@ -96,32 +105,43 @@ __device__ __forceinline__ void wf_pass(uint64_t *buf, uint32_t slot_stride, uin
   }
 }
 
-// levels [s0, lg) forward: input < 4p natural order, output < 4p bit-reversed order.  Ends with a barrier.
+// Gentleman-Sande butterfly on [0, 4p) values with the approximate Shoup quotient: x, y in [0, 4p) -> [0, 4p)
+__device__ __forceinline__ void bfly_inv_lazy(uint64_t &x, uint64_t &y, const Twiddle &t, uint64_t p, uint64_t four_p) {
+  const uint64_t s = x + y;
+  const uint64_t d = x - y + four_p;
+  x = s >= four_p ? s - four_p : s;
+  y = mul_shoup_approx(d, t, p);
+}
+
+// levels [s0, lg) forward: input < 4p (canonical when LAZY) natural order, output bit-reversed order, < 4p or (LAZY) any
+// 64-bit representative.  Ends with a barrier.
+template <bool LAZY>
 __device__ __noinline__ void wf_ntt_fwd(uint64_t *buf, uint32_t slot_stride, uint32_t nslots, uint32_t nb, uint32_t lg, uint32_t s0,
                                         const Twiddle *tab, uint64_t p) {
   uint32_t s = s0;
   while (lg - s >= 4) {
-    wf_pass<4, false>(buf, slot_stride, nslots, nb, lg, s, tab, p);
+    wf_pass<4, false, LAZY>(buf, slot_stride, nslots, nb, lg, s, tab, p);
     __syncthreads();
     s += 4;
   }
-  if (lg - s == 3) wf_pass<3, false>(buf, slot_stride, nslots, nb, lg, s, tab, p);
-  else if (lg - s == 2) wf_pass<2, false>(buf, slot_stride, nslots, nb, lg, s, tab, p);
-  else if (lg - s == 1) wf_pass<1, false>(buf, slot_stride, nslots, nb, lg, s, tab, p);
+  if (lg - s == 3) wf_pass<3, false, LAZY>(buf, slot_stride, nslots, nb, lg, s, tab, p);
+  else if (lg - s == 2) wf_pass<2, false, LAZY>(buf, slot_stride, nslots, nb, lg, s, tab, p);
+  else if (lg - s == 1) wf_pass<1, false, LAZY>(buf, slot_stride, nslots, nb, lg, s, tab, p);
   __syncthreads();
 }
-// all lg levels inverse: input < 2p bit-reversed order, output < 2p natural order, NOT scaled.  Ends with a barrier.
+// all lg levels inverse: input < 2p bit-reversed order, output natural order, < 2p or (LAZY) < 4p, NOT scaled.  Ends with a barrier.
+template <bool LAZY>
 __device__ __noinline__ void wf_ntt_inv(uint64_t *buf, uint32_t slot_stride, uint32_t nslots, uint32_t nb, uint32_t lg,
                                         const Twiddle *tab, uint64_t p) {
   uint32_t rem = lg;
   const uint32_t first = rem & 3;
-  if (first == 3) wf_pass<3, true>(buf, slot_stride, nslots, nb, lg, rem - 3, tab, p);
-  else if (first == 2) wf_pass<2, true>(buf, slot_stride, nslots, nb, lg, rem - 2, tab, p);
-  else if (first == 1) wf_pass<1, true>(buf, slot_stride, nslots, nb, lg, rem - 1, tab, p);
+  if (first == 3) wf_pass<3, true, LAZY>(buf, slot_stride, nslots, nb, lg, rem - 3, tab, p);
+  else if (first == 2) wf_pass<2, true, LAZY>(buf, slot_stride, nslots, nb, lg, rem - 2, tab, p);
+  else if (first == 1) wf_pass<1, true, LAZY>(buf, slot_stride, nslots, nb, lg, rem - 1, tab, p);
   if (first) __syncthreads();
   rem -= first;
   while (rem) {
-    wf_pass<4, true>(buf, slot_stride, nslots, nb, lg, rem - 4, tab, p);
+    wf_pass<4, true, LAZY>(buf, slot_stride, nslots, nb, lg, rem - 4, tab, p);
     __syncthreads();
     rem -= 4;
   }
@@ -175,6 +195,7 @@ __device__ __forceinline__ void wf_leaf(uint64_t *f /* WF_B words in shared memo
 
 // Shared body: buffer A of every slot holds canonical Newton coefficients c_k (k < n, zeros beyond); on return it holds
 // the monomial coefficients.  B is scratch of the same shape, hs a [nslots][WF_HMAX] staging area.
+template <bool LAZY>
 __device__ __forceinline__ void wf_newton_to_monomial(uint64_t *A, uint64_t *B, uint64_t *hs, const FastTables &T, uint32_t limb,
                                                       uint32_t nsl, uint32_t stride, const Twiddle *fw, const Twiddle *iv,
                                                       uint64_t p, const ModConst &mc) {
@@ -206,35 +227,40 @@ __device__ __forceinline__ void wf_newton_to_monomial(uint64_t *A, uint64_t *B, 
       B[s * stride + pad_idx(b * two_m + i)] = v;
       B[s * stride + pad_idx(b * two_m + m + i)] = v;
     }
-    if (shortp)
+    if (shortp) {   // the trailing block's own scratch range is free: stage its high coefficients and P there
       for (uint32_t t = threadIdx.x; t < h_last * nsl; t += blockDim.x) {
         const uint32_t s = t % nsl, i = t / nsl;
         hs[s * WF_HMAX + i] = A[s * stride + pad_idx(last * two_m + m + i)];
       }
+      for (uint32_t i = threadIdx.x; i <= m; i += blockDim.x) B[pad_idx(last * two_m + i)] = __ldg(Pn + i);
+    }
     __syncthreads();
     if (nbN) {
-      wf_ntt_fwd(B, stride, nsl, nbN, lg, 1, fw, p);
+      wf_ntt_fwd<LAZY>(B, stride, nsl, nbN, lg, 1, fw, p);
       for (uint32_t t = threadIdx.x; t < nbN * two_m * nsl; t += blockDim.x) {
         const uint32_t s = t % nsl, idx = t / nsl;
         uint64_t *w = B + s * stride + pad_idx(idx);
         *w = mul_shoup_lazy(*w, load_tw(Ph, idx), p);
       }
       __syncthreads();
-      wf_ntt_inv(B, stride, nsl, nbN, lg, iv, p);
+      wf_ntt_inv<LAZY>(B, stride, nsl, nbN, lg, iv, p);
       for (uint32_t t = threadIdx.x; t < nbN * two_m * nsl; t += blockDim.x) {
         const uint32_t s = t % nsl, idx = t / nsl;
-        uint64_t x = canon2(B[s * stride + pad_idx(idx)], p);
+        uint64_t x = canon4(B[s * stride + pad_idx(idx)], p);
         uint64_t *a = A + s * stride + pad_idx(idx);
         if ((idx & (two_m - 1)) < m) x = add_mod(x, *a, p);
         *a = x;
       }
     }
     if (shortp) {   // trailing block: out[j] = sum_{i < h_last, 0 <= j-i <= m} hi[i] * P[j-i]
+      const uint64_t *Ps = B + 0 * stride;   // slot 0's scratch holds P (staged above)
       for (uint32_t t = threadIdx.x; t < two_m * nsl; t += blockDim.x) {
         const uint32_t s = t % nsl, j = t / nsl;
         Acc192 acc;
         acc.clear();
-        for (uint32_t i = (j > m ? j - m : 0); i < h_last && i <= j; i++) acc.mac(hs[s * WF_HMAX + i], __ldg(Pn + (j - i)));
+#pragma unroll 4
+        for (uint32_t i = (j > m ? j - m : 0); i < h_last && i <= j; i++)
+          acc.mac(hs[s * WF_HMAX + i], Ps[pad_idx(last * two_m + j - i)]);
         uint64_t x = acc.reduce(mc);
         uint64_t *a = A + s * stride + pad_idx(last * two_m + j);
         if (j < m) x = add_mod(x, *a, p);
@@ -249,7 +275,7 @@ __device__ __forceinline__ void wf_newton_to_monomial(uint64_t *A, uint64_t *B, 
 // vectors ([element][L_R][N_R]: coef_stride = W, limb_stride = N_R, vec_stride = n*W, nslots = N_R) and per-constraint
 // constants ([vector][L_R][n]: coef_stride = 1, limb_stride = n, vec_stride = L_R*n, nslots = 1).
 // grid (nslots / SL, batch * L_R); SL divides nslots
-template <int SL>
+template <int SL, bool LAZY>
 __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict__ P, FastTables T, const uint64_t *__restrict__ Y,
                                                      uint64_t *__restrict__ C, size_t coef_stride, size_t limb_stride,
                                                      size_t vec_stride) {
@@ -274,7 +300,7 @@ __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict
   __syncthreads();
   if (wc) wf_wrapped(wr, A, n, nullptr, T.g_nat + (size_t)limb * n, n, S, wc, stride, nsl, mc);
   __syncthreads();
-  wf_ntt_fwd(A, stride, nsl, 1, T.logS, 0, fw, p);
+  wf_ntt_fwd<LAZY>(A, stride, nsl, 1, T.logS, 0, fw, p);
   {
     const Twiddle *Gh = T.Ghat + (size_t)limb * S;
     for (uint32_t t = threadIdx.x; t < S * nsl; t += blockDim.x) {
@@ -284,19 +310,19 @@ __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict
     }
   }
   __syncthreads();
-  wf_ntt_inv(A, stride, nsl, 1, T.logS, iv, p);
+  wf_ntt_inv<LAZY>(A, stride, nsl, 1, T.logS, iv, p);
   for (uint32_t t = threadIdx.x; t < S * nsl; t += blockDim.x) {
     const uint32_t s = t % nsl, i = t / nsl;
     uint64_t *w = A + s * stride + pad_idx(i);
     uint64_t x = 0;
     if (i < n) {
-      x = canon2(*w, p);
+      x = canon4(*w, p);
       if (i < wc) x = add_mod(x, wr[s * WF_WC_MAX + i], p);
     }
     *w = x;
   }
   __syncthreads();
-  wf_newton_to_monomial(A, B, hs, T, limb, nsl, stride, fw, iv, p, mc);
+  wf_newton_to_monomial<LAZY>(A, B, hs, T, limb, nsl, stride, fw, iv, p, mc);
   for (uint32_t t = threadIdx.x; t < n * nsl; t += blockDim.x) {
     const uint32_t s = t % nsl, i = t / nsl;
     C[goff + (size_t)i * coef_stride + s] = A[s * stride + pad_idx(i)];
@@ -305,7 +331,7 @@ __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict
 
 // H[i] (i < n-1) = coefficient i of the quotient of A*B by Z, A and B given by n monomial coefficients each
 // ([element][L_R][N_R]).  grid (N_R / SL, L_R); SL divides N_R
-template <int SL>
+template <int SL, bool LAZY>
 __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restrict__ P, FastTables T, const uint64_t *__restrict__ Ac,
                                                        const uint64_t *__restrict__ Bc, uint64_t *__restrict__ H) {
   extern __shared__ uint64_t sm[];
@@ -330,14 +356,15 @@ __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restri
   if (wc) wf_wrapped(wr, A, n, B, nullptr, n, S, wc, stride, nsl, mc);
   __syncthreads();
   // A and B are adjacent: one batch of 2*SL transforms (slot index SL + s addresses B's slot s)
-  wf_ntt_fwd(A, stride, 2 * SL, 1, T.logS, 0, fw, p);
+  wf_ntt_fwd<LAZY>(A, stride, 2 * SL, 1, T.logS, 0, fw, p);
   for (uint32_t t = threadIdx.x; t < S * nsl; t += blockDim.x) {
     const uint32_t s = t % nsl, i = t / nsl;
     uint64_t *w = A + s * stride + pad_idx(i);
-    *w = mul_mod(canon4(*w, p), canon4(B[s * stride + pad_idx(i)], p), mc);
+    const uint64_t b = B[s * stride + pad_idx(i)];
+    *w = LAZY ? mul_mod(reduce64(*w, mc), reduce64(b, mc), mc) : mul_mod(canon4(*w, p), canon4(b, p), mc);
   }
   __syncthreads();
-  wf_ntt_inv(A, stride, nsl, 1, T.logS, iv, p);
+  wf_ntt_inv<LAZY>(A, stride, nsl, 1, T.logS, iv, p);
   // u_i = coefficient 2n-2-i of A*B, i < n-1 (the dividend's top, reversed), zero-padded, into B
   const Twiddle invS = T.invS[limb];
   const uint32_t lu = n - 1;
@@ -355,7 +382,7 @@ __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restri
   const uint32_t wc2 = 2 * lu > S + 1 ? 2 * lu - 1 - S : 0;
   if (wc2) wf_wrapped(wr2, B, lu, nullptr, T.v_nat + (size_t)limb * n, lu, S, wc2, stride, nsl, mc);
   __syncthreads();
-  wf_ntt_fwd(B, stride, nsl, 1, T.logS, 0, fw, p);
+  wf_ntt_fwd<LAZY>(B, stride, nsl, 1, T.logS, 0, fw, p);
   {
     const Twiddle *Vh = T.Vhat + (size_t)limb * S;
     for (uint32_t t = threadIdx.x; t < S * nsl; t += blockDim.x) {
@@ -365,11 +392,11 @@ __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restri
     }
   }
   __syncthreads();
-  wf_ntt_inv(B, stride, nsl, 1, T.logS, iv, p);
+  wf_ntt_inv<LAZY>(B, stride, nsl, 1, T.logS, iv, p);
   for (uint32_t t = threadIdx.x; t < lu * nsl; t += blockDim.x) {
     const uint32_t s = t % nsl, i = t / nsl;
     const uint32_t k = lu - 1 - i;                      // H_i = rq_(n-2-i)
-    uint64_t x = canon2(B[s * stride + pad_idx(k)], p);
+    uint64_t x = canon4(B[s * stride + pad_idx(k)], p);
     if (k < wc2) x = add_mod(x, wr2[s * WF_WC_MAX + k], p);
     H[goff + (size_t)i * W + s] = x;
   }

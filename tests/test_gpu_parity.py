@@ -566,10 +566,13 @@ def test_fast_witness_map_equals_dense(n, monkeypatch):
     assert np.array_equal(res["dense"][1], res["fast"][1]), "quotient differs"
 
 
+@pytest.mark.parametrize("lazy", ["1", "0"])
 @pytest.mark.parametrize("n", [40, 129])
-def test_fast_witness_map_against_oracle(n, monkeypatch):
+def test_fast_witness_map_against_oracle(n, lazy, monkeypatch):
     """The quasi-linear path against the C oracle's restatement of interpolate / multiply / divide (polynomials.tcc), 54-bit
-    ring prime (C4)."""
+    ring prime (C4); with the correction-free butterflies (primes below 2^57) and with the corrected ones (RSG_WF_LAZY=0,
+    what a 58..61-bit ring prime gets)."""
+    monkeypatch.setenv("RSG_WF_LAZY", lazy)
     import ringsnark_b200 as rs
     from ringsnark_b200.params import CONFIGS
     cfg = CONFIGS["c4"]
