@@ -163,6 +163,11 @@ struct rsg_context {
   std::vector<std::vector<uint64_t>> h_fwdq;   // host copy of the forward twiddles mod q_j (witness_fast tables)
   int witness_mode = 0;             // 0 = auto, 1 = dense (RSG_WITNESS=dense), 2 = quasi-linear wherever it applies (RSG_WITNESS=fast)
   int wf_sl = 0;                    // RSG_WF_SL: slots per CTA of the quasi-linear kernels (0 = auto)
+  int lin_threads = 0;
+  // RSG_LIN_SPLITS / RSG_LIN_UNROLL / RSG_LIN_THREADS: tuning overrides of k_crs_lincomb's launch shape.  Measured on B200
+  // (C4): terms in flight per thread 1 / 2 / 3 / 4 / 8 -> 5836 / 5903 / 5980 / 5572 / 4300 GB/s on one 2063-term inner product
+  // (tools/lin_tune.py) and 2 / 3 / 4 -> 5820 / 4754 / 5493 GB/s inside the prover (bench.py): two is the robust choice
+  int lin_splits = 0, lin_unroll = 2;
   int wf_threads = 0;               // RSG_WF_THREADS: threads per CTA of the quasi-linear kernels (0 = auto)
   // scratch (grown on demand)
   uint64_t *d_plain = nullptr, *d_pntt = nullptr, *d_partial = nullptr;
@@ -381,6 +386,9 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (const char *m = getenv("RSG_MERGE")) c->merge_mode = atoi(m);
   if (const char *m = getenv("RSG_WITNESS")) c->witness_mode = !strcmp(m, "dense") ? 1 : (!strcmp(m, "fast") ? 2 : 0);
   if (const char *m = getenv("RSG_WF_SL")) c->wf_sl = atoi(m);
+  if (const char *m = getenv("RSG_LIN_SPLITS")) c->lin_splits = atoi(m);
+  if (const char *m = getenv("RSG_LIN_THREADS")) c->lin_threads = atoi(m);
+  if (const char *m = getenv("RSG_LIN_UNROLL")) c->lin_unroll = atoi(m);
   if (const char *m = getenv("RSG_WF_THREADS")) c->wf_threads = atoi(m);
   if (const char *m = getenv("RSG_PNTT_BUDGET_WORDS")) c->pntt_budget_words = std::max<size_t>(1, strtoull(m, nullptr, 10));   // tests: force chunking
   if ((rc = dev_alloc(c, &c->d_nz, MAX_LR, false))) return rc;
@@ -791,11 +799,12 @@ extern "C" int rsg_ntt(rsg_context *c, uint64_t *d, size_t batch, int which, siz
 static int launch_lincomb(rsg_context *c, const uint64_t *d_crs, const uint32_t *d_term, const uint32_t *d_pidx, size_t n_terms,
                           const uint64_t *d_pntt, uint64_t *d_out) {
   int rc;
-  const unsigned th = (unsigned)std::min<size_t>(256, c->N_E / 2);
+  const unsigned th = (unsigned)std::min<size_t>(c->lin_threads > 0 ? c->lin_threads : 256, c->N_E / 2);
   const unsigned gx = (unsigned)(c->N_E / 2 / th), gy = (unsigned)(c->L_R * c->L_E);
   // split the term range so that the grid has >= ~8 blocks per SM; each split streams >= 8 terms
   const unsigned base_blocks = gx * gy;
   unsigned splits = std::max(1u, (148u * 8 + base_blocks - 1) / base_blocks);
+  if (c->lin_splits > 0) splits = (unsigned)c->lin_splits;
   splits = (unsigned)std::min<size_t>(splits, (n_terms + 7) / 8);
   splits = std::max(1u, splits);
   const unsigned tps = (unsigned)((n_terms + splits - 1) / splits);
@@ -809,8 +818,16 @@ static int launch_lincomb(rsg_context *c, const uint64_t *d_crs, const uint32_t 
   c->st_lin_launches++;
   {
     LaunchScope ls(c, "k_crs_lincomb");
-    k_crs_lincomb<4><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, d_term, d_pidx, (uint32_t)n_terms, tps, d_pntt,
-                                                                 d_partial);
+    if (c->lin_unroll == 8)
+      k_crs_lincomb<8><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, d_term, d_pidx, (uint32_t)n_terms, tps, d_pntt, d_partial);
+    else if (c->lin_unroll == 1)
+      k_crs_lincomb<1><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, d_term, d_pidx, (uint32_t)n_terms, tps, d_pntt, d_partial);
+    else if (c->lin_unroll == 4)
+      k_crs_lincomb<4><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, d_term, d_pidx, (uint32_t)n_terms, tps, d_pntt, d_partial);
+    else if (c->lin_unroll == 3)
+      k_crs_lincomb<3><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, d_term, d_pidx, (uint32_t)n_terms, tps, d_pntt, d_partial);
+    else
+      k_crs_lincomb<2><<<dim3(gx, gy, splits), th, 0, c->stream>>>(c->d_params, d_crs, d_term, d_pidx, (uint32_t)n_terms, tps, d_pntt, d_partial);
   }
   CUDA_TRY(cudaGetLastError());
   if (splits > 1) {
