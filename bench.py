@@ -337,7 +337,8 @@ def run_gpu_arm(args, cfg_name, cfg):
             # traffic = DRAM bytes per launch from the committed ncu --set full capture (profiles/lincomb_traffic.json)
             "roofline": {"kernel": "k_crs_lincomb", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None,
-                         "traffic": traffic / lin_launches if traffic and lin_launches else None,
+                         # the committed capture is the 1-GPU workload; a sharded run has no capture of its own
+                         "traffic": traffic / lin_launches if traffic and lin_launches and world == 1 else None,
                          "algorithmic_bytes_per_launch": alg_bytes / lin_launches if lin_launches else None,
                          "launch_ms": lin_ms / lin_launches if lin_launches else None, "launches_per_step": lin_launches,
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": lin_ms,

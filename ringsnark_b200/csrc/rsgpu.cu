@@ -1318,7 +1318,8 @@ static bool wf_supported(const rsg_context *c, size_t n) {
 }
 static bool wf_use(const rsg_context *c, size_t n) {
   if (c->witness_mode == 1 || !wf_supported(c, n)) return false;
-  return c->witness_mode == 2 || n >= 64;                      // below that the dense products are a handful of launches of nothing
+  // measured on B200 (profiles/r1d_c5_sweep.json, N_R = 2^15): n = 256 dense 12.9 ms / quasi-linear 18.4 ms, n = 1024 185 / 50 ms
+  return c->witness_mode == 2 || n >= 320;
 }
 // forward negacyclic transform on the host, the device's table order (h_tables): natural in, bit-reversed out
 static void h_ntt_fwd(std::vector<uint64_t> &a, int lg, uint64_t p, const std::vector<uint64_t> &tw) {
@@ -1449,9 +1450,10 @@ static bool wf_lazy(const rsg_context *c) {
     if (p >= (1ull << 57)) return false;
   return true;
 }
-static unsigned wf_threads(const rsg_context *c, int sl) {
+static unsigned wf_threads(const rsg_context *c, int sl, uint32_t S) {
   if (c->wf_threads >= 32 && c->wf_threads <= 512) return (unsigned)c->wf_threads & ~31u;
-  return sl >= 4 ? 512u : (sl == 2 ? 256u : 128u);
+  // one radix-16 item per thread in a full-size pass: sl * S / 16 items
+  return (unsigned)std::min<size_t>(512, std::max<size_t>(128, (size_t)sl * S / 16));
 }
 template <int SL>
 static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
@@ -1459,7 +1461,7 @@ static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t
   const size_t smem = wf_smem_bytes(ft.S, SL);
   auto kern = wf_lazy(c) ? k_interp_fast<SL, true> : k_interp_fast<SL, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3((unsigned)(nslots / SL), (unsigned)(batch * c->L_R)), wf_threads(c, SL), smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride,
+  kern<<<dim3((unsigned)(nslots / SL), (unsigned)(batch * c->L_R)), wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride,
                                                                                                      limb_stride, vec_stride);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
@@ -1481,7 +1483,7 @@ static int wf_launch_quotient(rsg_context *c, const FastTables &ft, const uint64
   const size_t smem = wf_smem_bytes(ft.S, SL);
   auto kern = wf_lazy(c) ? k_quotient_fast<SL, true> : k_quotient_fast<SL, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3((unsigned)(c->N_R / SL), (unsigned)c->L_R), wf_threads(c, SL), smem, c->stream>>>(c->d_params, ft, A, B, H);
+  kern<<<dim3((unsigned)(c->N_R / SL), (unsigned)c->L_R), wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, A, B, H);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }

@@ -168,12 +168,16 @@ def test_lincomb_random_vs_oracle(gold):
     assert np.array_equal(out, want)
 
 
-@pytest.mark.parametrize("name", ["c1", "c3p", "c4s"])
-def test_reference_sized_cases(name):
+@pytest.mark.parametrize("name,witness", [("c1", "auto"), ("c3p", "auto"), ("c4s", "auto"), ("c4s", "fast"), ("c3p", "fast")])
+def test_reference_sized_cases(name, witness, monkeypatch):
     """Full-size parameter sets of the reference (N_E = 8192 / 16384, both plain-lift paths): fresh dump from the
-    compiled reference, then every prover inner product, the proof and the witness map must be bit-identical."""
+    compiled reference, then every prover inner product, the proof and the witness map must be bit-identical -- with the
+    witness map the library picks by itself and with the quasi-linear one forced (c4s: n = 33, two tree levels, one wrapped
+    coefficient; c3p: four ring limbs)."""
     if not os.path.exists(REF_HARNESS):
         pytest.skip("oracle/_ref/ref_harness not built (needs /root/reference at build time)")
+    if witness != "auto":
+        monkeypatch.setenv("RSG_WITNESS", witness)
     import ctypes as C
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, name + ".rsgv")
