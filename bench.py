@@ -57,9 +57,22 @@ def cpu_reference_sample(cfg_name, cfg, budget="default"):
     wit = run(["witness", f"n={n_s}", "reps=1"])
     lincomb_ms = lin["seconds"] * 1e3 / t_terms * terms_total
     witness_ms = wit["seconds"] * 1e3 * (n / n_s) ** 2
+    # SURVEY.md 8(d) "best-effort parallel": what the host cores could do if groth16::prover ran its inner products the way
+    # rinocchio.tcc:106-163 does (OpenMP sections) -- `ncpu` concurrent inner products of t_par terms each; the witness map
+    # stays on one thread (Polytools' pragmas are inert).  Reported next to the faithful number, not instead.
+    par = None
+    try:
+        t_par = max(16, t_terms // 8)
+        lp = run(["lincomb", f"terms={t_par}", "reps=1", f"threads={ncpu}"])
+        par = {"cores": ncpu, "lincomb_terms_per_s": lp["terms_per_s"], "lincomb_ms": terms_total / lp["terms_per_s"] * 1e3,
+               "value": terms_total / lp["terms_per_s"] * 1e3 + witness_ms,
+               "sample": f"{ncpu} concurrent inner products x {t_par} terms; witness map single-threaded as in the reference"}
+    except Exception as ex:
+        par = {"error": str(ex)[:200]}
     return {
         "value": lincomb_ms + witness_ms, "unit": UNIT, "cores": 1, "kind": "reference", "host_cpus": ncpu,
         "lincomb_ms_per_term": lin["seconds"] * 1e3 / t_terms, "lincomb_ms": lincomb_ms, "witness_ms": witness_ms,
+        "parallel_best_effort": par,
         "sample": (f"unmodified reference (SEAL 4.1.1, g++ -O3), 1 thread (groth16::prover has no OpenMP): inner_product on "
                    f"{t_terms} of {terms_total} terms x{terms_total / t_terms:.1f} (linear) + witness map at n={n_s} "
                    f"x{(n / n_s) ** 2:.1f} (quadratic in n) -> one {cfg_name} proof"),
