@@ -160,6 +160,15 @@ void rsg_r1cs_destroy(rsg_r1cs *r);
 /* assignment: n_io + n_aux ring elements; evals: 9n elements in rsg_witness_map's input order. */
 int rsg_r1cs_evaluate(rsg_context *ctx, const rsg_r1cs *r, const rsg_ringvec *assignment, rsg_ringvec *evals);
 
+/* ---- instance map with evaluation: r1cs_to_qrp_instance_map_with_evaluation (reductions/r1cs_to_qrp/r1cs_to_qrp.tcc:
+ * 75-116) with evaluate_all_lagrange_polynomials / compute_vanishing_polynomial (util/evaluation_domain.tcc:20-51) --
+ * the O(m^2) step of generator (groth16.tcc:11-12, rinocchio.tcc:12-13) and of every verifier call (groth16.tcc:127-128,
+ * rinocchio.tcc:220-221).  t = element t_first of `t` (must not hit a domain point in any slot: the caller keeps the
+ * reference's std::find check).  ABCt: 3 * (n_io + n_aux + 1) elements At | Bt | Ct indexed by variable (0 = constant
+ * wire); Ht: n + 1 elements 1, t, .., t^n; Zt: 1 element Z(t). ---- */
+int rsg_instance_map(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *t, size_t t_first, rsg_ringvec *ABCt, rsg_ringvec *Ht,
+                     rsg_ringvec *Zt);
+
 /* ---- groth16::prover (zk_proof_systems/groth16/groth16.tcc:69-115), whole prover in one call ----
  * The proving key's CRS vectors live in ONE arena; each vector may be a shard [lo, hi) of its terms (multi-GPU:
  * the partial proofs of all ranks are all-gathered and summed with rsg_enc_sum). */

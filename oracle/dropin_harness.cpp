@@ -156,8 +156,28 @@ int main(int argc, char **argv) {
       } catch (const std::exception &ex) {
         std::cerr << "reference verifier threw: " << ex.what() << std::endl;
       }
-      const bool ok = eqA && eqB && eqC && verified == verified_ref;
+      // the instance map with evaluation at the key's own s, reference loop vs device, element by element
+      t0 = now_s();
+      const auto inst_ref = ringsnark::r1cs_to_qrp_instance_map_with_evaluation<R>(cs, kp.vk.s.host());
+      const double t_inst_ref = now_s() - t0;
+      (void)ringsnark::r1cs_to_qrp_instance_map_with_evaluation<GR>(gcs, kp.vk.s);   // warm-up (per-n tables)
+      t0 = now_s();
+      const auto inst_gpu = ringsnark::r1cs_to_qrp_instance_map_with_evaluation<GR>(gcs, kp.vk.s);
+      bool eqI = inst_ref.At.size() == inst_gpu.At.size() && inst_ref.Ht.size() == inst_gpu.Ht.size();
+      auto same = [](const R &a, const GR &b) {
+        R x(a), y(b.host());
+        x.to_poly_inplace();
+        y.to_poly_inplace();
+        return x == y;
+      };
+      for (size_t i = 0; eqI && i < inst_ref.At.size(); i++)
+        eqI = same(inst_ref.At[i], inst_gpu.At[i]) && same(inst_ref.Bt[i], inst_gpu.Bt[i]) && same(inst_ref.Ct[i], inst_gpu.Ct[i]);
+      for (size_t i = 0; eqI && i < inst_ref.Ht.size(); i++) eqI = same(inst_ref.Ht[i], inst_gpu.Ht[i]);
+      eqI = eqI && same(inst_ref.Zt, inst_gpu.Zt);
+      const double t_inst_gpu = now_s() - t0;   // includes downloading every element for the comparison
+      const bool ok = eqA && eqB && eqC && verified == verified_ref && eqI;
       all_ok = all_ok && ok;
+      js << ",\"instance_map\":{\"bit_exact\":" << eqI << ",\"ref_s\":" << t_inst_ref << ",\"gpu_s\":" << t_inst_gpu << "}";
       js << ",\"groth16\":{\"bit_exact\":[" << eqA << "," << eqB << "," << eqC << "],\"verified\":" << (verified ? "true" : "false")
          << ",\"verified_ref\":" << (verified_ref ? "true" : "false") << ",\"generator_s\":" << t_gen << ",\"prover_ref_s\":" << t_ref
          << ",\"prover_gpu_s\":" << t_gpu << ",\"ok\":" << (ok ? "true" : "false") << "}";

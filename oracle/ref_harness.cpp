@@ -305,7 +305,24 @@ static int cmd_dump(const std::string &name, const std::string &out, uint64_t se
     w.put1("kat_root_Q0", tabQ[0].get_root());
     w.put1("kat_root_q0", tabt->get_root());
   }
-  w.put("timing_us", vector<uint64_t>{(uint64_t)(t_wit * 1e6), (uint64_t)(t_gen * 1e6), (uint64_t)(t_prove * 1e6)});
+  // (7) instance map with evaluation (r1cs_to_qrp.tcc:75-116) at a fresh exceptional point, as generator
+  //     (groth16.tcc:11-12) and verifier (groth16.tcc:127-128) call it.  Drawn AFTER everything above so that the ring
+  //     PRNG stream of (1)-(6) is what it was before this section existed.
+  double t_inst = 0;
+  {
+    const auto domain = ringsnark::get_evaluation_domain<R>(s.cs.num_constraints());
+    const R t = R::random_exceptional_element(domain);
+    t0 = now_s();
+    const auto inst = ringsnark::r1cs_to_qrp_instance_map_with_evaluation(s.cs, t);
+    t_inst = now_s() - t0;
+    put_ring(w, "inst_t", vector<R>{t});
+    put_ring(w, "inst_At", inst.At);
+    put_ring(w, "inst_Bt", inst.Bt);
+    put_ring(w, "inst_Ct", inst.Ct);
+    put_ring(w, "inst_Ht", inst.Ht);
+    put_ring(w, "inst_Zt", vector<R>{inst.Zt});
+  }
+  w.put("timing_us", vector<uint64_t>{(uint64_t)(t_wit * 1e6), (uint64_t)(t_gen * 1e6), (uint64_t)(t_prove * 1e6), (uint64_t)(t_inst * 1e6)});
   w.save(out);
   std::cerr << "case " << name << ": satisfied=" << sat << " verified=" << ok << " witness_map=" << t_wit
             << "s generator=" << t_gen << "s prover=" << t_prove << "s -> " << out << std::endl;

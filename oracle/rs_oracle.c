@@ -346,3 +346,53 @@ void ro_witness_H(size_t n, const uint64_t *aA, const uint64_t *aB, const uint64
     free(a); free(b); free(u); free(Z);
   }
 }
+
+/*
+ * r1cs_to_qrp_instance_map_with_evaluation, ringsnark/reductions/r1cs_to_qrp/r1cs_to_qrp.tcc:75-116, values only, as the
+ * reference computes it:
+ *   u[j] = prod_{i != j} (t - x_i) / prod_{i != j} (x_j - x_i)      evaluate_all_lagrange_polynomials,
+ *                                                                   util/evaluation_domain.tcc:20-41 (O(m^2), one division)
+ *   Zt   = prod_i (t - x_i)                                         compute_vanishing_polynomial, :43-51
+ *   At[idx] += u[i] * coeff  for every term of constraint i's a (likewise b, c)     r1cs_to_qrp.tcc:92-107
+ *   Ht[i] = t^i, i = 0..m                                           :109-113
+ * on the domain x_i = i (get_evaluation_domain).  t: [L_R][N_R]; CSR system as in ro-side tests: rows m*n + i, col 0 = constant
+ * wire, uint64 coefficients reduced mod q_j (multiply_poly_scalar_coeffmod semantics).  ABCt: [3][nvars1][W], Ht: [n+1][W],
+ * Zt: [W].  Returns 0, or -1 if some slot of t hits a domain point (the reference needs the divisions to exist).
+ */
+int ro_instance_map(size_t n, size_t nvars1, const uint32_t *row_ptr, const uint32_t *col, const uint64_t *coeff,
+                    const uint64_t *t, size_t N_R, size_t L_R, const uint64_t *q, uint64_t *ABCt, uint64_t *Ht, uint64_t *Zt) {
+  size_t W = N_R * L_R;
+  int bad = 0;
+  memset(ABCt, 0, 3 * nvars1 * W * 8);
+#pragma omp parallel
+  {
+    uint64_t *u = malloc((n ? n : 1) * 8);
+#pragma omp for schedule(static)
+    for (size_t w = 0; w < W; w++) {
+      uint64_t p = q[w / N_R], tv = t[w];
+      for (size_t j = 0; j < n; j++) {
+        uint64_t num = 1, den = 1;
+        for (size_t i = 0; i < n; i++) {
+          if (i == j) continue;
+          num = mulmod(num, submod(tv, i % p, p), p);
+          den = mulmod(den, submod(j % p, i % p, p), p);
+        }
+        uint64_t inv;
+        if (!ro_try_invert(den, p, &inv)) { bad = 1; inv = 0; }
+        u[j] = mulmod(num, inv, p);
+      }
+      uint64_t z = 1, pw = 1;
+      for (size_t i = 0; i < n; i++) z = mulmod(z, submod(tv, i % p, p), p);
+      Zt[w] = z;
+      for (size_t i = 0; i <= n; i++) { Ht[i * W + w] = pw; pw = mulmod(pw, tv, p); }
+      for (size_t m = 0; m < 3; m++)
+        for (size_t i = 0; i < n; i++)
+          for (size_t e = row_ptr[m * n + i]; e < row_ptr[m * n + i + 1]; e++) {
+            uint64_t *dst = ABCt + (m * nvars1 + col[e]) * W + w;
+            *dst = addmod(*dst, mulmod(u[i], coeff[e] % p, p), p);
+          }
+    }
+    free(u);
+  }
+  return bad ? -1 : 0;
+}

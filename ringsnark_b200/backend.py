@@ -156,6 +156,14 @@ class R1cs:
         check(self.ctx.lib.rsg_r1cs_evaluate(self.ctx.h, self.h, assignment.h, evals.h))
         return evals
 
+    def instance_map(self, t, t_first=0):
+        """r1cs_to_qrp_instance_map_with_evaluation (r1cs_to_qrp.tcc:75-116) at the ring element t[t_first].
+        Returns (ABCt [3*(vars+1)], Ht [n+1], Zt [1]) as device ring vectors."""
+        nv1 = self.n_io + self.n_aux + 1
+        ABCt, Ht, Zt = RingVec(self.ctx, 3 * nv1), RingVec(self.ctx, self.n + 1), RingVec(self.ctx, 1)
+        check(self.ctx.lib.rsg_instance_map(self.ctx.h, self.h, t.h, t_first, ABCt.h, Ht.h, Zt.h))
+        return ABCt, Ht, Zt
+
     def __del__(self):
         try:
             if self.h and self.ctx.h:

@@ -56,6 +56,7 @@ SIGNATURES = {
     "rsg_witness_map_r1cs": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "rsg_witness_map_groth16": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "rsg_interpolate": (_int, [_vp, _sz, _sz, _vp, _sz, _vp, _sz]),
+    "rsg_instance_map": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "rsg_vanishing": (_int, [_vp, _sz, _vp]),
     "rsg_r1cs_create": (_int, [_vp, _sz, _sz, _sz, _vp, _vp, _vp, _pp]),
     "rsg_r1cs_destroy": (None, [_vp]),

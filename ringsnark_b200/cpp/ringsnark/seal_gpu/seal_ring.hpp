@@ -10,8 +10,9 @@
 //   GPU : EncodingElem::inner_product (seal_ring.tcc:361-433), EncodingElem::operator*= (:509-548) and operator+=
 //         (:479-507), and -- through the explicit specialisation at the end of this file --
 //         r1cs_to_qrp_witness_map (reductions/r1cs_to_qrp/r1cs_to_qrp.tcc:148-259) including the sparse
-//         linear_combination::evaluate pass in front of it (relations/variable.tcc:246-254).
-//         There is no CPU fallback for these: without librsgpu.so and a CUDA device they throw.
+//         linear_combination::evaluate pass in front of it (relations/variable.tcc:246-254), and
+//         r1cs_to_qrp_instance_map_with_evaluation (r1cs_to_qrp.tcc:75-116: the O(m^2) step of setup and of every
+//         verification).  There is no CPU fallback for these: without librsgpu.so and a CUDA device they throw.
 //   host: ring elements that drivers build (circuits, assignments) are host values exactly as in the reference --
 //         this class keeps a ringsnark::seal::RingElem inside and forwards the element-wise operators to it, so the
 //         scalar/polynomial variant rules (seal_ring.tcc:105-263) and SealPoly::is_zero's prefix quirk
@@ -632,6 +633,86 @@ inline qrp_witness<seal_gpu::RingElem> r1cs_to_qrp_witness_map<seal_gpu::RingEle
   return qrp_witness<R>(cs.num_variables(), n, cs.num_inputs(), d1, d2, d3, full_variable_assignment, slice(coeffs, 0, n),
                         slice(coeffs, n, n), slice(coeffs, 2 * n, n), slice(coeffs, 3 * n, n), slice(coeffs, 4 * n, n),
                         slice(coeffs, 5 * n, n), Z, slice(H, 0, n + 1));
+}
+// =====================================================================================================================
+// the instance map with evaluation on the GPU.  Explicit specialisation of
+// reductions/r1cs_to_qrp/r1cs_to_qrp.hpp:48-50; generator (groth16.tcc:11-12, rinocchio.tcc:12-13) and verifier
+// (groth16.tcc:127-128, rinocchio.tcc:220-221) pick it up unedited.  Falls back to the reference's loop (as written,
+// r1cs_to_qrp.tcc:75-116) when a linear-term coefficient is a ring element rather than an integer.
+template <>
+inline qrp_instance_evaluation<seal_gpu::RingElem> r1cs_to_qrp_instance_map_with_evaluation<seal_gpu::RingElem>(
+    const r1cs_constraint_system<seal_gpu::RingElem> &cs, const seal_gpu::RingElem &t) {
+  using R = seal_gpu::RingElem;
+  namespace D = seal_gpu::detail;
+  auto &b = D::backend();
+  const auto domain = get_evaluation_domain<R>(cs.num_constraints());
+  const size_t n = cs.num_constraints(), nv1 = cs.num_variables() + 1;
+  // evaluate_all_lagrange_polynomials' guard (evaluation_domain.tcc:22-24)
+  for (size_t i = 0; i < domain->m; i++)
+    if (domain->get_domain_element(i) == t) throw std::invalid_argument("t cannot be one of the values in the domain");
+  bool scalar_coeffs = true;
+  std::vector<uint32_t> row_ptr{0}, col;
+  std::vector<uint64_t> coeff;
+  for (int m = 0; m < 3 && scalar_coeffs; m++)
+    for (size_t i = 0; i < n && scalar_coeffs; i++) {
+      const auto &lc = m == 0 ? cs.constraints[i].a : (m == 1 ? cs.constraints[i].b : cs.constraints[i].c);
+      for (const auto &lt : lc.terms) {
+        if (!lt.coeff.is_scalar()) {
+          scalar_coeffs = false;
+          break;
+        }
+        col.push_back((uint32_t)lt.index);
+        coeff.push_back(lt.coeff.get_scalar());
+      }
+      row_ptr.push_back((uint32_t)col.size());
+    }
+  if (!scalar_coeffs) {
+    std::vector<R> At(nv1, R::zero()), Bt(nv1, R::zero()), Ct(nv1, R::zero()), Ht;
+    const R Zt = domain->compute_vanishing_polynomial(t);
+    const std::vector<R> u = domain->evaluate_all_lagrange_polynomials(t);
+    for (size_t i = 0; i < n; ++i) {
+      for (const auto &lt : cs.constraints[i].a.terms) At[lt.index] += u[i] * lt.coeff;
+      for (const auto &lt : cs.constraints[i].b.terms) Bt[lt.index] += u[i] * lt.coeff;
+      for (const auto &lt : cs.constraints[i].c.terms) Ct[lt.index] += u[i] * lt.coeff;
+    }
+    R ti = R::one();
+    for (size_t i = 0; i < domain->m + 1; ++i) {
+      Ht.emplace_back(ti);
+      ti *= t;
+    }
+    return qrp_instance_evaluation<R>(domain, cs.num_variables(), domain->m, cs.num_inputs(), t, std::move(At), std::move(Bt),
+                                      std::move(Ct), std::move(Ht), Zt);
+  }
+  auto make_vec = [&](size_t count) {
+    auto v = std::make_shared<D::DevRing>();
+    D::check(rsg_ringvec_create(b.ctx, count ? count : 1, &v->v));
+    return v;
+  };
+  rsg_r1cs *r1cs = nullptr;
+  struct R1csGuard {
+    rsg_r1cs *&r;
+    ~R1csGuard() { rsg_r1cs_destroy(r); }
+  } guard{r1cs};
+  D::check(rsg_r1cs_create(b.ctx, n, cs.primary_input_size, cs.auxiliary_input_size, row_ptr.data(), col.data(), coeff.data(), &r1cs));
+  std::vector<uint64_t> tw;
+  t.append_words(tw);
+  auto tv = make_vec(1), ABCt = make_vec(3 * nv1), Ht = make_vec(n + 1), Zt = make_vec(1);
+  D::check(rsg_ringvec_upload(tv->v, 0, 1, tw.data()));
+  D::check(rsg_instance_map(b.ctx, r1cs, tv->v, 0, ABCt->v, Ht->v, Zt->v));
+  for (auto *v : {ABCt.get(), Ht.get(), Zt.get()}) {
+    const size_t cnt = rsg_ringvec_size(v->v);
+    v->zero.resize(cnt);
+    D::check(rsg_ringvec_is_zero_prefix(v->v, 0, cnt, v->zero.data()));
+  }
+  auto slice = [&](const std::shared_ptr<D::DevRing> &v, size_t first, size_t count) {
+    std::vector<R> out;
+    out.reserve(count);
+    for (size_t i = 0; i < count; i++) out.push_back(R::from_device(v, first + i));
+    return out;
+  };
+  return qrp_instance_evaluation<R>(domain, cs.num_variables(), domain->m, cs.num_inputs(), t, slice(ABCt, 0, nv1),
+                                    slice(ABCt, nv1, nv1), slice(ABCt, 2 * nv1, nv1), slice(Ht, 0, n + 1),
+                                    R::from_device(Zt, 0));
 }
 }  // namespace ringsnark
 

@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "witness.cuh"
 #include "witness_fast.cuh"
+#include "instance.cuh"
 #include "ringops.cuh"
 
 using namespace rsg;
@@ -139,6 +140,7 @@ struct WitnessTables {   // per constraint count n
   uint64_t *d_Z = nullptr;      // [L_R][n+1]
   std::vector<uint64_t> h_Z;    // [L_R][n+1]
   std::vector<uint64_t> h_u;    // [L_R][max(n-1,1)]  rev(Z)^-1 mod x^(n-1)
+  Twiddle *d_lagw = nullptr;    // [L_R][n] 1 / prod_{i != j} (j - i): Lagrange denominators (instance.cuh)
   bool fast_ready = false;      // quasi-linear path (witness_fast.cuh)
   FastTables ft;
 };
@@ -225,6 +227,10 @@ struct rsg_r1cs {
   size_t n, n_io, n_aux;
   uint32_t *d_row_ptr = nullptr, *d_col = nullptr;
   uint64_t *d_coeff = nullptr;
+  std::vector<uint32_t> h_row_ptr, h_col;   // host copy of the CSR system (the instance map transposes it on first use)
+  std::vector<uint64_t> h_coeff;
+  uint32_t *d_col_ptr = nullptr, *d_rows = nullptr;   // CSC of A | B | C over variables 0..n_io+n_aux (instance map)
+  uint64_t *d_ccoeff = nullptr;
   std::vector<uint64_t> h_const;   // [2][L_R][n]: constant-wire coefficient of A_i, B_i mod q_j
   uint64_t *d_cc = nullptr;        // [2][L_R][n]: its interpolant V^-1 * const, built on first use
 };
@@ -401,7 +407,7 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (void *p : c->owned) cudaFree(p);
-  for (auto &kv : c->wit) { cudaFree(kv.second.d_Vinv); cudaFree(kv.second.d_T); cudaFree(kv.second.d_Z); }
+  for (auto &kv : c->wit) { cudaFree(kv.second.d_Vinv); cudaFree(kv.second.d_T); cudaFree(kv.second.d_Z); }   // d_lagw / fast tables: c->owned
   cudaFree(c->d_plain); cudaFree(c->d_pntt); cudaFree(c->d_partial);
   cudaFree(c->d_term); cudaFree(c->d_pidx); cudaFree(c->d_eidx); cudaFree(c->d_flags); cudaFree(c->d_out_scratch);
   cudaFree(c->d_chunk); cudaFree(c->d_evals); cudaFree(c->d_wit); cudaFree(c->d_zk);
@@ -1680,6 +1686,9 @@ extern "C" int rsg_r1cs_create(rsg_context *c, size_t n, size_t n_io, size_t n_a
     if (h_col[t] > n_io + n_aux) return fail(RSG_ERR_ARG, "variable index out of range");
   CUDA_TRY(cudaSetDevice(c->device));
   rsg_r1cs *r = new rsg_r1cs{c, n, n_io, n_aux};
+  r->h_row_ptr.assign(h_row_ptr, h_row_ptr + 3 * n + 1);
+  r->h_col.assign(h_col, h_col + nnz);
+  r->h_coeff.assign(h_coeff, h_coeff + nnz);
   r->h_const.assign(2 * c->L_R * n, 0);
   for (size_t m = 0; m < 2; m++)
     for (size_t i = 0; i < n; i++)
@@ -1705,8 +1714,77 @@ extern "C" void rsg_r1cs_destroy(rsg_r1cs *r) {
   if (!r) return;
   cudaStreamSynchronize(r->ctx->stream);
   cudaFree(r->d_row_ptr); cudaFree(r->d_col); cudaFree(r->d_coeff); cudaFree(r->d_cc);
+  cudaFree(r->d_col_ptr); cudaFree(r->d_rows); cudaFree(r->d_ccoeff);
   delete r;
 }
+// ------------------------------------------------------------------------------------------------------------
+// instance map with evaluation (the O(m^2) step of setup and of every verification; instance.cuh)
+extern "C" int rsg_instance_map(rsg_context *c, rsg_r1cs *r, const rsg_ringvec *t, size_t t_first, rsg_ringvec *ABCt, rsg_ringvec *Ht,
+                                rsg_ringvec *Zt) {
+  if (!c || !r || !t || !ABCt || !Ht || !Zt) return fail(RSG_ERR_ARG, "null argument");
+  const size_t n = r->n, nv1 = r->n_io + r->n_aux + 1, W = c->ring_words();
+  if (t_first >= t->n || ABCt->n < 3 * nv1 || Ht->n < n + 1 || Zt->n < 1) return fail(RSG_ERR_ARG, "instance-map vector sizes");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  WitnessTables *wt;
+  int rc = get_witness_tables(c, n, &wt);
+  if (rc) return rc;
+  if (!wt->d_lagw) {   // 1 / prod_{i != j} (j - i) = (-1)^(n-1-j) / (j! (n-1-j)!)
+    std::vector<Twiddle> w(c->L_R * n);
+    for (size_t j = 0; j < c->L_R; j++) {
+      const uint64_t p = c->q[j];
+      std::vector<uint64_t> fact(n + 1, 1);
+      for (size_t i = 1; i <= n; i++) fact[i] = h_mulmod(fact[i - 1], i % p, p);
+      for (size_t x = 0; x < n; x++) {
+        uint64_t d = h_mulmod(fact[x], fact[n - 1 - x], p);
+        if ((n - 1 - x) & 1) d = (p - d) % p;
+        w[j * n + x] = h_twiddle(h_inv(d, p), p);
+      }
+    }
+    if ((rc = upload_vec(c, w, &wt->d_lagw))) return rc;
+  }
+  if (!r->d_col_ptr) {   // transpose the CSR rows (matrix, constraint) -> CSC columns (matrix, variable)
+    const size_t nnz = r->h_col.size();
+    std::vector<uint32_t> col_ptr(3 * nv1 + 1, 0), rows(std::max<size_t>(nnz, 1));
+    std::vector<uint64_t> cc(std::max<size_t>(nnz, 1));
+    for (size_t m = 0; m < 3; m++)
+      for (size_t i = 0; i < n; i++)
+        for (size_t e = r->h_row_ptr[m * n + i]; e < r->h_row_ptr[m * n + i + 1]; e++) col_ptr[m * nv1 + r->h_col[e] + 1]++;
+    for (size_t k = 0; k < 3 * nv1; k++) col_ptr[k + 1] += col_ptr[k];
+    std::vector<uint32_t> fill(col_ptr.begin(), col_ptr.end() - 1);
+    for (size_t m = 0; m < 3; m++)
+      for (size_t i = 0; i < n; i++)
+        for (size_t e = r->h_row_ptr[m * n + i]; e < r->h_row_ptr[m * n + i + 1]; e++) {
+          const uint32_t at = fill[m * nv1 + r->h_col[e]]++;
+          rows[at] = (uint32_t)i;
+          cc[at] = r->h_coeff[e];
+        }
+    void *v;
+    CUDA_TRY(cudaMalloc(&v, col_ptr.size() * 4)); r->d_col_ptr = (uint32_t *)v;
+    CUDA_TRY(cudaMalloc(&v, rows.size() * 4)); r->d_rows = (uint32_t *)v;
+    CUDA_TRY(cudaMalloc(&v, cc.size() * 8)); r->d_ccoeff = (uint64_t *)v;
+    CUDA_TRY(cudaMemcpy(r->d_col_ptr, col_ptr.data(), col_ptr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->d_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->d_ccoeff, cc.data(), cc.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if ((rc = ensure(c, &c->d_plain, &c->cap_plain, n * W))) return rc;   // u[0..n): the Lagrange basis at t
+  uint64_t *d_u = c->d_plain;
+  {
+    LaunchScope ls(c, "k_lagrange_at");
+    k_lagrange_at<<<dim3((unsigned)((c->N_R + 127) / 128), (unsigned)c->L_R), 128, 0, c->stream>>>(
+        c->d_modq, t->d + t_first * W, wt->d_lagw, (uint32_t)n, d_u, Ht->d, Zt->d, (uint32_t)c->N_R, (uint32_t)c->L_R);
+    CUDA_TRY(cudaGetLastError());
+  }
+  {
+    LaunchScope ls(c, "k_instance_accum");
+    const unsigned sblocks = (unsigned)((c->N_R + 127) / 128);
+    k_instance_accum<<<dim3((unsigned)nv1, 3, (unsigned)(c->L_R * sblocks)), 128, 0, c->stream>>>(
+        c->d_modq, r->d_col_ptr, r->d_rows, r->d_ccoeff, (uint32_t)nv1, d_u, ABCt->d, (uint32_t)c->N_R, (uint32_t)c->L_R);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return RSG_OK;
+}
+
 static int r1cs_eval_dev(rsg_context *c, const rsg_r1cs *r, const uint64_t *d_assign, uint64_t *d_evals) {
   const unsigned sblocks = (unsigned)((c->N_R + MM_THREADS - 1) / MM_THREADS);
   dim3 grid((unsigned)r->n, 3, (unsigned)(c->L_R * sblocks));

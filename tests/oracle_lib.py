@@ -116,3 +116,21 @@ def witness_H(aA, aB, aC, N_R, L_R, q, lens=None):
     hl = C.c_size_t(0)
     lib.ro_witness_H(n, aA, aB, aC, lens[0], lens[1], lens[2], N_R, L_R, c(q), H, C.byref(hl))
     return H, int(hl.value)
+
+
+def instance_map(n, n_vars, row_ptr, col, coeff, t, N_R, L_R, q):
+    """r1cs_to_qrp_instance_map_with_evaluation (r1cs_to_qrp.tcc:75-116): returns (ABCt [3][n_vars+1][W], Ht [n+1][W], Zt [W])."""
+    nv1 = n_vars + 1
+    W = N_R * L_R
+    ABCt = np.zeros((3 * nv1, W), dtype=np.uint64); Ht = np.zeros((n + 1, W), dtype=np.uint64); Zt = np.zeros(W, dtype=np.uint64)
+    rp = np.ascontiguousarray(row_ptr, dtype=np.uint32); cl = np.ascontiguousarray(col, dtype=np.uint32)
+    fn = lib.ro_instance_map
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                   C.c_void_p, C.c_void_p, C.c_void_p]
+    cf, tt, qq = c(coeff), c(t), c(q)
+    rc = fn(n, nv1, rp.ctypes.data, cl.ctypes.data, cf.ctypes.data, tt.ctypes.data, N_R, L_R, qq.ctypes.data,
+            ABCt.ctypes.data, Ht.ctypes.data, Zt.ctypes.data)
+    if rc:
+        raise ValueError("t hits a domain point in some slot")
+    return ABCt, Ht, Zt

@@ -30,6 +30,7 @@ def test_tiny_cases_both_systems(case):
     rc, res, err = run(case, 11)
     assert rc == 0 and res["ok"], (res, err[-1500:])
     assert res["groth16"]["bit_exact"] == [1, 1, 1]
+    assert res["instance_map"]["bit_exact"] == 1      # generator / verifier ran the device instance map (8(f) rank 3)
     assert res["rinocchio"]["bit_exact"] == [1] * 9
     assert res["groth16"]["verified"] == res["groth16"]["verified_ref"]
     assert res["rinocchio"]["verified"] == res["rinocchio"]["verified_ref"]
@@ -43,5 +44,6 @@ def test_reference_sized_cases(case, which):
     assert rc == 0 and res["ok"], (res, err[-1500:])
     if which in ("groth16", "both"):
         assert res["groth16"]["bit_exact"] == [1, 1, 1] and res["groth16"]["verified"]
+        assert res["instance_map"]["bit_exact"] == 1
     if which == "both":
         assert res["rinocchio"]["bit_exact"] == [1] * 9 and res["rinocchio"]["verified"]

@@ -614,3 +614,43 @@ def test_fast_witness_proofs_match_reference(gold, monkeypatch):
         assert ctx.stat("witness_fast_launches") > 0 or case.n < 2
     finally:
         ctx.close()
+
+
+def test_instance_map_matches_reference(gold):
+    """rsg_instance_map (instance.cuh: prefix x suffix products, constant denominators, transposed sparse product) against
+    the reference's r1cs_to_qrp_instance_map_with_evaluation (golden sections inst_*)."""
+    import ringsnark_b200 as rs
+    case, ctx = gold
+    nv1 = case.io + case.aux + 1
+    r1cs = rs.R1cs(ctx, case.n, case.io, case.aux, case.d["r1cs_row_ptr"], case.d["r1cs_col"], case.d["r1cs_coeff"])
+    t = ctx.ringvec_from(case.ring("inst_t")[0])
+    ABCt, Ht, Zt = r1cs.instance_map(t)
+    got = ABCt.download()
+    for m, k in enumerate(["At", "Bt", "Ct"]):
+        assert np.array_equal(got[m * nv1:(m + 1) * nv1], case.ring("inst_" + k)[0]), k
+    assert np.array_equal(Ht.download(), case.ring("inst_Ht")[0])
+    assert np.array_equal(Zt.download(), case.ring("inst_Zt")[0])
+
+
+@pytest.mark.parametrize("name,n", [("c4", 129), ("c3p", 65)])
+def test_instance_map_against_oracle(name, n):
+    """A synthetic system of the bench's shape at n = 129 / 65 (54-bit ring prime; four 43/44-bit limbs), random t: the
+    device instance map against the oracle's literal O(m^2) restatement."""
+    import ringsnark_b200 as rs
+    from ringsnark_b200.params import CONFIGS, synthetic_r1cs
+    cfg = CONFIGS[name]
+    N_R, q = 64, cfg["q"]
+    io, aux = n // 2 + 1, n + n // 2
+    row_ptr, col, coeff = synthetic_r1cs(n, io, aux, seed=3, use_const=True)
+    ctx = rs.Context(N_R, q, cfg["N_E"], cfg["Q"])
+    try:
+        r1cs = rs.R1cs(ctx, n, io, aux, row_ptr, col, coeff)
+        t = ctx.ringvec(1)
+        t.fill_uniform(77)
+        ABCt, Ht, Zt = r1cs.instance_map(t)
+        want = O.instance_map(n, io + aux, row_ptr, col, coeff, t.download()[0], N_R, len(q), q)
+        assert np.array_equal(ABCt.download(), want[0])
+        assert np.array_equal(Ht.download(), want[1])
+        assert np.array_equal(Zt.download()[0], want[2])
+    finally:
+        ctx.close()

@@ -143,3 +143,18 @@ def test_is_zero_quirk():
     assert not O.is_zero_quirk(w)
     w[8] = 0; w[7] = 1 << 63
     assert not O.is_zero_quirk(w)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=IDS)
+def test_instance_map_matches_reference(path):
+    """ro_instance_map (r1cs_to_qrp.tcc:75-116 + evaluation_domain.tcc:20-51 restated) against the reference's own
+    r1cs_to_qrp_instance_map_with_evaluation at a seeded exceptional point (golden sections inst_*)."""
+    case = Case(path)
+    n, nv1 = case.n, case.io + case.aux + 1
+    t = case.ring("inst_t")[0][0]
+    ABC, Ht, Zt = O.instance_map(n, nv1 - 1, case.d["r1cs_row_ptr"], case.d["r1cs_col"], case.d["r1cs_coeff"], t,
+                                 case.N_R, case.L_R, case.q)
+    for m, k in enumerate(["At", "Bt", "Ct"]):
+        assert np.array_equal(ABC[m * nv1:(m + 1) * nv1], case.ring("inst_" + k)[0]), k
+    assert np.array_equal(Ht, case.ring("inst_Ht")[0])
+    assert np.array_equal(Zt, case.ring("inst_Zt")[0][0])
