@@ -169,6 +169,22 @@ int rsg_r1cs_evaluate(rsg_context *ctx, const rsg_r1cs *r, const rsg_ringvec *as
 int rsg_instance_map(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *t, size_t t_first, rsg_ringvec *ABCt, rsg_ringvec *Ht,
                      rsg_ringvec *Zt);
 
+/* ---- (de)serialisation of encodings: a CRS / proving-key range or a proof.  The reference declares the stream
+ * operators (zk_proof_systems/r1cs_ppzksnark.hpp:43-47,142-146) and never defines them; the container is documented in
+ * ringsnark_b200/csrc/serialize.inl (magic, parameters and primes, payload in HBM layout, checksum, end mark).
+ * rsg_enc_file_* are host-only (no GPU needed); kind 1 = CRS range, 2 = proof.  Readers fail with RSG_ERR_ARG on foreign
+ * parameters, non-canonical words, checksum mismatch or truncation. ---- */
+#define RSG_FILE_CRS 1
+#define RSG_FILE_PROOF 2
+int rsg_enc_file_info(const char *path, uint64_t *info /* kind, N_R, L_R, N_E, L_E, n_elems */, uint64_t *q /* nullable, 8 */,
+                      uint64_t *Q /* nullable, 16 */);
+int rsg_enc_file_write(const char *path, uint64_t kind, size_t N_R, size_t L_R, const uint64_t *q, size_t N_E, size_t L_E,
+                       const uint64_t *Q, size_t n_elems, const uint64_t *h_words);
+int rsg_enc_file_read(const char *path, size_t N_R, size_t L_R, const uint64_t *q, size_t N_E, size_t L_E, const uint64_t *Q,
+                      size_t cap_elems, uint64_t *h_words, size_t *n_elems, uint64_t *kind);
+int rsg_crs_save(const rsg_crs *crs, size_t first, size_t count, const char *path);   /* HBM -> file, pinned staging */
+int rsg_crs_load(rsg_crs *crs, size_t first, const char *path, size_t *count);          /* file -> HBM */
+
 /* ---- groth16::prover (zk_proof_systems/groth16/groth16.tcc:69-115), whole prover in one call ----
  * The proving key's CRS vectors live in ONE arena; each vector may be a shard [lo, hi) of its terms (multi-GPU:
  * the partial proofs of all ranks are all-gathered and summed with rsg_enc_sum). */

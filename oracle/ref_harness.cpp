@@ -417,6 +417,24 @@ static int cmd_time(const std::string &name, const std::string &what, int argc, 
     std::sort(ts.begin(), ts.end());
     js << "{\"what\":\"witness\",\"case\":\"" << name << "\",\"n\":" << cspec.n << ",\"threads\":1,\"reps\":" << reps
        << ",\"seconds\":" << ts[ts.size() / 2] << "}";
+  } else if (what == "instance") {
+    // r1cs_to_qrp_instance_map_with_evaluation (r1cs_to_qrp.tcc:75-116): the O(m^2) step of generator and verifier
+    ringsnark::r1cs_constraint_system<R> cs;
+    vector<R> assignment;
+    cases::build_circuit<R, ringsnark::r1cs_constraint_system<R>, ringsnark::r1cs_constraint<R>,
+                         ringsnark::linear_combination<R>, ringsnark::variable<R>>(cspec, 1, cs, assignment, &make_elem);
+    const auto domain = ringsnark::get_evaluation_domain<R>(cs.num_constraints());
+    const R t = R::random_exceptional_element(domain);
+    vector<double> ts;
+    for (size_t r = 0; r < reps; r++) {
+      double t0 = now_s();
+      const auto inst = ringsnark::r1cs_to_qrp_instance_map_with_evaluation(cs, t);
+      ts.push_back(now_s() - t0);
+      if (inst.Ht.empty()) abort();
+    }
+    std::sort(ts.begin(), ts.end());
+    js << "{\"what\":\"instance\",\"case\":\"" << name << "\",\"n\":" << cspec.n << ",\"threads\":1,\"reps\":" << reps
+       << ",\"seconds\":" << ts[ts.size() / 2] << "}";
   } else if (what == "prover") {
     // full groth16::prover on a synthetic CRS of the right shape
     ringsnark::r1cs_constraint_system<R> cs;
@@ -464,7 +482,7 @@ int main(int argc, char **argv) {
       return rc;
     }
     if (argc >= 4 && std::string(argv[1]) == "time") return cmd_time(argv[2], argv[3], argc - 4, argv + 4);
-    std::cerr << "usage: ref_harness dump <case> <out.rsgv> [seed] | time <case> <prover|lincomb|witness> [terms=T n=N reps=R threads=T] | list\n";
+    std::cerr << "usage: ref_harness dump <case> <out.rsgv> [seed] | time <case> <prover|lincomb|witness|instance> [terms=T n=N reps=R threads=T] | list\n";
     return 2;
   } catch (const std::exception &ex) {
     std::cerr << "ref_harness: " << ex.what() << std::endl;

@@ -219,6 +219,18 @@ class Groth16ProvingKey:
             self.crs.upload(alpha, L.alpha_idx)
             self.crs.upload(beta, L.beta_idx)
 
+    def save(self, path):
+        """This rank's arena (its shard of every CRS vector, in layout order) -> one file (csrc/serialize.inl)."""
+        from . import serialize
+        serialize.save_crs(self.crs, path, 0, self.n_elems)
+
+    def load_file(self, path):
+        """Arena written by save() for the same (n, n_aux, rank, world) -> HBM."""
+        from . import serialize
+        got = serialize.load_crs(self.crs, path, 0)
+        if got != self.n_elems:
+            raise ValueError(f"{path} holds {got} encodings, this key shard needs {self.n_elems}")
+
     def prove(self, h_assignment=None, aux_kind=None, to_host=True, d_proof=None):
         """groth16::prover (groth16.tcc:69-115). h_assignment: host words [n_io+n_aux][L_R*N_R] (None = use what is
         already resident in self.assignment). Returns (proof words [3][enc_words] or None, n_used[3])."""

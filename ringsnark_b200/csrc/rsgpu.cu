@@ -1973,3 +1973,4 @@ extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg
   const uint64_t *vec[6] = {coeffs, coeffs + 3 * n * W, coeffs + n * W, coeffs + 4 * n * W, H, assignment->d + n_io * W};
   return groth16_lincombs_dev(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, d_proof, n_used);
 }
+#include "serialize.inl"
