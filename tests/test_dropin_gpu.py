@@ -16,10 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "dropin_harness")
 
 
-def run(case, seed, which="both", timeout=900):
+def run(case, seed, which="both", timeout=900, env=None):
     if not os.path.exists(HARNESS):
         pytest.skip("oracle/_ref/dropin_harness not built (needs /root/reference at build time)")
-    out = subprocess.run([HARNESS, case, str(seed), which], capture_output=True, text=True, timeout=timeout)
+    out = subprocess.run([HARNESS, case, str(seed), which], capture_output=True, text=True, timeout=timeout,
+                         env=dict(os.environ, **(env or {})))
     assert out.stdout.strip(), out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
     return out.returncode, res, out.stderr
@@ -47,3 +48,13 @@ def test_reference_sized_cases(case, which):
         assert res["instance_map"]["bit_exact"] == 1
     if which == "both":
         assert res["rinocchio"]["bit_exact"] == [1] * 9 and res["rinocchio"]["verified"]
+
+
+@pytest.mark.parametrize("witness", ["dense", "fast"])
+def test_medium_circuit_both_witness_paths(witness):
+    """C4 parameters at n = 129 (the largest circuit the reference proves in seconds): the unmodified prover template over
+    the GPU backend, with the dense and with the quasi-linear witness map, against the reference's proof on the same CRS."""
+    rc, res, err = run("c4m", 31, "groth16", env={"RSG_WITNESS": witness})
+    assert rc == 0 and res["ok"], (res, err[-1500:])
+    assert res["groth16"]["bit_exact"] == [1, 1, 1] and res["instance_map"]["bit_exact"] == 1
+    assert res["groth16"]["verified"] == res["groth16"]["verified_ref"]
