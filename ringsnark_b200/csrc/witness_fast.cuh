@@ -53,9 +53,24 @@ struct FastTables {              // device pointers; [L_R] major
 // LAZY (every ring prime below 2^57): butterflies without range corrections where the bound allows it -- forward values grow
 // by 4p per level from a canonical input (at most 13 levels here: < 53p < 2^64) and any 64-bit value is a valid operand of
 // the next Shoup multiplication; the inverse keeps its values in [0, 4p) with the three-product Shoup quotient.
-template <int RL, bool INVERSE, bool LAZY>
+// FUSE: element-wise work folded into a pass so that it costs no shared-memory round trip and no barrier of its own.
+enum : int {
+  WF_PLAIN = 0,
+  WF_LOAD_DUP = 1,       // first forward pass of a tree level: read (F_hi | F_hi) of block b from the coefficient buffer
+  WF_STORE_MUL = 2,      // last forward pass: multiply by the transformed constant before the store
+  WF_STORE_COMBINE = 4,  // last inverse pass of a tree level: F_lo + product straight into the coefficient buffer
+  WF_STORE_NEWTON = 8    // last inverse pass of the Newton-coefficient product: canonicalise, add the wrapped terms, cut at n
+};
+struct WfFuse {
+  uint64_t *coef = nullptr;        // LOAD_DUP (read) / STORE_COMBINE (read-modify-write): the slots' coefficient buffers
+  uint32_t m = 0;                  // half block size of the level
+  const Twiddle *mul = nullptr;    // STORE_MUL: constant for position idx of the slot buffer
+  const uint64_t *wr = nullptr;    // STORE_NEWTON: wrapped terms [slot][WF_WC_MAX]
+  uint32_t n = 0, wc = 0;
+};
+template <int RL, bool INVERSE, bool LAZY, int FUSE = WF_PLAIN>
 __device__ __forceinline__ void wf_pass(uint64_t *buf, uint32_t slot_stride, uint32_t nslots, uint32_t nb, uint32_t lg,
-                                        uint32_t s, const Twiddle *__restrict__ tab, uint64_t p) {
+                                        uint32_t s, const Twiddle *__restrict__ tab, uint64_t p, const WfFuse &f = WfFuse()) {
   constexpr int R = 1 << RL;
   const uint32_t lgi = lg - RL, lgg = lg - s - RL, g = 1u << lgg;
   const uint32_t per_slot = nb << lgi, total = per_slot * nslots;
@@ -67,8 +82,18 @@ __device__ __forceinline__ void wf_pass(uint64_t *buf, uint32_t slot_stride, uin
     const uint32_t base = (b << lg) + (blk << (lg - s)) + o;
     uint64_t *sp = buf + slot * slot_stride;
     uint64_t v[R];
+    if (FUSE & WF_LOAD_DUP) {
+      const uint64_t *cp = f.coef + slot * slot_stride;
+      const uint32_t two_m = 2 * f.m;
 #pragma unroll
-    for (int k = 0; k < R; k++) v[k] = sp[pad_idx(base + k * g)];
+      for (int k = 0; k < R; k++) {
+        const uint32_t idx = base + k * g, e = idx & (two_m - 1);
+        v[k] = cp[pad_idx(idx - e + f.m + (e & (f.m - 1)))];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; k++) v[k] = sp[pad_idx(base + k * g)];
+    }
     if (!INVERSE) {
 #pragma unroll
       for (int u = 0; u < RL; u++) {
@@ -100,8 +125,36 @@ __device__ __forceinline__ void wf_pass(uint64_t *buf, uint32_t slot_stride, uin
         }
       }
     }
+    if (FUSE & WF_STORE_MUL) {
 #pragma unroll
-    for (int k = 0; k < R; k++) sp[pad_idx(base + k * g)] = v[k];
+      for (int k = 0; k < R; k++) sp[pad_idx(base + k * g)] = mul_shoup_lazy(v[k], load_tw(f.mul, base + k * g), p);
+    } else if (FUSE & WF_STORE_COMBINE) {
+      uint64_t *cp = f.coef + slot * slot_stride;
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        const uint32_t idx = base + k * g;
+        uint64_t x = v[k] >= (p << 1) ? v[k] - (p << 1) : v[k];
+        x = x >= p ? x - p : x;
+        uint64_t *a = cp + pad_idx(idx);
+        if ((idx & (2 * f.m - 1)) < f.m) x = add_mod(x, *a, p);
+        *a = x;
+      }
+    } else if (FUSE & WF_STORE_NEWTON) {
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        const uint32_t idx = base + k * g;
+        uint64_t x = 0;
+        if (idx < f.n) {
+          x = v[k] >= (p << 1) ? v[k] - (p << 1) : v[k];
+          x = x >= p ? x - p : x;
+          if (idx < f.wc) x = add_mod(x, f.wr[slot * WF_WC_MAX + idx], p);
+        }
+        sp[pad_idx(idx)] = x;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; k++) sp[pad_idx(base + k * g)] = v[k];
+    }
   }
 }
 
@@ -145,6 +198,69 @@ __device__ __noinline__ void wf_ntt_inv(uint64_t *buf, uint32_t slot_stride, uin
     __syncthreads();
     rem -= 4;
   }
+}
+
+
+// ---- drivers with the element-wise steps fused into the first / last pass (see WfFuse) -------------------------------
+// forward, levels [0, lg), last pass multiplies by `mul` (lg >= 5)
+template <bool LAZY>
+__device__ __noinline__ void wf_fwd_mul(uint64_t *buf, uint32_t stride, uint32_t nslots, uint32_t lg, const Twiddle *tab, uint64_t p,
+                                        const Twiddle *mul) {
+  WfFuse f;
+  f.mul = mul;
+  uint32_t s = 0;
+  while (lg - s > 4) {
+    wf_pass<4, false, LAZY>(buf, stride, nslots, 1, lg, s, tab, p);
+    __syncthreads();
+    s += 4;
+  }
+  if (lg - s == 4) wf_pass<4, false, LAZY, WF_STORE_MUL>(buf, stride, nslots, 1, lg, s, tab, p, f);
+  else if (lg - s == 3) wf_pass<3, false, LAZY, WF_STORE_MUL>(buf, stride, nslots, 1, lg, s, tab, p, f);
+  else if (lg - s == 2) wf_pass<2, false, LAZY, WF_STORE_MUL>(buf, stride, nslots, 1, lg, s, tab, p, f);
+  else wf_pass<1, false, LAZY, WF_STORE_MUL>(buf, stride, nslots, 1, lg, s, tab, p, f);
+  __syncthreads();
+}
+// inverse, all lg levels (lg >= 5), the last pass (levels 3..0) finishes with FUSE
+template <bool LAZY, int FUSE>
+__device__ __noinline__ void wf_inv_fused(uint64_t *buf, uint32_t stride, uint32_t nslots, uint32_t nb, uint32_t lg, const Twiddle *tab,
+                                          uint64_t p, const WfFuse &f) {
+  uint32_t rem = lg;
+  const uint32_t first = rem & 3;
+  if (first == 3) wf_pass<3, true, LAZY>(buf, stride, nslots, nb, lg, rem - 3, tab, p);
+  else if (first == 2) wf_pass<2, true, LAZY>(buf, stride, nslots, nb, lg, rem - 2, tab, p);
+  else if (first == 1) wf_pass<1, true, LAZY>(buf, stride, nslots, nb, lg, rem - 1, tab, p);
+  if (first) __syncthreads();
+  rem -= first;
+  while (rem > 4) {
+    wf_pass<4, true, LAZY>(buf, stride, nslots, nb, lg, rem - 4, tab, p);
+    __syncthreads();
+    rem -= 4;
+  }
+  wf_pass<4, true, LAZY, FUSE>(buf, stride, nslots, nb, lg, 0, tab, p, f);
+  __syncthreads();
+}
+// forward of one tree level: levels [1, lg) of (F_hi | F_hi) read from the coefficient buffer, last pass times P-hat
+template <bool LAZY>
+__device__ __noinline__ void wf_level_fwd(uint64_t *buf, uint32_t stride, uint32_t nslots, uint32_t nb, uint32_t lg, const Twiddle *tab,
+                                          uint64_t p, const WfFuse &f) {
+  if (lg == 5) {
+    wf_pass<4, false, LAZY, WF_LOAD_DUP | WF_STORE_MUL>(buf, stride, nslots, nb, lg, 1, tab, p, f);
+    __syncthreads();
+    return;
+  }
+  wf_pass<4, false, LAZY, WF_LOAD_DUP>(buf, stride, nslots, nb, lg, 1, tab, p, f);
+  __syncthreads();
+  uint32_t s = 5;
+  while (lg - s > 4) {
+    wf_pass<4, false, LAZY>(buf, stride, nslots, nb, lg, s, tab, p);
+    __syncthreads();
+    s += 4;
+  }
+  if (lg - s == 4) wf_pass<4, false, LAZY, WF_STORE_MUL>(buf, stride, nslots, nb, lg, s, tab, p, f);
+  else if (lg - s == 3) wf_pass<3, false, LAZY, WF_STORE_MUL>(buf, stride, nslots, nb, lg, s, tab, p, f);
+  else if (lg - s == 2) wf_pass<2, false, LAZY, WF_STORE_MUL>(buf, stride, nslots, nb, lg, s, tab, p, f);
+  else wf_pass<1, false, LAZY, WF_STORE_MUL>(buf, stride, nslots, nb, lg, s, tab, p, f);
+  __syncthreads();
 }
 
 __device__ __forceinline__ uint64_t canon2(uint64_t x, uint64_t p) { return x >= p ? x - p : x; }
@@ -220,37 +336,23 @@ __device__ __forceinline__ void wf_newton_to_monomial(uint64_t *A, uint64_t *B, 
     const uint32_t nbN = nb_active - (shortp ? 1 : 0);
     const Twiddle *Ph = T.Phat + ((size_t)limb * T.levels + lvl) * S;
     const uint64_t *Pn = T.Pnat + ((size_t)limb * T.levels + lvl) * (S / 2 + 1);
-    // (a) F_hi of every transformed block, duplicated into both halves: the first butterfly level of (F_hi | 0) is a copy
-    for (uint32_t t = threadIdx.x; t < nbN * m * nsl; t += blockDim.x) {
-      const uint32_t s = t % nsl, r = t / nsl, b = r >> (lg - 1), i = r & (m - 1);
-      const uint64_t v = A[s * stride + pad_idx(b * two_m + m + i)];
-      B[s * stride + pad_idx(b * two_m + i)] = v;
-      B[s * stride + pad_idx(b * two_m + m + i)] = v;
-    }
     if (shortp) {   // the trailing block's own scratch range is free: stage its high coefficients and P there
       for (uint32_t t = threadIdx.x; t < h_last * nsl; t += blockDim.x) {
         const uint32_t s = t % nsl, i = t / nsl;
         hs[s * WF_HMAX + i] = A[s * stride + pad_idx(last * two_m + m + i)];
       }
       for (uint32_t i = threadIdx.x; i <= m; i += blockDim.x) B[pad_idx(last * two_m + i)] = __ldg(Pn + i);
+      if (!nbN) __syncthreads();
     }
-    __syncthreads();
     if (nbN) {
-      wf_ntt_fwd<LAZY>(B, stride, nsl, nbN, lg, 1, fw, p);
-      for (uint32_t t = threadIdx.x; t < nbN * two_m * nsl; t += blockDim.x) {
-        const uint32_t s = t % nsl, idx = t / nsl;
-        uint64_t *w = B + s * stride + pad_idx(idx);
-        *w = mul_shoup_lazy(*w, load_tw(Ph, idx), p);
-      }
-      __syncthreads();
-      wf_ntt_inv<LAZY>(B, stride, nsl, nbN, lg, iv, p);
-      for (uint32_t t = threadIdx.x; t < nbN * two_m * nsl; t += blockDim.x) {
-        const uint32_t s = t % nsl, idx = t / nsl;
-        uint64_t x = canon4(B[s * stride + pad_idx(idx)], p);
-        uint64_t *a = A + s * stride + pad_idx(idx);
-        if ((idx & (two_m - 1)) < m) x = add_mod(x, *a, p);
-        *a = x;
-      }
+      // (F_hi | 0) of every transformed block: its first butterfly level is a copy, so the first pass reads (F_hi | F_hi)
+      // straight from A; the last forward pass multiplies by P-hat; the last inverse pass adds F_lo and writes A
+      WfFuse f;
+      f.coef = A;
+      f.m = m;
+      f.mul = Ph;
+      wf_level_fwd<LAZY>(B, stride, nsl, nbN, lg, fw, p, f);
+      wf_inv_fused<LAZY, WF_STORE_COMBINE>(B, stride, nsl, nbN, lg, iv, p, f);
     }
     if (shortp) {   // trailing block: out[j] = sum_{i < h_last, 0 <= j-i <= m} hi[i] * P[j-i]
       const uint64_t *Ps = B + 0 * stride;   // slot 0's scratch holds P (staged above)
@@ -300,28 +402,14 @@ __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict
   __syncthreads();
   if (wc) wf_wrapped(wr, A, n, nullptr, T.g_nat + (size_t)limb * n, n, S, wc, stride, nsl, mc);
   __syncthreads();
-  wf_ntt_fwd<LAZY>(A, stride, nsl, 1, T.logS, 0, fw, p);
   {
-    const Twiddle *Gh = T.Ghat + (size_t)limb * S;
-    for (uint32_t t = threadIdx.x; t < S * nsl; t += blockDim.x) {
-      const uint32_t s = t % nsl, i = t / nsl;
-      uint64_t *w = A + s * stride + pad_idx(i);
-      *w = mul_shoup_lazy(*w, load_tw(Gh, i), p);
-    }
+    WfFuse f;
+    f.wr = wr;
+    f.n = n;
+    f.wc = wc;
+    wf_fwd_mul<LAZY>(A, stride, nsl, T.logS, fw, p, T.Ghat + (size_t)limb * S);
+    wf_inv_fused<LAZY, WF_STORE_NEWTON>(A, stride, nsl, 1, T.logS, iv, p, f);
   }
-  __syncthreads();
-  wf_ntt_inv<LAZY>(A, stride, nsl, 1, T.logS, iv, p);
-  for (uint32_t t = threadIdx.x; t < S * nsl; t += blockDim.x) {
-    const uint32_t s = t % nsl, i = t / nsl;
-    uint64_t *w = A + s * stride + pad_idx(i);
-    uint64_t x = 0;
-    if (i < n) {
-      x = canon4(*w, p);
-      if (i < wc) x = add_mod(x, wr[s * WF_WC_MAX + i], p);
-    }
-    *w = x;
-  }
-  __syncthreads();
   wf_newton_to_monomial<LAZY>(A, B, hs, T, limb, nsl, stride, fw, iv, p, mc);
   for (uint32_t t = threadIdx.x; t < n * nsl; t += blockDim.x) {
     const uint32_t s = t % nsl, i = t / nsl;
