@@ -1458,8 +1458,10 @@ static bool wf_lazy(const rsg_context *c) {
 }
 static unsigned wf_threads(const rsg_context *c, int sl, uint32_t S) {
   if (c->wf_threads >= 32 && c->wf_threads <= 512) return (unsigned)c->wf_threads & ~31u;
-  // one radix-16 item per thread in a full-size pass: sl * S / 16 items
-  return (unsigned)std::min<size_t>(512, std::max<size_t>(128, (size_t)sl * S / 16));
+  // a full-size pass has sl * S / 16 radix-16 items, the passes of the tree levels about half of that (n just above S/2
+  // leaves half of the buffer empty): one item per thread THERE, measured best on B200 (C4: 2 x 128 threads 3.32 ms for 8
+  // vectors, 2 x 256 3.49 ms, 4 x 512 3.82 ms; profiles/r1d_wf_tune.log) -- idle threads only lengthen the barriers
+  return (unsigned)std::min<size_t>(512, std::max<size_t>(64, (size_t)sl * S / 32));
 }
 template <int SL>
 static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
