@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict
     if ((pos >> LOGN) == h) sm[pad_idx(pos & (n - 1))] = src[k];
   }
   __syncthreads();
-  ntt_inverse_smem<LOGN>(sm, P->invq[j], p, LVL0, h);
+  // unsplit transform: values may stay in [0, 4p) (the exact Shoup multiplication by N^-1 below accepts any 64-bit word);
+  // the split one hands [0, 2p) values to k_intt_finish
+  ntt_inverse_smem<LOGN, LVL0 == 0>(sm, P->invq[j], p, LVL0, h);
   uint64_t *dst = plain + (((size_t)e * L_R + j) << (LOGN + LVL0)) + (size_t)h * n;
   if (LVL0 == 0) {
     const Twiddle invn = P->invN_q[j];

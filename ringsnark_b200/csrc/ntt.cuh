@@ -56,6 +56,15 @@ __device__ __forceinline__ void bfly_fwd_lazy(uint64_t &x, uint64_t &y, const Tw
   x = x + v;
 }
 
+// Gentleman-Sande butterfly on [0, 4p) values with the three-product Shoup quotient (one IMAD.WIDE + two IMAD.HI instead of a
+// full 64x64 high product): x, y in [0, 4p) -> [0, 4p), p < 2^61.
+__device__ __forceinline__ void bfly_inv_lazy(uint64_t &x, uint64_t &y, const Twiddle &t, uint64_t p, uint64_t four_p) {
+  const uint64_t s = x + y;
+  const uint64_t d = x - y + four_p;
+  x = s >= four_p ? s - four_p : s;
+  y = mul_shoup_approx(d, t, p);
+}
+
 // One pass = RL consecutive levels [S, S+RL) done in registers on 2^RL elements spaced g = n >> (S+RL) apart.
 // n = local transform size (1 << LOGN); `lvl0` = levels already applied outside (0 unless the polynomial was
 // pre-split in global memory), `blk` = index of this local block among the 1 << lvl0 blocks.
@@ -100,7 +109,10 @@ __device__ __forceinline__ void ntt_pass(uint64_t *sm, const Twiddle *tab, uint6
         for (int grp = 0; grp < (1 << u); grp++) {
           const Twiddle t = load_tw(tab, tbase + grp);
 #pragma unroll
-          for (int k = 0; k < half; k++) bfly_inv(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, two_p);
+          for (int k = 0; k < half; k++) {
+            if (LAZY) bfly_inv_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, four_p);
+            else bfly_inv(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, two_p);
+          }
         }
       }
     }
@@ -125,7 +137,7 @@ struct PassChain {   // levels [S, LOGN): radix-16 passes while four levels rema
     constexpr int REMAIN = LOGN - S;   // here S counts the levels already undone from the top
     if constexpr (REMAIN > 0) {
       constexpr int RL = (REMAIN % 4) ? (REMAIN % 4) : 4;
-      ntt_pass<LOGN, RL, REMAIN - RL, true, false>(sm, tab, p, lvl0, blk);
+      ntt_pass<LOGN, RL, REMAIN - RL, true, LAZY>(sm, tab, p, lvl0, blk);
       __syncthreads();
       PassChain<LOGN, S + RL, INVERSE, LAZY>::inv(sm, tab, p, lvl0, blk);
     }
@@ -140,11 +152,12 @@ __device__ __forceinline__ void ntt_forward_smem(uint64_t *sm, const Twiddle *ta
   PassChain<LOGN, 0, false, LAZY>::fwd(sm, tab, p, lvl0, blk);
 }
 
-// All LOGN levels, inverse (levels run LOGN-1 .. 0).  Input in [0, 2p), output lazy in [0, 2p), NOT yet scaled.
-template <int LOGN>
+// All LOGN levels, inverse (levels run LOGN-1 .. 0).  Input in [0, 2p), output lazy in [0, 2p) -- or [0, 4p) with LAZY
+// (bfly_inv_lazy, p < 2^61) --, NOT yet scaled.
+template <int LOGN, bool LAZY = false>
 __device__ __forceinline__ void ntt_inverse_smem(uint64_t *sm, const Twiddle *tab, uint64_t p, uint32_t lvl0,
                                                  uint32_t blk) {
-  PassChain<LOGN, 0, true, false>::inv(sm, tab, p, lvl0, blk);
+  PassChain<LOGN, 0, true, LAZY>::inv(sm, tab, p, lvl0, blk);
 }
 
 }  // namespace rsg

@@ -158,14 +158,6 @@ __device__ __forceinline__ void wf_pass(uint64_t *buf, uint32_t slot_stride, uin
   }
 }
 
-// Gentleman-Sande butterfly on [0, 4p) values with the approximate Shoup quotient: x, y in [0, 4p) -> [0, 4p)
-__device__ __forceinline__ void bfly_inv_lazy(uint64_t &x, uint64_t &y, const Twiddle &t, uint64_t p, uint64_t four_p) {
-  const uint64_t s = x + y;
-  const uint64_t d = x - y + four_p;
-  x = s >= four_p ? s - four_p : s;
-  y = mul_shoup_approx(d, t, p);
-}
-
 // levels [s0, lg) forward: input < 4p (canonical when LAZY) natural order, output bit-reversed order, < 4p or (LAZY) any
 // 64-bit representative.  Ends with a barrier.
 template <bool LAZY>
