@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict
   __syncthreads();
   // unsplit transform: values may stay in [0, 4p) (the exact Shoup multiplication by N^-1 below accepts any 64-bit word);
   // the split one hands [0, 2p) values to k_intt_finish
-  ntt_inverse_smem<LOGN, LVL0 == 0>(sm, P->invq[j], p, LVL0, h);
+  if (LVL0 == 0 && 2 * N_R <= n) ntt_inverse_smem_q02<LOGN, true>(sm, P->invq[j], p);   // first matrix row only: half the input is zero
+  else ntt_inverse_smem<LOGN, LVL0 == 0>(sm, P->invq[j], p, LVL0, h);
   uint64_t *dst = plain + (((size_t)e * L_R + j) << (LOGN + LVL0)) + (size_t)h * n;
   if (LVL0 == 0) {
     const Twiddle invn = P->invN_q[j];

@@ -160,4 +160,116 @@ __device__ __forceinline__ void ntt_inverse_smem(uint64_t *sm, const Twiddle *ta
   PassChain<LOGN, 0, true, LAZY>::inv(sm, tab, p, lvl0, blk);
 }
 
+// ---- inverse transform of a batch-encoded slot vector that uses the first matrix row only (N_R <= N_E / 2) ------------
+// BatchEncoder's index map (batchencoder.cpp:64-88) sends slot i of the first row to position bitrev((3^i mod 2N - 1) / 2).
+// 3 generates the residues = 1, 3 mod 8, so (3^i - 1) / 2 = 0, 1 mod 4: bit 1 of the natural index -- the second-highest bit of
+// the bit-reversed position -- is always 0.  Quarters 1 and 3 of the transform's input are therefore structurally zero:
+//   * every pass below the top two levels works inside a quarter: only the items of quarters 0 and 2 are run (half the
+//     butterflies of 12 of the 14 levels at N = 2^14);
+//   * in the last pass the butterflies of levels 3, 2 on the zero quarters vanish and level 1 (quarter 0 <-> 1, 2 <-> 3)
+//     degenerates to a copy and one multiplication.
+// Same residues as the dense transform: a butterfly on (0, 0) is (0, 0) and on (x, 0) is (x, x w).
+template <int LOGN, int RL, int S, bool LAZY>
+__device__ __forceinline__ void ntt_pass_inv_q02(uint64_t *sm, const Twiddle *tab, uint64_t p) {
+  static_assert(S >= 2, "the pass must stay inside a quarter");
+  constexpr uint32_t n = 1u << LOGN;
+  constexpr int R = 1 << RL;
+  constexpr uint32_t g = n >> (S + RL);
+  constexpr uint32_t items = n >> RL, quarter = items / 4;
+  const uint64_t two_p = p << 1, four_p = p << 2;
+  for (uint32_t it = threadIdx.x; it < 2 * quarter; it += blockDim.x) {
+    const uint32_t item = it < quarter ? it : it + quarter;     // items are block-major: quarter q = [q, q+1) * items/4
+    const uint32_t o = item & (g - 1);
+    const uint32_t b = item / g;
+    const uint32_t base = b * (n >> S) + o;
+    uint64_t *ptr = sm + pad_idx(base);
+    uint64_t v[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) v[k] = ptr[k * g + ((k * g) >> 4)];
+#pragma unroll
+    for (int u = RL - 1; u >= 0; u--) {
+      const int half = R >> (u + 1);
+      const uint32_t tbase = (1u << (S + u)) + (b << u);
+#pragma unroll
+      for (int grp = 0; grp < (1 << u); grp++) {
+        const Twiddle t = load_tw(tab, tbase + grp);
+#pragma unroll
+        for (int k = 0; k < half; k++) {
+          if (LAZY) bfly_inv_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, four_p);
+          else bfly_inv(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, two_p);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) ptr[k * g + ((k * g) >> 4)] = v[k];
+  }
+}
+// last pass: levels 3..0 on 16 elements spaced n/16 apart; elements 4..7 and 12..15 (quarters 1, 3) are zero on entry
+template <int LOGN, bool LAZY>
+__device__ __forceinline__ void ntt_pass_inv_top_q02(uint64_t *sm, const Twiddle *tab, uint64_t p) {
+  constexpr uint32_t n = 1u << LOGN;
+  constexpr uint32_t g = n >> 4;
+  const uint64_t two_p = p << 1, four_p = p << 2;
+  for (uint32_t item = threadIdx.x; item < g; item += blockDim.x) {
+    uint64_t *ptr = sm + pad_idx(item);
+    uint64_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = ((k >> 2) & 1) ? 0 : ptr[k * g + ((k * g) >> 4)];
+    // level 3 (pairs k, k+1) and level 2 (pairs k, k+2) inside the non-zero quarters only
+#pragma unroll
+    for (int u = 3; u >= 2; u--) {
+      const int half = 16 >> (u + 1);
+#pragma unroll
+      for (int grp = 0; grp < (1 << u); grp++) {
+        if (((grp * 2 * half) >> 2) & 1) continue;   // this group lies in quarter 1 or 3
+        const Twiddle t = load_tw(tab, (1u << u) + grp);
+#pragma unroll
+        for (int k = 0; k < half; k++) {
+          if (LAZY) bfly_inv_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, four_p);
+          else bfly_inv(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, two_p);
+        }
+      }
+    }
+    // level 1: (x, 0) -> (x, x w)
+#pragma unroll
+    for (int grp = 0; grp < 2; grp++) {
+      const Twiddle t = load_tw(tab, 2 + grp);
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[grp * 8 + k + 4] = LAZY ? mul_shoup_approx(v[grp * 8 + k], t, p) : mul_shoup_lazy(v[grp * 8 + k], t, p);
+    }
+    {   // level 0
+      const Twiddle t = load_tw(tab, 1);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (LAZY) bfly_inv_lazy(v[k], v[k + 8], t, p, four_p);
+        else bfly_inv(v[k], v[k + 8], t, p, two_p);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) ptr[k * g + ((k * g) >> 4)] = v[k];
+  }
+}
+template <int LOGN, int S, bool LAZY>
+struct PassChainInvQ02 {   // S counts the levels already undone from the bottom, as in PassChain::inv
+  static __device__ __forceinline__ void run(uint64_t *sm, const Twiddle *tab, uint64_t p) {
+    constexpr int REMAIN = LOGN - S;
+    if constexpr (REMAIN > 4) {
+      constexpr int RL = (REMAIN % 4) ? (REMAIN % 4) : 4;
+      ntt_pass_inv_q02<LOGN, RL, REMAIN - RL, LAZY>(sm, tab, p);
+      __syncthreads();
+      PassChainInvQ02<LOGN, S + RL, LAZY>::run(sm, tab, p);
+    } else {
+      static_assert(REMAIN == 4, "needs at least eight levels");
+      ntt_pass_inv_top_q02<LOGN, LAZY>(sm, tab, p);
+      __syncthreads();
+    }
+  }
+};
+// Input: canonical values in quarters 0 and 2 of the bit-reversed array (quarters 1, 3 are not read); output as
+// ntt_inverse_smem: natural order, lazy, not scaled.
+template <int LOGN, bool LAZY>
+__device__ __forceinline__ void ntt_inverse_smem_q02(uint64_t *sm, const Twiddle *tab, uint64_t p) {
+  PassChainInvQ02<LOGN, 0, LAZY>::run(sm, tab, p);
+}
+
 }  // namespace rsg
