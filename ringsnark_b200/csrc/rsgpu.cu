@@ -1442,11 +1442,13 @@ static int ensure_fast_tables(rsg_context *c, size_t n, WitnessTables *wt) {
   return RSG_OK;
 }
 // slots per CTA: a power of two dividing the slot count; both polynomial buffers of a CTA stay below ~100 KiB (2 CTAs/SM)
-static uint32_t wf_pick_sl(const rsg_context *c, uint32_t S, size_t nslots) {
-  // measured on B200 at C4 (n = 1031, S = 2048): 2 slots x 256 threads, two CTAs per SM, beats 4 x 512 by 12 %
+static uint32_t wf_pick_sl(const rsg_context *c, uint32_t S, size_t nslots, size_t vectors) {
+  // measured on B200 at C4 (n = 1031, S = 2048): 2 slots per CTA, two to three CTAs per SM, beats 4 x 512 threads by 12 %
   uint32_t sl = 2;
   if (c->wf_sl > 0) sl = (uint32_t)c->wf_sl;
   while (sl > 1 && (nslots % sl || wf_smem_bytes(S, sl) > (c->wf_sl > 0 ? 227 : 100) * 1024)) sl >>= 1;
+  // (one slot per CTA when a multi-GPU slot shard leaves less than two waves of CTAs was tried: 0.69 vs 0.65 ms at 4 GPUs)
+  (void)vectors;
   return sl;
 }
 // correction-free butterflies (witness_fast.cuh) need every ring prime below 2^57; RSG_WF_LAZY=0 forces the corrected ones
@@ -1479,7 +1481,7 @@ static int launch_interp_fast(rsg_context *c, WitnessTables *wt, const uint64_t 
   if (!batch) return RSG_OK;
   LaunchScope ls(c, name);
   c->st_wf++;
-  switch (wf_pick_sl(c, wt->ft.S, nslots)) {
+  switch (wf_pick_sl(c, wt->ft.S, nslots, batch * c->L_R)) {
     case 8: return wf_launch_interp<8>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
     case 4: return wf_launch_interp<4>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
     case 2: return wf_launch_interp<2>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
@@ -1498,7 +1500,7 @@ static int wf_launch_quotient(rsg_context *c, const FastTables &ft, const uint64
 static int launch_quotient_fast(rsg_context *c, WitnessTables *wt, const uint64_t *A, const uint64_t *B, uint64_t *H) {
   LaunchScope ls(c, "k_quotient_fast");
   c->st_wf++;
-  switch (wf_pick_sl(c, wt->ft.S, c->N_R)) {
+  switch (wf_pick_sl(c, wt->ft.S, c->N_R, c->L_R)) {
     case 8: return wf_launch_quotient<8>(c, wt->ft, A, B, H);
     case 4: return wf_launch_quotient<4>(c, wt->ft, A, B, H);
     case 2: return wf_launch_quotient<2>(c, wt->ft, A, B, H);
