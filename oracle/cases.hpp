@@ -27,6 +27,8 @@ struct CaseSpec {
   size_t n = 0, io = 0, aux = 0;
   bool use_const = false;       // constraints that touch the constant wire (reference verifier then rejects)
   bool quirks = false;          // scalar 0 / 1 / k inputs and a zero-prefix element among the assignment
+  bool ntt_demo = false;        // ONE constraint (x_1 + sum_i row^i x_(i+1)) * 1 = x_io with RING-ELEMENT coefficients, no
+                                // auxiliary input: the shape of benchmarks/bench_ntt_SEAL.cpp:29-55 (SURVEY 8(d) C2')
 };
 
 inline CaseSpec get_case(const std::string &name) {
@@ -46,6 +48,11 @@ inline CaseSpec get_case(const std::string &name) {
     c.n = 3; c.io = 2; c.aux = 4;
   } else if (name == "c1") {            // examples/example_SEAL.cpp
     c.N_R = 4096; c.ring_bits = {36, 36, 37}; c.N_E = 8192; c.n = 2; c.io = 5; c.aux = 1;
+  } else if (name == "c2p") {           // bench_ntt_SEAL.cpp shape, shortened (the reference uses io = N_R + 1 = 4097).
+    // NOT part of any test: with n = 1 and no auxiliary input the proof's C is an EMPTY encoding, and groth16::prover copies
+    // it into the proof -- ringsnark/seal/seal_ring.hpp:246 asserts !other.ciphertexts.empty(), so the reference built with
+    // assertions (as oracle/Makefile.ref builds it) aborts on this shape
+    c.N_R = 4096; c.ring_bits = {36, 36, 37}; c.N_E = 8192; c.n = 1; c.io = 258; c.aux = 0; c.ntt_demo = true; c.use_const = true;
   } else if (name == "c3p") {           // bench_mul circuit shape, N_R = 8192, N_E = 16384
     c.N_R = 8192; c.ring_bits = {43, 43, 44, 44, 44}; c.N_E = 16384; c.n = 4; c.io = 7; c.aux = 1;
   } else if (name == "c4s") {           // C4 parameters, small circuit (bench_plaintext_check size)
@@ -106,6 +113,27 @@ template <typename R, typename CS, typename Constraint, typename LC, typename Va
 void build_circuit(const CaseSpec &c, uint64_t seed, CS &cs, std::vector<R> &assignment,
                    R (*make_elem)(int kind)) {  // kind 0: uniform random element; 1: zero-prefix element (is_zero quirk)
   const size_t nv = c.io + c.aux;
+  if (c.ntt_demo) {
+    // sum = x_1 + row x_2 + row^2 x_3 + ... ; constraint sum * 1 = x_io (bench_ntt_SEAL.cpp:47-55): polynomial coefficients,
+    // the constant wire on the B side, n = 1 (domain {0}, Z = x, H = 0), no auxiliary input
+    if (c.n != 1 || c.aux != 0 || c.io < 3) throw std::invalid_argument("ntt_demo needs n = 1, aux = 0, io >= 3");
+    assignment.assign(nv, R(0));
+    for (size_t v = 0; v + 1 < c.io; v++) assignment[v] = make_elem(0);
+    cs.primary_input_size = c.io;
+    cs.auxiliary_input_size = 0;
+    const R rs = make_elem(0);
+    R row(rs);
+    LC sum = LC(Var(1));
+    R val = assignment[0];
+    for (size_t i = 1; i + 1 < c.io; i++) {
+      sum = sum + Var(i + 1) * row;
+      val += row * assignment[i];
+      row *= rs;
+    }
+    cs.add_constraint(Constraint(sum, LC((long)1), LC(Var(c.io))));
+    assignment[c.io - 1] = val;
+    return;
+  }
   if (nv < c.n + 1) throw std::invalid_argument("case has too few variables");
   const size_t nfree = nv - c.n;
   Wiring w(seed);

@@ -201,19 +201,23 @@ static int cmd_dump(const std::string &name, const std::string &out, uint64_t se
   // (1b) the constraint system itself in CSR form (rows m*n + i, m in {A,B,C}; col 0 = constant wire)
   {
     vector<uint64_t> row_ptr{0}, col, coeff;
+    bool scalar_coeffs = true;
     for (int m = 0; m < 3; m++)
       for (size_t i = 0; i < n; i++) {
         const auto &lc = m == 0 ? s.cs.constraints[i].a : (m == 1 ? s.cs.constraints[i].b : s.cs.constraints[i].c);
         for (const auto &lt : lc.terms) {
-          if (!lt.coeff.is_scalar()) throw std::logic_error("non-scalar linear-term coefficient");
+          if (!lt.coeff.is_scalar()) { scalar_coeffs = false; continue; }
           col.push_back(lt.index);
           coeff.push_back(lt.coeff.get_scalar());
         }
         row_ptr.push_back(col.size());
       }
-    w.put("r1cs_row_ptr", row_ptr);
-    w.put("r1cs_col", col);
-    w.put("r1cs_coeff", coeff);
+    w.put1("r1cs_scalar_coeffs", scalar_coeffs);   // 0: ring-element coefficients (bench_ntt shape) -- no CSR form exists
+    if (scalar_coeffs) {
+      w.put("r1cs_row_ptr", row_ptr);
+      w.put("r1cs_col", col);
+      w.put("r1cs_coeff", coeff);
+    }
   }
   put_ring(w, "primary_input", s.primary);
   put_ring(w, "auxiliary_input", s.auxiliary);
