@@ -33,6 +33,7 @@ extern "C" {
 #define RSG_ERR_STATE (-3)     /* context not set / handle misuse (reference: "context not set") */
 #define RSG_ERR_NOTINV (-4)    /* "element is not invertible in ring" (seal_ring.tcc:87-103) */
 #define RSG_ERR_UNSUPPORTED (-5)
+#define RSG_ERR_NOISE (-6)     /* decoding_error: a ciphertext has no noise budget left (seal_ring.tcc:445-453) */
 
 /* Per-term dispatch of EncodingElem::operator*= (seal_ring.tcc:509-548) decided by the host shim exactly as the
  * reference does: is_zero() (incl. the SealPoly::is_zero prefix quirk) -> SKIP; scalar 1 -> ONE (ciphertext taken
@@ -168,6 +169,17 @@ int rsg_r1cs_evaluate(rsg_context *ctx, const rsg_r1cs *r, const rsg_ringvec *as
  * wire); Ht: n + 1 elements 1, t, .., t^n; Zt: 1 element Z(t). ---- */
 int rsg_instance_map(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *t, size_t t_first, rsg_ringvec *ABCt, rsg_ringvec *Ht,
                      rsg_ringvec *Zt);
+
+/* ---- EncodingElem::decode (ringsnark/seal/seal_ring.tcc:435-477): the verifier's front half (groth16.tcc:121-123,
+ * rinocchio.tcc:205-217) for first-level BGV ciphertexts in NTT form with correction factor 1.  Per ring limb j:
+ * invariant noise budget (decryptor.cpp:383-461), c0 + c1 s, inverse NTT, exact base conversion q -> t
+ * (util/rns.cpp:466-539), BatchEncoder::decode (batchencoder.cpp:278-315), first N_R slots.
+ * h_sk: [L_R][L_E][N_E] words of the secret keys in NTT form (SecretKey::data() of limb j's context, first L_E limbs);
+ * encodings from HBM (d_enc) or from the host (h_enc), exactly one non-null; h_ring: [count][L_R][N_R];
+ * h_budget (nullable): [count][L_R] noise budgets in bits.  Returns RSG_ERR_NOISE (after filling both outputs) when some
+ * budget is <= 0, the reference's decoding_error.  An all-zero encoding (SEAL's empty ciphertext) decodes to zero. ---- */
+int rsg_decode(rsg_context *ctx, const uint64_t *h_sk, const uint64_t *d_enc, const uint64_t *h_enc, size_t count, uint64_t *h_ring,
+               int32_t *h_budget);
 
 /* ---- (de)serialisation of encodings: a CRS / proving-key range or a proof.  The reference declares the stream
  * operators (zk_proof_systems/r1cs_ppzksnark.hpp:43-47,142-146) and never defines them; the container is documented in

@@ -326,6 +326,39 @@ static int cmd_dump(const std::string &name, const std::string &out, uint64_t se
     put_ring(w, "inst_Ht", inst.Ht);
     put_ring(w, "inst_Zt", vector<R>{inst.Zt});
   }
+  // (8) EncodingElem::decode (seal_ring.tcc:435-477) of the three proof elements, as the verifier does first
+  //     (groth16.tcc:121-123): the secret keys in NTT form, the decoded ring elements and SEAL's invariant noise budgets
+  {
+    const auto &sk = kp.vk.sk_enc;
+    vector<uint64_t> skw, budgets, decoded_ok;
+    for (size_t j = 0; j < s.L_R; j++) skw.insert(skw.end(), sk[j].data().data(), sk[j].data().data() + s.L_E * s.N_E);
+    w.put("dec_sk", skw);   // [L_R][L_E][N_E]: first-level limbs of the key-level secret key
+    vector<R> dec;
+    for (const E *e : {&proof.A, &proof.B, &proof.C}) {
+      bool ok = false;
+      R r = R::zero();
+      if (!e->is_empty()) {
+        const auto &cts = EncAccess::cts(*e);
+        for (size_t j = 0; j < s.L_R; j++) {
+          seal::Decryptor d(E::get_contexts()[j], sk[j]);
+          budgets.push_back(cts[j].size() ? (uint64_t)d.invariant_noise_budget(cts[j]) : ~0ull);
+        }
+        try {
+          r = E::decode(sk, *e);
+          ok = true;
+        } catch (const std::exception &ex) {
+          std::cerr << "decode threw: " << ex.what() << std::endl;
+        }
+      } else {
+        for (size_t j = 0; j < s.L_R; j++) budgets.push_back(~0ull);
+      }
+      decoded_ok.push_back(ok);
+      dec.push_back(ok ? r.to_poly() : R::zero().to_poly());
+    }
+    put_ring(w, "dec_proof", dec);
+    w.put("dec_budget", budgets);   // [3][L_R]; ~0 = empty ciphertext (no budget defined)
+    w.put("dec_ok", decoded_ok);
+  }
   w.put("timing_us", vector<uint64_t>{(uint64_t)(t_wit * 1e6), (uint64_t)(t_gen * 1e6), (uint64_t)(t_prove * 1e6), (uint64_t)(t_inst * 1e6)});
   w.save(out);
   std::cerr << "case " << name << ": satisfied=" << sat << " verified=" << ok << " witness_map=" << t_wit

@@ -396,3 +396,91 @@ int ro_instance_map(size_t n, size_t nvars1, const uint32_t *row_ptr, const uint
   }
   return bad ? -1 : 0;
 }
+
+/*
+ * EncodingElem::decode, ringsnark/seal/seal_ring.tcc:435-477, for ONE ring limb (one BGV ciphertext of size 2, NTT form,
+ * first level, correction factor 1), values only:
+ *   budget  Decryptor::invariant_noise_budget   depends/SEAL/native/src/seal/decryptor.cpp:383-461
+ *           (c0 + c1 s, inverse NTT, CRT-compose, centred infinity norm, bitcount(Q) - bitcount(norm) - 1, floored at 0)
+ *   plain   Decryptor::bgv_decrypt               decryptor.cpp:189-231 with RNSTool::decrypt_modt = BaseConverter::
+ *           exact_convert_array, util/rns.cpp:466-539: temp_l = x_l (Q/Q_l)^-1 mod Q_l, v = (uint64)(sum_l double(temp_l) /
+ *           double(Q_l) + 0.5) summed in limb order, out = sum_l temp_l (Q/Q_l mod t) - v (Q mod t)  mod t
+ *   slots   BatchEncoder::decode                 batchencoder.cpp:278-315: forward NTT mod t, out[i] = temp[index_map[i]]
+ * ct: [2][L_E][N_E]; sk: [L_E][N_E] (NTT form); out: N_R slot values (seal_ring.tcc:466 keeps the first N_R).
+ * Returns the noise budget in bits.  Big integers: little-endian 64-bit words, at most 16 limbs.
+ */
+int ro_decode_limb(const uint64_t *ct, const uint64_t *sk, size_t N_E, size_t L_E, const uint64_t *Q, uint64_t t, size_t N_R,
+                   uint64_t *out) {
+  enum { MAXW = 16 };
+  uint64_t *phase = malloc(L_E * N_E * 8), *plain = malloc(N_E * 8), *map = malloc(N_E * 8);
+  for (size_t l = 0; l < L_E; l++) {
+    for (size_t i = 0; i < N_E; i++)
+      phase[l * N_E + i] = addmod(mulmod(ct[(L_E + l) * N_E + i], sk[l * N_E + i], Q[l]), ct[l * N_E + i], Q[l]);
+    ro_ntt_inverse(phase + l * N_E, N_E, Q[l]);
+  }
+  uint64_t inv_punct[MAXW], punct_mod_t[MAXW], Q_mod_t = 1, Qw[MAXW + 1] = {1}, halfw[MAXW];
+  for (size_t l = 0; l < L_E; l++) {
+    uint64_t pr = 1, pm = 1;
+    for (size_t k = 0; k < L_E; k++)
+      if (k != l) { pr = mulmod(pr, Q[k] % Q[l], Q[l]); pm = mulmod(pm, Q[k] % t, t); }
+    ro_try_invert(pr, Q[l], &inv_punct[l]);
+    punct_mod_t[l] = pm;
+    Q_mod_t = mulmod(Q_mod_t, Q[l] % t, t);
+    uint64_t carry = 0;
+    for (size_t w = 0; w < MAXW; w++) { u128 x = (u128)Qw[w] * Q[l] + carry; Qw[w] = (uint64_t)x; carry = (uint64_t)(x >> 64); }
+  }
+  int Qbits = 0;
+  for (int w = MAXW - 1; w >= 0; w--) if (Qw[w]) { Qbits = w * 64 + 64 - __builtin_clzll(Qw[w]); break; }
+  { uint64_t tmp[MAXW + 1], carry = 1;
+    for (size_t w = 0; w < MAXW; w++) { tmp[w] = Qw[w] + carry; carry = tmp[w] < carry; }
+    tmp[MAXW] = carry;
+    for (size_t w = 0; w < MAXW; w++) halfw[w] = (tmp[w] >> 1) | (tmp[w + 1] << 63); }
+  int norm_bits = 0;
+  for (size_t i = 0; i < N_E; i++) {
+    uint64_t temp[MAXW];
+    double agg = 0.0;
+    u128 acc = 0;
+    for (size_t l = 0; l < L_E; l++) {
+      temp[l] = mulmod(phase[l * N_E + i], inv_punct[l], Q[l]);
+      agg += (double)temp[l] / (double)Q[l];
+      acc = (acc + (u128)mulmod(temp[l] % t, punct_mod_t[l], t)) % t;
+    }
+    agg += 0.5;
+    uint64_t v = (uint64_t)agg;
+    plain[i] = submod((uint64_t)acc, mulmod(v % t, Q_mod_t, t), t);
+    /* CRT-compose: X = sum_l temp_l * (Q / Q_l)  mod Q  -- here through mixed radix digits (same integer in [0, Q)) */
+    uint64_t a[MAXW], X[MAXW] = {0};
+    for (size_t l = 0; l < L_E; l++) {
+      uint64_t x = phase[l * N_E + i];
+      for (size_t k = 0; k < l; k++) {
+        uint64_t inv;
+        ro_try_invert(Q[k] % Q[l], Q[l], &inv);
+        x = mulmod(submod(x, a[k] % Q[l], Q[l]), inv, Q[l]);
+      }
+      a[l] = x;
+    }
+    X[0] = a[L_E - 1];
+    for (int l = (int)L_E - 2; l >= 0; l--) {
+      uint64_t carry = a[l];
+      for (size_t w = 0; w < L_E; w++) { u128 x = (u128)X[w] * Q[l] + carry; X[w] = (uint64_t)x; carry = (uint64_t)(x >> 64); }
+    }
+    int ge = 1;
+    for (int w = (int)L_E - 1; w >= 0; w--) if (X[w] != halfw[w]) { ge = X[w] > halfw[w]; break; }
+    if (ge) {
+      uint64_t borrow = 0;
+      for (size_t w = 0; w < L_E; w++) {
+        uint64_t d = Qw[w] - X[w] - borrow;
+        borrow = (Qw[w] < X[w]) || (Qw[w] == X[w] && borrow);
+        X[w] = d;
+      }
+    }
+    for (int w = (int)L_E - 1; w >= 0; w--)
+      if (X[w]) { int nb = w * 64 + 64 - __builtin_clzll(X[w]); if (nb > norm_bits) norm_bits = nb; break; }
+  }
+  ro_ntt_forward(plain, N_E, t);
+  ro_batch_index_map(N_E, map);
+  for (size_t i = 0; i < N_R; i++) out[i] = plain[map[i]];
+  free(phase); free(plain); free(map);
+  int budget = Qbits - norm_bits - 1;
+  return budget < 0 ? 0 : budget;
+}

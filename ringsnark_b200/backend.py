@@ -121,6 +121,17 @@ class Context:
         check(self.lib.rsg_interpolate(self.h, n, batch, y.h, y_first, out.h, out_first))
         return out
 
+    def decode(self, sk, enc_words):
+        """EncodingElem::decode (seal_ring.tcc:435-477) of host encodings [count][enc_words] under the secret keys
+        sk [L_R][L_E][N_E] (NTT form).  Returns (ring words [count][L_R*N_R], noise budgets [count][L_R]); raises RsgError
+        (code -6) if some ciphertext has no noise budget left -- the reference's decoding_error."""
+        sk, enc = _u64(sk), _u64(enc_words)
+        count = enc.size // self.enc_words
+        ring = np.zeros((count, self.L_R * self.N_R), dtype=np.uint64)
+        budget = np.zeros((count, self.L_R), dtype=np.int32)
+        check(self.lib.rsg_decode(self.h, _ptr(sk), None, _ptr(enc), count, _ptr(ring), budget.ctypes.data_as(C.c_void_p)))
+        return ring, budget
+
     def vanishing(self, n):
         Z = np.zeros((self.L_R, n + 1), dtype=np.uint64)
         check(self.lib.rsg_vanishing(self.h, n, _ptr(Z)))

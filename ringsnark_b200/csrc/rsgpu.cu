@@ -16,6 +16,7 @@
 #include "witness.cuh"
 #include "witness_fast.cuh"
 #include "instance.cuh"
+#include "decode.cuh"
 #include "ringops.cuh"
 
 using namespace rsg;
@@ -203,6 +204,10 @@ struct rsg_context {
   uint64_t *d_ip = nullptr;         // the separate inner products of rsg_groth16_prove
   size_t cap_ip = 0;
   uint64_t exact_fallbacks = 0;     // how often a flagged prefix had to be resolved exactly
+  DecodeConsts *d_dec = nullptr;    // constants of rsg_decode (decode.cuh), built on first use
+  int Q_bits = 0;                   // bit length of Q = prod Q_l
+  uint64_t *d_decode = nullptr;     // rsg_decode scratch
+  size_t cap_decode = 0;
   uint64_t st_wf = 0, st_wd = 0;
   uint64_t st_lin_terms = 0, st_lin_plain = 0, st_lin_launches = 0, st_fwd_polys = 0, st_inv_polys = 0, st_merged = 0;
   bool f64_ntt = false;             // every Q_l < 2^49: forward NTTs of the plaintext pipeline run on the FP64 pipe
@@ -765,11 +770,16 @@ extern "C" int rsg_plain_to_ntt(rsg_context *c, const uint64_t *d_plain, size_t 
   std::lock_guard<std::mutex> g(c->mu);
   return launch_lift_ntt(c, d_plain, count, d_pntt);
 }
+static int ntt_dev(rsg_context *c, uint64_t *d, size_t batch, int which, size_t idx, int inverse);
 extern "C" int rsg_ntt(rsg_context *c, uint64_t *d, size_t batch, int which, size_t idx, int inverse) {
   if (!c) return fail(RSG_ERR_STATE, "context not set");
   if ((which == 0 && idx >= c->L_E) || (which == 1 && idx >= c->L_R) || which < 0 || which > 1) return fail(RSG_ERR_ARG, "bad modulus index");
   if (!batch) return RSG_OK;
   std::lock_guard<std::mutex> g(c->mu);
+  return ntt_dev(c, d, batch, which, idx, inverse);
+}
+// `batch` contiguous N_E-point polynomials, in place, canonical in and out; which = 0: mod Q_idx, 1: mod q_idx.  Caller holds c->mu.
+static int ntt_dev(rsg_context *c, uint64_t *d, size_t batch, int which, size_t idx, int inverse) {
   const uint64_t p = which == 0 ? c->Q[idx] : c->q[idx];
   const Twiddle *tab = which == 0 ? (inverse ? c->hp.invQ[idx] : c->hp.fwdQ[idx]) : (inverse ? c->hp.invq[idx] : c->hp.fwdq[idx]);
   const Twiddle invn = which == 0 ? c->hp.invN_Q[idx] : c->hp.invN_q[idx];
@@ -1721,6 +1731,121 @@ extern "C" void rsg_r1cs_destroy(rsg_r1cs *r) {
   cudaFree(r->d_col_ptr); cudaFree(r->d_rows); cudaFree(r->d_ccoeff);
   delete r;
 }
+// ------------------------------------------------------------------------------------------------------------
+// EncodingElem::decode on the device (decode.cuh)
+static int get_decode_consts(rsg_context *c) {
+  if (c->d_dec) return RSG_OK;
+  DecodeConsts K;
+  memset(&K, 0, sizeof(K));
+  const size_t L_E = c->L_E, L_R = c->L_R;
+  for (size_t l = 0; l < L_E; l++) {
+    uint64_t prod = 1;   // Q / Q_l mod Q_l
+    for (size_t k = 0; k < L_E; k++)
+      if (k != l) prod = h_mulmod(prod, c->Q[k] % c->Q[l], c->Q[l]);
+    K.inv_punct[l] = h_inv(prod, c->Q[l]);
+    for (size_t j = 0; j < L_R; j++) {
+      uint64_t pm = 1;
+      for (size_t k = 0; k < L_E; k++)
+        if (k != l) pm = h_mulmod(pm, c->Q[k] % c->q[j], c->q[j]);
+      K.punct_mod_t[j][l] = pm;
+    }
+    for (size_t k = 0; k < l; k++) K.garner_inv[l][k] = h_inv(c->Q[k] % c->Q[l], c->Q[l]);
+  }
+  for (size_t j = 0; j < L_R; j++) {
+    uint64_t qm = 1;
+    for (size_t k = 0; k < L_E; k++) qm = h_mulmod(qm, c->Q[k] % c->q[j], c->q[j]);
+    K.Q_mod_t[j] = qm;
+  }
+  K.Qw[0] = 1;   // Q = prod Q_l, little-endian words
+  for (size_t l = 0; l < L_E; l++) {
+    uint64_t carry = 0;
+    for (size_t w = 0; w < DEC_MAXW; w++) {
+      const u128 t = (u128)K.Qw[w] * c->Q[l] + carry;
+      K.Qw[w] = (uint64_t)t;
+      carry = (uint64_t)(t >> 64);
+    }
+  }
+  {   // (Q + 1) >> 1
+    uint64_t tmp[DEC_MAXW + 1] = {0}, carry = 1;
+    for (size_t w = 0; w < DEC_MAXW; w++) {
+      tmp[w] = K.Qw[w] + carry;
+      carry = tmp[w] < carry ? 1 : 0;
+    }
+    tmp[DEC_MAXW] = carry;
+    for (size_t w = 0; w < DEC_MAXW; w++) K.halfw[w] = (tmp[w] >> 1) | (tmp[w + 1] << 63);
+    c->Q_bits = 0;
+    for (int w = DEC_MAXW - 1; w >= 0; w--)
+      if (K.Qw[w]) { c->Q_bits = w * 64 + (64 - __builtin_clzll(K.Qw[w])); break; }
+  }
+  int rc = dev_alloc(c, &c->d_dec, 1);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpy(c->d_dec, &K, sizeof(K), cudaMemcpyHostToDevice));
+  return RSG_OK;
+}
+
+extern "C" int rsg_decode(rsg_context *c, const uint64_t *h_sk, const uint64_t *d_enc, const uint64_t *h_enc, size_t count,
+                          uint64_t *h_ring, int32_t *h_budget) {
+  if (!c || !h_sk || (!d_enc == !h_enc) || !h_ring) return fail(RSG_ERR_ARG, "null argument (exactly one of d_enc / h_enc)");
+  if (!count) return RSG_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = get_decode_consts(c);
+  if (rc) return rc;
+  const size_t E = c->enc_words(), N = c->N_E, L_E = c->L_E, L_R = c->L_R, W = c->ring_words();
+  // scratch: [enc (if from host) | sk | phase | plain | ring | bits]
+  const size_t need = (h_enc ? count * E : 0) + L_R * L_E * N + L_E * count * L_R * N + L_R * count * N + count * W + count * L_R;
+  if ((rc = ensure(c, &c->d_decode, &c->cap_decode, need))) return rc;
+  uint64_t *p = c->d_decode;
+  const uint64_t *enc = d_enc;
+  if (h_enc) {
+    CUDA_TRY(cudaMemcpyAsync(p, h_enc, count * E * 8, cudaMemcpyHostToDevice, c->stream));
+    enc = p;
+    p += count * E;
+  }
+  uint64_t *sk = p; p += L_R * L_E * N;
+  uint64_t *phase = p; p += L_E * count * L_R * N;
+  uint64_t *plain = p; p += L_R * count * N;
+  uint64_t *ring = p; p += count * W;
+  int *bits = (int *)p;
+  CUDA_TRY(cudaMemcpyAsync(sk, h_sk, L_R * L_E * N * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemsetAsync(bits, 0, count * L_R * sizeof(int), c->stream));
+  {
+    LaunchScope ls(c, "k_dec_phase");
+    k_dec_phase<<<dim3((unsigned)((N + 255) / 256), (unsigned)(L_E * L_R), (unsigned)count), 256, 0, c->stream>>>(c->d_params, enc, sk,
+                                                                                                              (uint32_t)count, phase);
+    CUDA_TRY(cudaGetLastError());
+  }
+  for (size_t l = 0; l < L_E; l++)
+    if ((rc = ntt_dev(c, phase + l * count * L_R * N, count * L_R, 0, l, 1))) return rc;
+  {
+    LaunchScope ls(c, "k_dec_modt");
+    k_dec_modt<<<dim3((unsigned)((N + 127) / 128), (unsigned)L_R, (unsigned)count), 128, 0, c->stream>>>(c->d_params, c->d_dec, phase,
+                                                                                                      (uint32_t)count, plain, bits);
+    CUDA_TRY(cudaGetLastError());
+  }
+  for (size_t j = 0; j < L_R; j++)
+    if ((rc = ntt_dev(c, plain + j * count * N, count, 1, j, 0))) return rc;
+  {
+    LaunchScope ls(c, "k_dec_gather");
+    k_dec_gather<<<dim3((unsigned)((c->N_R + 255) / 256), (unsigned)L_R, (unsigned)count), 256, 0, c->stream>>>(c->d_params, plain,
+                                                                                                             (uint32_t)count, ring);
+    CUDA_TRY(cudaGetLastError());
+  }
+  std::vector<int> hb(count * L_R);
+  CUDA_TRY(cudaMemcpyAsync(h_ring, ring, count * W * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(hb.data(), bits, hb.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  bool exhausted = false;
+  for (size_t k = 0; k < hb.size(); k++) {
+    const int budget = std::max(0, c->Q_bits - hb[k] - 1);   // decryptor.cpp:457-459
+    if (h_budget) h_budget[k] = budget;
+    exhausted = exhausted || budget <= 0;
+  }
+  // seal_ring.tcc:445-453: decoding_error when a ciphertext has no noise budget left
+  if (exhausted) return fail(RSG_ERR_NOISE, "a ciphertext has remaining noise budget <= 0");
+  return RSG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // instance map with evaluation (the O(m^2) step of setup and of every verification; instance.cuh)
 extern "C" int rsg_instance_map(rsg_context *c, rsg_r1cs *r, const rsg_ringvec *t, size_t t_first, rsg_ringvec *ABCt, rsg_ringvec *Ht,

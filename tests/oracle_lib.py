@@ -134,3 +134,18 @@ def instance_map(n, n_vars, row_ptr, col, coeff, t, N_R, L_R, q):
     if rc:
         raise ValueError("t hits a domain point in some slot")
     return ABCt, Ht, Zt
+
+
+def decode(enc, sk, N_R, L_R, q, N_E, L_E, Q):
+    """EncodingElem::decode (seal_ring.tcc:435-477) of one encoding [L_R][2][L_E][N_E] with the secret keys
+    [L_R][L_E][N_E]: returns (ring words [L_R*N_R], budgets [L_R])."""
+    enc, sk, Q = c(enc).reshape(L_R, 2 * L_E * N_E), c(sk).reshape(L_R, L_E * N_E), c(Q)
+    fn = lib.ro_decode_limb
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p]
+    out = np.zeros((L_R, N_R), dtype=np.uint64)
+    budgets = []
+    for j in range(L_R):
+        e, s = np.ascontiguousarray(enc[j]), np.ascontiguousarray(sk[j])
+        budgets.append(int(fn(e.ctypes.data, s.ctypes.data, N_E, L_E, Q.ctypes.data, int(q[j]), N_R, out[j].ctypes.data)))
+    return out.reshape(-1), budgets

@@ -212,6 +212,13 @@ def test_reference_sized_cases(name, witness, monkeypatch):
         aux = ctx.ringvec_from(aux_w)
         out, used = ctx.inner_product(delta_mid, aux, ctx.term_tags(aux, aux_t, aux_s))
         assert np.array_equal(out, ip[5])
+        # the verifier's front half: decode of the reference's proof, with SEAL's noise budgets
+        keep = [k for k in range(3) if int(case.d["dec_ok"][k])]
+        ring, budget = ctx.decode(case.d["dec_sk"], np.stack([case.enc("proof")[0][k] for k in keep]))
+        wb = case.d["dec_budget"].reshape(3, case.L_R)
+        for n_, k in enumerate(keep):
+            assert np.array_equal(ring[n_], case.ring("dec_proof")[0][k]), k
+            assert [int(x) for x in budget[n_]] == [int(x) for x in wb[k]], k
     finally:
         ctx.close()
 
@@ -652,5 +659,41 @@ def test_instance_map_against_oracle(name, n):
         assert np.array_equal(ABCt.download(), want[0])
         assert np.array_equal(Ht.download(), want[1])
         assert np.array_equal(Zt.download()[0], want[2])
+    finally:
+        ctx.close()
+
+
+def test_decode_matches_reference(gold):
+    """rsg_decode (decode.cuh) against the reference's EncodingElem::decode of its own proof: decoded ring elements and
+    SEAL's invariant noise budgets, bit for bit."""
+    case, ctx = gold
+    proof, sk = case.enc("proof")[0], case.d["dec_sk"]
+    keep = [k for k in range(3) if int(case.d["dec_ok"][k])]
+    ring, budget = ctx.decode(sk, np.stack([proof[k] for k in keep]))
+    want, wb = case.ring("dec_proof")[0], case.d["dec_budget"].reshape(3, case.L_R)
+    for n_, k in enumerate(keep):
+        assert np.array_equal(ring[n_], want[k]), k
+        assert [int(x) for x in budget[n_]] == [int(x) for x in wb[k]], k
+
+
+def test_decode_noise_exhausted_and_zero():
+    """A uniformly random 'ciphertext' has no noise budget: RSG_ERR_NOISE, the reference's decoding_error; an all-zero
+    encoding (SEAL's empty ciphertext) decodes to zero with the full budget."""
+    import ringsnark_b200 as rs
+    from ringsnark_b200.capi import RsgError
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c4"]
+    ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"])
+    try:
+        crs = ctx.crs(1)
+        crs.fill_uniform(5)
+        rng = np.random.default_rng(2)
+        sk = np.concatenate([rng.integers(0, int(p), size=cfg["N_E"], dtype=np.uint64) for p in cfg["Q"]])
+        with pytest.raises(RsgError) as ei:
+            ctx.decode(sk, crs.download(0, 1))
+        assert ei.value.code == -6
+        ring, budget = ctx.decode(sk, np.zeros((1, ctx.enc_words), dtype=np.uint64))
+        import math
+        assert not ring.any() and int(budget[0, 0]) == math.prod(int(p) for p in cfg["Q"]).bit_length() - 1
     finally:
         ctx.close()

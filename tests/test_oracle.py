@@ -158,3 +158,18 @@ def test_instance_map_matches_reference(path):
         assert np.array_equal(ABC[m * nv1:(m + 1) * nv1], case.ring("inst_" + k)[0]), k
     assert np.array_equal(Ht, case.ring("inst_Ht")[0])
     assert np.array_equal(Zt, case.ring("inst_Zt")[0][0])
+
+
+@pytest.mark.parametrize("path", GOLD, ids=IDS)
+def test_decode_matches_reference(path):
+    """ro_decode_limb (seal_ring.tcc:435-477 over SEAL's bgv_decrypt / exact_convert_array / invariant_noise_budget /
+    BatchEncoder::decode) against the reference's EncodingElem::decode of its own proof and SEAL's noise budgets."""
+    case = Case(path)
+    proof, sk = case.enc("proof")[0], case.d["dec_sk"]
+    want, budget = case.ring("dec_proof")[0], case.d["dec_budget"].reshape(3, case.L_R)
+    for k in range(3):
+        if not int(case.d["dec_ok"][k]):
+            continue
+        got, b = O.decode(proof[k], sk, case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)
+        assert np.array_equal(got, want[k]), k
+        assert b == [int(x) for x in budget[k]], k
