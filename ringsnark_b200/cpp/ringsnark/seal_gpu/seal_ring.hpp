@@ -17,8 +17,8 @@
 //         this class keeps a ringsnark::seal::RingElem inside and forwards the element-wise operators to it, so the
 //         scalar/polynomial variant rules (seal_ring.tcc:105-263) and SealPoly::is_zero's prefix quirk
 //         (depends/SEAL-Polytools/src/poly_arith.cpp:147-153) are the reference's own code, not a re-statement.
-//         Setup (keygen, encode) and verification (decode) delegate to ringsnark::seal::EncodingElem: SURVEY.md
-//         section 8 keeps them on the SEAL path.
+//         Setup (keygen, encode) delegates to ringsnark::seal::EncodingElem: SURVEY.md section 8 keeps it on the SEAL
+//         path.  EncodingElem::decode (the verifier's front half) runs on the GPU (rsg_decode).
 //   Ring elements PRODUCED by the GPU witness map stay in HBM (a RingElem then holds a ref-counted slice of a device
 //   vector plus its is_zero flag) and are fed to inner_product without a round trip; they are downloaded lazily only
 //   if host code looks at them.  Encodings live in HBM arenas: one arena per encode() call, so a proving-key vector
@@ -395,8 +395,26 @@ class EncodingElem {
     for (const auto &r : rs) hosts.push_back(r.host());
     return from_seal(SealEnc::encode(sk, hosts));
   }
-  // seal_ring.tcc:435-477 -- verify side: download, SEAL decrypts and decodes.
-  static RingElem decode(const SecretKey &sk, const EncodingElem &e) { return RingElem(SealEnc::decode(sk, e.to_seal())); }
+  // seal_ring.tcc:435-477 on the GPU: noise budget, c0 + c1 s, exact base conversion q -> t, batch
+  // decode -- rsg_decode, bit-identical to SEAL's Decryptor + BatchEncoder.  Empty / zero encodings (no arena) keep the
+  // reference's own handling.
+  static RingElem decode(const SecretKey &sk, const EncodingElem &e) {
+    if (!e.arena_) return RingElem(SealEnc::decode(sk, e.to_seal()));
+    auto &b = detail::backend();
+    if (sk.size() != b.L_R) throw std::invalid_argument("one secret key per ring limb expected");
+    std::vector<uint64_t> skw;
+    skw.reserve(b.L_R * b.L_E * b.N_E);
+    for (size_t j = 0; j < b.L_R; j++) skw.insert(skw.end(), sk[j].data().data(), sk[j].data().data() + b.L_E * b.N_E);
+    std::vector<uint64_t> w(b.ring_words);
+    std::vector<int32_t> budget(b.L_R, 0);
+    const int rc = rsg_decode(b.ctx, skw.data(), e.dptr(), nullptr, 1, w.data(), budget.data());
+    if (rc == RSG_ERR_NOISE)
+      for (size_t j = 0; j < b.L_R; j++)
+        if (budget[j] <= 0)
+          throw decoding_error("ciphertext #" + std::to_string(j) + " has remaining noise budget " + std::to_string(budget[j]) + " <= 0");
+    detail::check(rc);
+    return RingElem(polytools::SealPoly(RingElem::get_context(), w, &RingElem::get_context().first_parms_id()));
+  }
 
   // seal_ring.tcc:361-433 on the GPU.
   static EncodingElem inner_product(std::vector<EncodingElem>::const_iterator a_start,
