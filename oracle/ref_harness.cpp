@@ -472,6 +472,24 @@ static int cmd_time(const std::string &name, const std::string &what, int argc, 
     std::sort(ts.begin(), ts.end());
     js << "{\"what\":\"instance\",\"case\":\"" << name << "\",\"n\":" << cspec.n << ",\"threads\":1,\"reps\":" << reps
        << ",\"seconds\":" << ts[ts.size() / 2] << "}";
+  } else if (what == "decode") {
+    // EncodingElem::decode (seal_ring.tcc:435-477) of `terms` fresh encodings: noise budget + decrypt + batch decode each
+    auto keys = E::keygen();
+    vector<R> rs;
+    for (size_t i = 0; i < terms; i++) rs.push_back(R::random_element());
+    const auto encs = E::encode(std::get<1>(keys), rs);
+    vector<double> ts;
+    for (size_t r = 0; r < reps; r++) {
+      double t0 = now_s();
+      for (size_t i = 0; i < terms; i++) {
+        const R d = E::decode(std::get<1>(keys), encs[i]);
+        if (d != rs[i]) abort();
+      }
+      ts.push_back(now_s() - t0);
+    }
+    std::sort(ts.begin(), ts.end());
+    js << "{\"what\":\"decode\",\"case\":\"" << name << "\",\"encodings\":" << terms << ",\"threads\":1,\"reps\":" << reps
+       << ",\"seconds\":" << ts[ts.size() / 2] << ",\"ms_per_encoding\":" << 1e3 * ts[ts.size() / 2] / terms << "}";
   } else if (what == "prover") {
     // full groth16::prover on a synthetic CRS of the right shape
     ringsnark::r1cs_constraint_system<R> cs;
@@ -519,7 +537,7 @@ int main(int argc, char **argv) {
       return rc;
     }
     if (argc >= 4 && std::string(argv[1]) == "time") return cmd_time(argv[2], argv[3], argc - 4, argv + 4);
-    std::cerr << "usage: ref_harness dump <case> <out.rsgv> [seed] | time <case> <prover|lincomb|witness|instance> [terms=T n=N reps=R threads=T] | list\n";
+    std::cerr << "usage: ref_harness dump <case> <out.rsgv> [seed] | time <case> <prover|lincomb|witness|instance|decode> [terms=T n=N reps=R threads=T] | list\n";
     return 2;
   } catch (const std::exception &ex) {
     std::cerr << "ref_harness: " << ex.what() << std::endl;
