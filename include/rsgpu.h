@@ -128,7 +128,11 @@ int rsg_enc_sum(rsg_context *ctx, const uint64_t *d_parts, size_t parts, size_t 
  * coeffs: receives 6*n elements A_io,B_io,C_io,A_mid,B_mid,C_mid (qrp_witness order, qrp.hpp:171-181).
  * H: receives n+1 elements: (A*B - C)/Z in [0, n-1), zeros at n-1 and n (non-ZK call of groth16.tcc:82-84).
  * Interpolation on the domain {0..n-1} (util/polynomials.tcc:9-43), product and exact division by the monic
- * Z (util/polynomials.tcc:61-81, util/evaluation_domain.tcc:53-84); all slot-parallel on the GPU. */
+ * Z (util/polynomials.tcc:61-81, util/evaluation_domain.tcc:53-84); all slot-parallel on the GPU.
+ * Two implementations with identical (canonical) results: dense constant-matrix products for small n, and for
+ * 320 <= n <= 4112 the quasi-linear path of csrc/witness_fast.cuh (Newton coefficients by one negacyclic product,
+ * Newton -> monomial on the subproduct tree, quotient by two products).  RSG_WITNESS=dense|fast overrides the choice;
+ * rsg_context_stat("witness_fast_launches" / "witness_dense_launches") says which one ran. */
 int rsg_witness_map(rsg_context *ctx, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H);
 /* The zero-knowledge variant rinocchio::prover calls (rinocchio.tcc:88-93, r1cs_to_qrp.tcc:225-235):
  * h_d = 3 ring elements d1, d2, d3 (host words, [3][L_R][N_R]); H[i] += d2*A[i] + d1*B[i] (i < n), H[0] -= d3,
@@ -137,13 +141,13 @@ int rsg_witness_map_zk(rsg_context *ctx, size_t n, const rsg_ringvec *evals, con
                        rsg_ringvec *H);
 /* The same when `evals` IS the output of rsg_r1cs_evaluate(r1cs, .): then full = mid + io - (constant wire), interpolation
  * is linear, and the interpolants of the full assignment are formed from the other six instead of being computed
- * (6 instead of 8 matrix products per proof; identical residues). */
+ * (6 instead of 8 interpolations per proof; identical residues). */
 typedef struct rsg_r1cs rsg_r1cs;
 int rsg_witness_map_r1cs(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *evals, const uint64_t *h_d,
                          rsg_ringvec *coeffs, rsg_ringvec *H);
 /* The witness map as groth16::prover consumes it (groth16.tcc:82-112, non-ZK): coefficients_for_C_io / C_mid are never
  * read by that prover and C does not reach the quotient H (deg C < n = deg Z), so only A and B are interpolated
- * (4 matrix products).  The C_io / C_mid blocks of `coeffs` are left untouched. */
+ * (4 interpolations).  The C_io / C_mid blocks of `coeffs` are left untouched. */
 int rsg_witness_map_groth16(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H);
 /* util/polynomials.tcc:9-43 on its own: vectors of n ring elements; `batch` vectors back to back. */
 int rsg_interpolate(rsg_context *ctx, size_t n, size_t batch, const rsg_ringvec *y, size_t y_first, rsg_ringvec *out,
