@@ -35,6 +35,7 @@
 
 #include <ringsnark/seal/seal_ring.hpp>
 #include <ringsnark/reductions/r1cs_to_qrp/r1cs_to_qrp.hpp>
+#include <ringsnark/util/polynomials.hpp>
 
 #include "rsgpu.h"
 
@@ -733,5 +734,50 @@ inline qrp_instance_evaluation<seal_gpu::RingElem> r1cs_to_qrp_instance_map_with
                                     R::from_device(Zt, 0));
 }
 }  // namespace ringsnark
+
+// =====================================================================================================================
+// The verifier's three interpolations (groth16.tcc:147-153, rinocchio.tcc: the same shape): explicit specialisation of the
+// global function template interpolate (util/polynomials.hpp:17-18) for this backend's ring type.  On the evaluation
+// domain {0..n-1} -- the only point set the proof systems use -- it runs on the GPU (rsg_interpolate: the quasi-linear or
+// the dense kernels of the witness map); any other point set goes through the reference's own algorithm on the host
+// type.  With the device instance map and the device decode this takes groth16::verifier at the logistic-regression shape
+// (n = 1031) from minutes to well under a second.
+template <>
+inline std::vector<ringsnark::seal_gpu::RingElem> interpolate<ringsnark::seal_gpu::RingElem>(
+    const std::vector<ringsnark::seal_gpu::RingElem> &x, const std::vector<ringsnark::seal_gpu::RingElem> &y) {
+  using R = ringsnark::seal_gpu::RingElem;
+  namespace D = ringsnark::seal_gpu::detail;
+  const size_t n = x.size();
+  if (y.size() != n) throw std::invalid_argument("interpolate: mismatched sizes");
+  bool domain = n >= 1;
+  for (size_t i = 0; i < n && domain; i++) domain = x[i].is_scalar() && x[i].get_scalar() == i;
+  if (!domain) {
+    std::vector<R::Host> hx, hy;
+    hx.reserve(n);
+    hy.reserve(n);
+    for (const auto &e : x) hx.push_back(e.host());
+    for (const auto &e : y) hy.push_back(e.host());
+    const auto hc = interpolate<R::Host>(hx, hy);
+    return std::vector<R>(hc.begin(), hc.end());
+  }
+  auto &b = D::backend();
+  auto make_vec = [&](size_t count) {
+    auto v = std::make_shared<D::DevRing>();
+    D::check(rsg_ringvec_create(b.ctx, count, &v->v));
+    return v;
+  };
+  std::vector<uint64_t> w;
+  w.reserve(n * b.ring_words);
+  for (const auto &e : y) e.append_words(w);
+  auto yv = make_vec(n), out = make_vec(n);
+  D::check(rsg_ringvec_upload(yv->v, 0, n, w.data()));
+  D::check(rsg_interpolate(b.ctx, n, 1, yv->v, 0, out->v, 0));
+  out->zero.resize(n);
+  D::check(rsg_ringvec_is_zero_prefix(out->v, 0, n, out->zero.data()));
+  std::vector<R> coeffs;
+  coeffs.reserve(n);
+  for (size_t i = 0; i < n; i++) coeffs.push_back(R::from_device(out, i));
+  return coeffs;
+}
 
 #endif  // RINGSNARK_SEAL_GPU_RING_HPP
