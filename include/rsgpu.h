@@ -243,6 +243,9 @@ int rsg_crs_lincomb(rsg_context *ctx, const uint64_t *d_crs, const uint32_t *h_t
                     size_t n_terms, const uint64_t *d_plain_ntt, uint64_t *d_out);
 /* Timing hook: device milliseconds of the most recent kernels, by name, measured with CUDA events on the
  * context's stream when profiling is enabled. */
+/* Host-side API trace (environment RSG_TRACE=1): wall time and call count per entry point, process-wide.  Writes a text
+ * table into buf (nullable) and returns the size needed; reset != 0 clears the counters. */
+size_t rsg_trace_report(char *buf, size_t cap, int reset);
 int rsg_context_enable_timing(rsg_context *ctx, int on);
 int rsg_context_last_timing(rsg_context *ctx, const char *kernel, float *ms, uint64_t *launches);
 

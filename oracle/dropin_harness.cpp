@@ -245,9 +245,15 @@ int main(int argc, char **argv) {
         const auto kp = G::generator<GR, GE>(gcs);
         const double t_gen = now_s() - t0;
         (void)G::prover<GR, GE>(kp.pk, gprimary, gauxiliary);
+        rsg_trace_report(nullptr, 0, 1);
         t0 = now_s();
         const auto proof = G::prover<GR, GE>(kp.pk, gprimary, gauxiliary);
         const double t_prove = now_s() - t0;
+        {
+          std::vector<char> buf(rsg_trace_report(nullptr, 0, 0));
+          rsg_trace_report(buf.data(), buf.size(), 1);
+          std::cerr << "---- API trace of one groth16::prover call (RSG_TRACE=1) ----\n" << buf.data();
+        }
         bool verified = false;
         t0 = now_s();
         try {

@@ -74,6 +74,7 @@ SIGNATURES = {
     "rsg_plain_to_ntt": (_int, [_vp, _vp, _sz, _vp]),
     "rsg_ntt": (_int, [_vp, _vp, _sz, _int, _sz, _int]),
     "rsg_crs_lincomb": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "rsg_trace_report": (_sz, [C.c_char_p, _sz, _int]),
     "rsg_context_enable_timing": (_int, [_vp, _int]),
     "rsg_context_last_timing": (_int, [_vp, C.c_char_p, C.POINTER(C.c_float), C.POINTER(_u64)]),
 }

@@ -129,6 +129,48 @@ static void h_tables(int logn, uint64_t p, std::vector<Twiddle> &fwd, std::vecto
   }
 }
 
+// ---- host-side API trace (RSG_TRACE=1): wall time and call count per C entry point, process-wide; rsg_trace_report() ----
+#include <chrono>
+namespace {
+struct TraceRow { uint64_t calls = 0; double ms = 0; };
+std::mutex g_trace_mu;
+std::map<std::string, TraceRow> g_trace;
+inline bool trace_on() {
+  static const bool on = getenv("RSG_TRACE") && atoi(getenv("RSG_TRACE")) != 0;
+  return on;
+}
+struct ApiTrace {
+  const char *name;
+  std::chrono::steady_clock::time_point t0;
+  explicit ApiTrace(const char *n) : name(n) { if (trace_on()) t0 = std::chrono::steady_clock::now(); }
+  ~ApiTrace() {
+    if (!trace_on()) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> g(g_trace_mu);
+    TraceRow &r = g_trace[name];
+    r.calls++;
+    r.ms += ms;
+  }
+};
+}  // namespace
+#define RSG_TRACE_CALL() ApiTrace rsg_api_trace_(__func__)
+extern "C" size_t rsg_trace_report(char *buf, size_t cap, int reset) {
+  std::lock_guard<std::mutex> g(g_trace_mu);
+  std::string out;
+  for (auto &kv : g_trace) {
+    char line[160];
+    snprintf(line, sizeof line, "%-28s %8llu calls %10.3f ms\n", kv.first.c_str(), (unsigned long long)kv.second.calls, kv.second.ms);
+    out += line;
+  }
+  if (buf && cap) {
+    const size_t k = std::min(cap - 1, out.size());
+    memcpy(buf, out.data(), k);
+    buf[k] = 0;
+  }
+  if (reset) g_trace.clear();
+  return out.size() + 1;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 struct TimingRec {
   std::string name;
@@ -416,6 +458,7 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
   cudaFree(c->d_plain); cudaFree(c->d_pntt); cudaFree(c->d_partial);
   cudaFree(c->d_term); cudaFree(c->d_pidx); cudaFree(c->d_eidx); cudaFree(c->d_flags); cudaFree(c->d_out_scratch);
   cudaFree(c->d_chunk); cudaFree(c->d_evals); cudaFree(c->d_wit); cudaFree(c->d_zk);
+  cudaFree(c->d_decode);
   cudaFree(c->d_probe); cudaFree(c->d_probe_carry); cudaFree(c->d_nz); cudaFree(c->d_exact); cudaFree(c->d_ip);
   for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -479,6 +522,7 @@ extern "C" int rsg_context_last_timing(rsg_context *c, const char *kernel, float
 // ------------------------------------------------------------------------------------------------------------
 // arenas
 extern "C" int rsg_crs_create(rsg_context *c, size_t n, rsg_crs **out) {
+  RSG_TRACE_CALL();
   if (!c || !out) return fail(RSG_ERR_STATE, "context not set");
   CUDA_TRY(cudaSetDevice(c->device));
   rsg_crs *r = new rsg_crs{c, n, nullptr};
@@ -490,6 +534,7 @@ extern "C" int rsg_crs_create(rsg_context *c, size_t n, rsg_crs **out) {
   return RSG_OK;
 }
 extern "C" int rsg_crs_upload(rsg_crs *r, size_t first, size_t count, const uint64_t *h) {
+  RSG_TRACE_CALL();
   if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "CRS range");
   rsg_context *c = r->ctx;
   CUDA_TRY(cudaMemcpyAsync(r->d + first * c->enc_words(), h, count * c->enc_words() * 8, cudaMemcpyHostToDevice, c->stream));
@@ -497,6 +542,7 @@ extern "C" int rsg_crs_upload(rsg_crs *r, size_t first, size_t count, const uint
   return RSG_OK;
 }
 extern "C" int rsg_crs_download(const rsg_crs *r, size_t first, size_t count, uint64_t *h) {
+  RSG_TRACE_CALL();
   if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "CRS range");
   rsg_context *c = r->ctx;
   CUDA_TRY(cudaMemcpyAsync(h, r->d + first * c->enc_words(), count * c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -518,6 +564,7 @@ extern "C" int rsg_crs_fill_uniform(rsg_crs *r, uint64_t seed) {
 }
 extern "C" uint64_t *rsg_crs_device_ptr(rsg_crs *r) { return r ? r->d : nullptr; }
 extern "C" void rsg_crs_destroy(rsg_crs *r) {
+  RSG_TRACE_CALL();
   if (!r) return;
   cudaStreamSynchronize(r->ctx->stream);
   cudaFree(r->d);
@@ -525,6 +572,7 @@ extern "C" void rsg_crs_destroy(rsg_crs *r) {
 }
 
 extern "C" int rsg_ringvec_create(rsg_context *c, size_t n, rsg_ringvec **out) {
+  RSG_TRACE_CALL();
   if (!c || !out) return fail(RSG_ERR_STATE, "context not set");
   CUDA_TRY(cudaSetDevice(c->device));
   rsg_ringvec *r = new rsg_ringvec{c, n, nullptr};
@@ -537,6 +585,7 @@ extern "C" int rsg_ringvec_create(rsg_context *c, size_t n, rsg_ringvec **out) {
   return RSG_OK;
 }
 extern "C" int rsg_ringvec_upload(rsg_ringvec *r, size_t first, size_t count, const uint64_t *h) {
+  RSG_TRACE_CALL();
   if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "ringvec range");
   rsg_context *c = r->ctx;
   CUDA_TRY(cudaMemcpyAsync(r->d + first * c->ring_words(), h, count * c->ring_words() * 8, cudaMemcpyHostToDevice, c->stream));
@@ -544,6 +593,7 @@ extern "C" int rsg_ringvec_upload(rsg_ringvec *r, size_t first, size_t count, co
   return RSG_OK;
 }
 extern "C" int rsg_ringvec_download(const rsg_ringvec *r, size_t first, size_t count, uint64_t *h) {
+  RSG_TRACE_CALL();
   if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "ringvec range");
   rsg_context *c = r->ctx;
   CUDA_TRY(cudaMemcpyAsync(h, r->d + first * c->ring_words(), count * c->ring_words() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -558,6 +608,7 @@ extern "C" int rsg_ringvec_fill_uniform(rsg_ringvec *r, uint64_t seed) {
 extern "C" uint64_t *rsg_ringvec_device_ptr(rsg_ringvec *r) { return r ? r->d : nullptr; }
 extern "C" size_t rsg_ringvec_size(const rsg_ringvec *r) { return r ? r->n : 0; }
 extern "C" void rsg_ringvec_destroy(rsg_ringvec *r) {
+  RSG_TRACE_CALL();
   if (!r) return;
   cudaStreamSynchronize(r->ctx->stream);
   if (r->owned) cudaFree(r->d);
@@ -572,6 +623,7 @@ extern "C" int rsg_ringvec_wrap(rsg_context *c, uint64_t *d_words, size_t n, rsg
 }
 
 extern "C" int rsg_ringvec_is_zero_prefix(const rsg_ringvec *r, size_t first, size_t count, uint8_t *h_flags) {
+  RSG_TRACE_CALL();
   if (!r || first + count > r->n || !h_flags) return fail(RSG_ERR_ARG, "ringvec range");
   if (!count) return RSG_OK;
   rsg_context *c = r->ctx;
@@ -596,6 +648,7 @@ static dim3 ring_grid(const rsg_context *c, size_t count) {
 }
 extern "C" int rsg_ring_binop(rsg_context *c, int op, const rsg_ringvec *a, size_t a_first, const rsg_ringvec *b, size_t b_first,
                               rsg_ringvec *out, size_t out_first, size_t count) {
+  RSG_TRACE_CALL();
   if (!c || op < 0 || op > 2) return fail(RSG_ERR_ARG, "bad operator");
   if (!ring_range(a, a_first, count) || !ring_range(b, b_first, count) || !ring_range(out, out_first, count)) return fail(RSG_ERR_ARG, "ringvec range");
   if (!count) return RSG_OK;
@@ -640,6 +693,7 @@ extern "C" int rsg_ring_negate(rsg_context *c, const rsg_ringvec *a, size_t a_fi
 }
 extern "C" int rsg_ring_invert(rsg_context *c, const rsg_ringvec *a, size_t a_first, rsg_ringvec *out, size_t out_first, size_t count,
                                uint8_t *h_ok) {
+  RSG_TRACE_CALL();
   if (!c) return fail(RSG_ERR_STATE, "context not set");
   if (!ring_range(a, a_first, count) || !ring_range(out, out_first, count)) return fail(RSG_ERR_ARG, "ringvec range");
   if (!count) return RSG_OK;
@@ -1187,6 +1241,7 @@ static int inner_product_impl(rsg_context *c, const rsg_crs *crs, size_t crs_fir
 }
 extern "C" int rsg_inner_product(rsg_context *c, const rsg_crs *crs, size_t crs_first, const rsg_ringvec *coeffs, size_t coeff_first,
                                  size_t count, const uint8_t *h_tags, uint64_t *h_out, uint64_t *d_out, size_t *n_used) {
+  RSG_TRACE_CALL();
   if (!crs || !coeffs) return fail(RSG_ERR_ARG, "null argument");
   if (crs_first + count > crs->n || coeff_first + count > coeffs->n) return fail(RSG_ERR_ARG, "range");
   return inner_product_impl(c, crs, crs_first, nullptr, coeffs, coeff_first, nullptr, count, h_tags, h_out, d_out, n_used);
@@ -1194,6 +1249,7 @@ extern "C" int rsg_inner_product(rsg_context *c, const rsg_crs *crs, size_t crs_
 extern "C" int rsg_inner_product_idx(rsg_context *c, const rsg_crs *crs, const uint32_t *h_crs_idx, const rsg_ringvec *coeffs,
                                      const uint32_t *h_coeff_idx, size_t count, const uint8_t *h_tags, uint64_t *h_out,
                                      uint64_t *d_out, size_t *n_used) {
+  RSG_TRACE_CALL();
   if (!h_crs_idx || !h_coeff_idx) return fail(RSG_ERR_ARG, "null index list");
   return inner_product_impl(c, crs, 0, h_crs_idx, coeffs, 0, h_coeff_idx, count, h_tags, h_out, d_out, n_used);
 }
@@ -1208,12 +1264,14 @@ extern "C" int rsg_enc_sum(rsg_context *c, const uint64_t *d_parts, size_t parts
   return RSG_OK;
 }
 extern "C" int rsg_enc_add(rsg_context *c, uint64_t *d_acc, const uint64_t *d_other) {
+  RSG_TRACE_CALL();
   if (!c || !d_acc || !d_other) return fail(RSG_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> g(c->mu);
   CUDA_TRY(cudaSetDevice(c->device));
   return enc_add_fix(c, d_acc, d_other);
 }
 extern "C" int rsg_crs_copy(rsg_crs *dst, size_t dst_first, const rsg_crs *src, size_t src_first, size_t count) {
+  RSG_TRACE_CALL();
   if (!dst || !src || dst->ctx != src->ctx) return fail(RSG_ERR_ARG, "null or foreign arena");
   if (dst_first + count > dst->n || src_first + count > src->n) return fail(RSG_ERR_ARG, "CRS range");
   rsg_context *c = dst->ctx;
@@ -1553,6 +1611,7 @@ static int interpolate_dev(rsg_context *c, size_t n, WitnessTables *wt, const ui
 
 extern "C" int rsg_interpolate(rsg_context *c, size_t n, size_t batch, const rsg_ringvec *y, size_t y_first, rsg_ringvec *out,
                                size_t out_first) {
+  RSG_TRACE_CALL();
   if (!c || !y || !out) return fail(RSG_ERR_ARG, "null argument");
   if (y_first + batch * n > y->n || out_first + batch * n > out->n) return fail(RSG_ERR_ARG, "range");
   std::lock_guard<std::mutex> g(c->mu);
@@ -1564,6 +1623,7 @@ extern "C" int rsg_interpolate(rsg_context *c, size_t n, size_t batch, const rsg
 }
 
 extern "C" int rsg_vanishing(rsg_context *c, size_t n, uint64_t *h_Z) {
+  RSG_TRACE_CALL();
   if (!c || !h_Z) return fail(RSG_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> g(c->mu);
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1648,6 +1708,7 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
 
 extern "C" int rsg_witness_map_zk(rsg_context *c, size_t n, const rsg_ringvec *evals, const uint64_t *h_d, rsg_ringvec *coeffs,
                                   rsg_ringvec *H) {
+  RSG_TRACE_CALL();
   if (!c || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
   if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
   std::lock_guard<std::mutex> g(c->mu);
@@ -1663,6 +1724,7 @@ extern "C" int rsg_witness_map_zk(rsg_context *c, size_t n, const rsg_ringvec *e
 }
 extern "C" int rsg_witness_map_r1cs(rsg_context *c, rsg_r1cs *r1cs, const rsg_ringvec *evals, const uint64_t *h_d, rsg_ringvec *coeffs,
                                     rsg_ringvec *H) {
+  RSG_TRACE_CALL();
   if (!c || !r1cs || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
   const size_t n = r1cs->n;
   if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
@@ -1678,6 +1740,7 @@ extern "C" int rsg_witness_map_r1cs(rsg_context *c, rsg_r1cs *r1cs, const rsg_ri
   return witness_map_dev(c, n, evals->d, coeffs->d, H->d, d_zk, r1cs);
 }
 extern "C" int rsg_witness_map_groth16(rsg_context *c, rsg_r1cs *r1cs, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H) {
+  RSG_TRACE_CALL();
   if (!c || !r1cs || !evals || !coeffs || !H) return fail(RSG_ERR_ARG, "null argument");
   const size_t n = r1cs->n;
   if (evals->n < 9 * n || coeffs->n < 6 * n || H->n < n + 1) return fail(RSG_ERR_ARG, "witness-map vector sizes");
@@ -1694,6 +1757,7 @@ extern "C" int rsg_witness_map(rsg_context *c, size_t n, const rsg_ringvec *eval
 
 extern "C" int rsg_r1cs_create(rsg_context *c, size_t n, size_t n_io, size_t n_aux, const uint32_t *h_row_ptr, const uint32_t *h_col,
                                const uint64_t *h_coeff, rsg_r1cs **out) {
+  RSG_TRACE_CALL();
   if (!c || !h_row_ptr || !out || !n) return fail(RSG_ERR_ARG, "null argument");
   const size_t nnz = h_row_ptr[3 * n];
   for (size_t t = 0; t < nnz; t++)
@@ -1725,6 +1789,7 @@ extern "C" int rsg_r1cs_create(rsg_context *c, size_t n, size_t n_io, size_t n_a
   return RSG_OK;
 }
 extern "C" void rsg_r1cs_destroy(rsg_r1cs *r) {
+  RSG_TRACE_CALL();
   if (!r) return;
   cudaStreamSynchronize(r->ctx->stream);
   cudaFree(r->d_row_ptr); cudaFree(r->d_col); cudaFree(r->d_coeff); cudaFree(r->d_cc);
@@ -1785,6 +1850,7 @@ static int get_decode_consts(rsg_context *c) {
 
 extern "C" int rsg_decode(rsg_context *c, const uint64_t *h_sk, const uint64_t *d_enc, const uint64_t *h_enc, size_t count,
                           uint64_t *h_ring, int32_t *h_budget) {
+  RSG_TRACE_CALL();
   if (!c || !h_sk || (!d_enc == !h_enc) || !h_ring) return fail(RSG_ERR_ARG, "null argument (exactly one of d_enc / h_enc)");
   if (!count) return RSG_OK;
   std::lock_guard<std::mutex> g(c->mu);
@@ -1850,6 +1916,7 @@ extern "C" int rsg_decode(rsg_context *c, const uint64_t *h_sk, const uint64_t *
 // instance map with evaluation (the O(m^2) step of setup and of every verification; instance.cuh)
 extern "C" int rsg_instance_map(rsg_context *c, rsg_r1cs *r, const rsg_ringvec *t, size_t t_first, rsg_ringvec *ABCt, rsg_ringvec *Ht,
                                 rsg_ringvec *Zt) {
+  RSG_TRACE_CALL();
   if (!c || !r || !t || !ABCt || !Ht || !Zt) return fail(RSG_ERR_ARG, "null argument");
   const size_t n = r->n, nv1 = r->n_io + r->n_aux + 1, W = c->ring_words();
   if (t_first >= t->n || ABCt->n < 3 * nv1 || Ht->n < n + 1 || Zt->n < 1) return fail(RSG_ERR_ARG, "instance-map vector sizes");
@@ -1924,6 +1991,7 @@ static int r1cs_eval_dev(rsg_context *c, const rsg_r1cs *r, const uint64_t *d_as
   return RSG_OK;
 }
 extern "C" int rsg_r1cs_evaluate(rsg_context *c, const rsg_r1cs *r, const rsg_ringvec *assignment, rsg_ringvec *evals) {
+  RSG_TRACE_CALL();
   if (!c || !r || !assignment || !evals) return fail(RSG_ERR_ARG, "null argument");
   if (assignment->n < r->n_io + r->n_aux || evals->n < 9 * r->n) return fail(RSG_ERR_ARG, "vector sizes");
   std::lock_guard<std::mutex> g(c->mu);
@@ -2071,6 +2139,7 @@ static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_gr
 extern "C" int rsg_groth16_lincombs(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
                                     const uint64_t *const d_vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
                                     size_t *n_used) {
+  RSG_TRACE_CALL();
   if (!c || !crs || !L || !d_vec) return fail(RSG_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> g(c->mu);
   CUDA_TRY(cudaSetDevice(c->device));
@@ -2085,6 +2154,7 @@ extern "C" int rsg_groth16_lincombs(rsg_context *c, const rsg_crs *crs, const rs
 extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg_crs *crs, const rsg_groth16_layout *L,
                                  rsg_ringvec *assignment, const uint64_t *h_assignment, const uint8_t *h_aux_kind, uint64_t *h_proof,
                                  uint64_t *d_proof, size_t *n_used) {
+  RSG_TRACE_CALL();
   if (!c || !r1cs || !crs || !L || !assignment) return fail(RSG_ERR_ARG, "null argument");
   const size_t n = r1cs->n, n_io = r1cs->n_io, n_aux = r1cs->n_aux, W = c->ring_words();
   if (assignment->n < n_io + n_aux) return fail(RSG_ERR_ARG, "assignment too short");
