@@ -1528,10 +1528,11 @@ static bool wf_lazy(const rsg_context *c) {
 }
 static unsigned wf_threads(const rsg_context *c, int sl, uint32_t S) {
   if (c->wf_threads >= 32 && c->wf_threads <= 512) return (unsigned)c->wf_threads & ~31u;
-  // a full-size pass has sl * S / 16 radix-16 items, the passes of the tree levels about half of that (n just above S/2
-  // leaves half of the buffer empty): one item per thread THERE, measured best on B200 (C4: 2 x 128 threads 3.32 ms for 8
-  // vectors, 2 x 256 3.49 ms, 4 x 512 3.82 ms; profiles/r1d_wf_tune.log) -- idle threads only lengthen the barriers
-  return (unsigned)std::min<size_t>(512, std::max<size_t>(64, (size_t)sl * S / 32));
+  // a full-size pass has sl * S / 16 radix-16 items: one thread per item, at most 256 threads.  Measured on B200
+  // (profiles/r1d_wf_tune.log, r1d/r1e_c5_sweep.json; ms for 8 vectors): S = 512: 64 thr 11.5 / 128 thr 17.2; S = 2048 x 2 slots:
+  // 128 thr 51.5 / 256 thr 46.7 (N_R = 2^15) and 3.32 / 3.49 (N_R = 2^11); S = 4096: 128 thr 186 / 256 thr 113; S = 8192: 256 thr
+  // 302 / 512 thr 542 -- idle threads lengthen the barriers, too few warps expose the latencies
+  return (unsigned)std::min<size_t>(256, std::max<size_t>(64, (size_t)sl * S / 16));
 }
 template <int SL>
 static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
