@@ -248,6 +248,8 @@ struct rsg_context {
   uint64_t exact_fallbacks = 0;     // how often a flagged prefix had to be resolved exactly
   DecodeConsts *d_dec = nullptr;    // constants of rsg_decode (decode.cuh), built on first use
   int Q_bits = 0;                   // bit length of Q = prod Q_l
+  uint64_t *d_wfB = nullptr;        // witness_fast scratch buffers in global memory (S = 16384)
+  size_t cap_wfB = 0;
   uint64_t *d_decode = nullptr;     // rsg_decode scratch
   size_t cap_decode = 0;
   uint64_t st_wf = 0, st_wd = 0;
@@ -458,7 +460,7 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
   cudaFree(c->d_plain); cudaFree(c->d_pntt); cudaFree(c->d_partial);
   cudaFree(c->d_term); cudaFree(c->d_pidx); cudaFree(c->d_eidx); cudaFree(c->d_flags); cudaFree(c->d_out_scratch);
   cudaFree(c->d_chunk); cudaFree(c->d_evals); cudaFree(c->d_wit); cudaFree(c->d_zk);
-  cudaFree(c->d_decode);
+  cudaFree(c->d_decode); cudaFree(c->d_wfB);
   cudaFree(c->d_probe); cudaFree(c->d_probe_carry); cudaFree(c->d_nz); cudaFree(c->d_exact); cudaFree(c->d_ip);
   for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1385,7 +1387,7 @@ static bool wf_supported(const rsg_context *c, size_t n) {
   uint32_t S, logS, wc;
   wf_shape(n, &S, &logS, &wc);
   if (S > c->N_E) return false;                                // no 2S-th root of unity guaranteed beyond N_E
-  if (wf_smem_bytes(S, 1) > 227 * 1024) return false;
+  if (wf_smem_bytes(S, 1, true) > 227 * 1024) return false;      // even with the scratch buffer in global memory
   for (uint64_t p : c->q)
     if (p >= (1ull << 61)) return false;
   return true;
@@ -1510,7 +1512,10 @@ static int ensure_fast_tables(rsg_context *c, size_t n, WitnessTables *wt) {
   return RSG_OK;
 }
 // slots per CTA: a power of two dividing the slot count; both polynomial buffers of a CTA stay below ~100 KiB (2 CTAs/SM)
+// S = 16384: two S-word buffers per slot exceed an SM's shared memory; the scratch buffer then lives in global memory (L2)
+static bool wf_b_global(uint32_t S) { return wf_smem_bytes(S, 1, false) > 227 * 1024; }
 static uint32_t wf_pick_sl(const rsg_context *c, uint32_t S, size_t nslots, size_t vectors) {
+  if (wf_b_global(S)) return 1;
   // measured on B200 at C4 (n = 1031, S = 2048): 2 slots per CTA, two to three CTAs per SM, beats 4 x 512 threads by 12 %
   uint32_t sl = 2;
   if (c->wf_sl > 0) sl = (uint32_t)c->wf_sl;
@@ -1537,11 +1542,18 @@ static unsigned wf_threads(const rsg_context *c, int sl, uint32_t S) {
 template <int SL>
 static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
                             size_t coef_stride, size_t limb_stride, size_t vec_stride) {
-  const size_t smem = wf_smem_bytes(ft.S, SL);
+  const bool b_global = wf_b_global(ft.S);
+  const size_t smem = wf_smem_bytes(ft.S, SL, b_global);
+  const dim3 grid((unsigned)(nslots / SL), (unsigned)(batch * c->L_R));
+  uint64_t *gB = nullptr;
+  if (b_global) {
+    int rc = ensure(c, &c->d_wfB, &c->cap_wfB, (size_t)grid.x * grid.y * SL * wf_slot_stride(ft.S));
+    if (rc) return rc;
+    gB = c->d_wfB;
+  }
   auto kern = wf_lazy(c) ? k_interp_fast<SL, true> : k_interp_fast<SL, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3((unsigned)(nslots / SL), (unsigned)(batch * c->L_R)), wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride,
-                                                                                                     limb_stride, vec_stride);
+  kern<<<grid, wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride, limb_stride, vec_stride, gB);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -1559,10 +1571,18 @@ static int launch_interp_fast(rsg_context *c, WitnessTables *wt, const uint64_t 
 }
 template <int SL>
 static int wf_launch_quotient(rsg_context *c, const FastTables &ft, const uint64_t *A, const uint64_t *B, uint64_t *H) {
-  const size_t smem = wf_smem_bytes(ft.S, SL);
+  const bool b_global = wf_b_global(ft.S);
+  const size_t smem = wf_smem_bytes(ft.S, SL, b_global);
+  const dim3 grid((unsigned)(c->N_R / SL), (unsigned)c->L_R);
+  uint64_t *gB = nullptr;
+  if (b_global) {
+    int rc = ensure(c, &c->d_wfB, &c->cap_wfB, (size_t)grid.x * grid.y * SL * wf_slot_stride(ft.S));
+    if (rc) return rc;
+    gB = c->d_wfB;
+  }
   auto kern = wf_lazy(c) ? k_quotient_fast<SL, true> : k_quotient_fast<SL, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3((unsigned)(c->N_R / SL), (unsigned)c->L_R), wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, A, B, H);
+  kern<<<grid, wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, A, B, H, gB);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }

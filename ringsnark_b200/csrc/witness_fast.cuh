@@ -257,8 +257,10 @@ __device__ __noinline__ void wf_level_fwd(uint64_t *buf, uint32_t stride, uint32
 
 __device__ __forceinline__ uint64_t canon2(uint64_t x, uint64_t p) { return x >= p ? x - p : x; }
 __host__ __device__ constexpr uint32_t wf_slot_stride(uint32_t S) { return padded_words(S) + 1; }   // odd: slots land on different banks
-__host__ __device__ constexpr size_t wf_smem_bytes(uint32_t S, uint32_t SL) {
-  return ((size_t)2 * SL * wf_slot_stride(S) + (size_t)SL * (2 * WF_WC_MAX + WF_HMAX)) * 8;
+// two polynomial buffers per slot (coefficients A, scratch / second operand B) + the small staging areas; with b_global the
+// B buffers live in a per-CTA global scratch range instead (S = 16384: one buffer is 136 KiB, two do not fit an SM)
+__host__ __device__ constexpr size_t wf_smem_bytes(uint32_t S, uint32_t SL, bool b_global = false) {
+  return ((size_t)(b_global ? 1 : 2) * SL * wf_slot_stride(S) + (size_t)SL * (2 * WF_WC_MAX + WF_HMAX)) * 8;
 }
 
 // wr[slot][k] = sum_{i+j = k+S} u_i * v_j for k < wc: the coefficients a product modulo x^S + 1 folds back (with a minus
@@ -372,7 +374,7 @@ __device__ __forceinline__ void wf_newton_to_monomial(uint64_t *A, uint64_t *B, 
 template <int SL, bool LAZY>
 __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict__ P, FastTables T, const uint64_t *__restrict__ Y,
                                                      uint64_t *__restrict__ C, size_t coef_stride, size_t limb_stride,
-                                                     size_t vec_stride) {
+                                                     size_t vec_stride, uint64_t *gB) {
   extern __shared__ uint64_t sm[];
   const uint32_t L_R = P->L_R;
   const uint32_t v = blockIdx.y / L_R, limb = blockIdx.y - v * L_R;
@@ -380,7 +382,10 @@ __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict
   const uint32_t slot0 = blockIdx.x * SL;
   const uint32_t n = T.n, S = T.S, wc = T.wc;
   const uint32_t stride = wf_slot_stride(S);
-  uint64_t *A = sm, *B = sm + (size_t)SL * stride, *wr = B + (size_t)SL * stride, *hs = wr + (size_t)SL * 2 * WF_WC_MAX;
+  // gB != nullptr: the scratch buffers of this CTA are a private range of global memory (barriers order global accesses
+  // within the block just as they order shared ones; the range stays in L2)
+  uint64_t *A = sm, *B = gB ? gB + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SL * stride : sm + (size_t)SL * stride;
+  uint64_t *wr = sm + (size_t)(gB ? 1 : 2) * SL * stride, *hs = wr + (size_t)SL * 2 * WF_WC_MAX;
   const ModConst mc = P->q[limb];
   const uint64_t p = mc.p;
   const Twiddle *fw = P->fwdq[limb], *iv = P->invq[limb];
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict
 // ([element][L_R][N_R]).  grid (N_R / SL, L_R); SL divides N_R
 template <int SL, bool LAZY>
 __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restrict__ P, FastTables T, const uint64_t *__restrict__ Ac,
-                                                       const uint64_t *__restrict__ Bc, uint64_t *__restrict__ H) {
+                                                       const uint64_t *__restrict__ Bc, uint64_t *__restrict__ H, uint64_t *gB) {
   extern __shared__ uint64_t sm[];
   const uint32_t N_R = P->N_R, L_R = P->L_R, limb = blockIdx.y;
   const size_t W = (size_t)N_R * L_R;
@@ -421,7 +426,8 @@ __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restri
   const uint32_t slot0 = blockIdx.x * SL;
   const uint32_t n = T.n, S = T.S, wc = T.wc;
   const uint32_t stride = wf_slot_stride(S);
-  uint64_t *A = sm, *B = sm + (size_t)SL * stride, *wr = B + (size_t)SL * stride, *wr2 = wr + (size_t)SL * WF_WC_MAX;
+  uint64_t *A = sm, *B = gB ? gB + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SL * stride : sm + (size_t)SL * stride;
+  uint64_t *wr = sm + (size_t)(gB ? 1 : 2) * SL * stride, *wr2 = wr + (size_t)SL * WF_WC_MAX;
   const ModConst mc = P->q[limb];
   const uint64_t p = mc.p;
   const Twiddle *fw = P->fwdq[limb], *iv = P->invq[limb];
@@ -436,7 +442,12 @@ __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restri
   if (wc) wf_wrapped(wr, A, n, B, nullptr, n, S, wc, stride, nsl, mc);
   __syncthreads();
   // A and B are adjacent: one batch of 2*SL transforms (slot index SL + s addresses B's slot s)
-  wf_ntt_fwd<LAZY>(A, stride, 2 * SL, 1, T.logS, 0, fw, p);
+  if (gB) {
+    wf_ntt_fwd<LAZY>(A, stride, nsl, 1, T.logS, 0, fw, p);
+    wf_ntt_fwd<LAZY>(B, stride, nsl, 1, T.logS, 0, fw, p);
+  } else {
+    wf_ntt_fwd<LAZY>(A, stride, 2 * SL, 1, T.logS, 0, fw, p);
+  }
   for (uint32_t t = threadIdx.x; t < S * nsl; t += blockDim.x) {
     const uint32_t s = t % nsl, i = t / nsl;
     uint64_t *w = A + s * stride + pad_idx(i);

@@ -697,3 +697,13 @@ def test_decode_noise_exhausted_and_zero():
         assert not ring.any() and int(budget[0, 0]) == math.prod(int(p) for p in cfg["Q"]).bit_length() - 1
     finally:
         ctx.close()
+
+
+def test_fast_witness_map_global_scratch(monkeypatch):
+    """n = 4200 needs transforms of size 16384: two such buffers per slot exceed an SM's shared memory, so the scratch buffer
+    of each CTA lives in global memory (witness_fast.cuh, gB).  Same residues as the dense path."""
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c4"]
+    res = _witness_both_modes(monkeypatch, 16, cfg["q"], cfg["N_E"], cfg["Q"], 4200, seed=42)
+    assert np.array_equal(res["dense"][0], res["fast"][0]), "interpolants differ"
+    assert np.array_equal(res["dense"][1], res["fast"][1]), "quotient differs"
