@@ -1387,7 +1387,7 @@ static bool wf_supported(const rsg_context *c, size_t n) {
   uint32_t S, logS, wc;
   wf_shape(n, &S, &logS, &wc);
   if (S > c->N_E) return false;                                // no 2S-th root of unity guaranteed beyond N_E
-  if (wf_smem_bytes(S, 1, true) > 227 * 1024) return false;      // even with the scratch buffer in global memory
+  if (S > 32768) return false;
   for (uint64_t p : c->q)
     if (p >= (1ull << 61)) return false;
   return true;
@@ -1513,7 +1513,8 @@ static int ensure_fast_tables(rsg_context *c, size_t n, WitnessTables *wt) {
 }
 // slots per CTA: a power of two dividing the slot count; both polynomial buffers of a CTA stay below ~100 KiB (2 CTAs/SM)
 // S = 16384: two S-word buffers per slot exceed an SM's shared memory; the scratch buffer then lives in global memory (L2)
-static bool wf_b_global(uint32_t S) { return wf_smem_bytes(S, 1, false) > 227 * 1024; }
+static int wf_n_global(uint32_t S) { return wf_smem_bytes(S, 1, 0) <= 227 * 1024 ? 0 : (wf_smem_bytes(S, 1, 1) <= 227 * 1024 ? 1 : 2); }
+static bool wf_b_global(uint32_t S) { return wf_n_global(S) > 0; }
 static uint32_t wf_pick_sl(const rsg_context *c, uint32_t S, size_t nslots, size_t vectors) {
   if (wf_b_global(S)) return 1;
   // measured on B200 at C4 (n = 1031, S = 2048): 2 slots per CTA, two to three CTAs per SM, beats 4 x 512 threads by 12 %
@@ -1542,18 +1543,20 @@ static unsigned wf_threads(const rsg_context *c, int sl, uint32_t S) {
 template <int SL>
 static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
                             size_t coef_stride, size_t limb_stride, size_t vec_stride) {
-  const bool b_global = wf_b_global(ft.S);
-  const size_t smem = wf_smem_bytes(ft.S, SL, b_global);
+  const int n_global = wf_n_global(ft.S);
+  const size_t smem = wf_smem_bytes(ft.S, SL, n_global);
   const dim3 grid((unsigned)(nslots / SL), (unsigned)(batch * c->L_R));
-  uint64_t *gB = nullptr;
-  if (b_global) {
-    int rc = ensure(c, &c->d_wfB, &c->cap_wfB, (size_t)grid.x * grid.y * SL * wf_slot_stride(ft.S));
+  uint64_t *gB = nullptr, *gA = nullptr;
+  if (n_global) {
+    const size_t per = (size_t)grid.x * grid.y * SL * wf_slot_stride(ft.S);
+    int rc = ensure(c, &c->d_wfB, &c->cap_wfB, per * n_global);
     if (rc) return rc;
     gB = c->d_wfB;
+    if (n_global == 2) gA = c->d_wfB + per;
   }
   auto kern = wf_lazy(c) ? k_interp_fast<SL, true> : k_interp_fast<SL, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride, limb_stride, vec_stride, gB);
+  kern<<<grid, wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, Y, C, coef_stride, limb_stride, vec_stride, gB, gA);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -1571,18 +1574,20 @@ static int launch_interp_fast(rsg_context *c, WitnessTables *wt, const uint64_t 
 }
 template <int SL>
 static int wf_launch_quotient(rsg_context *c, const FastTables &ft, const uint64_t *A, const uint64_t *B, uint64_t *H) {
-  const bool b_global = wf_b_global(ft.S);
-  const size_t smem = wf_smem_bytes(ft.S, SL, b_global);
+  const int n_global = wf_n_global(ft.S);
+  const size_t smem = wf_smem_bytes(ft.S, SL, n_global);
   const dim3 grid((unsigned)(c->N_R / SL), (unsigned)c->L_R);
-  uint64_t *gB = nullptr;
-  if (b_global) {
-    int rc = ensure(c, &c->d_wfB, &c->cap_wfB, (size_t)grid.x * grid.y * SL * wf_slot_stride(ft.S));
+  uint64_t *gB = nullptr, *gA = nullptr;
+  if (n_global) {
+    const size_t per = (size_t)grid.x * grid.y * SL * wf_slot_stride(ft.S);
+    int rc = ensure(c, &c->d_wfB, &c->cap_wfB, per * n_global);
     if (rc) return rc;
     gB = c->d_wfB;
+    if (n_global == 2) gA = c->d_wfB + per;
   }
   auto kern = wf_lazy(c) ? k_quotient_fast<SL, true> : k_quotient_fast<SL, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, A, B, H, gB);
+  kern<<<grid, wf_threads(c, SL, ft.S), smem, c->stream>>>(c->d_params, ft, A, B, H, gB, gA);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }

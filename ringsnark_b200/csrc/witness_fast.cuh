@@ -257,10 +257,11 @@ __device__ __noinline__ void wf_level_fwd(uint64_t *buf, uint32_t stride, uint32
 
 __device__ __forceinline__ uint64_t canon2(uint64_t x, uint64_t p) { return x >= p ? x - p : x; }
 __host__ __device__ constexpr uint32_t wf_slot_stride(uint32_t S) { return padded_words(S) + 1; }   // odd: slots land on different banks
-// two polynomial buffers per slot (coefficients A, scratch / second operand B) + the small staging areas; with b_global the
-// B buffers live in a per-CTA global scratch range instead (S = 16384: one buffer is 136 KiB, two do not fit an SM)
-__host__ __device__ constexpr size_t wf_smem_bytes(uint32_t S, uint32_t SL, bool b_global = false) {
-  return ((size_t)(b_global ? 1 : 2) * SL * wf_slot_stride(S) + (size_t)SL * (2 * WF_WC_MAX + WF_HMAX)) * 8;
+// two polynomial buffers per slot (coefficients A, scratch / second operand B) + the small staging areas; the
+// buffers that do not fit an SM live in a per-CTA global scratch range instead (S = 16384: one buffer is 136 KiB)
+// n_global = 1: the scratch buffers, = 2: both buffers (S = 32768: even one buffer is 272 KiB) live in global memory.
+__host__ __device__ constexpr size_t wf_smem_bytes(uint32_t S, uint32_t SL, int n_global = 0) {
+  return ((size_t)(2 - n_global) * SL * wf_slot_stride(S) + (size_t)SL * (2 * WF_WC_MAX + WF_HMAX)) * 8;
 }
 
 // wr[slot][k] = sum_{i+j = k+S} u_i * v_j for k < wc: the coefficients a product modulo x^S + 1 folds back (with a minus
@@ -374,7 +375,7 @@ __device__ __forceinline__ void wf_newton_to_monomial(uint64_t *A, uint64_t *B, 
 template <int SL, bool LAZY>
 __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict__ P, FastTables T, const uint64_t *__restrict__ Y,
                                                      uint64_t *__restrict__ C, size_t coef_stride, size_t limb_stride,
-                                                     size_t vec_stride, uint64_t *gB) {
+                                                     size_t vec_stride, uint64_t *gB, uint64_t *gA) {
   extern __shared__ uint64_t sm[];
   const uint32_t L_R = P->L_R;
   const uint32_t v = blockIdx.y / L_R, limb = blockIdx.y - v * L_R;
@@ -384,8 +385,9 @@ __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict
   const uint32_t stride = wf_slot_stride(S);
   // gB != nullptr: the scratch buffers of this CTA are a private range of global memory (barriers order global accesses
   // within the block just as they order shared ones; the range stays in L2)
-  uint64_t *A = sm, *B = gB ? gB + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SL * stride : sm + (size_t)SL * stride;
-  uint64_t *wr = sm + (size_t)(gB ? 1 : 2) * SL * stride, *hs = wr + (size_t)SL * 2 * WF_WC_MAX;
+  const size_t cta_off = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SL * stride;
+  uint64_t *A = gA ? gA + cta_off : sm, *B = gB ? gB + cta_off : sm + (size_t)SL * stride;
+  uint64_t *wr = sm + (size_t)((gA ? 0 : 1) + (gB ? 0 : 1)) * SL * stride, *hs = wr + (size_t)SL * 2 * WF_WC_MAX;
   const ModConst mc = P->q[limb];
   const uint64_t p = mc.p;
   const Twiddle *fw = P->fwdq[limb], *iv = P->invq[limb];
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(512) k_interp_fast(const DevParams *__restrict
 // ([element][L_R][N_R]).  grid (N_R / SL, L_R); SL divides N_R
 template <int SL, bool LAZY>
 __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restrict__ P, FastTables T, const uint64_t *__restrict__ Ac,
-                                                       const uint64_t *__restrict__ Bc, uint64_t *__restrict__ H, uint64_t *gB) {
+                                                       const uint64_t *__restrict__ Bc, uint64_t *__restrict__ H, uint64_t *gB, uint64_t *gA) {
   extern __shared__ uint64_t sm[];
   const uint32_t N_R = P->N_R, L_R = P->L_R, limb = blockIdx.y;
   const size_t W = (size_t)N_R * L_R;
@@ -426,8 +428,9 @@ __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restri
   const uint32_t slot0 = blockIdx.x * SL;
   const uint32_t n = T.n, S = T.S, wc = T.wc;
   const uint32_t stride = wf_slot_stride(S);
-  uint64_t *A = sm, *B = gB ? gB + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SL * stride : sm + (size_t)SL * stride;
-  uint64_t *wr = sm + (size_t)(gB ? 1 : 2) * SL * stride, *wr2 = wr + (size_t)SL * WF_WC_MAX;
+  const size_t cta_off = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SL * stride;
+  uint64_t *A = gA ? gA + cta_off : sm, *B = gB ? gB + cta_off : sm + (size_t)SL * stride;
+  uint64_t *wr = sm + (size_t)((gA ? 0 : 1) + (gB ? 0 : 1)) * SL * stride, *wr2 = wr + (size_t)SL * WF_WC_MAX;
   const ModConst mc = P->q[limb];
   const uint64_t p = mc.p;
   const Twiddle *fw = P->fwdq[limb], *iv = P->invq[limb];

@@ -707,3 +707,13 @@ def test_fast_witness_map_global_scratch(monkeypatch):
     res = _witness_both_modes(monkeypatch, 16, cfg["q"], cfg["N_E"], cfg["Q"], 4200, seed=42)
     assert np.array_equal(res["dense"][0], res["fast"][0]), "interpolants differ"
     assert np.array_equal(res["dense"][1], res["fast"][1]), "quotient differs"
+
+
+def test_fast_witness_map_all_global(monkeypatch):
+    """n = 8300 at N_E = 2^15 needs transforms of size 32768: neither buffer of a slot fits shared memory, both live in the
+    CTA's global scratch range.  Same residues as the dense path."""
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c5s"]
+    res = _witness_both_modes(monkeypatch, 16, cfg["q"], cfg["N_E"], cfg["Q"], 8300, seed=43)
+    assert np.array_equal(res["dense"][0], res["fast"][0]), "interpolants differ"
+    assert np.array_equal(res["dense"][1], res["fast"][1]), "quotient differs"

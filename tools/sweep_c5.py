@@ -4,7 +4,7 @@ one B200, with the parity checks the survey asks for at sizes the reference cann
   * lincomb: T terms over a synthetic uniform CRS; the first 8 terms are re-derived by the C oracle (multiply_plain + add);
     linearity over the whole range: ip(crs, a + b) == ip(crs, a) + ip(crs, b) is NOT an identity of the reference (the lift
     is centred per plaintext), so the check used is split invariance: ip over [0,T) == ip[0,T/2) + ip[T/2,T).
-  * witness map at n up to 4096 (quasi-linear path): the identity A(r) B(r) - C(r) = H(r) Z(r) at a random point r per
+  * witness map at n up to 8192 on 2^15 slots and 16384 on 2^11 slots (quasi-linear path): the identity A(r) B(r) - C(r) = H(r) Z(r) at a random point r per
     sampled slot, evaluated on the host with Python integers from the downloaded coefficients, and equality with the
     dense path at the n where the dense path is affordable.
 Writes one JSON object to stdout (and to argv[1] if given).  GPU only: the product path has no CPU fallback."""
@@ -81,7 +81,8 @@ def main():
 
     # ---- witness-map sweep (quasi-linear path), identity at a random point
     rng = np.random.default_rng(5)
-    for n in (256, 1024, 2048, 4096):
+    for n, N_R in ((256, N_R), (1024, N_R), (2048, N_R), (4096, N_R), (8192, N_R), (16384, 2048)):
+        # n = 16384 (both buffers of a slot in global memory) on 2048 slots only: at 2^15 slots its vectors need > 130 GB
         os.environ["RSG_WITNESS"] = "fast"
         ctx = rs.Context(N_R, q, N_E, Q)
         ev = ctx.ringvec(9 * n); ev.fill_uniform(100 + n)
@@ -115,7 +116,7 @@ def main():
             for k in range(n, -1, -1):
                 Z_r = (Z_r * r + Z[k]) % p
             ok = ok and (A_r * B_r - C_r) % p == H_r * Z_r % p
-        rec = {"n": n, "interp_ms_8_vectors": round(t_int, 3), "quotient_ms": round(t_quo, 3),
+        rec = {"n": n, "N_R": N_R, "interp_ms_8_vectors": round(t_int, 3), "quotient_ms": round(t_quo, 3),
                "witness_ms": round(t_int + t_quo, 3), "identity_AB_minus_C_eq_HZ": bool(ok),
                "Wref_modmuls": 44 * n * n * N_R * L_R,
                "Wref_Gmodmul_per_s": round(44 * n * n * N_R * L_R / (t_int + t_quo) / 1e6, 1)}
