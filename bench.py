@@ -70,7 +70,7 @@ def cpu_reference_sample(cfg_name, cfg, budget="default"):
     except Exception as ex:
         par = {"error": str(ex)[:200]}
     return {
-        "value": lincomb_ms + witness_ms, "unit": UNIT, "cores": 1, "kind": "reference", "host_cpus": ncpu,
+        "value": lincomb_ms + witness_ms, "unit": UNIT, "cores": 1, "kind": "reference", "host_cpus": ncpu, "extrapolated": True,
         "lincomb_ms_per_term": lin["seconds"] * 1e3 / t_terms, "lincomb_ms": lincomb_ms, "witness_ms": witness_ms,
         "parallel_best_effort": par,
         "sample": (f"unmodified reference (SEAL 4.1.1, g++ -O3), 1 thread (groth16::prover has no OpenMP): inner_product on "
@@ -79,24 +79,54 @@ def cpu_reference_sample(cfg_name, cfg, budget="default"):
     }
 
 
+REF_FULL_CASES = ("c1", "c3p", "c4s", "c4m", "c4")     # shapes oracle/cases.hpp knows: groth16::prover is run WHOLE on these
+
+
+def cpu_reference_full(cfg_name, cfg):
+    """ONE whole run of the unmodified reference's groth16::prover (zk_proof_systems/groth16/groth16.tcc:69-115) on this
+    box's host cores: witness map + six inner products + additions, synthetic CRS of the right shape, CRS generation
+    excluded.  Measured, not extrapolated (C4: 4-10 minutes on one core -- the reference prover is single-threaded)."""
+    if not os.path.exists(REF_HARNESS) or cfg_name not in REF_FULL_CASES:
+        return None
+    out = subprocess.run([REF_HARNESS, "time", cfg_name, "prover", "reps=1"], capture_output=True, text=True, timeout=3400)
+    if out.returncode != 0:
+        raise RuntimeError(out.stderr[-400:])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    return {"value": r["seconds"] * 1e3, "unit": UNIT, "cores": 1, "kind": "reference", "host_cpus": os.cpu_count() or 1,
+            "extrapolated": False,
+            "sample": (f"measured: one whole groth16::prover call of the unmodified reference (SEAL 4.1.1, g++ -O3) on the "
+                       f"{cfg_name} shape, n={r['n']}, io={r['io']}, aux={r['aux']}, 1 thread (groth16::prover has no OpenMP)")}
+
+
 def run_reference_arm(args, cfg_name, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.time()
-    vals, last = [], None
-    for _ in range(max(1, min(args.steps, 2))):      # each "step" is a fresh bounded sample
-        last = cpu_reference_sample(cfg_name, cfg, budget="small")
-        if last is None:
-            emit({"impl": "reference", "unavailable": "oracle/_ref/ref_harness not built (needs /root/reference at build time)"})
-            return
-        vals.append(last["value"])
-    v = statistics.median(vals)
-    last["value"] = v
+    if not os.path.exists(REF_HARNESS):
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_harness not built (needs /root/reference at build time)"})
+        return
+    last = None
+    if os.environ.get("RSG_REF_SAMPLE", "full") == "full":
+        try:
+            last = cpu_reference_full(cfg_name, cfg)    # one measured run, whatever --steps says: a step is 4-10 minutes
+        except Exception as ex:
+            sys.stderr.write(f"bench.py: full reference run failed ({ex}); falling back to the bounded sample\n")
+    steps_run = 1
+    if last is None:
+        vals = []
+        for _ in range(max(1, min(args.steps, 2))):      # each "step" is a fresh bounded sample
+            last = cpu_reference_sample(cfg_name, cfg, budget="small")
+            vals.append(last["value"])
+        last["value"] = statistics.median(vals)
+        last["extrapolated"] = True
+        steps_run = len(vals)
+    v = last["value"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_run,
+        "warmup": 0, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(cfg_name, cfg, args.gpus),
+        "extrapolated": bool(last.get("extrapolated")),
         "cpu_baseline": last,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
@@ -123,7 +153,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for ln in self.proc.stdout:
                 self.rows.append([x.strip() for x in ln.split(",")])
@@ -173,6 +203,98 @@ def make_assignment(cfg, row_ptr, col, coeff, seed):
     return x.astype(np.uint64).reshape(nv, len(q) * N_R)
 
 
+def proof_checksum(words):
+    """64-bit position-weighted checksum of the proof words: equal for every world size when the CRS is seeded by global
+    term index (Groth16ProvingKey.fill_synthetic)."""
+    import numpy as np
+    w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1)
+    k = (np.arange(w.size, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+    with np.errstate(over="ignore"):
+        return "%016x" % int(np.bitwise_xor.reduce(w * k))
+
+
+def parity_single(ctx, r1cs, pk, cfg, proof, rs, seed=7):
+    """Outside every timed region: is the proof the bench just timed the reference's proof?
+      witness_identity        A(r) B(r) - C(r) = H(r) Z(r) at a random point, on the device's witness-map output
+                              (r1cs_to_qrp.tcc:148-259), for a few slots of every ring limb;
+      oracle_subrange_terms   the lincomb kernels over a 32-term sub-range of every CRS vector (the same static launch
+                              sequence, through rsg_groth16_lincombs) against the C oracle (seal_ring.tcc:361-433);
+      shard_sum_equals_proof  the partial proofs of 4 term shards sum (mod Q_l) to the timed proof, word for word."""
+    import ctypes as C
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from ringsnark_b200.backend import Groth16Layout, NONE, groth16_shard_layout
+    from ringsnark_b200.capi import check
+    n, io, aux = cfg["n"], cfg["io"], cfg["aux"]
+    q, Q = [int(x) for x in cfg["q"]], [int(x) for x in cfg["Q"]]
+    N_R, L_R, W, E = cfg["N_R"], len(q), ctx.ring_words, ctx.enc_words
+    out = {}
+    evals = r1cs.evaluate(pk.assignment)
+    coeffs, H = ctx.ringvec(6 * n), ctx.ringvec(n + 1)
+    check(ctx.lib.rsg_witness_map_r1cs(ctx.h, r1cs.h, evals.h, None, coeffs.h, H.h))
+    cw = coeffs.download().reshape(6, n, L_R, N_R)      # A_io, B_io, C_io, A_mid, B_mid, C_mid
+    hw = H.download().reshape(n + 1, L_R, N_R)
+    rng = np.random.default_rng(seed)
+    ok = True
+    for j, p in enumerate(q):
+        for slot in [int(x) for x in rng.integers(0, N_R, size=4)]:
+            r = int(rng.integers(n + 1, p))
+
+            def ev(col):
+                acc = 0
+                for v in reversed(col):
+                    acc = (acc * r + int(v)) % p
+                return acc
+            A = (ev(cw[0, :, j, slot]) + ev(cw[3, :, j, slot])) % p
+            B = (ev(cw[1, :, j, slot]) + ev(cw[4, :, j, slot])) % p
+            Cc = (ev(cw[2, :, j, slot]) + ev(cw[5, :, j, slot])) % p
+            Z = 1
+            for i in range(n):
+                Z = Z * (r - i) % p
+            ok = ok and (A * B - Cc) % p == ev(hw[:, j, slot]) * Z % p
+    out["witness_identity"] = bool(ok)
+
+    base = {0: 0, 1: 3 * n, 2: n, 3: 4 * n}               # A_io, A_mid, B_io, B_mid inside `coeffs`
+    d_c, d_h, d_a = coeffs.device_ptr(), H.device_ptr(), pk.assignment.device_ptr() + io * W * 8
+
+    def lincombs(s, t, m, alpha):
+        """partial proof over s_pows[s0:s1), delta_ts[t0:t1), delta_mid[m0:m1) of the one arena"""
+        L = Groth16Layout()
+        L.s_pows_off, L.s_pows_lo, L.s_pows_hi = s[0], s[0], s[1]
+        L.delta_ts_off, L.delta_ts_lo, L.delta_ts_hi = n + 1 + t[0], t[0], t[1]
+        L.delta_mid_off, L.delta_mid_lo, L.delta_mid_hi = 2 * n + 2 + m[0], m[0], m[1]
+        L.alpha_idx, L.beta_idx = (2 * n + 2 + aux, 2 * n + 3 + aux) if alpha else (NONE, NONE)
+        ptrs = [d_c + (base[k] + s[0]) * W * 8 for k in range(4)] + [d_h + t[0] * W * 8, d_a + m[0] * W * 8]
+        return ctx.groth16_lincombs(pk.crs, L, n, aux, ptrs)[0]
+
+    T, a = min(32, n - 2, aux), min(100, max(0, n - 2 - 32))
+    part = lincombs((a, a + T), (a, a + T), (a, a + T), False)
+    tags = np.full(T, 2, dtype=np.uint8)
+    ipk = lambda crs_first, words: O.inner_product(pk.crs.download(crs_first, T), words, tags, N_R, L_R, q, ctx.N_E, ctx.L_E, Q)[0]
+    cw2 = cw.reshape(6, n, W)
+    aux_w = pk.assignment.download(io + a, T)
+    want = [O.enc_add(ipk(a, cw2[0, a:a + T]), ipk(a, cw2[3, a:a + T]), L_R, ctx.N_E, ctx.L_E, Q),
+            O.enc_add(ipk(a, cw2[1, a:a + T]), ipk(a, cw2[4, a:a + T]), L_R, ctx.N_E, ctx.L_E, Q),
+            O.enc_add(ipk(n + 1 + a, hw.reshape(n + 1, W)[a:a + T]), ipk(2 * n + 2 + a, aux_w), L_R, ctx.N_E, ctx.L_E, Q)]
+    out["oracle_subrange_terms"] = T if all(np.array_equal(part[e], want[e]) for e in range(3)) else 0
+
+    import torch
+    world = 4
+    parts = torch.zeros(world * 3 * E, dtype=torch.int64, device="cuda")
+    for r_ in range(world):
+        d = groth16_shard_layout(n, aux, r_, world)
+        p_ = lincombs((d["s_pows_lo"], d["s_pows_hi"]), (d["delta_ts_lo"], d["delta_ts_hi"]), (d["delta_mid_lo"], d["delta_mid_hi"]), r_ == 0)
+        parts[r_ * 3 * E:(r_ + 1) * 3 * E] = torch.from_numpy(p_.reshape(-1).view(np.int64))
+    total = torch.zeros(3 * E, dtype=torch.int64, device="cuda")
+    ctx.enc_sum(parts.data_ptr(), world, 3, total.data_ptr())
+    ctx.sync()
+    torch.cuda.synchronize()
+    out["shard_sum_equals_proof"] = bool(np.array_equal(total.cpu().numpy().view(np.uint64), np.asarray(proof).reshape(-1)))
+    out["ok"] = bool(out["witness_identity"] and out["oracle_subrange_terms"] and out["shard_sum_equals_proof"])
+    return out
+
+
 def run_gpu_arm(args, cfg_name, cfg):
     import numpy as np
     import torch
@@ -190,23 +312,29 @@ def run_gpu_arm(args, cfg_name, cfg):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, io, aux = cfg["n"], cfg["io"], cfg["aux"]
+    SEED = 0xB200
     stream = torch.cuda.Stream()
     row_ptr, col, coeff = synthetic_r1cs(n, io, aux, seed=1)
-    h_assign_np = make_assignment(cfg, row_ptr, col, coeff, seed=0xB200)
+    h_assign_np = make_assignment(cfg, row_ptr, col, coeff, seed=SEED)
     import ctypes as C
     from ringsnark_b200.capi import check
     single = world == 1
+
+    def make_single():
+        cx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"], device=local)
+        cx.set_stream(stream.cuda_stream)
+        r1 = rs.R1cs(cx, n, io, aux, row_ptr, col, coeff)
+        key = rs.Groth16ProvingKey(cx, r1, 0, 1)
+        key.fill_synthetic(SEED)            # the SAME CRS words for every world size (seeded by global term index)
+        key.assignment.upload(h_assign_np)
+        return cx, r1, key
+
     if single:
-        ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"], device=local)
-        ctx.set_stream(stream.cuda_stream)
+        ctx, r1cs, pk = make_single()
         ctxs = [ctx]
-        r1cs = rs.R1cs(ctx, n, io, aux, row_ptr, col, coeff)
-        pk = rs.Groth16ProvingKey(ctx, r1cs, 0, 1)
-        pk.crs.fill_uniform(0xB200)
         layout = pk.layout
         h_assign = torch.from_numpy(h_assign_np.view(np.int64)).pin_memory()
         h_proof = torch.empty(3 * ctx.enc_words, dtype=torch.int64).pin_memory()
-        pk.assignment.upload(h_assign_np)
         d_final = torch.zeros(3 * ctx.enc_words, dtype=torch.int64, device="cuda")
         h_assign_ptr = h_assign.numpy().view(np.uint64)
         h_proof_np = h_proof.numpy().view(np.uint64)
@@ -222,13 +350,17 @@ def run_gpu_arm(args, cfg_name, cfg):
                     C.c_void_p(h_proof_np.ctypes.data) if host_io else None,
                     C.c_void_p(d_final.data_ptr()), used))
                 return [int(u) for u in used]
+
+        def final_words():
+            torch.cuda.synchronize()
+            return d_final.cpu().numpy().view(np.uint64)
     else:
         # slot-sharded witness map -> all-to-all -> term-sharded lincombs -> all-gather + modular add (distributed.py)
         from ringsnark_b200.distributed import ShardedGroth16Prover, slot_shard
         sp = ShardedGroth16Prover(cfg, (row_ptr, col, coeff), rank, world, device=local, stream=stream.cuda_stream)
         ctx = sp.ctxP
         ctxs = [sp.ctxP, sp.ctxW]
-        sp.crs.fill_uniform(0xB200 + rank)
+        sp.fill_synthetic(SEED)
         layout = sp.layout
         h_shard = torch.from_numpy(slot_shard(h_assign_np, sp.L_R, sp.N_R, rank, world).view(np.int64)).pin_memory()
         h_aux = torch.from_numpy(np.ascontiguousarray(h_assign_np[io + sp.m_lo:io + sp.m_hi]).view(np.int64)).pin_memory()
@@ -251,6 +383,10 @@ def run_gpu_arm(args, cfg_name, cfg):
                     h_proof.copy_(sp.t_final, non_blocking=True)
                 return used
 
+        def final_words():
+            torch.cuda.synchronize()
+            return sp.t_final.cpu().numpy().view(np.uint64)
+
     def barrier():
         torch.cuda.synchronize()
         if dist:
@@ -265,20 +401,16 @@ def run_gpu_arm(args, cfg_name, cfg):
         return float(t.item())
 
     used = None
-    for _ in range(args.warmup):
+    for _ in range(max(3, args.warmup)):
         used = prove(False)
         prove(True)
     barrier()
 
-    # ---- timed region 1: device-resident inputs ("value"), with per-kernel event timing for the roofline
+    # ---- timed region 1: device-resident inputs ("value"); NO per-launch instrumentation inside it
     sampler = ClockSampler(local)
     sampler.start()
-    for cx in ctxs:
-        cx.enable_timing(True)
+    time.sleep(0.05)
     l0 = sum(cx.launch_count() for cx in ctxs)
-    stat_names = ("lincomb_terms", "lincomb_plain_terms", "lincomb_launches", "ntt_forward_polys", "ntt_inverse_polys",
-                  "merged_lincombs", "exact_fallbacks")
-    st0 = {k: sum(cx.stat(k) for cx in ctxs) for k in stat_names}
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -288,19 +420,6 @@ def run_gpu_arm(args, cfg_name, cfg):
     barrier()
     ms_dev = reduce_max(ev0.elapsed_time(ev1) / args.steps)
     launches = sum(cx.launch_count() for cx in ctxs) - l0
-    stats = {k: (sum(cx.stat(k) for cx in ctxs) - st0[k]) / args.steps for k in stat_names}   # per proof, this rank
-    kern = {}
-    for name in ("k_crs_lincomb", "k_lift_fwd_ntt", "k_encode_intt", "k_interp_fast", "k_quotient_fast", "k_modmat_interp",
-                 "k_modmat_divZ", "k_conv_top",
-                 "k_r1cs_eval", "k_enc_sum", "k_enc_add", "k_is_zero_prefix", "k_probe", "k_probe_eval", "k_full_from_parts",
-                 "k_c1_nonzero", "k_zero_transparent"):
-        ms = cnt = 0
-        for cx in ctxs:
-            m_, c_ = cx.timing(name)
-            ms, cnt = ms + m_, cnt + c_
-        kern[name] = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps}
-    for cx in ctxs:
-        cx.enable_timing(False)
 
     # ---- timed region 2: through the C ABI with host buffers ("e2e")
     barrier()
@@ -312,15 +431,65 @@ def run_gpu_arm(args, cfg_name, cfg):
     ms_e2e = reduce_max((time.perf_counter() - t0) * 1e3 / args.steps)
     clocks = sampler.stop()
 
-    # ---- roofline of the dominant kernel (k_crs_lincomb): algorithmic bytes per step / its device time per step
+    # ---- separate profiled pass (per-launch CUDA events on the launching streams): kernel breakdown + roofline inputs
+    psteps = max(1, min(args.steps, 5))
+    stat_names = ("lincomb_terms", "lincomb_plain_terms", "lincomb_launches", "ntt_forward_polys", "ntt_inverse_polys",
+                  "merged_lincombs", "exact_fallbacks", "fast_proofs", "fast_fallbacks")
+    for cx in ctxs:
+        cx.enable_timing(True)
+    st0 = {k: sum(cx.stat(k) for cx in ctxs) for k in stat_names}
+    barrier()
+    for _ in range(psteps):
+        prove(False)
+    barrier()
+    stats = {k: (sum(cx.stat(k) for cx in ctxs) - st0[k]) / psteps for k in stat_names}   # per proof, this rank
+    kern = {}
+    for name in ("k_crs_lincomb", "k_lift_fwd_ntt", "k_encode_intt", "k_interp_fast", "k_quotient_fast", "k_modmat_interp",
+                 "k_modmat_divZ", "k_conv_top", "k_centre_add",
+                 "k_r1cs_eval", "k_enc_sum", "k_enc_add", "k_is_zero_prefix", "k_probe", "k_probe_eval", "k_full_from_parts",
+                 "k_c1_nonzero", "k_zero_transparent"):
+        ms = cnt = 0
+        for cx in ctxs:
+            m_, c_ = cx.timing(name)
+            ms, cnt = ms + m_, cnt + c_
+        kern[name] = {"ms_per_step": ms / psteps, "launches_per_step": cnt / psteps}
+    for cx in ctxs:
+        cx.enable_timing(False)
+
+    # ---- parity, outside every timed region
+    proof_words = final_words()
+    checksum = proof_checksum(proof_words)
+    parity = None
+    if single:
+        try:
+            parity = parity_single(ctx, r1cs, pk, cfg, proof_words, rs)
+        except Exception as ex:
+            parity = {"ok": False, "error": repr(ex)[:300]}
+    else:
+        # rank 0 rebuilds the SAME key unsharded and proves on one GPU: the N-rank proof must equal it word for word
+        parity = {"ok": True}
+        if rank == 0:
+            try:
+                cx1, r11, pk1 = make_single()
+                one, _ = pk1.prove()
+                cx1.sync()
+                same = bool(np.array_equal(one.reshape(-1), proof_words))
+                parity = {"ok": same, "n_rank_proof_equals_1gpu_proof": same, "checksum_1gpu": proof_checksum(one)}
+                del pk1, r11
+                cx1.close()
+            except Exception as ex:
+                parity = {"ok": False, "error": repr(ex)[:300]}
+        barrier()
+
+    # ---- roofline of the HBM-bound kernel (k_crs_lincomb): algorithmic bytes per step / its device time per step
     L_R, L_E, N_E = len(cfg["q"]), len(cfg["Q"]), cfg["N_E"]
+    logN = N_E.bit_length() - 1
     row = L_R * L_E * N_E * 8
-    ones = [1 if layout.alpha_idx != rs.backend.NONE else 0, 1 if layout.beta_idx != rs.backend.NONE else 0, 0]
-    # alpha / beta are added by k_enc_add, every other term is streamed by k_crs_lincomb: 3 words per slot per term
-    # (2 CRS + 1 NTT-domain plaintext) + one 2-word output per launch
-    # counted by the library (rsg_context_stat): the merged A / B passes stream each s_pows element ONCE for io + mid
+    # every streamed term: 2 CRS words per slot, + 1 NTT-domain plaintext word unless the term is a bare ciphertext (alpha /
+    # beta / scalar-1 inputs), + one 2-word output per output encoding; counted by the library
     lin_launches = stats["lincomb_launches"]
-    alg_bytes = row * (2 * stats["lincomb_terms"] + stats["lincomb_plain_terms"] + 2 * lin_launches)
+    n_outputs = 3 if stats["fast_proofs"] else lin_launches
+    alg_bytes = row * (2 * stats["lincomb_terms"] + stats["lincomb_plain_terms"] + 2 * n_outputs)
     lin_ms = kern["k_crs_lincomb"]["ms_per_step"]
     peaks = {}
     try:
@@ -334,40 +503,62 @@ def run_gpu_arm(args, cfg_name, cfg):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "lincomb_traffic.json"))).get("dram_bytes_per_step")
     except Exception:
         pass
-    ntt_butterflies = (stats["ntt_forward_polys"] + stats["ntt_inverse_polys"]) * (N_E // 2) * (N_E.bit_length() - 1)
-    ntt_ms = kern["k_lift_fwd_ntt"]["ms_per_step"] + kern["k_encode_intt"]["ms_per_step"]
+    # NTT work actually done: forward transforms are dense; the batch-encode inverse transform skips the structurally zero
+    # quarters when N_R <= N_E / 2 (ntt.cuh: 12 levels at half width, level 1 as N/4 products, level 0 dense)
+    dense = (N_E // 2) * logN
+    inv_each = dense if (2 * cfg["N_R"] > N_E or logN > 14) else (logN - 2) * (N_E // 4) + N_E // 4 + N_E // 2
+    fwd_bfly = stats["ntt_forward_polys"] * dense
+    inv_bfly = stats["ntt_inverse_polys"] * inv_each
+    fwd_ms, inv_ms = kern["k_lift_fwd_ntt"]["ms_per_step"], kern["k_encode_intt"]["ms_per_step"]
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    pipe_peak = 148 * 64 * sm_max * 1e6          # lane-instructions / s of the FP64 (= of the IMAD) pipe at the maximum clock
+    f64 = all(int(x) < (1 << 49) for x in cfg["Q"]) and os.environ.get("RSG_NTT") != "int"
+    per_bfly = 10.0 if f64 else 13.0             # pipe instructions per butterfly incl. re-centring / corrections
+    ntt_ach = fwd_bfly * per_bfly / (fwd_ms * 1e-3) if fwd_ms else 0.0
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": ms_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": ms_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(cfg_name, cfg, world),
             "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(h_proof.numel() * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            # per launch: algorithmic bytes / average launch duration (the per-step sums divided by the launches per step);
-            # traffic = DRAM bytes per launch from the committed ncu --set full capture (profiles/lincomb_traffic.json)
+            "parity_checked": bool(parity and parity.get("ok")), "parity": parity, "proof_checksum": checksum,
+            # per launch: algorithmic bytes / average launch duration, both from the separate profiled pass (CUDA events on
+            # the launching stream); traffic = DRAM bytes per launch from the committed ncu --set full capture
             "roofline": {"kernel": "k_crs_lincomb", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None,
-                         # the committed capture is the 1-GPU workload; a sharded run has no capture of its own
                          "traffic": traffic / lin_launches if traffic and lin_launches and world == 1 else None,
                          "algorithmic_bytes_per_launch": alg_bytes / lin_launches if lin_launches else None,
                          "launch_ms": lin_ms / lin_launches if lin_launches else None, "launches_per_step": lin_launches,
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": lin_ms,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"},
+            "roofline_ntt": {"kernel": "k_lift_fwd_ntt_f64" if f64 else "k_lift_fwd_ntt", "bound": "fp64 pipe" if f64 else "int32 pipe",
+                             "achieved": ntt_ach / 1e12, "peak": pipe_peak / 1e12, "unit": "T lane-instr/s",
+                             "frac": ntt_ach / pipe_peak if pipe_peak else None, "instr_per_butterfly_model": per_bfly,
+                             "butterflies_per_step": fwd_bfly, "kernel_ms_per_step": fwd_ms,
+                             "peak_source": f"148 SM x 64 lanes x {sm_max:.0f} MHz (maximum SM clock)"},
             "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()},
-            "ntt": {"butterflies_per_step": ntt_butterflies, "gbutterflies_per_s": ntt_butterflies / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None},
+            "ntt": {"forward_butterflies_per_step": fwd_bfly, "inverse_butterflies_per_step": inv_bfly,
+                    "forward_gbutterflies_per_s": fwd_bfly / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
+                    "inverse_gbutterflies_per_s": inv_bfly / (inv_ms * 1e-3) / 1e9 if inv_ms else None},
             "terms_per_step": used,
             "work_per_step": stats,
+            "modes": {k: os.environ.get(k) for k in ("RSG_FAST", "RSG_LIN", "RSG_OVERLAP", "RSG_NTT", "RSG_LT_CTAS") if os.environ.get(k)},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_reference_sample(cfg_name, cfg)
+                cb = cpu_reference_sample(cfg_name, cfg)
+                line["cpu_baseline"] = cb
+                if cb and cb.get("parallel_best_effort"):
+                    line["cpu_baseline_parallel"] = cb["parallel_best_effort"]     # inner products on all host cores
             except Exception as ex:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"error": str(ex)[:200]}
         emit(line)
     if single:
+        del pk, r1cs
         ctx.close()
     else:
         sp.close()

@@ -71,6 +71,10 @@ int rsg_crs_create(rsg_context *ctx, size_t n_elems, rsg_crs **out);            
 int rsg_crs_upload(rsg_crs *crs, size_t first, size_t count, const uint64_t *h_words);       /* count encodings */
 int rsg_crs_download(const rsg_crs *crs, size_t first, size_t count, uint64_t *h_words);
 int rsg_crs_fill_uniform(rsg_crs *crs, uint64_t seed);   /* synthetic CRS: uniform residues, generated on device */
+/* The same stream of words for a SHARD: elements [first, first + count) of this arena receive what elements
+ * [virtual_first, virtual_first + count) of an arena filled by rsg_crs_fill_uniform(seed) hold -- every rank of a multi-GPU
+ * run then proves over the same CRS as the single-GPU run (bench.py checks the proofs word for word). */
+int rsg_crs_fill_uniform_at(rsg_crs *crs, size_t first, size_t count, uint64_t virtual_first, uint64_t seed);
 uint64_t *rsg_crs_device_ptr(rsg_crs *crs);
 void rsg_crs_destroy(rsg_crs *crs);
 

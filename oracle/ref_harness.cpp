@@ -263,12 +263,17 @@ static int cmd_dump(const std::string &name, const std::string &out, uint64_t se
   double t_prove = now_s() - t0;
   put_enc_vec(w, "proof", vector<E>{proof.A, proof.B, proof.C}, s.L_R, s.L_E, s.N_E);
   bool ok = false;
-  try {
-    ok = ringsnark::groth16::verifier(kp.vk, s.primary, proof);
-  } catch (const std::exception &ex) {
-    std::cerr << "verifier threw: " << ex.what() << std::endl;
+  // an EMPTY proof element (C2': n = 1, no auxiliary input -> C is the empty sum) makes the reference verifier index an empty
+  // ciphertext vector (seal_ring.tcc:435-445 only asserts the size): not runnable, recorded as verified = 2
+  const bool has_empty = proof.A.is_empty() || proof.B.is_empty() || proof.C.is_empty();
+  if (!has_empty) {
+    try {
+      ok = ringsnark::groth16::verifier(kp.vk, s.primary, proof);
+    } catch (const std::exception &ex) {
+      std::cerr << "verifier threw: " << ex.what() << std::endl;
+    }
   }
-  w.put1("verified", ok);
+  w.put1("verified", has_empty ? 2 : (uint64_t)ok);
 
   // (6) primitive-level known answers from SEAL itself for term 0 / ring limb 0 of (s_pows, A_mid-like poly):
   //     BatchEncoder::encode output (batchencoder.cpp:110-149) and transform_to_ntt_inplace output
@@ -526,7 +531,7 @@ static int cmd_time(const std::string &name, const std::string &what, int argc, 
 int main(int argc, char **argv) {
   try {
     if (argc >= 2 && std::string(argv[1]) == "list") {
-      for (const char *n : {"tiny_fast", "tiny_slow", "tiny_quirks", "tiny_full", "c1", "c3p", "c4s", "c4m", "c4"}) std::cout << n << "\n";
+      for (const char *n : {"tiny_fast", "tiny_slow", "tiny_quirks", "tiny_full", "c1", "c2p", "c3p", "c4s", "c4m", "c4"}) std::cout << n << "\n";
       return 0;
     }
     if (argc >= 4 && std::string(argv[1]) == "dump") {

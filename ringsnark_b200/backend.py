@@ -105,6 +105,20 @@ class Context:
                                          _ptr(out) if to_host else None, C.c_void_p(d_out) if d_out else None, C.byref(used)))
         return out, int(used.value)
 
+    def groth16_lincombs(self, crs, layout, n, n_aux, d_vec, aux_kind=None, to_host=True, d_proof=None):
+        """The six inner products + operator+= chain of groth16.tcc:89-112 over the term ranges of `layout` from
+        device-resident coefficient vectors: d_vec = 6 device pointers (A_io, A_mid, B_io, B_mid, H, aux), each at the
+        FIRST element of its range.  Returns (proof words [3][enc_words] or None, n_used[3])."""
+        out = np.empty((3, self.enc_words), dtype=np.uint64) if to_host else None
+        used = (C.c_size_t * 3)()
+        ptrs = (C.c_void_p * 6)(*[int(p) for p in d_vec])
+        if aux_kind is not None:
+            aux_kind = np.ascontiguousarray(aux_kind, dtype=np.uint8)
+        check(self.lib.rsg_groth16_lincombs(self.h, crs.h, C.byref(layout), n, n_aux, ptrs,
+                                            _ptr(aux_kind) if aux_kind is not None else None,
+                                            _ptr(out) if to_host else None, C.c_void_p(d_proof) if d_proof else None, used))
+        return out, [int(u) for u in used]
+
     def enc_sum(self, d_parts, parts, n_enc, d_out):
         """Modular sum of `parts` blocks of n_enc encodings (device pointers): runs after the NCCL all-gather."""
         check(self.lib.rsg_enc_sum(self.h, C.c_void_p(d_parts), parts, n_enc, C.c_void_p(d_out)))
@@ -230,6 +244,17 @@ class Groth16ProvingKey:
             self.crs.upload(alpha, L.alpha_idx)
             self.crs.upload(beta, L.beta_idx)
 
+    def fill_synthetic(self, seed):
+        """Synthetic CRS (uniform residues) that is the SAME key for every (rank, world): each shard range is filled with
+        the words the unsharded arena [s_pows (n+1) | delta_ts (n+1) | delta_mid (n_aux) | alpha | beta] would hold."""
+        L, n, aux = self.layout, self.r1cs.n, self.r1cs.n_aux
+        self.crs.fill_uniform_at(L.s_pows_off, L.s_pows_hi - L.s_pows_lo, L.s_pows_lo, seed)
+        self.crs.fill_uniform_at(L.delta_ts_off, L.delta_ts_hi - L.delta_ts_lo, n + 1 + L.delta_ts_lo, seed)
+        self.crs.fill_uniform_at(L.delta_mid_off, L.delta_mid_hi - L.delta_mid_lo, 2 * n + 2 + L.delta_mid_lo, seed)
+        if L.alpha_idx != NONE:
+            self.crs.fill_uniform_at(L.alpha_idx, 1, 2 * n + 2 + aux, seed)
+            self.crs.fill_uniform_at(L.beta_idx, 1, 2 * n + 3 + aux, seed)
+
     def save(self, path):
         """This rank's arena (its shard of every CRS vector, in layout order) -> one file (csrc/serialize.inl)."""
         from . import serialize
@@ -283,6 +308,10 @@ class Crs(_Arena):
 
     def fill_uniform(self, seed):
         check(self.ctx.lib.rsg_crs_fill_uniform(self.h, seed))
+
+    def fill_uniform_at(self, first, count, virtual_first, seed):
+        """Elements [first, first+count) := elements [virtual_first, ...) of an arena filled by fill_uniform(seed)."""
+        check(self.ctx.lib.rsg_crs_fill_uniform_at(self.h, first, count, virtual_first, seed))
 
     def device_ptr(self):
         return int(self.ctx.lib.rsg_crs_device_ptr(self.h) or 0)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "rsg_crs_upload": (_int, [_vp, _sz, _sz, _vp]),
     "rsg_crs_download": (_int, [_vp, _sz, _sz, _vp]),
     "rsg_crs_fill_uniform": (_int, [_vp, _u64]),
+    "rsg_crs_fill_uniform_at": (_int, [_vp, _sz, _sz, _u64, _u64]),
     "rsg_crs_device_ptr": (_vp, [_vp]),
     "rsg_crs_destroy": (None, [_vp]),
     "rsg_ringvec_create": (_int, [_vp, _sz, _pp]),

@@ -48,16 +48,14 @@ __device__ __forceinline__ uint64_t canon4(uint64_t x, uint64_t p) {  // [0,4p) 
 // LVL0 = 1 each CTA owns one HALF: the inverse transform's levels LOGN..1 stay inside a half (they are the independent
 // sub-transforms of the bit-reversed input), the CTA leaves its lazy values in `plain`, and k_intt_finish applies the
 // last level (pairs i, i + N/2) together with the N^-1 scaling SEAL merges into it (util/dwthandler.h:60-73).
-template <int LOGN, int LVL0>
-__global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict__ P, const uint64_t *__restrict__ ring,
-                                                     const uint32_t *__restrict__ elem_idx,
-                                                     uint64_t *__restrict__ plain) {
+// encode_body: the work of one CTA.  CENTRE: store the centred representative v - t for v >= ceil(t/2) (two's complement
+// int64) instead of the residue -- what the centred lift of evaluator.cpp:2220-2259 consumes (prover_fast.cuh).
+template <int LOGN, int LVL0, bool CENTRE>
+__device__ __forceinline__ void encode_body(const DevParams *__restrict__ P, const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
+                                            uint32_t j, uint32_t h) {
   extern __shared__ uint64_t sm[];
   constexpr uint32_t n = 1u << LOGN;
-  const uint32_t j = blockIdx.y, e = blockIdx.x >> LVL0, h = blockIdx.x & ((1u << LVL0) - 1);
-  const uint32_t N_R = P->N_R, L_R = P->L_R;
-  const uint32_t src_e = elem_idx ? elem_idx[e] : e;
-  const uint64_t *src = ring + ((size_t)src_e * L_R + j) * N_R;
+  const uint32_t N_R = P->N_R;
   const uint64_t p = P->q[j].p;
   for (uint32_t i = threadIdx.x; i < padded_words(n); i += blockDim.x) sm[i] = 0;
   __syncthreads();
@@ -71,20 +69,37 @@ __global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict
   // the split one hands [0, 2p) values to k_intt_finish
   if (LVL0 == 0 && 2 * N_R <= n) ntt_inverse_smem_q02<LOGN, true>(sm, P->invq[j], p);   // first matrix row only: half the input is zero
   else ntt_inverse_smem<LOGN, LVL0 == 0>(sm, P->invq[j], p, LVL0, h);
-  uint64_t *dst = plain + (((size_t)e * L_R + j) << (LOGN + LVL0)) + (size_t)h * n;
   if (LVL0 == 0) {
     const Twiddle invn = P->invN_q[j];
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = mul_shoup(sm[pad_idx(i)], invn, p);
+    const uint64_t thr = P->thr[j];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      uint64_t v = mul_shoup(sm[pad_idx(i)], invn, p);
+      if (CENTRE) v = v >= thr ? v - p : v;
+      dst[i] = v;
+    }
   } else {
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = sm[pad_idx(i)];   // lazy, < 2p
   }
+}
+
+template <int LOGN, int LVL0>
+__global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict__ P, const uint64_t *__restrict__ ring,
+                                                     const uint32_t *__restrict__ elem_idx,
+                                                     uint64_t *__restrict__ plain) {
+  const uint32_t j = blockIdx.y, e = blockIdx.x >> LVL0, h = blockIdx.x & ((1u << LVL0) - 1);
+  const uint32_t N_R = P->N_R, L_R = P->L_R;
+  const uint32_t src_e = elem_idx ? elem_idx[e] : e;
+  const uint64_t *src = ring + ((size_t)src_e * L_R + j) * N_R;
+  uint64_t *dst = plain + (((size_t)e * L_R + j) << (LOGN + LVL0)) + ((size_t)h << LOGN);
+  encode_body<LOGN, LVL0, false>(P, src, dst, j, h);
 }
 
 // Last Gentleman-Sande level of a split inverse transform + scaling: (x, y) -> ((x + y) N^-1, (x - y) w N^-1), canonical.
 // data: `polys` polynomials of 2*half words, values < 2p.  which_q: per-polynomial modulus index = poly % n_mod.
 __global__ void __launch_bounds__(256) k_intt_finish(uint64_t *__restrict__ data, uint32_t half, size_t polys,
                                                      const ModConst *__restrict__ mods, const Twiddle *__restrict__ invn,
-                                                     const Twiddle *__restrict__ invnw, uint32_t n_mod, uint32_t fixed_mod) {
+                                                     const Twiddle *__restrict__ invnw, uint32_t n_mod, uint32_t fixed_mod,
+                                                     uint32_t centre = 0) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= polys * half) return;
   const size_t poly = t / half;
@@ -95,8 +110,14 @@ __global__ void __launch_bounds__(256) k_intt_finish(uint64_t *__restrict__ data
   const uint64_t x = d[i], y = d[i + half];
   uint64_t s2 = x + y;
   s2 = s2 >= two_p ? s2 - two_p : s2;
-  d[i] = mul_shoup(s2, invn[mi], p);
-  d[i + half] = mul_shoup(x - y + two_p, invnw[mi], p);
+  uint64_t a = mul_shoup(s2, invn[mi], p), b = mul_shoup(x - y + two_p, invnw[mi], p);
+  if (centre) {   // centred representatives (two's complement), threshold ceil(p / 2) as context.cpp:329
+    const uint64_t thr = (p + 1) >> 1;
+    a = a >= thr ? a - p : a;
+    b = b >= thr ? b - p : b;
+  }
+  d[i] = a;
+  d[i + half] = b;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -109,12 +130,14 @@ __global__ void __launch_bounds__(256) k_intt_finish(uint64_t *__restrict__ data
 // NTT_Q is linear, so two inner products over the same CRS range share one transform and one CRS pass.
 template <int LOGN, int LVL0, bool LAZY>
 __global__ void __launch_bounds__(512) k_lift_fwd_ntt(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
-                                                      uint32_t is_signed, uint64_t *__restrict__ out) {
+                                                      uint32_t is_signed, uint64_t *__restrict__ out,
+                                                      const uint8_t *__restrict__ slot_skip = nullptr) {
   extern __shared__ uint64_t sm[];
   constexpr uint32_t n = 1u << LOGN;
   const uint32_t L_R = P->L_R, L_E = P->L_E;
   const uint32_t h = blockIdx.x & ((1u << LVL0) - 1), el = blockIdx.x >> LVL0;
   const uint32_t e = el / L_E, l = el - e * L_E, j = blockIdx.y;
+  if (slot_skip && slot_skip[e]) return;   // term skipped on the device (prover_fast.cuh): nothing reads this slot
   const ModConst m = P->Q[l];
   const uint64_t thr = P->thr[j], tm = P->tmodQ[j][l];
   const uint64_t *src = plain + (((size_t)e * L_R + j) << (LOGN + LVL0));
@@ -182,12 +205,14 @@ struct LiftIoF64 {
 
 template <int LOGN, int LVL0, bool SIGNED>
 __global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
-                                                          uint64_t *__restrict__ out) {
+                                                          uint64_t *__restrict__ out,
+                                                          const uint8_t *__restrict__ slot_skip = nullptr) {
   extern __shared__ double smf[];
   constexpr uint32_t n = 1u << LOGN;
   const uint32_t L_R = P->L_R, L_E = P->L_E;
   const uint32_t h = blockIdx.x & ((1u << LVL0) - 1), el = blockIdx.x >> LVL0;
   const uint32_t e = el / L_E, l = el - e * L_E, j = blockIdx.y;
+  if (slot_skip && slot_skip[e]) return;   // term skipped on the device (prover_fast.cuh): nothing reads this slot
   LiftIoF64<SIGNED> io;
   io.m = P->Q[l];
   io.pd = (double)io.m.p;
@@ -266,12 +291,15 @@ template <int UNROLL>
 __global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
                                                      const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
                                                      uint32_t n_terms, uint32_t terms_per_split,
-                                                     const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial) {
+                                                     const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
+                                                     const uint32_t *__restrict__ zoff = nullptr,
+                                                     const uint8_t *__restrict__ slot_skip = nullptr) {
   const uint32_t N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
   const uint32_t x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const uint32_t j = blockIdx.y / L_E, l = blockIdx.y - j * L_E;
-  const uint32_t t0 = blockIdx.z * terms_per_split;
-  const uint32_t t1 = min(n_terms, t0 + terms_per_split);
+  // zoff (prover_fast.cuh): split z sums the terms [zoff[z], zoff[z+1]) -- several outputs in one launch
+  const uint32_t t0 = zoff ? zoff[blockIdx.z] : blockIdx.z * terms_per_split;
+  const uint32_t t1 = zoff ? zoff[blockIdx.z + 1] : min(n_terms, t0 + terms_per_split);
   const size_t poly = (size_t)N_E;                       // words per (k, l) row
   const size_t ct_words = 2 * (size_t)L_E * poly;        // one ciphertext
   const size_t enc_words = (size_t)L_R * ct_words;       // one encoding
@@ -292,6 +320,10 @@ __global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict
       const uint32_t ci = __ldg(term + t + u);
       pi[u] = __ldg(pidx + t + u);
       const uint64_t *c = crs + (size_t)ci * enc_words + c_off;
+      if (slot_skip && pi[u] != 0xFFFFFFFFu && slot_skip[pi[u]]) {   // skipped on the device: contributes nothing
+        c0[u] = c1[u] = pp[u] = make_ulonglong2(0, 0);
+        continue;
+      }
       c0[u] = ld_stream(c);
       c1[u] = ld_stream(c + k_stride);
       if (pi[u] != 0xFFFFFFFFu) pp[u] = ld_stream(pntt + (size_t)pi[u] * p_stride + p_off);
@@ -307,6 +339,7 @@ __global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict
   }
   for (; t < t1; t++) {
     const uint32_t ci = __ldg(term + t), pi = __ldg(pidx + t);
+    if (slot_skip && pi != 0xFFFFFFFFu && slot_skip[pi]) continue;
     const uint64_t *c = crs + (size_t)ci * enc_words + c_off;
     const ulonglong2 c0 = ld_stream(c), c1 = ld_stream(c + k_stride);
     const ulonglong2 pp = pi != 0xFFFFFFFFu ? ld_stream(pntt + (size_t)pi * p_stride + p_off) : make_ulonglong2(1, 1);
@@ -498,12 +531,14 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 __global__ void __launch_bounds__(256) k_fill_uniform(uint64_t *__restrict__ dst, size_t words, uint32_t row_words,
                                                       const ModConst *__restrict__ mods, uint32_t n_mods,
-                                                      uint32_t rows_per_mod_cycle, uint64_t seed) {
+                                                      uint32_t rows_per_mod_cycle, uint64_t seed, uint64_t w_base = 0) {
+  // w_base: index of dst[0] in the virtual (unsharded) array -- a shard filled with its global offset holds the same
+  // words the whole array would (w_base must be a multiple of n_mods * rows_per_mod_cycle * row_words)
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride) {
     const size_t row = w / row_words;
     const uint64_t p = mods[(row / rows_per_mod_cycle) % n_mods].p;
-    dst[w] = __umul64hi(splitmix64(seed ^ (w * 0xD1342543DE82EF95ull)), p);
+    dst[w] = __umul64hi(splitmix64(seed ^ ((w + w_base) * 0xD1342543DE82EF95ull)), p);
   }
 }
 

@@ -1,0 +1,380 @@
+// The ringGroth16 prover's lincomb phase as ONE static launch sequence (groth16.tcc:89-112, seal_ring.tcc:361-433):
+// no host round trip between the witness map and the proof.  Which terms an inner product skips (RingElem::is_zero with
+// SealPoly::is_zero's prefix quirk, seal_ring.tcc:390-396 / poly_arith.cpp:147-153) is decided on the device and carried as
+// per-element flags that every later kernel honours, instead of compacted term lists built on the host; the
+// transparent-ciphertext rule (seal_ring.tcc:493-504) is watched by probe sums and any candidate sends the whole call to
+// the exact host-driven path of rsgpu.cu (which is what ran for every proof in round 1).
+//
+// Element ids: the prover's six coefficient vectors over this shard's term ranges, back to back
+//     [A_io (nS) | A_mid (nS) | B_io (nS) | B_mid (nS) | H (nH) | aux (nM)]
+// NTT slots (one centred plaintext polynomial each, [L_R][N_E] int64):
+//     [A merged (nS) | B merged (nS) | H (nH) | aux (nM)]
+// merged: centred(io) + centred(mid) -- the two inner products over the same s_pows range share one transform and one pass
+// over the CRS (see lincomb_merged in rsgpu.cu for the argument).
+#pragma once
+#include "kernels.cuh"
+
+namespace rsg {
+
+constexpr uint32_t FP_SKIP = 1;   // element flag: the reference skips this term
+constexpr uint32_t FP_ONE = 2;    // element flag: scalar 1 -- the ciphertext is taken unchanged (seal_ring.tcc:525-528)
+
+struct FastVec {
+  const uint64_t *base;   // address element 0 of the vector WOULD have (only [lo, lo + count) is read)
+  uint32_t lo, count, eid0;
+};
+struct FastTable {
+  FastVec vec[6];           // A_io, A_mid, B_io, B_mid, H, aux
+  uint32_t nS, nH, nM, n_elems, n_parts, n_slots;
+  uint32_t crs_off[6];      // arena index of the CRS element multiplying element 0 of each vector's range
+  const uint8_t *aux_kind;  // device copy of h_aux_kind (absolute auxiliary index), null = all RSG_AUX_POLY
+  uint32_t alpha_idx, beta_idx;   // arena index or 0xFFFFFFFF
+};
+// status words (device, copied back once per proof)
+constexpr int FPS_CANDIDATE = 0;   // a probe sum vanished somewhere: resolve on the exact path
+constexpr int FPS_COUNT0 = 1;      // [1..6]: summed terms per inner product
+constexpr int FPS_WORDS = 8;
+
+__device__ __forceinline__ void fast_locate(const FastTable &T, uint32_t eid, uint32_t &k, uint32_t &i) {
+  k = 0;
+#pragma unroll
+  for (int v = 1; v < 6; v++)
+    if (eid >= T.vec[v].eid0) k = v;
+  i = T.vec[k].lo + (eid - T.vec[k].eid0);
+}
+
+// elem_flag[eid] (FP_SKIP / FP_ONE), slot_skip of the H / aux slots, and the per-inner-product term counts.
+// grid (n_elems), 256 threads.
+__global__ void __launch_bounds__(256) k_term_flags(const DevParams *__restrict__ P, FastTable T, uint8_t *__restrict__ elem_flag,
+                                                    uint8_t *__restrict__ slot_skip, uint32_t *__restrict__ status) {
+  uint32_t k, i;
+  fast_locate(T, blockIdx.x, k, i);
+  const uint32_t W = P->N_R * P->L_R;
+  uint32_t kind = 0xFF;
+  if (k == 5 && T.aux_kind) kind = T.aux_kind[i];
+  uint32_t flag;
+  if (kind == 0xFF) {   // polynomial: bytes [0, W + 7) all zero  <=>  SealPoly::is_zero says "zero"
+    const uint64_t *src = T.vec[k].base + (size_t)i * W;
+    const uint32_t bytes = W + 7, full = min(bytes / 8, W), rem = bytes % 8;
+    uint32_t nz = 0;
+    for (uint32_t w = threadIdx.x; w < full; w += blockDim.x) nz |= (src[w] != 0);
+    if (threadIdx.x == 0 && rem && full < W) nz |= ((src[full] & ((1ull << (8 * rem)) - 1)) != 0);
+    flag = __syncthreads_or((int)nz) ? 0 : FP_SKIP;
+  } else {
+    flag = kind == 0 ? FP_SKIP : (kind == 1 ? FP_ONE : 0);   // RSG_TERM_SKIP / ONE / GENERAL
+  }
+  if (threadIdx.x == 0) {
+    elem_flag[blockIdx.x] = (uint8_t)flag;
+    if (blockIdx.x >= T.n_parts) slot_skip[2 * T.nS + (blockIdx.x - T.n_parts)] = flag ? 1 : 0;   // ONE: no plaintext either
+    if (!(flag & FP_SKIP)) atomicAdd(status + FPS_COUNT0 + k, 1u);
+  }
+}
+
+// Batch encode of every element that needs a plaintext, centred output.  Parts of the merged pairs go to `parts`
+// [n_parts][L_R][N_E], the H / aux elements straight to their NTT slot.  grid (n_elems << LVL0, L_R).
+template <int LOGN, int LVL0>
+__global__ void __launch_bounds__(512) k_encode_fast(const DevParams *__restrict__ P, FastTable T, const uint8_t *__restrict__ elem_flag,
+                                                     uint64_t *__restrict__ parts, uint64_t *__restrict__ nttsrc) {
+  const uint32_t eid = blockIdx.x >> LVL0, h = blockIdx.x & ((1u << LVL0) - 1), j = blockIdx.y;
+  if (elem_flag[eid]) return;
+  uint32_t k, i;
+  fast_locate(T, eid, k, i);
+  const uint32_t N_R = P->N_R, L_R = P->L_R;
+  const uint64_t *src = T.vec[k].base + ((size_t)i * L_R + j) * N_R;
+  uint64_t *poly = eid < T.n_parts ? parts + (((size_t)eid * L_R + j) << (LOGN + LVL0))
+                                   : nttsrc + (((size_t)(2 * T.nS + eid - T.n_parts) * L_R + j) << (LOGN + LVL0));
+  encode_body<LOGN, LVL0, true>(P, src, poly + ((size_t)h << LOGN), j, h);
+}
+
+// Merged slots: nttsrc[m] = parts[X] + parts[Y] (int64), a skipped part counts as absent; slot_skip[m] = both skipped.
+// grid (2 nS, L_R), 256 threads.
+__global__ void __launch_bounds__(256) k_centre_add_fast(const DevParams *__restrict__ P, FastTable T, const uint8_t *__restrict__ elem_flag,
+                                                         const uint64_t *__restrict__ parts, uint64_t *__restrict__ nttsrc,
+                                                         uint8_t *__restrict__ slot_skip) {
+  const uint32_t m = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_R = P->L_R, nS = T.nS;
+  const uint32_t ex = m < nS ? m : 2 * nS + (m - nS), ey = ex + nS;
+  const bool sx = elem_flag[ex] != 0, sy = elem_flag[ey] != 0;
+  if (threadIdx.x == 0 && j == 0) slot_skip[m] = sx && sy;
+  if (sx && sy) return;
+  const ulonglong2 *a = reinterpret_cast<const ulonglong2 *>(parts + ((size_t)ex * L_R + j) * N_E);
+  const ulonglong2 *b = reinterpret_cast<const ulonglong2 *>(parts + ((size_t)ey * L_R + j) * N_E);
+  ulonglong2 *o = reinterpret_cast<ulonglong2 *>(nttsrc + ((size_t)m * L_R + j) * N_E);
+  for (uint32_t i = threadIdx.x; i < N_E / 2; i += blockDim.x) {
+    ulonglong2 x = sx ? make_ulonglong2(0, 0) : a[i];
+    if (!sy) {
+      const ulonglong2 y = b[i];
+      x.x += y.x; x.y += y.y;
+    }
+    o[i] = x;
+  }
+}
+
+// pval[eid][j] = NTT_{Q_0}(lift(part))[0] = sum_i part_i psi^i mod Q_0 for the parts of the merged pairs (centred input):
+// the one NTT-domain word the probe needs per term.  grid (n_parts, L_R).
+__global__ void __launch_bounds__(256) k_probe_eval_fast(const DevParams *__restrict__ P, const uint8_t *__restrict__ elem_flag,
+                                                         const uint64_t *__restrict__ parts, const uint64_t *__restrict__ psi_pow,
+                                                         uint64_t *__restrict__ pval) {
+  __shared__ uint64_t part[8];
+  const uint32_t g = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_R = P->L_R;
+  if (elem_flag[g]) return;
+  const ModConst m = P->Q[0];
+  const uint64_t *src = parts + ((size_t)g * L_R + j) * N_E;
+  Acc192 acc;
+  acc.clear();
+  for (uint32_t i = threadIdx.x; i < N_E; i += blockDim.x) {
+    const long long sv = (long long)src[i];
+    const uint64_t r = reduce64((uint64_t)(sv < 0 ? -sv : sv), m);
+    acc.mac(sv < 0 ? neg_mod(r, m.p) : r, __ldg(psi_pow + i));
+  }
+  uint64_t s = acc.reduce(m);
+#pragma unroll
+  for (int off = 16; off; off >>= 1) s = add_mod(s, __shfl_xor_sync(0xFFFFFFFFu, s, off), m.p);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = part[0];
+    for (int w = 1; w < 8; w++) t = add_mod(t, part[w], m.p);
+    pval[(size_t)g * L_R + j] = t;
+  }
+}
+
+// Probe of every inner product at one fixed slot (k = 1, l = 0, x = 0; see k_probe in kernels.cuh): running sums of the c1
+// contributions over the non-skipped terms; status[FPS_CANDIDATE] is raised when a running sum vanishes at a term.
+// totals[k][j] receives the whole sum, prefix (nullable, [6][L_R][max(nS, nH, nM)] with stride `pstride`) every running sum.
+// grid (6, L_R), 256 threads.
+__global__ void __launch_bounds__(256) k_probe_fast(const DevParams *__restrict__ P, FastTable T, const uint64_t *__restrict__ crs,
+                                                    const uint8_t *__restrict__ elem_flag, const uint64_t *__restrict__ pval,
+                                                    const uint64_t *__restrict__ pntt, uint64_t *__restrict__ totals,
+                                                    uint64_t *__restrict__ prefix, uint32_t pstride, uint32_t *__restrict__ status) {
+  __shared__ uint64_t warp_tot[8];
+  __shared__ uint64_t run;
+  const uint32_t k = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
+  const ModConst m = P->Q[0];
+  const size_t ct_words = 2 * (size_t)L_E * N_E, enc_words = (size_t)L_R * ct_words;
+  const size_t c_off = (size_t)j * ct_words + (size_t)L_E * N_E;   // k = 1, l = 0, x = 0
+  const uint32_t n_terms = T.vec[k].count, eid0 = T.vec[k].eid0;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t cand = 0;
+  if (threadIdx.x == 0) run = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_terms; base += 256) {
+    const uint32_t t = base + threadIdx.x;
+    uint64_t v = 0;
+    bool live = false;
+    if (t < n_terms) {
+      const uint32_t eid = eid0 + t, fl = elem_flag[eid];
+      live = !(fl & FP_SKIP);
+      if (live) {
+        const uint64_t cw = crs[(size_t)(T.crs_off[k] + t) * enc_words + c_off];
+        if (fl & FP_ONE) v = cw;
+        else if (eid < T.n_parts) v = mul_mod(cw, pval[(size_t)eid * L_R + j], m);
+        else v = mul_mod(cw, pntt[(size_t)(2 * T.nS + eid - T.n_parts) * L_R * L_E * N_E + (size_t)j * L_E * N_E], m);
+      }
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, v, off);
+      if (lane >= off) v = add_mod(v, o, m.p);
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    uint64_t pre = run;
+    for (uint32_t w = 0; w < warp; w++) pre = add_mod(pre, warp_tot[w], m.p);
+    v = add_mod(v, pre, m.p);
+    if (live && v == 0) cand = 1;
+    if (prefix && t < n_terms) prefix[((size_t)k * L_R + j) * pstride + t] = live ? v : ~0ull;   // ~0: no term here
+    __syncthreads();
+    if (threadIdx.x == 255) run = v;
+    __syncthreads();
+  }
+  if (__syncthreads_or((int)cand) && threadIdx.x == 0) atomicOr(status + FPS_CANDIDATE, 1u);
+  if (threadIdx.x == 0) totals[k * L_R + j] = run;
+}
+// The operator+= chains of groth16.tcc:89-112 at the probe slot: A = (ip0 += ip1) += alpha, B = (ip2 += ip3) += beta,
+// C = ip4 += ip5; a vanishing intermediate or final sum is a transparent-ciphertext candidate.  One block of 32 threads.
+__global__ void k_probe_chain(const DevParams *__restrict__ P, FastTable T, const uint64_t *__restrict__ crs,
+                              const uint64_t *__restrict__ totals, uint32_t *__restrict__ status) {
+  const uint32_t L_R = P->L_R, L_E = P->L_E, N_E = P->N_E;
+  const uint64_t p = P->Q[0].p;
+  const size_t ct_words = 2 * (size_t)L_E * N_E, enc_words = (size_t)L_R * ct_words;
+  for (uint32_t w = threadIdx.x; w < 3 * L_R; w += blockDim.x) {
+    const uint32_t e = w / L_R, j = w - e * L_R, a = 2 * e, b = a + 1;
+    if (status[FPS_COUNT0 + a] + status[FPS_COUNT0 + b] == 0) continue;   // both inner products empty: nothing was added
+    uint64_t s = add_mod(totals[a * L_R + j], totals[b * L_R + j], p);
+    bool cand = s == 0;
+    const uint32_t extra = e == 0 ? T.alpha_idx : (e == 1 ? T.beta_idx : 0xFFFFFFFFu);
+    if (extra != 0xFFFFFFFFu) {
+      s = add_mod(s, crs[(size_t)extra * enc_words + (size_t)j * ct_words + (size_t)L_E * N_E], p);
+      cand = cand || s == 0;
+    }
+    if (cand) atomicOr(status + FPS_CANDIDATE, 1u);
+  }
+}
+
+// out[e][w] = sum over the splits z in [zr[e], zr[e+1]) of partial[z][w] mod Q_l(w), e < n_out.  grid (pairs / 256, n_out).
+__global__ void __launch_bounds__(256) k_enc_sum_ranges(const DevParams *__restrict__ P, const uint64_t *__restrict__ partial,
+                                                        const uint32_t *__restrict__ zr, uint64_t *__restrict__ out) {
+  const uint32_t N_E = P->N_E, L_E = P->L_E, e = blockIdx.y;
+  const size_t enc_words = (size_t)P->L_R * 2 * L_E * N_E;
+  const size_t w = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (w >= enc_words) return;
+  const uint64_t p = P->Q[(uint32_t)((w / N_E) % L_E)].p;
+  const uint32_t z0 = zr[e], z1 = zr[e + 1];
+  ulonglong2 acc = make_ulonglong2(0, 0);
+  for (uint32_t z = z0; z < z1; z++) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(partial + (size_t)z * enc_words + w);
+    acc.x = add_mod(acc.x, v.x, p);
+    acc.y = add_mod(acc.y, v.y, p);
+  }
+  *reinterpret_cast<ulonglong2 *>(out + (size_t)e * enc_words + w) = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_crs_lincomb_tma: the streaming multiply-accumulate of k_crs_lincomb fed by the TMA engine instead of by the threads'
+// own loads.  A persistent CTA (128 threads, <= 64 registers) owns a sequence of work items (split z, row (j, l), chunk of
+// LT_XC consecutive x); per term one elected thread issues three 1-D bulk copies (cp.async.bulk: c0 chunk, c1 chunk,
+// NTT-domain plaintext chunk, 2 KiB each) into a ring of LT_STAGES shared-memory stages guarded by full / empty
+// mbarriers; the 128 threads multiply-accumulate out of shared memory into 192-bit accumulators.  The bytes in flight
+// ((LT_STAGES - 1) x 6 KiB per CTA) live in shared memory, not in registers, so one such CTA fits on an SM NEXT TO a
+// forward-NTT CTA (FP64-bound, 136 KiB of shared memory) and the HBM-bound stream runs under the transforms of the next
+// group of terms.  Same sums, same single Barrett reduction per output word as k_crs_lincomb.
+constexpr int LT_XC = 256;
+constexpr int LT_STAGES = 12;
+constexpr int LT_THREADS = 128;
+constexpr size_t LT_SMEM = (size_t)LT_STAGES * 3 * LT_XC * 8 + 2 * LT_STAGES * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Walks the (item, term) sequence of one CTA; the producer and the consumers each advance their own copy.
+struct LtCursor {
+  uint32_t item, t, t1;
+  size_t c_off, p_off;
+};
+
+__global__ void __launch_bounds__(LT_THREADS) k_crs_lincomb_tma(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
+                                                                const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
+                                                                const uint32_t *__restrict__ zoff, uint32_t Z,
+                                                                const uint8_t *__restrict__ slot_skip,
+                                                                const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial) {
+  extern __shared__ __align__(128) uint64_t lt_sm[];
+  uint64_t *full = lt_sm + (size_t)LT_STAGES * 3 * LT_XC, *empty = full + LT_STAGES;
+  const uint32_t N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
+  const uint32_t rows = L_R * L_E, nxc = N_E / LT_XC, per_z = rows * nxc, n_items = Z * per_z;
+  const size_t poly = N_E, ct_words = 2 * (size_t)L_E * poly, enc_words = (size_t)L_R * ct_words;
+  const size_t k_stride = (size_t)L_E * poly, p_stride = (size_t)L_R * L_E * poly;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LT_STAGES; s++) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, LT_THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto open_item = [&](LtCursor &c) {   // c.item < n_items
+    const uint32_t z = c.item / per_z, rem = c.item - z * per_z, row = rem / nxc, xc = rem - row * nxc;
+    const uint32_t j = row / L_E, l = row - j * L_E;
+    c.c_off = (size_t)j * ct_words + (size_t)l * poly + (size_t)xc * LT_XC;
+    c.p_off = ((size_t)j * L_E + l) * poly + (size_t)xc * LT_XC;
+    c.t = zoff[z];
+    c.t1 = zoff[z + 1];
+  };
+  auto skipped = [&](uint32_t t) {
+    const uint32_t pi = __ldg(pidx + t);
+    return slot_skip && pi != 0xFFFFFFFFu && slot_skip[pi];
+  };
+
+  // ---- producer state (thread 0 only)
+  LtCursor pc;
+  pc.item = blockIdx.x;
+  pc.t = pc.t1 = 0;
+  bool p_open = false;
+  uint32_t p_fill = 0;   // stages filled so far
+  auto produce = [&]() {   // fetch the next live term of this CTA's sequence into stage p_fill % LT_STAGES
+    for (;;) {
+      if (!p_open) {
+        if (pc.item >= n_items) return;
+        open_item(pc);
+        p_open = true;
+      }
+      while (pc.t < pc.t1 && skipped(pc.t)) pc.t++;
+      if (pc.t < pc.t1) break;
+      pc.item += gridDim.x;
+      p_open = false;
+    }
+    const uint32_t s = p_fill % LT_STAGES, use = p_fill / LT_STAGES;
+    if (use) mbar_wait(empty + s, (use - 1) & 1);
+    const uint32_t ci = __ldg(term + pc.t), pi = __ldg(pidx + pc.t);
+    uint64_t *dst = lt_sm + (size_t)s * 3 * LT_XC;
+    const uint64_t *c = crs + (size_t)ci * enc_words + pc.c_off;
+    const uint32_t row_bytes = LT_XC * 8;
+    mbar_expect_tx(full + s, pi != 0xFFFFFFFFu ? 3 * row_bytes : 2 * row_bytes);
+    bulk_g2s(dst, c, row_bytes, full + s);
+    bulk_g2s(dst + LT_XC, c + k_stride, row_bytes, full + s);
+    if (pi != 0xFFFFFFFFu) bulk_g2s(dst + 2 * LT_XC, pntt + (size_t)pi * p_stride + pc.p_off, row_bytes, full + s);
+    p_fill++;
+    pc.t++;
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < LT_STAGES - 1; s++) produce();
+
+  // ---- consumers (all threads)
+  uint32_t c_use = 0;   // stages consumed so far
+  LtCursor cc;
+  for (cc.item = blockIdx.x; cc.item < n_items; cc.item += gridDim.x) {
+    open_item(cc);
+    Acc192 a00, a01, a10, a11;
+    a00.clear(); a01.clear(); a10.clear(); a11.clear();
+    for (; cc.t < cc.t1; cc.t++) {
+      if (skipped(cc.t)) continue;
+      if (threadIdx.x == 0) produce();   // refills the stage everybody left one term ago
+      const uint32_t s = c_use % LT_STAGES;
+      mbar_wait(full + s, (c_use / LT_STAGES) & 1);
+      const uint64_t *st = lt_sm + (size_t)s * 3 * LT_XC + 2 * threadIdx.x;
+      const ulonglong2 c0 = *reinterpret_cast<const ulonglong2 *>(st);
+      const ulonglong2 c1 = *reinterpret_cast<const ulonglong2 *>(st + LT_XC);
+      ulonglong2 pp = make_ulonglong2(1, 1);
+      if (__ldg(pidx + cc.t) != 0xFFFFFFFFu) pp = *reinterpret_cast<const ulonglong2 *>(st + 2 * LT_XC);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(empty + s);
+      c_use++;
+      a00.mac(c0.x, pp.x);
+      a01.mac(c0.y, pp.y);
+      a10.mac(c1.x, pp.x);
+      a11.mac(c1.y, pp.y);
+    }
+    const uint32_t z = cc.item / per_z, row = (cc.item - z * per_z) / nxc, l = row % L_E;
+    const ModConst m = P->Q[l];
+    uint64_t *o = partial + (size_t)z * enc_words + cc.c_off + 2 * threadIdx.x;
+    *reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(a00.reduce(m), a01.reduce(m));
+    *reinterpret_cast<ulonglong2 *>(o + k_stride) = make_ulonglong2(a10.reduce(m), a11.reduce(m));
+  }
+}
+
+}  // namespace rsg

@@ -18,6 +18,7 @@
 #include "instance.cuh"
 #include "decode.cuh"
 #include "ringops.cuh"
+#include "prover_fast.cuh"
 
 using namespace rsg;
 typedef unsigned __int128 u128;
@@ -172,8 +173,8 @@ extern "C" size_t rsg_trace_report(char *buf, size_t cap, int reset) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-struct TimingRec {
-  std::string name;
+struct TimingRec {   // pooled: the events of a record are created once and reused by later timed passes
+  const char *name;
   cudaEvent_t a, b;
 };
 
@@ -203,7 +204,8 @@ struct rsg_context {
   std::mutex mu;
   uint64_t launches = 0;
   bool timing = false;
-  std::vector<TimingRec> recs;
+  std::vector<TimingRec> recs;      // event pool; the first n_recs entries belong to the current timed pass
+  size_t n_recs = 0;
   std::map<size_t, WitnessTables> wit;
   std::vector<std::vector<uint64_t>> h_fwdq;   // host copy of the forward twiddles mod q_j (witness_fast tables)
   int witness_mode = 0;             // 0 = auto, 1 = dense (RSG_WITNESS=dense), 2 = quasi-linear wherever it applies (RSG_WITNESS=fast)
@@ -225,7 +227,7 @@ struct rsg_context {
   size_t cap_chunk = 0;
   uint64_t *d_evals = nullptr, *d_wit = nullptr;   // prover scratch: 9n evaluations; [6n coeffs | n+1 H]
   size_t cap_evals = 0, cap_wit = 0;
-  size_t pntt_budget_words = (size_t)4 << 27;      // 4 GiB of NTT-domain plaintexts per chunk
+  size_t pntt_budget_words = (size_t)8 << 27;      // 8 GiB of NTT-domain plaintexts per chunk
   uint8_t *d_flags = nullptr;
   size_t cap_flags = 0;
   uint64_t *d_zk = nullptr;         // d1, d2, d3 of the zero-knowledge witness map
@@ -254,6 +256,23 @@ struct rsg_context {
   size_t cap_decode = 0;
   uint64_t st_wf = 0, st_wd = 0;
   uint64_t st_lin_terms = 0, st_lin_plain = 0, st_lin_launches = 0, st_fwd_polys = 0, st_inv_polys = 0, st_merged = 0;
+  // ---- static-plan prover (prover_fast.cuh)
+  int fast_mode = 1;                // RSG_FAST=0: always the host-driven exact path
+  int lin_mode = 0;                 // RSG_LIN=tma: k_crs_lincomb_tma instead of k_crs_lincomb (0 = ldg, 1 = tma)
+  int lt_ctas = 2;                  // RSG_LT_CTAS: persistent CTAs per SM of k_crs_lincomb_tma
+  int overlap_mode = 0;             // RSG_OVERLAP=1: lincomb of one term group on a second stream under the next group's NTTs
+  int fast_splits = 0;              // RSG_FAST_SPLITS: number of term chunks of the one-launch lincomb (0 = auto)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_phase[8] = {};     // NTT group done (stream -> stream2)
+  cudaEvent_t ev_join = nullptr;    // stream2 -> stream
+  struct FastPlan *fplan = nullptr; // cached index arrays of the last layout
+  uint8_t *d_fp_flags = nullptr;    // [n_elems elem_flag | n_slots slot_skip]
+  size_t cap_fp_flags = 0;
+  uint64_t *d_fp_parts = nullptr, *d_fp_nttsrc = nullptr;
+  size_t cap_fp_parts = 0, cap_fp_nttsrc = 0;
+  uint64_t *d_fp_totals = nullptr;  // [6][MAX_LR] probe totals
+  uint32_t *d_fp_status = nullptr, *h_fp_status = nullptr;   // FPS_WORDS device words + pinned host mirror
+  uint64_t st_fast = 0, st_fast_fallback = 0;
   bool f64_ntt = false;             // every Q_l < 2^49: forward NTTs of the plaintext pipeline run on the FP64 pipe
   int ntt_mode = 0;                 // 0 = auto; RSG_NTT=int forces the integer kernel
   size_t enc_words() const { return L_R * 2 * L_E * N_E; }
@@ -288,18 +307,27 @@ struct LaunchScope {   // counts launches and optionally brackets them with even
   rsg_context *c;
   const char *name;
   cudaEvent_t a = nullptr, b = nullptr;
-  LaunchScope(rsg_context *ctx, const char *nm) : c(ctx), name(nm) {
+  cudaStream_t st;
+  LaunchScope(rsg_context *ctx, const char *nm, cudaStream_t on = nullptr) : c(ctx), name(nm), st(on ? on : ctx->stream) {
     c->launches++;
     if (c->timing) {
-      cudaEventCreate(&a);
-      cudaEventCreate(&b);
-      cudaEventRecord(a, c->stream);
+      if (c->n_recs == c->recs.size()) {
+        TimingRec r{nm, nullptr, nullptr};
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        c->recs.push_back(r);
+      }
+      TimingRec &r = c->recs[c->n_recs];
+      r.name = nm;
+      a = r.a;
+      b = r.b;
+      cudaEventRecord(a, st);
     }
   }
   ~LaunchScope() {
-    if (c->timing) {
-      cudaEventRecord(b, c->stream);
-      c->recs.push_back({name, a, b});
+    if (c->timing && a) {
+      cudaEventRecord(b, st);
+      c->n_recs++;
     }
   }
 };
@@ -439,6 +467,11 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
     if ((rc = upload_vec(c, pw, &c->d_psi_pow))) return rc;
   }
   if (const char *m = getenv("RSG_MERGE")) c->merge_mode = atoi(m);
+  if (const char *m = getenv("RSG_FAST")) c->fast_mode = atoi(m);
+  if (const char *m = getenv("RSG_LIN")) c->lin_mode = !strcmp(m, "tma") ? 1 : 0;
+  if (const char *m = getenv("RSG_LT_CTAS")) c->lt_ctas = std::max(1, atoi(m));
+  if (const char *m = getenv("RSG_OVERLAP")) c->overlap_mode = atoi(m);
+  if (const char *m = getenv("RSG_FAST_SPLITS")) c->fast_splits = atoi(m);
   if (const char *m = getenv("RSG_WITNESS")) c->witness_mode = !strcmp(m, "dense") ? 1 : (!strcmp(m, "fast") ? 2 : 0);
   if (const char *m = getenv("RSG_WF_SL")) c->wf_sl = atoi(m);
   if (const char *m = getenv("RSG_LIN_SPLITS")) c->lin_splits = atoi(m);
@@ -451,6 +484,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   return RSG_OK;
 }
 
+static void fast_release(rsg_context *c);
 extern "C" void rsg_context_destroy(rsg_context *c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -463,6 +497,7 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
   cudaFree(c->d_decode); cudaFree(c->d_wfB);
   cudaFree(c->d_probe); cudaFree(c->d_probe_carry); cudaFree(c->d_nz); cudaFree(c->d_exact); cudaFree(c->d_ip);
   for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  fast_release(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -492,30 +527,37 @@ extern "C" uint64_t rsg_context_stat(const rsg_context *c, const char *name) {
   if (n == "exact_fallbacks") return c->exact_fallbacks;
   if (n == "witness_fast_launches") return c->st_wf;      // k_interp_fast / k_quotient_fast launches
   if (n == "witness_dense_launches") return c->st_wd;     // k_modmat* / k_conv_top launches
+  if (n == "fast_proofs") return c->st_fast;              // lincomb phases run as the static launch sequence (prover_fast.cuh)
+  if (n == "fast_fallbacks") return c->st_fast_fallback;  // ... of which a probe candidate sent to the exact path
   return 0;
 }
 extern "C" int rsg_context_enable_timing(rsg_context *c, int on) {
   if (!c) return fail(RSG_ERR_STATE, "context not set");
   std::lock_guard<std::mutex> g(c->mu);
+  cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-  c->recs.clear();
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  c->n_recs = 0;   // the pooled events are reused
   c->timing = on != 0;
   return RSG_OK;
 }
 extern "C" int rsg_context_last_timing(rsg_context *c, const char *kernel, float *ms, uint64_t *launches) {
   if (!c) return fail(RSG_ERR_STATE, "context not set");
   std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->stream2) CUDA_TRY(cudaStreamSynchronize(c->stream2));
   float total = 0;
   uint64_t n = 0;
-  for (auto &r : c->recs)
-    if (!kernel || r.name == kernel) {
+  for (size_t i = 0; i < c->n_recs; i++) {
+    const TimingRec &r = c->recs[i];
+    if (!kernel || !strcmp(r.name, kernel)) {
       float t = 0;
       CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
       total += t;
       n++;
     }
+  }
   if (ms) *ms = total;
   if (launches) *launches = n;
   return RSG_OK;
@@ -552,10 +594,11 @@ extern "C" int rsg_crs_download(const rsg_crs *r, size_t first, size_t count, ui
   return RSG_OK;
 }
 static int fill_uniform(rsg_context *c, uint64_t *d, size_t words, uint32_t row_words, const ModConst *mods, uint32_t n_mods,
-                        uint64_t seed) {
+                        uint64_t seed, uint64_t w_base = 0) {
   std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   LaunchScope ls(c, "k_fill_uniform");
-  k_fill_uniform<<<148 * 8, 256, 0, c->stream>>>(d, words, row_words, mods, n_mods, 1, seed);
+  k_fill_uniform<<<148 * 8, 256, 0, c->stream>>>(d, words, row_words, mods, n_mods, 1, seed, w_base);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -563,6 +606,13 @@ extern "C" int rsg_crs_fill_uniform(rsg_crs *r, uint64_t seed) {
   if (!r) return fail(RSG_ERR_ARG, "null CRS");
   rsg_context *c = r->ctx;
   return fill_uniform(c, r->d, r->n * c->enc_words(), (uint32_t)c->N_E, c->d_modQ, (uint32_t)c->L_E, seed);
+}
+extern "C" int rsg_crs_fill_uniform_at(rsg_crs *r, size_t first, size_t count, uint64_t virtual_first, uint64_t seed) {
+  if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "CRS range");
+  if (!count) return RSG_OK;
+  rsg_context *c = r->ctx;
+  return fill_uniform(c, r->d + first * c->enc_words(), count * c->enc_words(), (uint32_t)c->N_E, c->d_modQ, (uint32_t)c->L_E, seed,
+                      virtual_first * c->enc_words());
 }
 extern "C" uint64_t *rsg_crs_device_ptr(rsg_crs *r) { return r ? r->d : nullptr; }
 extern "C" void rsg_crs_destroy(rsg_crs *r) {
@@ -765,10 +815,10 @@ static int set_smem_attrs() {
 
 // split inverse transforms leave the last level to this kernel; fixed_mod = 0xFFFFFFFF: modulus = polynomial index % n_mod
 static int launch_intt_finish(rsg_context *c, uint64_t *d, size_t polys, const ModConst *mods, const Twiddle *invn,
-                              const Twiddle *invnw, uint32_t n_mod, uint32_t fixed_mod) {
+                              const Twiddle *invnw, uint32_t n_mod, uint32_t fixed_mod, uint32_t centre = 0) {
   const uint32_t half = (uint32_t)(c->N_E / 2);
   LaunchScope ls(c, "k_intt_finish");
-  k_intt_finish<<<(unsigned)((polys * half + 255) / 256), 256, 0, c->stream>>>(d, half, polys, mods, invn, invnw, n_mod, fixed_mod);
+  k_intt_finish<<<(unsigned)((polys * half + 255) / 256), 256, 0, c->stream>>>(d, half, polys, mods, invn, invnw, n_mod, fixed_mod, centre);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
@@ -2025,15 +2075,332 @@ extern "C" int rsg_r1cs_evaluate(rsg_context *c, const rsg_r1cs *r, const rsg_ri
   return r1cs_eval_dev(c, r, assignment->d, evals->d);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// The lincomb phase as a static launch sequence (prover_fast.cuh).  Index arrays depend only on the layout, the circuit
+// shape and the caller's scalar tags, so they are built once and cached.
+struct FastPlan {
+  rsg_groth16_layout L;
+  size_t n = 0, n_aux = 0;
+  bool has_kind = false;
+  std::vector<uint8_t> kind;
+  FastTable T;                 // vec[].base filled per call
+  uint32_t n_terms = 0, Z = 0;
+  uint32_t grp_z[5] = {0};     // split ranges of the term groups A | B | H | aux
+  uint32_t *d_idx = nullptr;   // [term n_terms | pidx n_terms | zoff Z+1 | zr 4]
+  uint8_t *d_kind = nullptr;
+};
+static void fast_release(rsg_context *c) {
+  if (c->fplan) {
+    cudaFree(c->fplan->d_idx);
+    cudaFree(c->fplan->d_kind);
+    delete c->fplan;
+    c->fplan = nullptr;
+  }
+  cudaFree(c->d_fp_flags); cudaFree(c->d_fp_parts); cudaFree(c->d_fp_nttsrc); cudaFree(c->d_fp_totals); cudaFree(c->d_fp_status);
+  if (c->h_fp_status) cudaFreeHost(c->h_fp_status);
+  for (auto &e : c->ev_phase) if (e) cudaEventDestroy(e);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+}
+
+static int fast_get_plan(rsg_context *c, const rsg_groth16_layout *L, size_t n, size_t n_aux, const uint8_t *h_aux_kind, FastPlan **out) {
+  const size_t NONE = (size_t)-1;
+  const size_t m_lo = L->delta_mid_lo, m_hi = std::min(L->delta_mid_hi, n_aux);
+  const size_t nM = m_hi > m_lo ? m_hi - m_lo : 0;
+  FastPlan *fp = c->fplan;
+  if (fp && fp->n == n && fp->n_aux == n_aux && !memcmp(&fp->L, L, sizeof(*L)) && fp->has_kind == (h_aux_kind != nullptr) &&
+      (!h_aux_kind || !memcmp(fp->kind.data(), h_aux_kind + m_lo, nM))) {
+    *out = fp;
+    return RSG_OK;
+  }
+  if (fp) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(fp->d_idx);
+    cudaFree(fp->d_kind);
+    delete fp;
+    c->fplan = nullptr;
+  }
+  fp = new FastPlan();
+  fp->L = *L; fp->n = n; fp->n_aux = n_aux;
+  fp->has_kind = h_aux_kind != nullptr;
+  if (h_aux_kind) fp->kind.assign(h_aux_kind + m_lo, h_aux_kind + m_lo + nM);
+  const size_t s_lo = L->s_pows_lo, s_hi = std::min(L->s_pows_hi, n), t_lo = L->delta_ts_lo, t_hi = std::min(L->delta_ts_hi, n + 1);
+  const uint32_t nS = (uint32_t)(s_hi > s_lo ? s_hi - s_lo : 0), nH = (uint32_t)(t_hi > t_lo ? t_hi - t_lo : 0);
+  FastTable &T = fp->T;
+  memset(&T, 0, sizeof(T));
+  T.nS = nS; T.nH = nH; T.nM = (uint32_t)nM;
+  T.n_parts = 4 * nS;
+  T.n_elems = T.n_parts + nH + (uint32_t)nM;
+  T.n_slots = 2 * nS + nH + (uint32_t)nM;
+  const uint32_t lo[6] = {(uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)t_lo, (uint32_t)m_lo};
+  const uint32_t cnt[6] = {nS, nS, nS, nS, nH, (uint32_t)nM};
+  const size_t off[6] = {L->s_pows_off, L->s_pows_off, L->s_pows_off, L->s_pows_off, L->delta_ts_off, L->delta_mid_off};
+  uint32_t eid = 0;
+  for (int k = 0; k < 6; k++) {
+    T.vec[k].lo = lo[k]; T.vec[k].count = cnt[k]; T.vec[k].eid0 = eid;
+    T.crs_off[k] = (uint32_t)off[k];
+    eid += cnt[k];
+  }
+  T.alpha_idx = L->alpha_idx == NONE ? 0xFFFFFFFFu : (uint32_t)L->alpha_idx;
+  T.beta_idx = L->beta_idx == NONE ? 0xFFFFFFFFu : (uint32_t)L->beta_idx;
+  // term groups A | B | H | aux; the outputs are A, B, C = H + aux
+  std::vector<uint32_t> term, pidx, grp_t{0};
+  for (uint32_t i = 0; i < nS; i++) { term.push_back(T.crs_off[0] + i); pidx.push_back(i); }
+  if (T.alpha_idx != 0xFFFFFFFFu) { term.push_back(T.alpha_idx); pidx.push_back(0xFFFFFFFFu); }
+  grp_t.push_back((uint32_t)term.size());
+  for (uint32_t i = 0; i < nS; i++) { term.push_back(T.crs_off[2] + i); pidx.push_back(nS + i); }
+  if (T.beta_idx != 0xFFFFFFFFu) { term.push_back(T.beta_idx); pidx.push_back(0xFFFFFFFFu); }
+  grp_t.push_back((uint32_t)term.size());
+  for (uint32_t i = 0; i < nH; i++) { term.push_back(T.crs_off[4] + i); pidx.push_back(2 * nS + i); }
+  grp_t.push_back((uint32_t)term.size());
+  for (uint32_t i = 0; i < nM; i++) {
+    const uint8_t kd = h_aux_kind ? h_aux_kind[m_lo + i] : (uint8_t)RSG_AUX_POLY;
+    term.push_back(T.crs_off[5] + i);
+    pidx.push_back(kd == RSG_TERM_ONE ? 0xFFFFFFFFu : 2 * nS + nH + i);   // a SKIP tag is honoured through slot_skip
+  }
+  grp_t.push_back((uint32_t)term.size());
+  fp->n_terms = (uint32_t)term.size();
+  // near-equal term chunks that never straddle a group: ~ 148 x 8 CTAs of k_crs_lincomb in one launch
+  const uint32_t base_blocks = (uint32_t)std::max<size_t>(1, (c->N_E / 512) * c->L_R * c->L_E);
+  uint32_t want = c->fast_splits > 0 ? (uint32_t)c->fast_splits : std::max(4u, (148u * 8 * 4 + base_blocks - 1) / base_blocks);
+  const uint32_t chunk = std::max(8u, (fp->n_terms + want - 1) / std::max(1u, want));
+  std::vector<uint32_t> zoff{0};
+  for (int g = 0; g < 4; g++) {
+    const uint32_t t0 = grp_t[g], t1 = grp_t[g + 1], len = t1 - t0;
+    fp->grp_z[g] = (uint32_t)zoff.size() - 1;
+    if (!len) continue;
+    const uint32_t pieces = (len + chunk - 1) / chunk, per = (len + pieces - 1) / pieces;
+    for (uint32_t a = t0; a < t1; a += per) zoff.push_back(std::min(t1, a + per));
+  }
+  fp->Z = (uint32_t)zoff.size() - 1;
+  fp->grp_z[4] = fp->Z;
+  const uint32_t zr[4] = {fp->grp_z[0], fp->grp_z[1], fp->grp_z[2], fp->grp_z[4]};   // outputs A, B, C
+  std::vector<uint32_t> idx;
+  idx.insert(idx.end(), term.begin(), term.end());
+  idx.insert(idx.end(), pidx.begin(), pidx.end());
+  idx.insert(idx.end(), zoff.begin(), zoff.end());
+  idx.insert(idx.end(), zr, zr + 4);
+  void *v = nullptr;
+  cudaError_t e = cudaMalloc(&v, idx.size() * 4);
+  if (e != cudaSuccess) { delete fp; return fail(RSG_ERR_CUDA, cudaGetErrorString(e)); }
+  fp->d_idx = (uint32_t *)v;
+  e = cudaMemcpy(fp->d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h_aux_kind && n_aux) {
+    // the device copy is indexed by ABSOLUTE auxiliary index like the host array
+    e = cudaMalloc(&v, n_aux);
+    if (e == cudaSuccess) {
+      fp->d_kind = (uint8_t *)v;
+      std::vector<uint8_t> all(n_aux, (uint8_t)RSG_AUX_POLY);
+      memcpy(all.data() + m_lo, h_aux_kind + m_lo, nM);
+      e = cudaMemcpy(fp->d_kind, all.data(), n_aux, cudaMemcpyHostToDevice);
+    }
+  }
+  if (e != cudaSuccess) { cudaFree(fp->d_idx); cudaFree(fp->d_kind); delete fp; return fail(RSG_ERR_CUDA, cudaGetErrorString(e)); }
+  T.aux_kind = fp->d_kind;
+  c->fplan = fp;
+  *out = fp;
+  return RSG_OK;
+}
+
+static bool fast_applies(const rsg_context *c, const rsg_groth16_layout *L, size_t n, size_t n_aux) {
+  if (!c->fast_mode || !c->merge_mode) return false;
+  const size_t s_lo = L->s_pows_lo, s_hi = std::min(L->s_pows_hi, n), t_lo = L->delta_ts_lo, t_hi = std::min(L->delta_ts_hi, n + 1);
+  const size_t m_lo = L->delta_mid_lo, m_hi = std::min(L->delta_mid_hi, n_aux);
+  const size_t nS = s_hi > s_lo ? s_hi - s_lo : 0, nH = t_hi > t_lo ? t_hi - t_lo : 0, nM = m_hi > m_lo ? m_hi - m_lo : 0;
+  const size_t slots = 2 * nS + nH + nM;
+  if (!slots || slots > (1u << 24)) return false;
+  return slots * c->L_R * c->L_E * c->N_E <= c->pntt_budget_words;   // larger term sets go through the chunked path
+}
+
+template <int LG, int LV>
+static int fast_set_attr() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done[dev]) return RSG_OK;
+  CUDA_TRY(cudaFuncSetAttribute(k_encode_fast<LG, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)padded_words(1u << LG) * 8));
+  done[dev] = true;
+  return RSG_OK;
+}
+
+// NTT slots [s0, s0 + count) of the fast path
+static int fast_launch_ntt(rsg_context *c, const uint64_t *nttsrc, uint32_t s0, uint32_t count, const uint8_t *slot_skip) {
+  if (!count) return RSG_OK;
+  const size_t poly = c->L_R * c->N_E, per_general = poly * c->L_E;
+  const unsigned th = ntt_threads(c->logN);
+  const size_t sm = ntt_smem(c->logN);
+  const unsigned split = c->logN > 14 ? 2 : 1;
+  c->st_fwd_polys += (uint64_t)count * c->L_R * c->L_E;
+  dim3 grid((unsigned)(count * c->L_E * split), (unsigned)c->L_R);
+  bool lazy = true;
+  for (uint64_t p : c->Q) lazy = lazy && p < (1ull << 58);
+  const uint64_t *src = nttsrc + (size_t)s0 * poly;
+  uint64_t *dst = c->d_pntt + (size_t)s0 * per_general;
+  const uint8_t *sk = slot_skip + s0;
+  LaunchScope ls(c, "k_lift_fwd_ntt");
+  if (c->f64_ntt && c->ntt_mode != 1) {
+    DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
+                             k_lift_fwd_ntt_f64<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk); });
+  } else {
+    DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
+                             if (lazy) k_lift_fwd_ntt<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, 1u, dst, sk);
+                             else k_lift_fwd_ntt<LG, LV, false><<<grid, th, sm, c->stream>>>(c->d_params, src, 1u, dst, sk); });
+  }
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+
+// splits [z0, z1) of the plan's term chunks -> partial[z]
+static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, const uint64_t *d_crs, uint32_t z0, uint32_t z1, const uint8_t *slot_skip,
+                               cudaStream_t st) {
+  if (z1 <= z0) return RSG_OK;
+  const uint32_t *d_term = fp->d_idx, *d_pidx = fp->d_idx + fp->n_terms, *d_zoff = fp->d_idx + 2 * fp->n_terms;
+  uint64_t *partial = c->d_partial + (size_t)z0 * c->enc_words();
+  c->st_lin_launches++;
+  LaunchScope ls(c, "k_crs_lincomb", st);
+  if (c->lin_mode == 1 && c->N_E % LT_XC == 0) {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev]) {
+      CUDA_TRY(cudaFuncSetAttribute(k_crs_lincomb_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM));
+      CUDA_TRY(cudaFuncSetAttribute(k_crs_lincomb_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      attr_done[dev] = true;
+    }
+    const size_t items = (size_t)(z1 - z0) * c->L_R * c->L_E * (c->N_E / LT_XC);
+    const unsigned grid = (unsigned)std::min<size_t>(items, (size_t)148 * c->lt_ctas);
+    k_crs_lincomb_tma<<<grid, LT_THREADS, LT_SMEM, st>>>(c->d_params, d_crs, d_term, d_pidx, d_zoff + z0, z1 - z0, slot_skip, c->d_pntt, partial);
+  } else {
+    const unsigned th = (unsigned)std::min<size_t>(c->lin_threads > 0 ? c->lin_threads : 256, c->N_E / 2);
+    const dim3 grid((unsigned)(c->N_E / 2 / th), (unsigned)(c->L_R * c->L_E), z1 - z0);
+    k_crs_lincomb<2><<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+
+// Returns RSG_OK with *candidate = 1 when a probe sum vanished (the caller then runs the exact path).  Synchronises once.
+static int groth16_lincombs_fast(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
+                                 const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *out,
+                                 size_t *n_used, int *candidate) {
+  int rc;
+  FastPlan *fp;
+  if ((rc = fast_get_plan(c, L, n, n_aux, h_aux_kind, &fp))) return rc;
+  FastTable T = fp->T;
+  for (int k = 0; k < 6; k++) T.vec[k].base = vec[k];
+  const size_t poly = c->L_R * c->N_E, per_general = poly * c->L_E, E = c->enc_words();
+  if ((rc = ensure(c, &c->d_fp_flags, &c->cap_fp_flags, (size_t)T.n_elems + T.n_slots + 64))) return rc;
+  if ((rc = ensure(c, &c->d_fp_parts, &c->cap_fp_parts, std::max<size_t>(1, (size_t)T.n_parts * poly)))) return rc;
+  if ((rc = ensure(c, &c->d_fp_nttsrc, &c->cap_fp_nttsrc, (size_t)T.n_slots * poly))) return rc;
+  if ((rc = ensure(c, &c->d_pntt, &c->cap_pntt, (size_t)T.n_slots * per_general))) return rc;
+  if ((rc = ensure(c, &c->d_pval, &c->cap_pval, std::max<size_t>((size_t)T.n_parts * c->L_R, 1024)))) return rc;
+  if ((rc = ensure(c, &c->d_partial, &c->cap_partial, (size_t)fp->Z * E))) return rc;
+  if (!c->d_fp_status) {
+    void *v = nullptr;
+    CUDA_TRY(cudaMalloc(&v, FPS_WORDS * 4));
+    c->d_fp_status = (uint32_t *)v;
+    CUDA_TRY(cudaMalloc(&v, 6 * MAX_LR * 8));
+    c->d_fp_totals = (uint64_t *)v;
+    CUDA_TRY(cudaHostAlloc(&v, FPS_WORDS * 4, cudaHostAllocDefault));
+    c->h_fp_status = (uint32_t *)v;
+  }
+  uint8_t *elem_flag = c->d_fp_flags, *slot_skip = c->d_fp_flags + T.n_elems;
+  cudaStream_t st = c->stream;
+  CUDA_TRY(cudaMemsetAsync(c->d_fp_status, 0, FPS_WORDS * 4, st));
+  {
+    LaunchScope ls(c, "k_is_zero_prefix");
+    k_term_flags<<<T.n_elems, 256, 0, st>>>(c->d_params, T, elem_flag, slot_skip, c->d_fp_status);
+  }
+  const unsigned th = ntt_threads(c->logN);
+  const size_t sm = ntt_smem(c->logN);
+  const unsigned split = c->logN > 14 ? 2 : 1;
+  c->st_inv_polys += (uint64_t)T.n_elems * c->L_R;
+  {
+    LaunchScope ls(c, "k_encode_intt");
+    DISPATCH_LOGN(c->logN, { if ((rc = fast_set_attr<LG, LV>())) return rc;
+                             k_encode_fast<LG, LV><<<dim3(T.n_elems * split, (unsigned)c->L_R), th, sm, st>>>(c->d_params, T, elem_flag, c->d_fp_parts,
+                                                                                                          c->d_fp_nttsrc); });
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (split > 1) {   // last inverse level + N^-1 + centring of the two plaintext regions
+    if (T.n_parts && (rc = launch_intt_finish(c, c->d_fp_parts, (size_t)T.n_parts * c->L_R, c->d_modq, c->d_invN_q, c->d_invNw_q, (uint32_t)c->L_R,
+                                             0xFFFFFFFFu, 1u)))
+      return rc;
+    if (T.nH + T.nM && (rc = launch_intt_finish(c, c->d_fp_nttsrc + (size_t)2 * T.nS * poly, (size_t)(T.nH + T.nM) * c->L_R, c->d_modq, c->d_invN_q,
+                                               c->d_invNw_q, (uint32_t)c->L_R, 0xFFFFFFFFu, 1u)))
+      return rc;
+  }
+  if (T.nS) {
+    LaunchScope ls(c, "k_centre_add");
+    k_centre_add_fast<<<dim3(2 * T.nS, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, elem_flag, c->d_fp_parts, c->d_fp_nttsrc, slot_skip);
+    CUDA_TRY(cudaGetLastError());
+  }
+  c->st_lin_terms += fp->n_terms;
+  c->st_lin_plain += T.n_slots;
+  c->st_merged += T.nS ? 2 : 0;
+  if (c->overlap_mode) {
+    // term groups A | B | H | aux: the transforms of group g+1 run on the main stream while the (HBM-bound) lincomb of group g
+    // streams on the second one
+    if (!c->stream2) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+      for (auto &e : c->ev_phase) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    const uint32_t s0[5] = {0, T.nS, 2 * T.nS, 2 * T.nS + T.nH, T.n_slots};
+    for (int g = 0; g < 4; g++) {
+      if ((rc = fast_launch_ntt(c, c->d_fp_nttsrc, s0[g], s0[g + 1] - s0[g], slot_skip))) return rc;
+      CUDA_TRY(cudaEventRecord(c->ev_phase[g], st));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_phase[g], 0));
+      if ((rc = fast_launch_lincomb(c, fp, crs->d, fp->grp_z[g], fp->grp_z[g + 1], slot_skip, c->stream2))) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_join, c->stream2));
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
+  } else {
+    if ((rc = fast_launch_ntt(c, c->d_fp_nttsrc, 0, T.n_slots, slot_skip))) return rc;
+    if ((rc = fast_launch_lincomb(c, fp, crs->d, 0, fp->Z, slot_skip, st))) return rc;
+  }
+  {
+    LaunchScope ls(c, "k_enc_sum");
+    const size_t pairs = E / 2;
+    k_enc_sum_ranges<<<dim3((unsigned)((pairs + 255) / 256), 3), 256, 0, st>>>(c->d_params, c->d_partial, fp->d_idx + 2 * fp->n_terms + fp->Z + 1, out);
+  }
+  if (T.n_parts) {
+    LaunchScope ls(c, "k_probe_eval");
+    k_probe_eval_fast<<<dim3(T.n_parts, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, elem_flag, c->d_fp_parts, c->d_psi_pow, c->d_pval);
+  }
+  {
+    LaunchScope ls(c, "k_probe");
+    k_probe_fast<<<dim3(6, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, crs->d, elem_flag, c->d_pval, c->d_pntt, c->d_fp_totals, nullptr, 0u,
+                                                            c->d_fp_status);
+  }
+  {
+    LaunchScope ls(c, "k_probe");
+    k_probe_chain<<<1, 32, 0, st>>>(c->d_params, T, crs->d, c->d_fp_totals, c->d_fp_status);
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(c->h_fp_status, c->d_fp_status, FPS_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 3 * E * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const uint32_t *hs = c->h_fp_status;
+  *candidate = hs[FPS_CANDIDATE] != 0;
+  if (n_used) {
+    n_used[0] = (size_t)hs[FPS_COUNT0 + 0] + hs[FPS_COUNT0 + 1] + (T.alpha_idx != 0xFFFFFFFFu);
+    n_used[1] = (size_t)hs[FPS_COUNT0 + 2] + hs[FPS_COUNT0 + 3] + (T.beta_idx != 0xFFFFFFFFu);
+    n_used[2] = (size_t)hs[FPS_COUNT0 + 4] + hs[FPS_COUNT0 + 5];
+  }
+  c->st_fast++;
+  return RSG_OK;
+}
 // ------------------------------------------------------------------------------------------------------------
 // groth16::prover (groth16.tcc:69-115): the witness map, then the reference's own sequence of six inner products combined
 // with operator+= (kept separate, not fused into three, because the transparent-ciphertext rule is order-dependent).
 // The six inner products + operator+= chain of groth16.tcc:89-112 over this shard's term ranges.  vec[k] (k = A_io, A_mid,
 // B_io, B_mid, H, aux) is the address element 0 of that coefficient vector WOULD have: only the elements of the shard's
 // ranges ([s_lo, min(s_hi, n)) for the first four, [t_lo, min(t_hi, n+1)) for H, [m_lo, min(m_hi, n_aux)) for aux) are read.
-static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
-                                const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
-                                size_t *n_used) {
+static int groth16_lincombs_exact(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
+                                  const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
+                                  size_t *n_used) {
   int rc;
   const size_t W = c->ring_words();
   const size_t NONE = (size_t)-1;
@@ -2160,6 +2527,26 @@ static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_gr
   if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 3 * c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
+}
+
+// The static launch sequence first; the host-driven exact path when it does not apply (RSG_FAST=0, term set above the
+// NTT-plaintext budget) or when a probe sum vanished (transparent-ciphertext candidate, seal_ring.tcc:493-504).
+static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
+                                const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
+                                size_t *n_used) {
+  if (fast_applies(c, L, n, n_aux)) {
+    int rc;
+    uint64_t *out = d_proof;
+    if (!out) {
+      if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 3 * c->enc_words()))) return rc;
+      out = c->d_out_scratch;
+    }
+    int candidate = 0;
+    if ((rc = groth16_lincombs_fast(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, out, n_used, &candidate))) return rc;
+    if (!candidate) return RSG_OK;
+    c->st_fast_fallback++;
+  }
+  return groth16_lincombs_exact(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, d_proof, n_used);
 }
 
 extern "C" int rsg_groth16_lincombs(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,

@@ -128,13 +128,29 @@ class ShardedGroth16Prover:
         check(lib.rsg_witness_map_groth16(ctx.h, self.r1csW.h, self.rv_evals, self.rv_coeffs, self.rv_H))
         return self.t_wit.index_select(0, self.idx)
 
-    def lincomb_phase(self, recv, h_proof_ptr=None):
-        """Phase 3 from the received buffer [world, 5, per, L_R, S]; leaves the partial proof in t_part."""
+    def fill_synthetic(self, seed):
+        """Synthetic CRS that is the SAME key for every world size (backend.Groth16ProvingKey.fill_synthetic)."""
+        L, n, aux = self.layout, self.n, self.aux
+        self.crs.fill_uniform_at(L.s_pows_off, L.s_pows_hi - L.s_pows_lo, L.s_pows_lo, seed)
+        self.crs.fill_uniform_at(L.delta_ts_off, L.delta_ts_hi - L.delta_ts_lo, n + 1 + L.delta_ts_lo, seed)
+        self.crs.fill_uniform_at(L.delta_mid_off, L.delta_mid_hi - L.delta_mid_lo, 2 * n + 2 + L.delta_mid_lo, seed)
+        if L.alpha_idx != NONE:
+            self.crs.fill_uniform_at(L.alpha_idx, 1, 2 * n + 2 + aux, seed)
+            self.crs.fill_uniform_at(L.beta_idx, 1, 2 * n + 3 + aux, seed)
+
+    def lincomb_phase(self, recv, h_proof_ptr=None, aux_kind=None):
+        """Phase 3 from the received buffer [world, 5, per, L_R, S]; leaves the partial proof in t_part.
+        aux_kind (nullable): RSG_TERM_* / RSG_AUX_POLY per ABSOLUTE auxiliary index, as rsg_groth16_prove takes it."""
         full = unpack(recv, self.world, self.per, self.L_R, self.S).contiguous()
         self._full = full   # keep alive until the kernels have run
         ptrs = (C.c_void_p * 6)(*[full[v].data_ptr() for v in range(5)], self.t_aux.data_ptr())
         used = (C.c_size_t * 3)()
-        check(self.ctxP.lib.rsg_groth16_lincombs(self.ctxP.h, self.crs.h, C.byref(self.layout), self.n, self.aux, ptrs, None,
+        if aux_kind is not None:
+            aux_kind = np.ascontiguousarray(aux_kind, dtype=np.uint8)
+            assert aux_kind.size == self.aux
+        self._aux_kind = aux_kind
+        check(self.ctxP.lib.rsg_groth16_lincombs(self.ctxP.h, self.crs.h, C.byref(self.layout), self.n, self.aux, ptrs,
+                                                 aux_kind.ctypes.data_as(C.c_void_p) if aux_kind is not None else None,
                                                  C.c_void_p(h_proof_ptr) if h_proof_ptr else None,
                                                  C.c_void_p(self.t_part.data_ptr()), used))
         return [int(u) for u in used]
@@ -147,5 +163,8 @@ class ShardedGroth16Prover:
         for ctx, h in self._wraps:
             ctx.lib.rsg_ringvec_destroy(h)
         self._wraps = []
+        # device objects first, then their contexts (their __del__ skips the free once the context handle is gone)
+        for obj in (self.r1csW, self.crs):
+            obj.__del__()
         self.ctxW.close()
         self.ctxP.close()

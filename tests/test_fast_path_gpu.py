@@ -1,0 +1,211 @@
+"""GPU tests of the static-plan prover (csrc/prover_fast.cuh): the one-launch-sequence lincomb phase, the TMA-fed
+streaming kernel and the two-stream overlap must give the reference's proof bit for bit -- and fall back to the exact
+host-driven path whenever a transparent-ciphertext candidate shows up (seal_ring.tcc:493-504)."""
+import glob
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from rsgv import Case
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.rsgv")))
+IDS = [os.path.basename(g)[:-5] for g in GOLD]
+REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+MODES = {
+    "exact": {"RSG_FAST": "0"},
+    "fast": {},
+    "fast_tma": {"RSG_LIN": "tma"},
+    "fast_overlap": {"RSG_OVERLAP": "1"},
+    "fast_tma_overlap": {"RSG_LIN": "tma", "RSG_OVERLAP": "1"},
+    "fast_tma_1cta": {"RSG_LIN": "tma", "RSG_LT_CTAS": "1", "RSG_FAST_SPLITS": "3"},
+}
+
+
+def _set_mode(monkeypatch, mode):
+    for k in ("RSG_FAST", "RSG_LIN", "RSG_OVERLAP", "RSG_LT_CTAS", "RSG_FAST_SPLITS"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in MODES[mode].items():
+        monkeypatch.setenv(k, v)
+
+
+def _aux_kind(case):
+    _, tag, scalar = case.ring("auxiliary_input")
+    kind = np.full(case.aux, 0xFF, dtype=np.uint8)
+    for i in range(case.aux):
+        if int(tag[i]) == 0:
+            s = int(scalar[i])
+            kind[i] = 0 if s == 0 else (1 if s == 1 else 2)
+    return kind
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("path", GOLD, ids=IDS)
+def test_golden_proofs_every_mode(path, mode, monkeypatch):
+    """Every golden case of the reference (fast / slow lift, scalar 0 / 1 / k inputs, zero-prefix elements, the constant wire,
+    a transparent prefix) through rsg_groth16_prove in every mode of the lincomb phase."""
+    import ringsnark_b200 as rs
+    _set_mode(monkeypatch, mode)
+    case = Case(path)
+    ctx = rs.Context(case.N_R, case.q, case.N_E, case.Q)
+    try:
+        r1cs = rs.R1cs(ctx, case.n, case.io, case.aux, case.d["r1cs_row_ptr"], case.d["r1cs_col"], case.d["r1cs_coeff"])
+        pk = rs.Groth16ProvingKey(ctx, r1cs)
+        pk.load(case.enc("crs_s_pows")[0], case.enc("crs_delta_ts")[0], case.enc("crs_delta_mid")[0],
+                case.enc("crs_alpha")[0], case.enc("crs_beta")[0])
+        assignment = np.concatenate([case.ring("primary_input")[0], case.ring("auxiliary_input")[0]])
+        for _ in range(2):   # the second call reuses the cached plan
+            proof, used = pk.prove(assignment, _aux_kind(case))
+            assert np.array_equal(proof, case.enc("proof")[0])
+        if mode == "exact":
+            assert ctx.stat("fast_proofs") == 0
+        else:
+            assert ctx.stat("fast_proofs") == 2
+            # tiny_transp: a prefix of <s_pows, A_io> is transparent -> the probe must send the call to the exact path
+            assert (ctx.stat("fast_fallbacks") > 0) == (int(case.seed) == 11)
+        del pk, r1cs
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("cfg_name", ["c4m", "c5s", "c1"])
+def test_synthetic_proofs_every_mode(cfg_name, monkeypatch):
+    """Reference-sized parameter sets (N_E = 2^14 on the FP64 pipe, 2^15 split transforms on the integer pipe, 2 ring limbs at
+    2^13) with a synthetic CRS: every mode gives the words of the exact path, and a 3-way term sharding sums to them."""
+    import torch
+    import ringsnark_b200 as rs
+    from ringsnark_b200.params import CONFIGS, synthetic_r1cs
+    cfg = CONFIGS[cfg_name]
+    n, io, aux = cfg["n"], cfg["io"], cfg["aux"]
+    row_ptr, col, coeff = synthetic_r1cs(n, io, aux, seed=3)
+    proofs = {}
+    for mode in MODES:
+        _set_mode(monkeypatch, mode)
+        ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"])
+        try:
+            r1cs = rs.R1cs(ctx, n, io, aux, row_ptr, col, coeff)
+            pk = rs.Groth16ProvingKey(ctx, r1cs)
+            pk.fill_synthetic(5)
+            pk.assignment.fill_uniform(6)
+            proofs[mode], used = pk.prove()
+            assert used == [2 * n + 1, 2 * n + 1, (n - 1) + aux], (mode, used)
+            if mode == "fast":   # term shards of the same key: partial proofs sum to the proof
+                E = ctx.enc_words
+                parts = torch.zeros(3 * 3 * E, dtype=torch.int64, device="cuda")
+                for r in range(3):
+                    pkr = rs.Groth16ProvingKey(ctx, r1cs, r, 3)
+                    pkr.fill_synthetic(5)
+                    pkr.assignment.fill_uniform(6)
+                    p, _ = pkr.prove()
+                    parts[r * 3 * E:(r + 1) * 3 * E] = torch.from_numpy(p.reshape(-1).view(np.int64))
+                    del pkr
+                total = torch.zeros(3 * E, dtype=torch.int64, device="cuda")
+                ctx.enc_sum(parts.data_ptr(), 3, 3, total.data_ptr())
+                ctx.sync()
+                torch.cuda.synchronize()
+                assert np.array_equal(total.cpu().numpy().view(np.uint64), proofs[mode].reshape(-1))
+            del pk, r1cs
+        finally:
+            ctx.close()
+    for mode in MODES:
+        assert np.array_equal(proofs[mode], proofs["exact"]), mode
+
+
+def test_fill_uniform_at_matches_whole_arena():
+    import ringsnark_b200 as rs
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c1"]
+    ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"])
+    try:
+        whole = ctx.crs(7)
+        whole.fill_uniform(99)
+        piece = ctx.crs(3)
+        piece.fill_uniform_at(0, 2, 4, 99)     # elements 4, 5 of the virtual arena
+        piece.fill_uniform_at(2, 1, 1, 99)     # element 1
+        w = whole.download()
+        p = piece.download()
+        assert np.array_equal(p[0], w[4]) and np.array_equal(p[1], w[5]) and np.array_equal(p[2], w[1])
+        Q = np.asarray(cfg["Q"], dtype=np.uint64)
+        assert (w.reshape(7, ctx.L_R, 2, ctx.L_E, ctx.N_E) < Q[None, None, None, :, None]).all()
+        del whole, piece
+    finally:
+        ctx.close()
+
+
+def test_c2p_ring_element_coefficients():
+    """SURVEY.md 8(d) C2' (benchmarks/bench_ntt_SEAL.cpp:29-55 restated): ONE constraint whose linear combination has
+    RING-ELEMENT coefficients, no auxiliary input -- the domain is {0}, H = 0 and the proof's C is the EMPTY encoding.  The
+    system has no CSR form with scalar coefficients, so the path runs from the reference's evaluation vectors: witness map,
+    the prover's inner products and the += chain against the reference's dump (built with -DNDEBUG: the reference asserts
+    on copying an empty encoding)."""
+    if not os.path.exists(REF_HARNESS):
+        pytest.skip("oracle/_ref/ref_harness not built (needs /root/reference at build time)")
+    import ringsnark_b200 as rs
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "c2p.rsgv")
+        subprocess.check_call([REF_HARNESS, "dump", "c2p", path, "31"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        case = Case(path)
+    assert int(case.d["r1cs_scalar_coeffs"][0]) == 0 and case.n == 1 and case.aux == 0
+    ctx = rs.Context(case.N_R, case.q, case.N_E, case.Q)
+    try:
+        n = case.n
+        order = ["A_mid", "B_mid", "C_mid", "A_io", "B_io", "C_io", "A_full", "B_full", "C_full"]
+        ev = ctx.ringvec_from(np.concatenate([case.ring("eval_" + k)[0] for k in order]))
+        coeffs, H = ctx.witness_map(n, ev)
+        got = coeffs.download()
+        for idx, k in enumerate(["A_io", "B_io", "C_io", "A_mid", "B_mid", "C_mid"]):
+            words, tag, scalar = case.ring("wit_" + k)
+            for i in range(n):   # the reference keeps scalar coefficients as scalars: compare slot-wise values
+                want = words[i] if int(tag[i]) else np.concatenate([np.full(case.N_R, int(scalar[i]) % int(p), dtype=np.uint64) for p in case.q])
+                assert np.array_equal(got[idx * n + i], want), (k, i)
+        s_pows = ctx.crs_from(case.enc("crs_s_pows")[0])
+        delta_ts = ctx.crs_from(case.enc("crs_delta_ts")[0])
+        ip, ip_size = case.enc("ip")
+        jobs = [(s_pows, coeffs, 0, "wit_A_io"), (s_pows, coeffs, 3 * n, "wit_A_mid"), (s_pows, coeffs, n, "wit_B_io"),
+                (s_pows, coeffs, 4 * n, "wit_B_mid")]
+        outs = []
+        for k, (crs, vec, first, name) in enumerate(jobs):
+            _, tag, scalar = case.ring(name)
+            tags = ctx.term_tags(vec, tag, scalar, first=first, count=n)
+            out, used = ctx.inner_product(crs, vec, tags, coeff_first=first)
+            assert (used == 0) == (int(ip_size[k][0]) == 2 ** 64 - 1), k
+            if used:
+                assert np.array_equal(out, ip[k]), k
+            outs.append((out, used))
+        # H = 0: every term of <delta_ts, H> is skipped -> the empty encoding, like the reference's C
+        _, tag, scalar = case.ring("wit_H")
+        tags = ctx.term_tags(H, tag, scalar, first=0, count=len(tag))
+        out, used = ctx.inner_product(delta_ts, H, tags)
+        assert used == 0 and int(ip_size[4][0]) == 2 ** 64 - 1
+        proof, psize = case.enc("proof")
+        assert int(psize[2][0]) == 2 ** 64 - 1          # the reference's C is empty
+        # A = ip0 + ip1 + alpha, B = ip2 + ip3 + beta through the C ABI's operator+=
+        import torch
+        for e, extra in enumerate(("crs_alpha", "crs_beta")):
+            acc = None
+            for (o, used) in outs[2 * e:2 * e + 2]:
+                if not used:
+                    continue
+                t = torch.from_numpy(o.view(np.int64)).cuda()
+                if acc is None:
+                    acc = t.clone()
+                else:
+                    assert ctx.lib.rsg_enc_add(ctx.h, acc.data_ptr(), t.data_ptr()) == 0
+            t = torch.from_numpy(np.ascontiguousarray(case.enc(extra)[0][0]).view(np.int64)).cuda()
+            if acc is None:
+                acc = t.clone()
+            else:
+                assert ctx.lib.rsg_enc_add(ctx.h, acc.data_ptr(), t.data_ptr()) == 0
+            ctx.sync()
+            torch.cuda.synchronize()
+            assert np.array_equal(acc.cpu().numpy().view(np.uint64), proof[e]), e
+        del s_pows, delta_ts, ev, coeffs, H
+    finally:
+        ctx.close()
