@@ -204,9 +204,8 @@ struct LiftIoF64 {
 };
 
 template <int LOGN, int LVL0, bool SIGNED>
-__global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
-                                                          uint64_t *__restrict__ out,
-                                                          const uint8_t *__restrict__ slot_skip = nullptr) {
+__device__ __forceinline__ void lift_fwd_ntt_f64_body(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
+                                                      uint64_t *__restrict__ out, const uint8_t *__restrict__ slot_skip) {
   extern __shared__ double smf[];
   constexpr uint32_t n = 1u << LOGN;
   const uint32_t L_R = P->L_R, L_E = P->L_E;
@@ -234,6 +233,20 @@ __global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__res
     __syncthreads();
   }
   PassChainF<LOGN, 0, LVL0 == 0>::fwd(smf, tab, io.pd, io.pinv, LVL0, h, tw0, io);
+}
+template <int LOGN, int LVL0, bool SIGNED>
+__global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
+                                                          uint64_t *__restrict__ out,
+                                                          const uint8_t *__restrict__ slot_skip = nullptr) {
+  lift_fwd_ntt_f64_body<LOGN, LVL0, SIGNED>(P, plain, out, slot_skip);
+}
+// The same transform capped at 96 registers (a few twiddles spill to L1): 512 x 96 = 48 Ki registers leave room for one
+// 256-thread CTA of k_crs_lincomb_r64 on the same SM, so the HBM-bound stream of one term group runs UNDER the FP64-bound
+// transforms of the next (prover_fast.cuh, RSG_OVERLAP).
+template <int LOGN, int LVL0, bool SIGNED>
+__global__ void __maxnreg__(96) k_lift_fwd_ntt_f64_r96(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
+                                                       uint64_t *__restrict__ out, const uint8_t *__restrict__ slot_skip) {
+  lift_fwd_ntt_f64_body<LOGN, LVL0, SIGNED>(P, plain, out, slot_skip);
 }
 
 // Raw NTT of `batch` polynomials; grid (batch << LVL0).  In place for LVL0 = 0.  For LVL0 = 1 the forward transform reads
@@ -288,12 +301,11 @@ __device__ __forceinline__ ulonglong2 ld_stream(const uint64_t *p) {
 }
 
 template <int UNROLL>
-__global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
-                                                     const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
-                                                     uint32_t n_terms, uint32_t terms_per_split,
-                                                     const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
-                                                     const uint32_t *__restrict__ zoff = nullptr,
-                                                     const uint8_t *__restrict__ slot_skip = nullptr) {
+__device__ __forceinline__ void crs_lincomb_body(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
+                                                 const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
+                                                 uint32_t n_terms, uint32_t terms_per_split,
+                                                 const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
+                                                 const uint32_t *__restrict__ zoff, const uint8_t *__restrict__ slot_skip) {
   const uint32_t N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
   const uint32_t x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const uint32_t j = blockIdx.y / L_E, l = blockIdx.y - j * L_E;
@@ -352,6 +364,24 @@ __global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict
   uint64_t *o = partial + (size_t)blockIdx.z * enc_words + c_off;
   *reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(a00.reduce(m), a01.reduce(m));
   *reinterpret_cast<ulonglong2 *>(o + k_stride) = make_ulonglong2(a10.reduce(m), a11.reduce(m));
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
+                                                     const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
+                                                     uint32_t n_terms, uint32_t terms_per_split,
+                                                     const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
+                                                     const uint32_t *__restrict__ zoff = nullptr,
+                                                     const uint8_t *__restrict__ slot_skip = nullptr) {
+  crs_lincomb_body<UNROLL>(P, crs, term, pidx, n_terms, terms_per_split, pntt, partial, zoff, slot_skip);
+}
+// 64 registers x 256 threads = 16 Ki registers: the CTA that fits next to k_lift_fwd_ntt_f64_r96 on one SM.
+__global__ void __maxnreg__(64) k_crs_lincomb_r64(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
+                                                  const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
+                                                  uint32_t n_terms, uint32_t terms_per_split,
+                                                  const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
+                                                  const uint32_t *__restrict__ zoff, const uint8_t *__restrict__ slot_skip) {
+  crs_lincomb_body<2>(P, crs, term, pidx, n_terms, terms_per_split, pntt, partial, zoff, slot_skip);
 }
 
 // out[w] = sum_s parts[s][w] mod Q_l(w): the modular-add kernel (after split-K or after the NCCL all-gather).

@@ -87,54 +87,59 @@ __global__ void __launch_bounds__(512) k_encode_fast(const DevParams *__restrict
 }
 
 // Merged slots: nttsrc[m] = parts[X] + parts[Y] (int64), a skipped part counts as absent; slot_skip[m] = both skipped.
+// While both parts stream through, the one NTT-domain word the probe needs of EACH part is evaluated directly:
+// pval[eid][j] = NTT_{Q_0}(lift(part))[0] = sum_i part_i psi^i mod Q_0 (the parts' own transforms are never formed).
 // grid (2 nS, L_R), 256 threads.
 __global__ void __launch_bounds__(256) k_centre_add_fast(const DevParams *__restrict__ P, FastTable T, const uint8_t *__restrict__ elem_flag,
                                                          const uint64_t *__restrict__ parts, uint64_t *__restrict__ nttsrc,
-                                                         uint8_t *__restrict__ slot_skip) {
+                                                         uint8_t *__restrict__ slot_skip, const uint64_t *__restrict__ psi_pow,
+                                                         uint64_t *__restrict__ pval) {
+  __shared__ uint64_t red[2][8];
   const uint32_t m = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_R = P->L_R, nS = T.nS;
   const uint32_t ex = m < nS ? m : 2 * nS + (m - nS), ey = ex + nS;
   const bool sx = elem_flag[ex] != 0, sy = elem_flag[ey] != 0;
   if (threadIdx.x == 0 && j == 0) slot_skip[m] = sx && sy;
   if (sx && sy) return;
+  const ModConst m0 = P->Q[0];
   const ulonglong2 *a = reinterpret_cast<const ulonglong2 *>(parts + ((size_t)ex * L_R + j) * N_E);
   const ulonglong2 *b = reinterpret_cast<const ulonglong2 *>(parts + ((size_t)ey * L_R + j) * N_E);
+  const ulonglong2 *pw = reinterpret_cast<const ulonglong2 *>(psi_pow);
   ulonglong2 *o = reinterpret_cast<ulonglong2 *>(nttsrc + ((size_t)m * L_R + j) * N_E);
+  auto lift0 = [&](uint64_t v) {   // centred int64 -> residue mod Q_0
+    const long long sv = (long long)v;
+    const uint64_t r = reduce64((uint64_t)(sv < 0 ? -sv : sv), m0);
+    return sv < 0 ? neg_mod(r, m0.p) : r;
+  };
+  Acc192 ax, ay;
+  ax.clear(); ay.clear();
   for (uint32_t i = threadIdx.x; i < N_E / 2; i += blockDim.x) {
-    ulonglong2 x = sx ? make_ulonglong2(0, 0) : a[i];
+    const ulonglong2 w = __ldg(pw + i);
+    ulonglong2 x = make_ulonglong2(0, 0);
+    if (!sx) {
+      x = a[i];
+      ax.mac(lift0(x.x), w.x);
+      ax.mac(lift0(x.y), w.y);
+    }
     if (!sy) {
       const ulonglong2 y = b[i];
+      ay.mac(lift0(y.x), w.x);
+      ay.mac(lift0(y.y), w.y);
       x.x += y.x; x.y += y.y;
     }
     o[i] = x;
   }
-}
-
-// pval[eid][j] = NTT_{Q_0}(lift(part))[0] = sum_i part_i psi^i mod Q_0 for the parts of the merged pairs (centred input):
-// the one NTT-domain word the probe needs per term.  grid (n_parts, L_R).
-__global__ void __launch_bounds__(256) k_probe_eval_fast(const DevParams *__restrict__ P, const uint8_t *__restrict__ elem_flag,
-                                                         const uint64_t *__restrict__ parts, const uint64_t *__restrict__ psi_pow,
-                                                         uint64_t *__restrict__ pval) {
-  __shared__ uint64_t part[8];
-  const uint32_t g = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_R = P->L_R;
-  if (elem_flag[g]) return;
-  const ModConst m = P->Q[0];
-  const uint64_t *src = parts + ((size_t)g * L_R + j) * N_E;
-  Acc192 acc;
-  acc.clear();
-  for (uint32_t i = threadIdx.x; i < N_E; i += blockDim.x) {
-    const long long sv = (long long)src[i];
-    const uint64_t r = reduce64((uint64_t)(sv < 0 ? -sv : sv), m);
-    acc.mac(sv < 0 ? neg_mod(r, m.p) : r, __ldg(psi_pow + i));
-  }
-  uint64_t s = acc.reduce(m);
+  uint64_t s0 = ax.reduce(m0), s1 = ay.reduce(m0);
 #pragma unroll
-  for (int off = 16; off; off >>= 1) s = add_mod(s, __shfl_xor_sync(0xFFFFFFFFu, s, off), m.p);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  for (int off = 16; off; off >>= 1) {
+    s0 = add_mod(s0, __shfl_xor_sync(0xFFFFFFFFu, s0, off), m0.p);
+    s1 = add_mod(s1, __shfl_xor_sync(0xFFFFFFFFu, s1, off), m0.p);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint64_t t = part[0];
-    for (int w = 1; w < 8; w++) t = add_mod(t, part[w], m.p);
-    pval[(size_t)g * L_R + j] = t;
+  if (threadIdx.x < 2) {
+    uint64_t t = red[threadIdx.x][0];
+    for (int w = 1; w < 8; w++) t = add_mod(t, red[threadIdx.x][w], m0.p);
+    pval[(size_t)(threadIdx.x ? ey : ex) * L_R + j] = t;
   }
 }
 

@@ -262,6 +262,8 @@ struct rsg_context {
   int lt_ctas = 2;                  // RSG_LT_CTAS: persistent CTAs per SM of k_crs_lincomb_tma
   int overlap_mode = 0;             // RSG_OVERLAP=1: lincomb of one term group on a second stream under the next group's NTTs
   int fast_splits = 0;              // RSG_FAST_SPLITS: number of term chunks of the one-launch lincomb (0 = auto)
+  int ntt_half = 0;                 // RSG_NTT_HALF=1 (experiment, see fast_launch_ntt)
+  int overlap_chunks = 4;           // RSG_OVERLAP_CHUNKS: term chunks (<= 128 terms each) per overlap phase
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_phase[8] = {};     // NTT group done (stream -> stream2)
   cudaEvent_t ev_join = nullptr;    // stream2 -> stream
@@ -472,6 +474,8 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (const char *m = getenv("RSG_LT_CTAS")) c->lt_ctas = std::max(1, atoi(m));
   if (const char *m = getenv("RSG_OVERLAP")) c->overlap_mode = atoi(m);
   if (const char *m = getenv("RSG_FAST_SPLITS")) c->fast_splits = atoi(m);
+  if (const char *m = getenv("RSG_NTT_HALF")) c->ntt_half = atoi(m);
+  if (const char *m = getenv("RSG_OVERLAP_CHUNKS")) c->overlap_chunks = std::max(1, atoi(m));
   if (const char *m = getenv("RSG_WITNESS")) c->witness_mode = !strcmp(m, "dense") ? 1 : (!strcmp(m, "fast") ? 2 : 0);
   if (const char *m = getenv("RSG_WF_SL")) c->wf_sl = atoi(m);
   if (const char *m = getenv("RSG_LIN_SPLITS")) c->lin_splits = atoi(m);
@@ -794,6 +798,7 @@ static int set_smem_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_r96<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done[dev] = true;
@@ -2087,6 +2092,7 @@ struct FastPlan {
   FastTable T;                 // vec[].base filled per call
   uint32_t n_terms = 0, Z = 0;
   uint32_t grp_z[5] = {0};     // split ranges of the term groups A | B | H | aux
+  std::vector<uint32_t> zs0, zs1;   // NTT slots [zs0[z], zs1[z]) feed the terms of split z
   uint32_t *d_idx = nullptr;   // [term n_terms | pidx n_terms | zoff Z+1 | zr 4]
   uint8_t *d_kind = nullptr;
 };
@@ -2164,7 +2170,8 @@ static int fast_get_plan(rsg_context *c, const rsg_groth16_layout *L, size_t n, 
   // near-equal term chunks that never straddle a group: ~ 148 x 8 CTAs of k_crs_lincomb in one launch
   const uint32_t base_blocks = (uint32_t)std::max<size_t>(1, (c->N_E / 512) * c->L_R * c->L_E);
   uint32_t want = c->fast_splits > 0 ? (uint32_t)c->fast_splits : std::max(4u, (148u * 8 * 4 + base_blocks - 1) / base_blocks);
-  const uint32_t chunk = std::max(8u, (fp->n_terms + want - 1) / std::max(1u, want));
+  uint32_t chunk = std::max(8u, (fp->n_terms + want - 1) / std::max(1u, want));
+  if (c->overlap_mode && c->fast_splits <= 0) chunk = std::min(chunk, 128u);   // phases are built from whole chunks
   std::vector<uint32_t> zoff{0};
   for (int g = 0; g < 4; g++) {
     const uint32_t t0 = grp_t[g], t1 = grp_t[g + 1], len = t1 - t0;
@@ -2175,6 +2182,13 @@ static int fast_get_plan(rsg_context *c, const rsg_groth16_layout *L, size_t n, 
   }
   fp->Z = (uint32_t)zoff.size() - 1;
   fp->grp_z[4] = fp->Z;
+  for (uint32_t z = 0; z < fp->Z; z++) {
+    uint32_t a = 0xFFFFFFFFu, b = 0;
+    for (uint32_t t = zoff[z]; t < zoff[z + 1]; t++)
+      if (pidx[t] != 0xFFFFFFFFu) { a = std::min(a, pidx[t]); b = std::max(b, pidx[t] + 1); }
+    fp->zs0.push_back(a == 0xFFFFFFFFu ? 0 : a);
+    fp->zs1.push_back(a == 0xFFFFFFFFu ? 0 : b);
+  }
   const uint32_t zr[4] = {fp->grp_z[0], fp->grp_z[1], fp->grp_z[2], fp->grp_z[4]};   // outputs A, B, C
   std::vector<uint32_t> idx;
   idx.insert(idx.end(), term.begin(), term.end());
@@ -2225,7 +2239,7 @@ static int fast_set_attr() {
 }
 
 // NTT slots [s0, s0 + count) of the fast path
-static int fast_launch_ntt(rsg_context *c, const uint64_t *nttsrc, uint32_t s0, uint32_t count, const uint8_t *slot_skip) {
+static int fast_launch_ntt(rsg_context *c, const uint64_t *nttsrc, uint32_t s0, uint32_t count, const uint8_t *slot_skip, bool lowreg = false) {
   if (!count) return RSG_OK;
   const size_t poly = c->L_R * c->N_E, per_general = poly * c->L_E;
   const unsigned th = ntt_threads(c->logN);
@@ -2239,9 +2253,20 @@ static int fast_launch_ntt(rsg_context *c, const uint64_t *nttsrc, uint32_t s0, 
   uint64_t *dst = c->d_pntt + (size_t)s0 * per_general;
   const uint8_t *sk = slot_skip + s0;
   LaunchScope ls(c, "k_lift_fwd_ntt");
+  if (c->ntt_half && c->logN == 14 && c->f64_ntt && c->ntt_mode != 1) {
+    // experiment (RSG_NTT_HALF=1): two 2^13-point CTAs of 256 threads per polynomial (first level fused into the load, as at
+    // N_E = 2^15) -- two independent CTAs per SM instead of one, so one CTA's barriers and loads hide behind the other's math
+    int rc = set_smem_attrs<13, 1>();
+    if (rc) return rc;
+    k_lift_fwd_ntt_f64<13, 1, true><<<dim3((unsigned)(count * c->L_E * 2), (unsigned)c->L_R), 256, (size_t)padded_words(1u << 13) * 8, c->stream>>>(
+        c->d_params, src, dst, sk);
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   if (c->f64_ntt && c->ntt_mode != 1) {
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
-                             k_lift_fwd_ntt_f64<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk); });
+                             if (lowreg) k_lift_fwd_ntt_f64_r96<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk);
+                             else k_lift_fwd_ntt_f64<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk); });
   } else {
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
                              if (lazy) k_lift_fwd_ntt<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, 1u, dst, sk);
@@ -2253,7 +2278,7 @@ static int fast_launch_ntt(rsg_context *c, const uint64_t *nttsrc, uint32_t s0, 
 
 // splits [z0, z1) of the plan's term chunks -> partial[z]
 static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, const uint64_t *d_crs, uint32_t z0, uint32_t z1, const uint8_t *slot_skip,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool lowreg = false) {
   if (z1 <= z0) return RSG_OK;
   const uint32_t *d_term = fp->d_idx, *d_pidx = fp->d_idx + fp->n_terms, *d_zoff = fp->d_idx + 2 * fp->n_terms;
   uint64_t *partial = c->d_partial + (size_t)z0 * c->enc_words();
@@ -2274,7 +2299,8 @@ static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, const uint64_
   } else {
     const unsigned th = (unsigned)std::min<size_t>(c->lin_threads > 0 ? c->lin_threads : 256, c->N_E / 2);
     const dim3 grid((unsigned)(c->N_E / 2 / th), (unsigned)(c->L_R * c->L_E), z1 - z0);
-    k_crs_lincomb<2><<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip);
+    if (lowreg) k_crs_lincomb_r64<<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip);
+    else k_crs_lincomb<2><<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip);
   }
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
@@ -2333,26 +2359,36 @@ static int groth16_lincombs_fast(rsg_context *c, const rsg_crs *crs, const rsg_g
   }
   if (T.nS) {
     LaunchScope ls(c, "k_centre_add");
-    k_centre_add_fast<<<dim3(2 * T.nS, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, elem_flag, c->d_fp_parts, c->d_fp_nttsrc, slot_skip);
+    k_centre_add_fast<<<dim3(2 * T.nS, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, elem_flag, c->d_fp_parts, c->d_fp_nttsrc, slot_skip,
+                                                                        c->d_psi_pow, c->d_pval);
     CUDA_TRY(cudaGetLastError());
   }
   c->st_lin_terms += fp->n_terms;
   c->st_lin_plain += T.n_slots;
   c->st_merged += T.nS ? 2 : 0;
   if (c->overlap_mode) {
-    // term groups A | B | H | aux: the transforms of group g+1 run on the main stream while the (HBM-bound) lincomb of group g
-    // streams on the second one
+    // Phases of ~overlap_terms terms (whole term chunks): the transforms of phase p+1 run on the main stream while the
+    // HBM-bound lincomb of phase p streams on the second one.  The register-capped kernel pair (96 x 512 + 64 x 256 = 64 Ki
+    // registers) lets one lincomb CTA sit on each SM next to the transform CTA; the last phase's lincomb runs alone.
     if (!c->stream2) {
       CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
       for (auto &e : c->ev_phase) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     }
-    const uint32_t s0[5] = {0, T.nS, 2 * T.nS, 2 * T.nS + T.nH, T.n_slots};
-    for (int g = 0; g < 4; g++) {
-      if ((rc = fast_launch_ntt(c, c->d_fp_nttsrc, s0[g], s0[g + 1] - s0[g], slot_skip))) return rc;
-      CUDA_TRY(cudaEventRecord(c->ev_phase[g], st));
-      CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_phase[g], 0));
-      if ((rc = fast_launch_lincomb(c, fp, crs->d, fp->grp_z[g], fp->grp_z[g + 1], slot_skip, c->stream2))) return rc;
+    const bool lowreg = c->overlap_mode == 1;
+    const uint32_t per_phase = (uint32_t)std::max(1, c->overlap_chunks);
+    uint32_t ntt_done = 0;   // slots [0, ntt_done) have been launched
+    int pe = 0;
+    for (uint32_t z0 = 0; z0 < fp->Z; z0 += per_phase, pe = (pe + 1) % 8) {
+      const uint32_t z1 = std::min(fp->Z, z0 + per_phase);
+      uint32_t s_end = ntt_done;
+      for (uint32_t z = z0; z < z1; z++) s_end = std::max(s_end, fp->zs1[z]);
+      if (z1 == fp->Z) s_end = T.n_slots;
+      if (s_end > ntt_done && (rc = fast_launch_ntt(c, c->d_fp_nttsrc, ntt_done, s_end - ntt_done, slot_skip, lowreg))) return rc;
+      ntt_done = s_end;
+      CUDA_TRY(cudaEventRecord(c->ev_phase[pe], st));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_phase[pe], 0));
+      if ((rc = fast_launch_lincomb(c, fp, crs->d, z0, z1, slot_skip, c->stream2, lowreg))) return rc;
     }
     CUDA_TRY(cudaEventRecord(c->ev_join, c->stream2));
     CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
@@ -2364,10 +2400,6 @@ static int groth16_lincombs_fast(rsg_context *c, const rsg_crs *crs, const rsg_g
     LaunchScope ls(c, "k_enc_sum");
     const size_t pairs = E / 2;
     k_enc_sum_ranges<<<dim3((unsigned)((pairs + 255) / 256), 3), 256, 0, st>>>(c->d_params, c->d_partial, fp->d_idx + 2 * fp->n_terms + fp->Z + 1, out);
-  }
-  if (T.n_parts) {
-    LaunchScope ls(c, "k_probe_eval");
-    k_probe_eval_fast<<<dim3(T.n_parts, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, elem_flag, c->d_fp_parts, c->d_psi_pow, c->d_pval);
   }
   {
     LaunchScope ls(c, "k_probe");

@@ -531,14 +531,15 @@ def test_merged_inner_products(gold, budget, monkeypatch):
             pk = _pk(case, ctx)
             proof, _ = pk.prove(_assignment(case), _aux_kind(case))
             proofs.append(proof)
-            stats.append((ctx.stat("merged_lincombs"), ctx.stat("lincomb_terms"), ctx.stat("exact_fallbacks")))
+            stats.append((ctx.stat("merged_lincombs"), ctx.stat("lincomb_terms"), ctx.stat("exact_fallbacks"), ctx.stat("fast_proofs")))
         finally:
             ctx.close()
     assert np.array_equal(proofs[0], case.enc("proof")[0])
     assert np.array_equal(proofs[1], case.enc("proof")[0])
     assert stats[1][0] == 0
     if int(case.seed) != 11:                       # tiny_transp un-merges after the probe flags a transparent prefix
-        assert stats[0][0] >= 1 and stats[0][1] < stats[1][1]
+        # (the static-plan path counts the CRS elements of its term ranges, skipped or not; the host-list path counts streamed ones)
+        assert stats[0][0] >= 1 and (stats[0][3] > 0 or stats[0][1] < stats[1][1])
     else:
         assert stats[0][2] > 0
 
