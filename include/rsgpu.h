@@ -189,6 +189,18 @@ int rsg_instance_map(rsg_context *ctx, rsg_r1cs *r1cs, const rsg_ringvec *t, siz
 int rsg_decode(rsg_context *ctx, const uint64_t *h_sk, const uint64_t *d_enc, const uint64_t *h_enc, size_t count, uint64_t *h_ring,
                int32_t *h_budget);
 
+/* ---- EncodingElem::encode (ringsnark/seal/seal_ring.tcc:324-359): BatchEncoder::encode + Encryptor::encrypt_symmetric (BGV,
+ * depends/SEAL/native/src/seal/encryptor.cpp:242-312, util/rlwe.cpp:276-390) of ring elements [first, first + count) of
+ * `elems` straight into encodings [out_first, ...) of the arena `out` -- the CRS never exists on the host.
+ * h_sk: [L_R][L_E][N_E] secret keys in NTT form (as rsg_decode).  h_seeds: [count][L_R][8] words -- per (element, ring limb)
+ * the 64-byte seed SEAL's random generator factory would hand to that encryption's bootstrap PRNG (randomgen.h:440-448:
+ * fresh system randomness per call, or the factory's fixed seed for a seeded context).  Randomness is SEAL's Blake2xbPRNG
+ * and SEAL's samplers (uniform with rejection, centred binomial), so a seeded context gives SEAL's ciphertext words bit
+ * for bit.  Scalar ring elements must be uploaded as polynomials with every slot set (RingElem::to_poly, as the reference
+ * does at seal_ring.tcc:343-344).  Requires L_E * N_E to be a multiple of 512. ---- */
+int rsg_encode(rsg_context *ctx, const uint64_t *h_sk, const rsg_ringvec *elems, size_t first, size_t count, const uint64_t *h_seeds,
+               rsg_crs *out, size_t out_first);
+
 /* ---- (de)serialisation of encodings: a CRS / proving-key range or a proof.  The reference declares the stream
  * operators (zk_proof_systems/r1cs_ppzksnark.hpp:43-47,142-146) and never defines them; the container is documented in
  * ringsnark_b200/csrc/serialize.inl (magic, parameters and primes, payload in HBM layout, checksum, end mark).

@@ -484,3 +484,116 @@ int ro_decode_limb(const uint64_t *ct, const uint64_t *sk, size_t N_E, size_t L_
   int budget = Qbits - norm_bits - 1;
   return budget < 0 ? 0 : budget;
 }
+
+/* ======================================================================================================================
+ * EncodingElem::encode (ringsnark/seal/seal_ring.tcc:324-359): BatchEncoder::encode + Encryptor::encrypt_symmetric
+ * (depends/SEAL/native/src/seal/encryptor.cpp:242-312 -> util/rlwe.cpp:276-390) for one (ring element, ring limb).
+ * Randomness is SEAL's Blake2xbPRNG (randomgen.cpp:201-211): the byte stream of a seed is the concatenation over
+ * counter = 0, 1, 2, ... of blake2xb(outlen = 4096, in = counter as 8 LE bytes, key = the 64 seed bytes)
+ * (util/blake2xb.c: root hash with the XOF parameter block, then one BLAKE2b call per 64 output bytes with node_offset = block
+ * index; util/blake2b.c is RFC 7693).
+ * ==================================================================================================================== */
+static const uint64_t B2_IV[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                                  0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+static const uint8_t B2_SIGMA[12][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+static inline uint64_t rotr64(uint64_t x, int r) { return (x >> r) | (x << (64 - r)); }
+/* one BLAKE2b compression: h (8 words) absorbs the 128-byte block m (16 LE words); t = bytes hashed so far incl. this block */
+static void b2_compress(uint64_t h[8], const uint64_t m[16], uint64_t t, int last) {
+  uint64_t v[16];
+  for (int i = 0; i < 8; i++) { v[i] = h[i]; v[i + 8] = B2_IV[i]; }
+  v[12] ^= t;
+  if (last) v[14] = ~v[14];
+#define B2_G(a, b, c, d, x, y)          \
+  v[a] = v[a] + v[b] + (x); v[d] = rotr64(v[d] ^ v[a], 32); v[c] = v[c] + v[d]; v[b] = rotr64(v[b] ^ v[c], 24); \
+  v[a] = v[a] + v[b] + (y); v[d] = rotr64(v[d] ^ v[a], 16); v[c] = v[c] + v[d]; v[b] = rotr64(v[b] ^ v[c], 63);
+  for (int r = 0; r < 12; r++) {
+    const uint8_t *s = B2_SIGMA[r];
+    B2_G(0, 4, 8, 12, m[s[0]], m[s[1]]) B2_G(1, 5, 9, 13, m[s[2]], m[s[3]]) B2_G(2, 6, 10, 14, m[s[4]], m[s[5]])
+    B2_G(3, 7, 11, 15, m[s[6]], m[s[7]]) B2_G(0, 5, 10, 15, m[s[8]], m[s[9]]) B2_G(1, 6, 11, 12, m[s[10]], m[s[11]])
+    B2_G(2, 7, 8, 13, m[s[12]], m[s[13]]) B2_G(3, 4, 9, 14, m[s[14]], m[s[15]])
+  }
+#undef B2_G
+  for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+/* one 4096-byte PRNG buffer: out[512] words = blake2xb(4096, counter, key = seed) */
+void ro_blake2xb_buffer(const uint64_t seed[8], uint64_t counter, uint64_t *out) {
+  uint64_t h[8], m[16], root[8];
+  /* root: digest 64, key 64, fanout 1, depth 1, leaf 0 | node_offset 0, xof_length 4096 | node_depth 0, inner 0 */
+  for (int i = 0; i < 8; i++) h[i] = B2_IV[i];
+  h[0] ^= 0x40ull | (0x40ull << 8) | (1ull << 16) | (1ull << 24);
+  h[1] ^= 4096ull << 32;
+  for (int i = 0; i < 16; i++) m[i] = i < 8 ? seed[i] : 0;   /* the key, padded to one block */
+  b2_compress(h, m, 128, 0);
+  for (int i = 0; i < 16; i++) m[i] = 0;
+  m[0] = counter;
+  b2_compress(h, m, 136, 1);
+  for (int i = 0; i < 8; i++) root[i] = h[i];
+  for (uint64_t b = 0; b < 64; b++) {
+    /* digest 64, key 0, fanout 0, depth 0, leaf_length 64 | node_offset b, xof_length 4096 | node_depth 0, inner_length 64 */
+    for (int i = 0; i < 8; i++) h[i] = B2_IV[i];
+    h[0] ^= 0x40ull | (64ull << 32);
+    h[1] ^= b | (4096ull << 32);
+    h[2] ^= 64ull << 8;
+    for (int i = 0; i < 16; i++) m[i] = i < 8 ? root[i] : 0;
+    b2_compress(h, m, 64, 1);
+    for (int i = 0; i < 8; i++) out[b * 8 + i] = h[i];
+  }
+}
+/* bytes [off, off + n) of the PRNG stream of `seed` */
+void ro_prng_bytes(const uint64_t seed[8], uint64_t off, size_t n, uint8_t *out) {
+  uint64_t buf[512];
+  uint64_t have = (uint64_t)-1;
+  for (size_t k = 0; k < n; k++) {
+    const uint64_t pos = off + k, ctr = pos / 4096;
+    if (ctr != have) { ro_blake2xb_buffer(seed, ctr, buf); have = ctr; }
+    out[k] = ((const uint8_t *)buf)[pos % 4096];
+  }
+}
+/* slots: N_R values mod t of ring limb j; sk: [L_E][N_E] secret key (NTT form, first L_E limbs); seed: what the context's
+ * random generator factory hands to every PRNG it creates (randomgen.h:440-448); ct: [2][L_E][N_E]. */
+void ro_encrypt_limb(const uint64_t *slots, size_t N_R, uint64_t t, size_t N_E, size_t L_E, const uint64_t *Q, const uint64_t *sk,
+                     const uint64_t seed[8], uint64_t *ct) {
+  uint64_t *plain = malloc(N_E * 8), *pntt = malloc(L_E * N_E * 8), *e = malloc(N_E * 8);
+  ro_batch_encode(slots, N_R, N_E, t, plain);                    /* batchencoder.cpp:110-149 */
+  ro_plain_lift_ntt(plain, N_E, t, Q, L_E, pntt);                /* encryptor.cpp:260-308: same lift as transform_to_ntt */
+  /* rlwe.cpp:321-328: bootstrap PRNG -> 64-byte public seed -> ciphertext PRNG */
+  uint64_t pub[8];
+  ro_prng_bytes(seed, 0, 64, (uint8_t *)pub);
+  /* rlwe.cpp:339 -> sample_poly_uniform (rlwe.cpp:106-131): bulk fill, then rejected words redrawn from the same stream */
+  uint64_t *c0 = ct, *c1 = ct + L_E * N_E;
+  ro_prng_bytes(pub, 0, L_E * N_E * 8, (uint8_t *)c1);
+  uint64_t extra_off = (uint64_t)L_E * N_E * 8;
+  for (size_t l = 0; l < L_E; l++) {
+    const uint64_t max_multiple = 0xFFFFFFFFFFFFFFFFull - (0xFFFFFFFFFFFFFFFFull % Q[l]) - 1;
+    for (size_t i = 0; i < N_E; i++) {
+      uint64_t r = c1[l * N_E + i];
+      while (r >= max_multiple) { ro_prng_bytes(pub, extra_off, 8, (uint8_t *)&r); extra_off += 8; }
+      c1[l * N_E + i] = r % Q[l];
+    }
+  }
+  /* rlwe.cpp:354 -> sample_poly_cbd (rlwe.cpp:68-104): 6 bytes of the BOOTSTRAP stream per coefficient */
+  uint8_t *nb = malloc(6 * N_E);
+  ro_prng_bytes(seed, 64, 6 * N_E, nb);
+  for (size_t l = 0; l < L_E; l++) {
+    for (size_t i = 0; i < N_E; i++) {
+      const uint8_t *x = nb + 6 * i;
+      const int noise = __builtin_popcount(x[0]) + __builtin_popcount(x[1]) + __builtin_popcount(x[2] & 0x1F) - __builtin_popcount(x[3]) -
+                        __builtin_popcount(x[4]) - __builtin_popcount(x[5] & 0x1F);
+      e[i] = noise < 0 ? Q[l] - (uint64_t)(-noise) : (uint64_t)noise;
+    }
+    ro_ntt_forward(e, N_E, Q[l]);                                /* rlwe.cpp:366 */
+    const uint64_t tq = t % Q[l];
+    for (size_t i = 0; i < N_E; i++) {
+      uint64_t v = addmod(mulmod(sk[l * N_E + i], c1[l * N_E + i], Q[l]), mulmod(e[i], tq, Q[l]), Q[l]);   /* a s + t e */
+      v = v ? Q[l] - v : 0;                                      /* rlwe.cpp:386 */
+      c0[l * N_E + i] = addmod(v, pntt[l * N_E + i], Q[l]);      /* encryptor.cpp:310-311 */
+    }
+  }
+  free(plain); free(pntt); free(e); free(nb);
+}

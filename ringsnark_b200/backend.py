@@ -146,6 +146,16 @@ class Context:
         check(self.lib.rsg_decode(self.h, _ptr(sk), None, _ptr(enc), count, _ptr(ring), budget.ctypes.data_as(C.c_void_p)))
         return ring, budget
 
+    def encode(self, sk, elems, seeds, out=None, first=0, count=None, out_first=0):
+        """EncodingElem::encode (seal_ring.tcc:324-359) of device ring elements into a CRS arena.  sk: [L_R][L_E][N_E] (NTT
+        form); seeds: [count][L_R][8] words (what SEAL's random generator factory would seed each encryption with)."""
+        count = len(elems) - first if count is None else count
+        out = out or Crs(self, count)
+        sk, seeds = _u64(sk), _u64(seeds)
+        assert seeds.size == count * self.L_R * 8
+        check(self.lib.rsg_encode(self.h, _ptr(sk), elems.h, first, count, _ptr(seeds), out.h, out_first))
+        return out
+
     def vanishing(self, n):
         Z = np.zeros((self.L_R, n + 1), dtype=np.uint64)
         check(self.lib.rsg_vanishing(self.h, n, _ptr(Z)))

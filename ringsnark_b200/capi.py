@@ -59,6 +59,7 @@ SIGNATURES = {
     "rsg_interpolate": (_int, [_vp, _sz, _sz, _vp, _sz, _vp, _sz]),
     "rsg_instance_map": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "rsg_decode": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "rsg_encode": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz]),
     "rsg_enc_file_info": (_int, [C.c_char_p, _vp, _vp, _vp]),
     "rsg_enc_file_write": (_int, [C.c_char_p, C.c_uint64, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _vp]),
     "rsg_enc_file_read": (_int, [C.c_char_p, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp]),

@@ -389,12 +389,47 @@ class EncodingElem {
     return out;
   }
 
-  // seal_ring.tcc:324-359 -- setup side: SEAL encodes and encrypts, the ciphertexts go straight into one HBM arena.
+  // seal_ring.tcc:324-359 on the GPU: batch encode + symmetric BGV encryption by rsg_encode, straight
+  // into ONE HBM arena -- the CRS never exists on the host.  Randomness is SEAL's: per (element, ring limb) the 64-byte seed the
+  // context's random generator factory would hand out (randomgen.h:440-448 -- fresh system randomness, or the fixed seed of a
+  // seeded factory, in which case the ciphertext words equal SEAL's bit for bit).  RSG_ENCODE=seal keeps SEAL's own path.
   static std::vector<EncodingElem> encode(const SecretKey &sk, const std::vector<RingElem> &rs) {
-    std::vector<RingElem::Host> hosts;
-    hosts.reserve(rs.size());
-    for (const auto &r : rs) hosts.push_back(r.host());
-    return from_seal(SealEnc::encode(sk, hosts));
+    auto &b = detail::backend();
+    const char *mode = std::getenv("RSG_ENCODE");
+    if ((mode && std::string(mode) == "seal") || (b.L_E * b.N_E) % 512 != 0) {
+      std::vector<RingElem::Host> hosts;
+      hosts.reserve(rs.size());
+      for (const auto &r : rs) hosts.push_back(r.host());
+      return from_seal(SealEnc::encode(sk, hosts));
+    }
+    std::vector<EncodingElem> out(rs.size());
+    if (rs.empty()) return out;
+    if (sk.size() != b.L_R) throw std::invalid_argument("one secret key per ring limb expected");
+    std::vector<uint64_t> skw;
+    skw.reserve(b.L_R * b.L_E * b.N_E);
+    for (size_t j = 0; j < b.L_R; j++) skw.insert(skw.end(), sk[j].data().data(), sk[j].data().data() + b.L_E * b.N_E);
+    std::vector<uint64_t> w;
+    w.reserve(rs.size() * b.ring_words);
+    for (const auto &r : rs) r.append_words(w);   // scalars as polynomials with every slot set (seal_ring.tcc:343-344)
+    auto ring = std::make_shared<detail::DevRing>();
+    detail::check(rsg_ringvec_create(b.ctx, rs.size(), &ring->v));
+    detail::check(rsg_ringvec_upload(ring->v, 0, rs.size(), w.data()));
+    auto &ctxs = SealEnc::get_contexts();
+    std::vector<uint64_t> seeds(rs.size() * b.L_R * 8);
+    for (size_t j = 0; j < b.L_R; j++) {
+      auto factory = ctxs[j].first_context_data()->parms().random_generator();
+      if (!factory) factory = ::seal::UniformRandomGeneratorFactory::DefaultFactory();
+      for (size_t i = 0; i < rs.size(); i++) {
+        ::seal::prng_seed_type seed;
+        if (factory->use_random_seed()) ::seal::random_bytes(reinterpret_cast<::seal::seal_byte *>(seed.data()), ::seal::prng_seed_byte_count);
+        else seed = factory->default_seed();
+        std::copy(seed.begin(), seed.end(), seeds.begin() + (i * b.L_R + j) * 8);
+      }
+    }
+    auto arena = detail::new_arena(rs.size());
+    detail::check(rsg_encode(b.ctx, skw.data(), ring->v, 0, rs.size(), seeds.data(), arena->c, 0));
+    for (size_t i = 0; i < rs.size(); i++) out[i] = EncodingElem(arena, i);
+    return out;
   }
   // seal_ring.tcc:435-477 on the GPU: noise budget, c0 + c1 s, exact base conversion q -> t, batch
   // decode -- rsg_decode, bit-identical to SEAL's Decryptor + BatchEncoder.  Empty / zero encodings (no arena) keep the

@@ -19,6 +19,7 @@
 #include "decode.cuh"
 #include "ringops.cuh"
 #include "prover_fast.cuh"
+#include "encode.cuh"
 
 using namespace rsg;
 typedef unsigned __int128 u128;
@@ -254,6 +255,8 @@ struct rsg_context {
   size_t cap_wfB = 0;
   uint64_t *d_decode = nullptr;     // rsg_decode scratch
   size_t cap_decode = 0;
+  uint64_t *d_encode = nullptr;     // rsg_encode scratch
+  size_t cap_encode = 0;
   uint64_t st_wf = 0, st_wd = 0;
   uint64_t st_lin_terms = 0, st_lin_plain = 0, st_lin_launches = 0, st_fwd_polys = 0, st_inv_polys = 0, st_merged = 0;
   // ---- static-plan prover (prover_fast.cuh)
@@ -498,7 +501,7 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
   cudaFree(c->d_plain); cudaFree(c->d_pntt); cudaFree(c->d_partial);
   cudaFree(c->d_term); cudaFree(c->d_pidx); cudaFree(c->d_eidx); cudaFree(c->d_flags); cudaFree(c->d_out_scratch);
   cudaFree(c->d_chunk); cudaFree(c->d_evals); cudaFree(c->d_wit); cudaFree(c->d_zk);
-  cudaFree(c->d_decode); cudaFree(c->d_wfB);
+  cudaFree(c->d_decode); cudaFree(c->d_wfB); cudaFree(c->d_encode);
   cudaFree(c->d_probe); cudaFree(c->d_probe_carry); cudaFree(c->d_nz); cudaFree(c->d_exact); cudaFree(c->d_ip);
   for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   fast_release(c);
@@ -1990,6 +1993,79 @@ extern "C" int rsg_decode(rsg_context *c, const uint64_t *h_sk, const uint64_t *
   }
   // seal_ring.tcc:445-453: decoding_error when a ciphertext has no noise budget left
   if (exhausted) return fail(RSG_ERR_NOISE, "a ciphertext has remaining noise budget <= 0");
+  return RSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// EncodingElem::encode on the device (encode.cuh)
+extern "C" int rsg_encode(rsg_context *c, const uint64_t *h_sk, const rsg_ringvec *elems, size_t first, size_t count,
+                          const uint64_t *h_seeds, rsg_crs *out, size_t out_first) {
+  RSG_TRACE_CALL();
+  if (!c || !h_sk || !elems || !h_seeds || !out) return fail(RSG_ERR_ARG, "null argument");
+  if (first + count > elems->n || out_first + count > out->n) return fail(RSG_ERR_ARG, "range");
+  if ((c->L_E * c->N_E) % 512) return fail(RSG_ERR_UNSUPPORTED, "L_E * N_E must be a multiple of 512 (one PRNG buffer = 512 words)");
+  if (!count) return RSG_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc;
+  const size_t L_R = c->L_R, L_E = c->L_E, N_E = c->N_E, poly = L_R * N_E, per_general = poly * L_E, W = c->ring_words();
+  const size_t chunk = std::min<size_t>(count, std::max<size_t>(1, std::min<size_t>(256, c->pntt_budget_words / per_general)));
+  const uint32_t nb_boot = (uint32_t)((64 + 6 * N_E + 4095) / 4096), nb_ct = (uint32_t)(L_E * N_E / 512);
+  const size_t boot_stride = (size_t)nb_boot * 512, S = chunk * L_R;
+  // scratch: [sk | seeds | boot | roots | noise | err]
+  const size_t n_sk = L_R * L_E * N_E, n_seeds = S * 8, n_boot = S * boot_stride, n_roots = S * std::max(nb_boot, nb_ct) * 8,
+               n_noise = S * L_E * N_E;
+  if ((rc = ensure(c, &c->d_encode, &c->cap_encode, n_sk + n_seeds + n_boot + n_roots + n_noise + 8))) return rc;
+  if ((rc = ensure(c, &c->d_plain, &c->cap_plain, chunk * poly))) return rc;
+  if ((rc = ensure(c, &c->d_pntt, &c->cap_pntt, chunk * per_general))) return rc;
+  uint64_t *d_sk = c->d_encode, *d_seeds = d_sk + n_sk, *d_boot = d_seeds + n_seeds, *d_roots = d_boot + n_boot, *d_noise = d_roots + n_roots;
+  uint32_t *d_err = (uint32_t *)(d_noise + n_noise);
+  cudaStream_t st = c->stream;
+  CUDA_TRY(cudaMemcpyAsync(d_sk, h_sk, n_sk * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(d_err, 0, 8, st));
+  for (size_t e0 = 0; e0 < count; e0 += chunk) {
+    const size_t ne = std::min(chunk, count - e0), ns = ne * L_R;
+    const uint32_t n_streams = (uint32_t)ns;
+    // BatchEncoder::encode + the centred lift and forward NTTs of encryptor.cpp:260-308 (the prover's own kernels)
+    if ((rc = launch_encode(c, elems->d + (first + e0) * W, nullptr, ne, c->d_plain))) return rc;
+    if ((rc = launch_lift_ntt(c, c->d_plain, ne, c->d_pntt))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_seeds, h_seeds + e0 * L_R * 8, ns * 8 * 8, cudaMemcpyHostToDevice, st));
+    {   // bootstrap streams: public seed + noise bytes
+      LaunchScope ls(c, "k_b2x");
+      const size_t nr = ns * nb_boot;
+      k_b2x_roots<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(d_seeds, 8, n_streams, nb_boot, d_roots);
+      k_b2x_blocks<<<(unsigned)((nr * 64 + 127) / 128), 128, 0, st>>>(d_roots, n_streams, nb_boot, d_boot, boot_stride);
+    }
+    uint64_t *arena = out->d;
+    {   // ciphertext streams, keyed by the public seeds: the bulk of sample_poly_uniform lands in c1
+      LaunchScope ls(c, "k_b2x");
+      const size_t nr = ns * nb_ct;
+      k_b2x_roots<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(d_boot, boot_stride, n_streams, nb_ct, d_roots);
+      k_b2x_blocks<<<(unsigned)((nr * 64 + 127) / 128), 128, 0, st>>>(d_roots, n_streams, nb_ct,
+                                                                     arena + (out_first + e0) * c->enc_words() + L_E * N_E, 2 * L_E * N_E);
+    }
+    {
+      LaunchScope ls(c, "k_enc_uniform_fix");
+      k_enc_uniform_fix<<<n_streams, 256, 0, st>>>(c->d_params, arena, out_first + e0, d_boot, boot_stride, d_err);
+    }
+    {
+      LaunchScope ls(c, "k_enc_noise");
+      k_enc_noise<<<dim3((unsigned)((N_E + 255) / 256), n_streams), 256, 0, st>>>(c->d_params, d_boot, boot_stride, n_streams, d_noise);
+    }
+    CUDA_TRY(cudaGetLastError());
+    for (size_t l = 0; l < L_E; l++)
+      if ((rc = ntt_dev(c, d_noise + l * ns * N_E, ns, 0, l, 0))) return rc;
+    {
+      LaunchScope ls(c, "k_enc_finish");
+      k_enc_finish<<<dim3((unsigned)((N_E + 255) / 256), (unsigned)L_E, n_streams), 256, 0, st>>>(c->d_params, arena, out_first + e0, d_sk, d_noise,
+                                                                                                 c->d_pntt, n_streams);
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  uint32_t err = 0;
+  CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (err) return fail(RSG_ERR_UNSUPPORTED, "uniform sampling: more redraws than the device list holds");
   return RSG_OK;
 }
 

@@ -149,3 +149,26 @@ def decode(enc, sk, N_R, L_R, q, N_E, L_E, Q):
         e, s = np.ascontiguousarray(enc[j]), np.ascontiguousarray(sk[j])
         budgets.append(int(fn(e.ctypes.data, s.ctypes.data, N_E, L_E, Q.ctypes.data, int(q[j]), N_R, out[j].ctypes.data)))
     return out.reshape(-1), budgets
+
+
+def prng_bytes(seed, off, n):
+    """Bytes [off, off+n) of SEAL's Blake2xbPRNG stream for the 8-word seed (randomgen.cpp:201-211, util/blake2xb.c)."""
+    seed = c(seed)
+    out = np.zeros(n, dtype=np.uint8)
+    lib.ro_prng_bytes.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p]
+    lib.ro_prng_bytes(seed.ctypes.data, off, n, out.ctypes.data)
+    return out
+
+
+def encode(ring, sk, seeds, N_R, L_R, q, N_E, L_E, Q):
+    """EncodingElem::encode (seal_ring.tcc:324-359) of one ring element [L_R*N_R] under the secret keys [L_R][L_E][N_E];
+    seeds: [L_R][8] words, the seed every PRNG of ring limb j's context starts from.  Returns [L_R][2][L_E][N_E] words."""
+    ring, sk, Q, seeds = c(ring).reshape(L_R, N_R), c(sk).reshape(L_R, L_E * N_E), c(Q), c(seeds).reshape(L_R, 8)
+    fn = lib.ro_encrypt_limb
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    out = np.zeros((L_R, 2 * L_E * N_E), dtype=np.uint64)
+    for j in range(L_R):
+        r, s, sd = np.ascontiguousarray(ring[j]), np.ascontiguousarray(sk[j]), np.ascontiguousarray(seeds[j])
+        fn(r.ctypes.data, N_R, int(q[j]), N_E, L_E, Q.ctypes.data, s.ctypes.data, sd.ctypes.data, out[j].ctypes.data)
+    return out.reshape(-1)

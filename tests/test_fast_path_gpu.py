@@ -212,3 +212,103 @@ def test_c2p_ring_element_coefficients():
         del s_pows, delta_ts, ev, coeffs, H
     finally:
         ctx.close()
+
+
+def _seeds(case_seed, count, L_R):
+    """cases.hpp::make_enc_contexts seeds limb j's factory with {seed, j + 1, 0xB200, 0...}; a seeded factory hands the same
+    seed to every PRNG it creates (randomgen.h:440-448)."""
+    s = np.zeros((count, L_R, 8), dtype=np.uint64)
+    for j in range(L_R):
+        s[:, j, 0], s[:, j, 1], s[:, j, 2] = int(case_seed), j + 1, 0xB200
+    return s
+
+
+@pytest.mark.parametrize("path", GOLD, ids=IDS)
+def test_encode_reproduces_reference_crs(path):
+    """EncodingElem::encode on the GPU (rsg_encode): decode the reference's CRS elements with the C oracle, encode the ring
+    elements again on the GPU under the same secret keys and seeds -> SEAL's ciphertext words, bit for bit (Blake2xb PRNG,
+    uniform and centred-binomial samplers, c0 = -(a s + t e) + m)."""
+    import ringsnark_b200 as rs
+    case = Case(path)
+    ctx = rs.Context(case.N_R, case.q, case.N_E, case.Q)
+    try:
+        sk = case.d["dec_sk"]
+        want = np.concatenate([case.enc("crs_s_pows")[0], case.enc("crs_delta_mid")[0][:3], case.enc("crs_alpha")[0], case.enc("crs_beta")[0]])
+        rings = np.stack([O.decode(w, sk, case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)[0] for w in want])
+        vec = ctx.ringvec_from(rings)
+        crs = ctx.encode(sk, vec, _seeds(case.seed, len(want), case.L_R))
+        got = crs.download()
+        for i in range(len(want)):
+            assert np.array_equal(got[i], want[i]), i
+        # and the verifier's front half gives the ring elements back
+        ring2, budget = ctx.decode(sk, got)
+        assert np.array_equal(ring2, rings)
+        del vec, crs
+    finally:
+        ctx.close()
+
+
+def test_encode_redraws_against_oracle():
+    """sample_poly_uniform's rejection loop (rlwe.cpp:120-127) practically never fires for SEAL's default primes (just below a
+    power of two: ~2^-31 per word); with primes near 0.75 * 2^60 one word in 64 is redrawn, some of them twice.  GPU against
+    the C oracle (pinned to SEAL on the bulk path by the golden CRS)."""
+    import ringsnark_b200 as rs
+    N_R, N_E = 128, 256
+
+    def primes(start, count):
+        out, k = [], start // 512
+        while len(out) < count:
+            p = k * 512 + 1
+            if pow(2, p - 1, p) == 1 and pow(3, p - 1, p) == 1 and pow(5, p - 1, p) == 1:
+                out.append(p)
+            k += 1
+        return out
+
+    Q = primes(3 << 58, 4)
+    q = primes(1 << 24, 2)
+    ctx = rs.Context(N_R, q, N_E, Q)
+    try:
+        rng = np.random.default_rng(4)
+        L_R, L_E, count = 2, 4, 5
+        sk = np.stack([np.stack([rng.integers(0, Ql, size=N_E, dtype=np.uint64) for Ql in Q]) for _ in range(L_R)])
+        rings = np.stack([np.concatenate([rng.integers(0, qj, size=N_R, dtype=np.uint64) for qj in q]) for _ in range(count)])
+        seeds = rng.integers(0, 2 ** 63, size=(count, L_R, 8), dtype=np.uint64)
+        n_rej = 0
+        for i in range(count):
+            pub = O.prng_bytes(seeds[i, 0], 0, 64).view(np.uint64)
+            bulk = O.prng_bytes(pub, 0, L_E * N_E * 8).view(np.uint64).reshape(L_E, N_E)
+            for l, Ql in enumerate(Q):
+                n_rej += int((bulk[l] >= np.uint64((2 ** 64 - 1) - ((2 ** 64 - 1) % Ql) - 1)).sum())
+        assert n_rej > 20          # the case really exercises the redraws
+        vec = ctx.ringvec_from(rings)
+        got = ctx.encode(sk, vec, seeds).download()
+        for i in range(count):
+            want = O.encode(rings[i], sk, seeds[i], N_R, L_R, q, N_E, L_E, Q)
+            assert np.array_equal(got[i], want), i
+        del vec
+    finally:
+        ctx.close()
+
+
+def test_encode_round_trip_full_size():
+    """C4 parameters (N_E = 2^14, 8 limbs): decode(encode(r)) = r with fresh noise budget, 40 elements, distinct seeds."""
+    import ringsnark_b200 as rs
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c4"]
+    ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"])
+    try:
+        rng = np.random.default_rng(9)
+        count = 40
+        sk = np.stack([rng.integers(0, int(Ql), size=ctx.N_E, dtype=np.uint64) for Ql in cfg["Q"]])[None]
+        vec = ctx.ringvec(count)
+        vec.fill_uniform(11)
+        seeds = rng.integers(0, 2 ** 63, size=(count, 1, 8), dtype=np.uint64)
+        crs = ctx.encode(sk, vec, seeds)
+        ring, budget = ctx.decode(sk, crs.download())
+        assert np.array_equal(ring, vec.download())
+        assert (budget > 200).all()
+        one = O.encode(vec.download(3, 1)[0], sk, seeds[3], ctx.N_R, 1, cfg["q"], ctx.N_E, ctx.L_E, cfg["Q"])
+        assert np.array_equal(crs.download(3, 1)[0], one)
+        del vec, crs
+    finally:
+        ctx.close()

@@ -173,3 +173,18 @@ def test_decode_matches_reference(path):
         got, b = O.decode(proof[k], sk, case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)
         assert np.array_equal(got, want[k]), k
         assert b == [int(x) for x in budget[k]], k
+
+
+@pytest.mark.parametrize("path", GOLD, ids=IDS)
+def test_oracle_encode_reproduces_reference_crs(path):
+    """ro_encrypt_limb (Blake2xb PRNG, uniform + centred-binomial samplers, BGV symmetric encryption) against the CRS the
+    unmodified reference generator produced with seeded contexts: decode every checked element, encode it again -> same words."""
+    case = Case(path)
+    sk = case.d["dec_sk"]
+    seeds = np.array([[int(case.seed), j + 1, 0xB200, 0, 0, 0, 0, 0] for j in range(case.L_R)], dtype=np.uint64)
+    for name in ("crs_s_pows", "crs_delta_ts", "crs_delta_mid", "crs_alpha", "crs_beta"):
+        words = case.enc(name)[0]
+        for idx in range(min(2, len(words))):
+            ring, _ = O.decode(words[idx], sk, case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)
+            enc = O.encode(ring, sk, seeds, case.N_R, case.L_R, case.q, case.N_E, case.L_E, case.Q)
+            assert np.array_equal(enc, words[idx]), (name, idx)
