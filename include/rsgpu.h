@@ -34,6 +34,8 @@ extern "C" {
 #define RSG_ERR_NOTINV (-4)    /* "element is not invertible in ring" (seal_ring.tcc:87-103) */
 #define RSG_ERR_UNSUPPORTED (-5)
 #define RSG_ERR_NOISE (-6)     /* decoding_error: a ciphertext has no noise budget left (seal_ring.tcc:445-453) */
+#define RSG_ERR_TRANSPARENT (-7) /* a fused prover met a transparent-ciphertext candidate (seal_ring.tcc:493-504): the outputs are
+                                  * NOT valid; redo the proof with the per-inner-product entry points, which resolve it exactly */
 
 /* Per-term dispatch of EncodingElem::operator*= (seal_ring.tcc:509-548) decided by the host shim exactly as the
  * reference does: is_zero() (incl. the SealPoly::is_zero prefix quirk) -> SKIP; scalar 1 -> ONE (ciphertext taken
@@ -197,7 +199,7 @@ int rsg_decode(rsg_context *ctx, const uint64_t *h_sk, const uint64_t *d_enc, co
  * fresh system randomness per call, or the factory's fixed seed for a seeded context).  Randomness is SEAL's Blake2xbPRNG
  * and SEAL's samplers (uniform with rejection, centred binomial), so a seeded context gives SEAL's ciphertext words bit
  * for bit.  Scalar ring elements must be uploaded as polynomials with every slot set (RingElem::to_poly, as the reference
- * does at seal_ring.tcc:343-344).  Requires L_E * N_E to be a multiple of 512. ---- */
+ * does at seal_ring.tcc:343-344). ---- */
 int rsg_encode(rsg_context *ctx, const uint64_t *h_sk, const rsg_ringvec *elems, size_t first, size_t count, const uint64_t *h_seeds,
                rsg_crs *out, size_t out_first);
 
@@ -233,6 +235,29 @@ typedef struct {
 int rsg_groth16_prove(rsg_context *ctx, const rsg_r1cs *r1cs, const rsg_crs *crs, const rsg_groth16_layout *layout,
                       rsg_ringvec *assignment, const uint64_t *h_assignment, const uint8_t *h_aux_kind,
                       uint64_t *h_proof, uint64_t *d_proof, size_t *n_used);
+
+/* The same prover over CRS vectors that live in DIFFERENT arenas -- what the generator templates produce: one
+ * EncodingElem::encode call, hence one arena, per vector (groth16.tcc:36-55).  refs[0..4] = s_pows[0..n], delta_ts[0..n],
+ * delta_mid[0..n_aux), alpha, beta: the arena and the index of the FIRST encoding of each.  Returns RSG_ERR_TRANSPARENT when a
+ * probe sum vanished and RSG_ERR_UNSUPPORTED when the term set exceeds the NTT-plaintext budget; the caller then forms the proof
+ * from rsg_inner_product / rsg_enc_add as the template does. */
+typedef struct {
+  const rsg_crs *crs;
+  size_t first;
+} rsg_crs_ref;
+int rsg_groth16_prove_refs(rsg_context *ctx, const rsg_r1cs *r1cs, const rsg_crs_ref refs[5], rsg_ringvec *assignment,
+                           const uint64_t *h_assignment, const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
+                           size_t *n_used);
+/* rinocchio::prover (zk_proof_systems/rinocchio/rinocchio.tcc:74-190) in one call.  refs[0..5] = s_pows[0..n],
+ * alpha_s_pows[0..n], beta_prods[0..n_aux), beta_rv_ts, beta_rw_ts, beta_ry_ts (the last three only read in zero-knowledge mode
+ * with auxiliary inputs).  h_d: the prover's d1, d2, d3 ([3][L_R][N_R] host words, RingElem::random_invertible_element drawn by
+ * the caller in the reference's order) or NULL for the non-zero-knowledge proof (rinocchio.tcc:81-90).  Outputs: 9 encodings
+ * A, alpha_A, B, alpha_B, C, alpha_C, D, alpha_D, F (proof order, rinocchio.hpp); F is all-zero words (the reference's empty
+ * encoding) without auxiliary inputs.  Each coefficient is batch-encoded and transformed ONCE and multiplied into both the
+ * s_pows and the alpha_s_pows stream.  Error returns as rsg_groth16_prove_refs. */
+int rsg_rinocchio_prove(rsg_context *ctx, const rsg_r1cs *r1cs, const rsg_crs_ref refs[6], rsg_ringvec *assignment,
+                        const uint64_t *h_assignment, const uint8_t *h_aux_kind, const uint64_t *h_d, uint64_t *h_proof,
+                        uint64_t *d_proof, size_t *n_used);
 
 /* The second half of rsg_groth16_prove on its own (the multi-GPU driver runs the witness map sharded by SLOT, exchanges
  * the coefficients with one all-to-all, and then calls this on every rank's TERM shard): the six inner products and the

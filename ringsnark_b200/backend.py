@@ -294,6 +294,48 @@ class Groth16ProvingKey:
         return out, [int(u) for u in used]
 
 
+class CrsRef(C.Structure):
+    """rsg_crs_ref (include/rsgpu.h): an arena handle and the index of the first encoding of a key vector."""
+    _fields_ = [("crs", C.c_void_p), ("first", C.c_size_t)]
+
+
+def rinocchio_prove(ctx, r1cs, refs, assignment, h_d=None, aux_kind=None, h_assignment=None):
+    """rinocchio::prover (rinocchio.tcc:74-190) in one call (rsg_rinocchio_prove).  refs: six (Crs, first) pairs -- s_pows,
+    alpha_s_pows, beta_prods, beta_rv_ts, beta_rw_ts, beta_ry_ts; h_d: [3][L_R*N_R] words d1, d2, d3 or None (non-ZK).
+    Returns (proof words [9][enc_words], n_used[9])."""
+    arr = (CrsRef * 6)()
+    for k, (crs, first) in enumerate(refs):
+        arr[k].crs, arr[k].first = (crs.h if crs is not None else None), first
+    out = np.empty((9, ctx.enc_words), dtype=np.uint64)
+    used = (C.c_size_t * 9)()
+    if h_d is not None:
+        h_d = _u64(h_d)
+    if aux_kind is not None:
+        aux_kind = np.ascontiguousarray(aux_kind, dtype=np.uint8)
+    if h_assignment is not None:
+        h_assignment = _u64(h_assignment)
+    check(ctx.lib.rsg_rinocchio_prove(ctx.h, r1cs.h, arr, assignment.h, _ptr(h_assignment) if h_assignment is not None else None,
+                                      _ptr(aux_kind) if aux_kind is not None else None, _ptr(h_d) if h_d is not None else None,
+                                      _ptr(out), None, used))
+    return out, [int(u) for u in used]
+
+
+def groth16_prove_refs(ctx, r1cs, refs, assignment, aux_kind=None, h_assignment=None):
+    """groth16::prover over key vectors in different arenas (rsg_groth16_prove_refs): refs = five (Crs, first) pairs."""
+    arr = (CrsRef * 5)()
+    for k, (crs, first) in enumerate(refs):
+        arr[k].crs, arr[k].first = (crs.h if crs is not None else None), first
+    out = np.empty((3, ctx.enc_words), dtype=np.uint64)
+    used = (C.c_size_t * 3)()
+    if aux_kind is not None:
+        aux_kind = np.ascontiguousarray(aux_kind, dtype=np.uint8)
+    if h_assignment is not None:
+        h_assignment = _u64(h_assignment)
+    check(ctx.lib.rsg_groth16_prove_refs(ctx.h, r1cs.h, arr, assignment.h, _ptr(h_assignment) if h_assignment is not None else None,
+                                         _ptr(aux_kind) if aux_kind is not None else None, _ptr(out), None, used))
+    return out, [int(u) for u in used]
+
+
 class _Arena:
     def __len__(self):
         return self.n

@@ -70,6 +70,8 @@ SIGNATURES = {
     "rsg_r1cs_destroy": (None, [_vp]),
     "rsg_r1cs_evaluate": (_int, [_vp, _vp, _vp, _vp]),
     "rsg_groth16_prove": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rsg_groth16_prove_refs": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rsg_rinocchio_prove": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rsg_groth16_lincombs": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "rsg_ringvec_wrap": (_int, [_vp, _vp, _sz, _pp]),
     "rsg_batch_encode": (_int, [_vp, _vp, _sz, _vp]),

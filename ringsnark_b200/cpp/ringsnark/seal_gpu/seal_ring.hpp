@@ -304,6 +304,21 @@ class EncodingElem {
   EncodingElem(std::shared_ptr<detail::DevEnc> arena, size_t idx) : arena_(std::move(arena)), idx_(idx) {}
   [[nodiscard]] bool is_empty() const { return !arena_ && !zero_; }
   [[nodiscard]] bool is_zero_ciphertext() const { return zero_; }
+  // (arena handle, index) of this encoding -- null handle for empty / zero encodings; used by the fused provers
+  [[nodiscard]] const rsg_crs *arena_handle() const { return arena_ ? arena_->c : nullptr; }
+  [[nodiscard]] size_t arena_index() const { return idx_; }
+  // true when [begin, end) are consecutive encodings of ONE arena (what one encode() call returns)
+  static bool contiguous(std::vector<EncodingElem>::const_iterator begin, std::vector<EncodingElem>::const_iterator end, rsg_crs_ref *ref) {
+    ref->crs = nullptr;
+    ref->first = 0;
+    if (begin == end) return true;
+    if (!begin->arena_) return false;
+    for (auto it = begin; it != end; ++it)
+      if (it->arena_ != begin->arena_ || it->idx_ != begin->idx_ + (size_t)(it - begin)) return false;
+    ref->crs = begin->arena_->c;
+    ref->first = begin->idx_;
+    return true;
+  }
 
   /* Static (seal_ring.hpp:254-341) */
   static std::tuple<PublicKey, SecretKey> keygen() { return SealEnc::keygen(); }
@@ -396,7 +411,7 @@ class EncodingElem {
   static std::vector<EncodingElem> encode(const SecretKey &sk, const std::vector<RingElem> &rs) {
     auto &b = detail::backend();
     const char *mode = std::getenv("RSG_ENCODE");
-    if ((mode && std::string(mode) == "seal") || (b.L_E * b.N_E) % 512 != 0) {
+    if (mode && std::string(mode) == "seal") {
       std::vector<RingElem::Host> hosts;
       hosts.reserve(rs.size());
       for (const auto &r : rs) hosts.push_back(r.host());
@@ -814,5 +829,7 @@ inline std::vector<ringsnark::seal_gpu::RingElem> interpolate<ringsnark::seal_gp
   for (size_t i = 0; i < n; i++) coeffs.push_back(R::from_device(out, i));
   return coeffs;
 }
+
+#include "provers.hpp"
 
 #endif  // RINGSNARK_SEAL_GPU_RING_HPP

@@ -116,13 +116,20 @@ __global__ void __launch_bounds__(128) k_b2x_blocks(const uint64_t *__restrict__
 // stream's seed.  256 threads.
 constexpr int ENC_MAX_REJ = 256;
 __global__ void __launch_bounds__(256) k_enc_uniform_fix(const DevParams *__restrict__ P, uint64_t *__restrict__ arena_first, size_t enc_first,
-                                                         const uint64_t *__restrict__ pub_seeds, size_t seed_stride, uint32_t *__restrict__ err) {
+                                                         const uint64_t *__restrict__ pub_seeds, size_t seed_stride, uint32_t *__restrict__ err,
+                                                         const uint64_t *__restrict__ bulk, size_t bulk_stride) {
   __shared__ uint32_t n_rej;
   __shared__ uint32_t pos[ENC_MAX_REJ];
   const uint32_t s = blockIdx.x, L_E = P->L_E, N_E = P->N_E, L_R = P->L_R;
   const size_t ct_words = 2 * (size_t)L_E * N_E;
   uint64_t *c1 = arena_first + (enc_first * L_R + s) * ct_words + (size_t)L_E * N_E;   // stream s = (element, ring limb)
   const uint32_t words = L_E * N_E;
+  // bulk (nullable): the stream's first `words` words when they were generated aside (L_E * N_E not a whole number of
+  // 512-word PRNG buffers); otherwise they already sit in c1
+  if (bulk) {
+    const uint64_t *src = bulk + (size_t)s * bulk_stride;
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) c1[w] = src[w];
+  }
   if (threadIdx.x == 0) n_rej = 0;
   __syncthreads();
   for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) {

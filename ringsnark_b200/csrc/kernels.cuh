@@ -305,7 +305,8 @@ __device__ __forceinline__ void crs_lincomb_body(const DevParams *__restrict__ P
                                                  const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
                                                  uint32_t n_terms, uint32_t terms_per_split,
                                                  const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
-                                                 const uint32_t *__restrict__ zoff, const uint8_t *__restrict__ slot_skip) {
+                                                 const uint32_t *__restrict__ zoff, const uint8_t *__restrict__ slot_skip,
+                                                 const uint64_t *const *__restrict__ term_ptr = nullptr) {
   const uint32_t N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
   const uint32_t x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const uint32_t j = blockIdx.y / L_E, l = blockIdx.y - j * L_E;
@@ -329,9 +330,9 @@ __device__ __forceinline__ void crs_lincomb_body(const DevParams *__restrict__ P
     uint32_t pi[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
-      const uint32_t ci = __ldg(term + t + u);
       pi[u] = __ldg(pidx + t + u);
-      const uint64_t *c = crs + (size_t)ci * enc_words + c_off;
+      // term_ptr (prover_fast.cuh): the encodings of a term list may live in different arenas -- one device pointer per term
+      const uint64_t *c = (term_ptr ? term_ptr[t + u] : crs + (size_t)__ldg(term + t + u) * enc_words) + c_off;
       if (slot_skip && pi[u] != 0xFFFFFFFFu && slot_skip[pi[u]]) {   // skipped on the device: contributes nothing
         c0[u] = c1[u] = pp[u] = make_ulonglong2(0, 0);
         continue;
@@ -350,9 +351,9 @@ __device__ __forceinline__ void crs_lincomb_body(const DevParams *__restrict__ P
     }
   }
   for (; t < t1; t++) {
-    const uint32_t ci = __ldg(term + t), pi = __ldg(pidx + t);
+    const uint32_t pi = __ldg(pidx + t);
     if (slot_skip && pi != 0xFFFFFFFFu && slot_skip[pi]) continue;
-    const uint64_t *c = crs + (size_t)ci * enc_words + c_off;
+    const uint64_t *c = (term_ptr ? term_ptr[t] : crs + (size_t)__ldg(term + t) * enc_words) + c_off;
     const ulonglong2 c0 = ld_stream(c), c1 = ld_stream(c + k_stride);
     const ulonglong2 pp = pi != 0xFFFFFFFFu ? ld_stream(pntt + (size_t)pi * p_stride + p_off) : make_ulonglong2(1, 1);
     a00.mac(c0.x, pp.x);
@@ -372,16 +373,18 @@ __global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict
                                                      uint32_t n_terms, uint32_t terms_per_split,
                                                      const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
                                                      const uint32_t *__restrict__ zoff = nullptr,
-                                                     const uint8_t *__restrict__ slot_skip = nullptr) {
-  crs_lincomb_body<UNROLL>(P, crs, term, pidx, n_terms, terms_per_split, pntt, partial, zoff, slot_skip);
+                                                     const uint8_t *__restrict__ slot_skip = nullptr,
+                                                     const uint64_t *const *__restrict__ term_ptr = nullptr) {
+  crs_lincomb_body<UNROLL>(P, crs, term, pidx, n_terms, terms_per_split, pntt, partial, zoff, slot_skip, term_ptr);
 }
 // 64 registers x 256 threads = 16 Ki registers: the CTA that fits next to k_lift_fwd_ntt_f64_r96 on one SM.
 __global__ void __maxnreg__(64) k_crs_lincomb_r64(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
                                                   const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
                                                   uint32_t n_terms, uint32_t terms_per_split,
                                                   const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
-                                                  const uint32_t *__restrict__ zoff, const uint8_t *__restrict__ slot_skip) {
-  crs_lincomb_body<2>(P, crs, term, pidx, n_terms, terms_per_split, pntt, partial, zoff, slot_skip);
+                                                  const uint32_t *__restrict__ zoff, const uint8_t *__restrict__ slot_skip,
+                                                  const uint64_t *const *__restrict__ term_ptr) {
+  crs_lincomb_body<2>(P, crs, term, pidx, n_terms, terms_per_split, pntt, partial, zoff, slot_skip, term_ptr);
 }
 
 // out[w] = sum_s parts[s][w] mod Q_l(w): the modular-add kernel (after split-K or after the NCCL all-gather).

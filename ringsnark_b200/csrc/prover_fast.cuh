@@ -23,23 +23,32 @@ struct FastVec {
   const uint64_t *base;   // address element 0 of the vector WOULD have (only [lo, lo + count) is read)
   uint32_t lo, count, eid0;
 };
+constexpr int FP_MAXV = 8;    // coefficient vectors per plan
+constexpr int FP_MAXIP = 12;  // inner products per plan
 struct FastTable {
-  FastVec vec[6];           // A_io, A_mid, B_io, B_mid, H, aux
-  uint32_t nS, nH, nM, n_elems, n_parts, n_slots;
-  uint32_t crs_off[6];      // arena index of the CRS element multiplying element 0 of each vector's range
-  const uint8_t *aux_kind;  // device copy of h_aux_kind (absolute auxiliary index), null = all RSG_AUX_POLY
-  uint32_t alpha_idx, beta_idx;   // arena index or 0xFFFFFFFF
+  // ringGroth16: A_io, A_mid, B_io, B_mid (the merged pairs, nS elements each), H, aux.
+  // Rinocchio (nS = 0, no merged pairs): A_mid, B_mid, C_mid, H, Z, aux, D = (d1, d2, d3).
+  FastVec vec[FP_MAXV];
+  uint32_t n_vec;
+  uint32_t nS, n_elems, n_parts, n_slots;
+  const uint8_t *kind[FP_MAXV];   // per vector (nullable = every element is a polynomial): RSG_TERM_* / RSG_AUX_POLY per ABSOLUTE
+                                  // element index -- scalars the caller holds (seal_ring.tcc:514-529)
+  uint32_t n_ip;
+  uint32_t ip_vec[FP_MAXIP];      // inner product p multiplies vector ip_vec[p] ...
+  const uint64_t *ip_base[FP_MAXIP];   // ... by the contiguous CRS encodings starting here (element 0 of the vector's RANGE);
+                                       // pointers, not arena indices: the vectors of a key may come from different encode() calls
+  const uint64_t *alpha, *beta;   // ringGroth16: the bare encodings added to A and B, or null
 };
 // status words (device, copied back once per proof)
 constexpr int FPS_CANDIDATE = 0;   // a probe sum vanished somewhere: resolve on the exact path
-constexpr int FPS_COUNT0 = 1;      // [1..6]: summed terms per inner product
-constexpr int FPS_WORDS = 8;
+constexpr int FPS_COUNT0 = 1;      // [1 .. FP_MAXV]: non-skipped elements per coefficient vector
+constexpr int FPS_WORDS = 16;
 
 __device__ __forceinline__ void fast_locate(const FastTable &T, uint32_t eid, uint32_t &k, uint32_t &i) {
   k = 0;
 #pragma unroll
-  for (int v = 1; v < 6; v++)
-    if (eid >= T.vec[v].eid0) k = v;
+  for (int v = 1; v < FP_MAXV; v++)
+    if (v < (int)T.n_vec && eid >= T.vec[v].eid0) k = v;
   i = T.vec[k].lo + (eid - T.vec[k].eid0);
 }
 
@@ -51,7 +60,7 @@ __global__ void __launch_bounds__(256) k_term_flags(const DevParams *__restrict_
   fast_locate(T, blockIdx.x, k, i);
   const uint32_t W = P->N_R * P->L_R;
   uint32_t kind = 0xFF;
-  if (k == 5 && T.aux_kind) kind = T.aux_kind[i];
+  if (T.kind[k]) kind = T.kind[k][i];
   uint32_t flag;
   if (kind == 0xFF) {   // polynomial: bytes [0, W + 7) all zero  <=>  SealPoly::is_zero says "zero"
     const uint64_t *src = T.vec[k].base + (size_t)i * W;
@@ -145,15 +154,15 @@ __global__ void __launch_bounds__(256) k_centre_add_fast(const DevParams *__rest
 
 // Probe of every inner product at one fixed slot (k = 1, l = 0, x = 0; see k_probe in kernels.cuh): running sums of the c1
 // contributions over the non-skipped terms; status[FPS_CANDIDATE] is raised when a running sum vanishes at a term.
-// totals[k][j] receives the whole sum, prefix (nullable, [6][L_R][max(nS, nH, nM)] with stride `pstride`) every running sum.
-// grid (6, L_R), 256 threads.
-__global__ void __launch_bounds__(256) k_probe_fast(const DevParams *__restrict__ P, FastTable T, const uint64_t *__restrict__ crs,
+// totals[p][j] receives the whole sum of inner product p, prefix (nullable, [n_ip][L_R][pstride]) every running sum.
+// grid (n_ip, L_R), 256 threads.
+__global__ void __launch_bounds__(256) k_probe_fast(const DevParams *__restrict__ P, FastTable T,
                                                     const uint8_t *__restrict__ elem_flag, const uint64_t *__restrict__ pval,
                                                     const uint64_t *__restrict__ pntt, uint64_t *__restrict__ totals,
                                                     uint64_t *__restrict__ prefix, uint32_t pstride, uint32_t *__restrict__ status) {
   __shared__ uint64_t warp_tot[8];
   __shared__ uint64_t run;
-  const uint32_t k = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
+  const uint32_t ip = blockIdx.x, k = T.ip_vec[ip], j = blockIdx.y, N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
   const ModConst m = P->Q[0];
   const size_t ct_words = 2 * (size_t)L_E * N_E, enc_words = (size_t)L_R * ct_words;
   const size_t c_off = (size_t)j * ct_words + (size_t)L_E * N_E;   // k = 1, l = 0, x = 0
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(256) k_probe_fast(const DevParams *__restrict_
       const uint32_t eid = eid0 + t, fl = elem_flag[eid];
       live = !(fl & FP_SKIP);
       if (live) {
-        const uint64_t cw = crs[(size_t)(T.crs_off[k] + t) * enc_words + c_off];
+        const uint64_t cw = T.ip_base[ip][(size_t)t * enc_words + c_off];
         if (fl & FP_ONE) v = cw;
         else if (eid < T.n_parts) v = mul_mod(cw, pval[(size_t)eid * L_R + j], m);
         else v = mul_mod(cw, pntt[(size_t)(2 * T.nS + eid - T.n_parts) * L_R * L_E * N_E + (size_t)j * L_E * N_E], m);
@@ -187,33 +196,92 @@ __global__ void __launch_bounds__(256) k_probe_fast(const DevParams *__restrict_
     for (uint32_t w = 0; w < warp; w++) pre = add_mod(pre, warp_tot[w], m.p);
     v = add_mod(v, pre, m.p);
     if (live && v == 0) cand = 1;
-    if (prefix && t < n_terms) prefix[((size_t)k * L_R + j) * pstride + t] = live ? v : ~0ull;   // ~0: no term here
+    if (prefix && t < n_terms) prefix[((size_t)ip * L_R + j) * pstride + t] = live ? v : ~0ull;   // ~0: no term here
     __syncthreads();
     if (threadIdx.x == 255) run = v;
     __syncthreads();
   }
   if (__syncthreads_or((int)cand) && threadIdx.x == 0) atomicOr(status + FPS_CANDIDATE, 1u);
-  if (threadIdx.x == 0) totals[k * L_R + j] = run;
+  if (threadIdx.x == 0) totals[ip * L_R + j] = run;
 }
 // The operator+= chains of groth16.tcc:89-112 at the probe slot: A = (ip0 += ip1) += alpha, B = (ip2 += ip3) += beta,
 // C = ip4 += ip5; a vanishing intermediate or final sum is a transparent-ciphertext candidate.  One block of 32 threads.
-__global__ void k_probe_chain(const DevParams *__restrict__ P, FastTable T, const uint64_t *__restrict__ crs,
+__global__ void k_probe_chain(const DevParams *__restrict__ P, FastTable T,
                               const uint64_t *__restrict__ totals, uint32_t *__restrict__ status) {
   const uint32_t L_R = P->L_R, L_E = P->L_E, N_E = P->N_E;
   const uint64_t p = P->Q[0].p;
-  const size_t ct_words = 2 * (size_t)L_E * N_E, enc_words = (size_t)L_R * ct_words;
+  const size_t ct_words = 2 * (size_t)L_E * N_E;
   for (uint32_t w = threadIdx.x; w < 3 * L_R; w += blockDim.x) {
     const uint32_t e = w / L_R, j = w - e * L_R, a = 2 * e, b = a + 1;
     if (status[FPS_COUNT0 + a] + status[FPS_COUNT0 + b] == 0) continue;   // both inner products empty: nothing was added
     uint64_t s = add_mod(totals[a * L_R + j], totals[b * L_R + j], p);
     bool cand = s == 0;
-    const uint32_t extra = e == 0 ? T.alpha_idx : (e == 1 ? T.beta_idx : 0xFFFFFFFFu);
-    if (extra != 0xFFFFFFFFu) {
-      s = add_mod(s, crs[(size_t)extra * enc_words + (size_t)j * ct_words + (size_t)L_E * N_E], p);
+    const uint64_t *extra = e == 0 ? T.alpha : (e == 1 ? T.beta : nullptr);
+    if (extra) {
+      s = add_mod(s, extra[(size_t)j * ct_words + (size_t)L_E * N_E], p);
       cand = cand || s == 0;
     }
     if (cand) atomicOr(status + FPS_CANDIDATE, 1u);
   }
+}
+
+// rinocchio::prover's shifts at the probe slot (rinocchio.tcc:166-186).  Inner products: 0 a, 1 alpha_a, 2 b, 3 alpha_b, 4 c,
+// 5 alpha_c, 6 d, 7 alpha_d, 8 z, 9 alpha_z, 10 f.  X += d_k * Y: candidate when the NTT-domain sum vanishes at the slot.
+// dhat[k][j]: NTT-domain plaintext of d_k at (l = 0, x = 0) = pntt of D's slots.  One block of 32 threads.
+struct RinoShift {
+  const uint64_t *beta_ts[3];   // beta_rv_ts, beta_rw_ts, beta_ry_ts (one encoding each)
+};
+__global__ void k_probe_chain_rino(const DevParams *__restrict__ P, RinoShift R,
+                                   const uint64_t *__restrict__ pntt, uint32_t d_slot0, const uint64_t *__restrict__ totals,
+                                   uint32_t *__restrict__ status, uint32_t shifts) {
+  const uint32_t L_R = P->L_R, L_E = P->L_E, N_E = P->N_E;
+  const ModConst m = P->Q[0];
+  const size_t ct_words = 2 * (size_t)L_E * N_E;
+  for (uint32_t j = threadIdx.x; j < L_R; j += blockDim.x) {
+    uint64_t dh[3];
+    for (int k = 0; k < 3; k++) dh[k] = pntt[(size_t)(d_slot0 + k) * L_R * L_E * N_E + (size_t)j * L_E * N_E];
+    bool cand = false;
+    for (int e = 0; e < 6; e++) {   // a, alpha_a, b, alpha_b, c, alpha_c  +=  d_(e/2) * (z | alpha_z)
+      const uint64_t s = add_mod(totals[e * L_R + j], mul_mod(totals[(8 + (e & 1)) * L_R + j], dh[e / 2], m), m.p);
+      cand = cand || s == 0;
+    }
+    uint64_t f = shifts > 1 ? totals[10 * L_R + j] : 1;
+    for (int k = 0; k < 3 && shifts > 1; k++) {
+      const uint64_t cw = R.beta_ts[k][(size_t)j * ct_words + (size_t)L_E * N_E];
+      f = add_mod(f, mul_mod(cw, dh[k], m), m.p);
+      cand = cand || f == 0;
+    }
+    if (cand) atomicOr(status + FPS_CANDIDATE, 1u);
+  }
+}
+// The nine proof elements from the eleven inner products ip[11][E] (order as above) and the three shift plaintexts:
+//   out = [a + d1 z, alpha_a + d1 alpha_z, b + d2 z, alpha_b + d2 alpha_z, c + d3 z, alpha_c + d3 alpha_z, d, alpha_d,
+//          f + d1 beta_rv_ts + d2 beta_rw_ts + d3 beta_ry_ts]                                   (rinocchio.tcc:166-190)
+// zk = 0: no shifts (out = the inner products); zk = 1: the six z / alpha_z shifts; zk = 2: also the three shifts of f (auxiliary
+// inputs present).  Without auxiliary inputs f is all-zero words = the reference's empty encoding.  grid (E / 512, 9).
+__global__ void __launch_bounds__(256) k_rino_combine(const DevParams *__restrict__ P, const uint64_t *__restrict__ ip, RinoShift R,
+                                                      const uint64_t *__restrict__ pntt, uint32_t d_slot0, uint32_t zk,
+                                                      uint64_t *__restrict__ out) {
+  const uint32_t N_E = P->N_E, L_E = P->L_E, L_R = P->L_R, e = blockIdx.y;
+  const size_t ct_words = 2 * (size_t)L_E * N_E, E = (size_t)L_R * ct_words;
+  const size_t w = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (w >= E) return;
+  const uint32_t j = (uint32_t)(w / ct_words), l = (uint32_t)((w / N_E) % L_E), x = (uint32_t)(w % N_E);
+  const ModConst m = P->Q[l];
+  const uint32_t src = e < 8 ? e : 10;
+  ulonglong2 acc = *reinterpret_cast<const ulonglong2 *>(ip + (size_t)src * E + w);
+  if (zk) {
+    auto dhat = [&](int k) { return *reinterpret_cast<const ulonglong2 *>(pntt + ((size_t)(d_slot0 + k) * L_R + j) * L_E * N_E + (size_t)l * N_E + x); };
+    auto fma2 = [&](const uint64_t *y, int k) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(y + w), d = dhat(k);
+      acc.x = add_mod(acc.x, mul_mod(v.x, d.x, m), m.p);
+      acc.y = add_mod(acc.y, mul_mod(v.y, d.y, m), m.p);
+    };
+    if (e < 6) fma2(ip + (size_t)(8 + (e & 1)) * E, e / 2);
+    else if (e == 8 && zk > 1)
+      for (int k = 0; k < 3; k++) fma2(R.beta_ts[k], k);
+  }
+  *reinterpret_cast<ulonglong2 *>(out + (size_t)e * E + w) = acc;
 }
 
 // out[e][w] = sum over the splits z in [zr[e], zr[e+1]) of partial[z][w] mod Q_l(w), e < n_out.  grid (pairs / 256, n_out).
@@ -282,8 +350,8 @@ struct LtCursor {
   size_t c_off, p_off;
 };
 
-__global__ void __launch_bounds__(LT_THREADS) k_crs_lincomb_tma(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
-                                                                const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,
+__global__ void __launch_bounds__(LT_THREADS) k_crs_lincomb_tma(const DevParams *__restrict__ P, const uint64_t *const *__restrict__ term_ptr,
+                                                                const uint32_t *__restrict__ pidx,
                                                                 const uint32_t *__restrict__ zoff, uint32_t Z,
                                                                 const uint8_t *__restrict__ slot_skip,
                                                                 const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial) {
@@ -335,9 +403,9 @@ __global__ void __launch_bounds__(LT_THREADS) k_crs_lincomb_tma(const DevParams 
     }
     const uint32_t s = p_fill % LT_STAGES, use = p_fill / LT_STAGES;
     if (use) mbar_wait(empty + s, (use - 1) & 1);
-    const uint32_t ci = __ldg(term + pc.t), pi = __ldg(pidx + pc.t);
+    const uint32_t pi = __ldg(pidx + pc.t);
     uint64_t *dst = lt_sm + (size_t)s * 3 * LT_XC;
-    const uint64_t *c = crs + (size_t)ci * enc_words + pc.c_off;
+    const uint64_t *c = term_ptr[pc.t] + pc.c_off;
     const uint32_t row_bytes = LT_XC * 8;
     mbar_expect_tx(full + s, pi != 0xFFFFFFFFu ? 3 * row_bytes : 2 * row_bytes);
     bulk_g2s(dst, c, row_bytes, full + s);

@@ -186,6 +186,7 @@ struct WitnessTables {   // per constraint count n
   std::vector<uint64_t> h_Z;    // [L_R][n+1]
   std::vector<uint64_t> h_u;    // [L_R][max(n-1,1)]  rev(Z)^-1 mod x^(n-1)
   Twiddle *d_lagw = nullptr;    // [L_R][n] 1 / prod_{i != j} (j - i): Lagrange denominators (instance.cuh)
+  uint64_t *d_Zvec = nullptr;   // [n+1][L_R][N_R]: coefficients_for_Z as ring elements (every slot = the constant), rinocchio
   bool fast_ready = false;      // quasi-linear path (witness_fast.cuh)
   FastTables ft;
 };
@@ -497,7 +498,7 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (void *p : c->owned) cudaFree(p);
-  for (auto &kv : c->wit) { cudaFree(kv.second.d_Vinv); cudaFree(kv.second.d_T); cudaFree(kv.second.d_Z); }   // d_lagw / fast tables: c->owned
+  for (auto &kv : c->wit) { cudaFree(kv.second.d_Vinv); cudaFree(kv.second.d_T); cudaFree(kv.second.d_Z); cudaFree(kv.second.d_Zvec); }   // d_lagw / fast tables: c->owned
   cudaFree(c->d_plain); cudaFree(c->d_pntt); cudaFree(c->d_partial);
   cudaFree(c->d_term); cudaFree(c->d_pidx); cudaFree(c->d_eidx); cudaFree(c->d_flags); cudaFree(c->d_out_scratch);
   cudaFree(c->d_chunk); cudaFree(c->d_evals); cudaFree(c->d_wit); cudaFree(c->d_zk);
@@ -2003,23 +2004,24 @@ extern "C" int rsg_encode(rsg_context *c, const uint64_t *h_sk, const rsg_ringve
   RSG_TRACE_CALL();
   if (!c || !h_sk || !elems || !h_seeds || !out) return fail(RSG_ERR_ARG, "null argument");
   if (first + count > elems->n || out_first + count > out->n) return fail(RSG_ERR_ARG, "range");
-  if ((c->L_E * c->N_E) % 512) return fail(RSG_ERR_UNSUPPORTED, "L_E * N_E must be a multiple of 512 (one PRNG buffer = 512 words)");
   if (!count) return RSG_OK;
   std::lock_guard<std::mutex> g(c->mu);
   CUDA_TRY(cudaSetDevice(c->device));
   int rc;
   const size_t L_R = c->L_R, L_E = c->L_E, N_E = c->N_E, poly = L_R * N_E, per_general = poly * L_E, W = c->ring_words();
   const size_t chunk = std::min<size_t>(count, std::max<size_t>(1, std::min<size_t>(256, c->pntt_budget_words / per_general)));
-  const uint32_t nb_boot = (uint32_t)((64 + 6 * N_E + 4095) / 4096), nb_ct = (uint32_t)(L_E * N_E / 512);
-  const size_t boot_stride = (size_t)nb_boot * 512, S = chunk * L_R;
-  // scratch: [sk | seeds | boot | roots | noise | err]
+  const uint32_t nb_boot = (uint32_t)((64 + 6 * N_E + 4095) / 4096), nb_ct = (uint32_t)((L_E * N_E + 511) / 512);
+  const bool aside = (L_E * N_E) % 512 != 0;   // the bulk of sample_poly_uniform is not a whole number of PRNG buffers
+  const size_t boot_stride = (size_t)nb_boot * 512, bulk_stride = (size_t)nb_ct * 512, S = chunk * L_R;
+  // scratch: [sk | seeds | boot | roots | noise | bulk (if aside) | err]
   const size_t n_sk = L_R * L_E * N_E, n_seeds = S * 8, n_boot = S * boot_stride, n_roots = S * std::max(nb_boot, nb_ct) * 8,
-               n_noise = S * L_E * N_E;
-  if ((rc = ensure(c, &c->d_encode, &c->cap_encode, n_sk + n_seeds + n_boot + n_roots + n_noise + 8))) return rc;
+               n_noise = S * L_E * N_E, n_bulk = aside ? S * bulk_stride : 0;
+  if ((rc = ensure(c, &c->d_encode, &c->cap_encode, n_sk + n_seeds + n_boot + n_roots + n_noise + n_bulk + 8))) return rc;
   if ((rc = ensure(c, &c->d_plain, &c->cap_plain, chunk * poly))) return rc;
   if ((rc = ensure(c, &c->d_pntt, &c->cap_pntt, chunk * per_general))) return rc;
   uint64_t *d_sk = c->d_encode, *d_seeds = d_sk + n_sk, *d_boot = d_seeds + n_seeds, *d_roots = d_boot + n_boot, *d_noise = d_roots + n_roots;
-  uint32_t *d_err = (uint32_t *)(d_noise + n_noise);
+  uint64_t *d_bulk = d_noise + n_noise;
+  uint32_t *d_err = (uint32_t *)(d_bulk + n_bulk);
   cudaStream_t st = c->stream;
   CUDA_TRY(cudaMemcpyAsync(d_sk, h_sk, n_sk * 8, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemsetAsync(d_err, 0, 8, st));
@@ -2041,12 +2043,14 @@ extern "C" int rsg_encode(rsg_context *c, const uint64_t *h_sk, const rsg_ringve
       LaunchScope ls(c, "k_b2x");
       const size_t nr = ns * nb_ct;
       k_b2x_roots<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(d_boot, boot_stride, n_streams, nb_ct, d_roots);
-      k_b2x_blocks<<<(unsigned)((nr * 64 + 127) / 128), 128, 0, st>>>(d_roots, n_streams, nb_ct,
-                                                                     arena + (out_first + e0) * c->enc_words() + L_E * N_E, 2 * L_E * N_E);
+      if (aside) k_b2x_blocks<<<(unsigned)((nr * 64 + 127) / 128), 128, 0, st>>>(d_roots, n_streams, nb_ct, d_bulk, bulk_stride);
+      else k_b2x_blocks<<<(unsigned)((nr * 64 + 127) / 128), 128, 0, st>>>(d_roots, n_streams, nb_ct,
+                                                                          arena + (out_first + e0) * c->enc_words() + L_E * N_E, 2 * L_E * N_E);
     }
     {
       LaunchScope ls(c, "k_enc_uniform_fix");
-      k_enc_uniform_fix<<<n_streams, 256, 0, st>>>(c->d_params, arena, out_first + e0, d_boot, boot_stride, d_err);
+      k_enc_uniform_fix<<<n_streams, 256, 0, st>>>(c->d_params, arena, out_first + e0, d_boot, boot_stride, d_err, aside ? d_bulk : nullptr,
+                                                   bulk_stride);
     }
     {
       LaunchScope ls(c, "k_enc_noise");
@@ -2161,24 +2165,24 @@ extern "C" int rsg_r1cs_evaluate(rsg_context *c, const rsg_r1cs *r, const rsg_ri
 // The lincomb phase as a static launch sequence (prover_fast.cuh).  Index arrays depend only on the layout, the circuit
 // shape and the caller's scalar tags, so they are built once and cached.
 struct FastPlan {
-  rsg_groth16_layout L;
-  size_t n = 0, n_aux = 0;
-  bool has_kind = false;
-  std::vector<uint8_t> kind;
+  std::vector<uint8_t> key;    // what the plan was built from (layout, shape, tags): cache check
   FastTable T;                 // vec[].base filled per call
-  uint32_t n_terms = 0, Z = 0;
-  uint32_t grp_z[5] = {0};     // split ranges of the term groups A | B | H | aux
+  uint32_t n_terms = 0, Z = 0, n_out = 0;
   std::vector<uint32_t> zs0, zs1;   // NTT slots [zs0[z], zs1[z]) feed the terms of split z
-  uint32_t *d_idx = nullptr;   // [term n_terms | pidx n_terms | zoff Z+1 | zr 4]
-  uint8_t *d_kind = nullptr;
+  uint32_t *d_idx = nullptr;   // [(unused) n_terms | pidx n_terms | zoff Z+1 | zr n_out+1]
+  const uint64_t **d_tptr = nullptr;   // device pointer of every term's encoding
+  uint8_t *d_kind = nullptr;   // device copies of the per-vector kind arrays
 };
+static void fast_free_plan(FastPlan *fp) {
+  if (!fp) return;
+  cudaFree(fp->d_idx);
+  cudaFree((void *)fp->d_tptr);
+  cudaFree(fp->d_kind);
+  delete fp;
+}
 static void fast_release(rsg_context *c) {
-  if (c->fplan) {
-    cudaFree(c->fplan->d_idx);
-    cudaFree(c->fplan->d_kind);
-    delete c->fplan;
-    c->fplan = nullptr;
-  }
+  fast_free_plan(c->fplan);
+  c->fplan = nullptr;
   cudaFree(c->d_fp_flags); cudaFree(c->d_fp_parts); cudaFree(c->d_fp_nttsrc); cudaFree(c->d_fp_totals); cudaFree(c->d_fp_status);
   if (c->h_fp_status) cudaFreeHost(c->h_fp_status);
   for (auto &e : c->ev_phase) if (e) cudaEventDestroy(e);
@@ -2186,78 +2190,98 @@ static void fast_release(rsg_context *c) {
   if (c->stream2) cudaStreamDestroy(c->stream2);
 }
 
-static int fast_get_plan(rsg_context *c, const rsg_groth16_layout *L, size_t n, size_t n_aux, const uint8_t *h_aux_kind, FastPlan **out) {
-  const size_t NONE = (size_t)-1;
-  const size_t m_lo = L->delta_mid_lo, m_hi = std::min(L->delta_mid_hi, n_aux);
-  const size_t nM = m_hi > m_lo ? m_hi - m_lo : 0;
+// What a plan is built from: the coefficient vectors' ranges and scalar tags, and per output the list of (inner product,
+// optional bare CRS element appended as a scalar-1 term).
+struct FastSpec {
+  uint32_t n_vec = 0, nS = 0;
+  uint32_t lo[FP_MAXV] = {0}, count[FP_MAXV] = {0};
+  const uint8_t *kind[FP_MAXV] = {nullptr};   // host, ABSOLUTE index, nullable; kind_len = elements of the whole vector
+  size_t kind_len[FP_MAXV] = {0};
+  uint32_t n_ip = 0, ip_vec[FP_MAXIP] = {0};
+  const uint64_t *ip_base[FP_MAXIP] = {nullptr};   // device address of the CRS encoding multiplying element 0 of the vector's RANGE
+  // term groups in output order: group g sums inner products grp_ip[g][0..1] (second may be 0xFFFFFFFF) + an optional bare CRS
+  // encoding; merged = the two inner products are the io / mid halves of a merged pair (one slot per term)
+  uint32_t n_grp = 0, grp_ip[FP_MAXIP][2], grp_out[FP_MAXIP];
+  const uint64_t *grp_extra[FP_MAXIP] = {nullptr};
+  bool grp_merged[FP_MAXIP] = {false};
+  uint32_t n_out = 0;
+  const uint64_t *alpha = nullptr, *beta = nullptr;
+};
+
+static int fast_build_plan(rsg_context *c, const FastSpec &sp, const std::vector<uint8_t> &key, FastPlan **out) {
   FastPlan *fp = c->fplan;
-  if (fp && fp->n == n && fp->n_aux == n_aux && !memcmp(&fp->L, L, sizeof(*L)) && fp->has_kind == (h_aux_kind != nullptr) &&
-      (!h_aux_kind || !memcmp(fp->kind.data(), h_aux_kind + m_lo, nM))) {
-    *out = fp;
-    return RSG_OK;
-  }
+  if (fp && fp->key == key) { *out = fp; return RSG_OK; }
   if (fp) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(fp->d_idx);
-    cudaFree(fp->d_kind);
-    delete fp;
+    fast_free_plan(fp);
     c->fplan = nullptr;
   }
   fp = new FastPlan();
-  fp->L = *L; fp->n = n; fp->n_aux = n_aux;
-  fp->has_kind = h_aux_kind != nullptr;
-  if (h_aux_kind) fp->kind.assign(h_aux_kind + m_lo, h_aux_kind + m_lo + nM);
-  const size_t s_lo = L->s_pows_lo, s_hi = std::min(L->s_pows_hi, n), t_lo = L->delta_ts_lo, t_hi = std::min(L->delta_ts_hi, n + 1);
-  const uint32_t nS = (uint32_t)(s_hi > s_lo ? s_hi - s_lo : 0), nH = (uint32_t)(t_hi > t_lo ? t_hi - t_lo : 0);
+  fp->key = key;
   FastTable &T = fp->T;
   memset(&T, 0, sizeof(T));
-  T.nS = nS; T.nH = nH; T.nM = (uint32_t)nM;
-  T.n_parts = 4 * nS;
-  T.n_elems = T.n_parts + nH + (uint32_t)nM;
-  T.n_slots = 2 * nS + nH + (uint32_t)nM;
-  const uint32_t lo[6] = {(uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)t_lo, (uint32_t)m_lo};
-  const uint32_t cnt[6] = {nS, nS, nS, nS, nH, (uint32_t)nM};
-  const size_t off[6] = {L->s_pows_off, L->s_pows_off, L->s_pows_off, L->s_pows_off, L->delta_ts_off, L->delta_mid_off};
+  T.n_vec = sp.n_vec; T.nS = sp.nS;
+  T.n_parts = 4 * sp.nS;
   uint32_t eid = 0;
-  for (int k = 0; k < 6; k++) {
-    T.vec[k].lo = lo[k]; T.vec[k].count = cnt[k]; T.vec[k].eid0 = eid;
-    T.crs_off[k] = (uint32_t)off[k];
-    eid += cnt[k];
+  size_t kind_bytes = 0;
+  for (uint32_t k = 0; k < sp.n_vec; k++) {
+    T.vec[k].lo = sp.lo[k]; T.vec[k].count = sp.count[k]; T.vec[k].eid0 = eid;
+    eid += sp.count[k];
+    if (sp.kind[k]) kind_bytes += sp.kind_len[k];
   }
-  T.alpha_idx = L->alpha_idx == NONE ? 0xFFFFFFFFu : (uint32_t)L->alpha_idx;
-  T.beta_idx = L->beta_idx == NONE ? 0xFFFFFFFFu : (uint32_t)L->beta_idx;
-  // term groups A | B | H | aux; the outputs are A, B, C = H + aux
-  std::vector<uint32_t> term, pidx, grp_t{0};
-  for (uint32_t i = 0; i < nS; i++) { term.push_back(T.crs_off[0] + i); pidx.push_back(i); }
-  if (T.alpha_idx != 0xFFFFFFFFu) { term.push_back(T.alpha_idx); pidx.push_back(0xFFFFFFFFu); }
-  grp_t.push_back((uint32_t)term.size());
-  for (uint32_t i = 0; i < nS; i++) { term.push_back(T.crs_off[2] + i); pidx.push_back(nS + i); }
-  if (T.beta_idx != 0xFFFFFFFFu) { term.push_back(T.beta_idx); pidx.push_back(0xFFFFFFFFu); }
-  grp_t.push_back((uint32_t)term.size());
-  for (uint32_t i = 0; i < nH; i++) { term.push_back(T.crs_off[4] + i); pidx.push_back(2 * nS + i); }
-  grp_t.push_back((uint32_t)term.size());
-  for (uint32_t i = 0; i < nM; i++) {
-    const uint8_t kd = h_aux_kind ? h_aux_kind[m_lo + i] : (uint8_t)RSG_AUX_POLY;
-    term.push_back(T.crs_off[5] + i);
-    pidx.push_back(kd == RSG_TERM_ONE ? 0xFFFFFFFFu : 2 * nS + nH + i);   // a SKIP tag is honoured through slot_skip
+  T.n_elems = eid;
+  T.n_slots = eid - T.n_parts + 2 * sp.nS;
+  T.n_ip = sp.n_ip;
+  for (uint32_t p = 0; p < sp.n_ip; p++) { T.ip_vec[p] = sp.ip_vec[p]; T.ip_base[p] = sp.ip_base[p]; }
+  T.alpha = sp.alpha; T.beta = sp.beta;
+  const size_t E = c->enc_words();
+  auto slot_of = [&](uint32_t k, uint32_t i, bool merged, uint32_t pair) -> uint32_t {   // i = index inside the range
+    if (merged) return pair * sp.nS + i;                        // merged pair 0 (A) / 1 (B)
+    return 2 * sp.nS + (T.vec[k].eid0 + i - T.n_parts);
+  };
+  std::vector<const uint64_t *> term;
+  std::vector<uint32_t> pidx, grp_t{0};
+  for (uint32_t g = 0; g < sp.n_grp; g++) {
+    const uint32_t p0 = sp.grp_ip[g][0], p1 = sp.grp_ip[g][1];
+    if (sp.grp_merged[g]) {   // one term per element of the pair
+      const uint32_t k = sp.ip_vec[p0];
+      for (uint32_t i = 0; i < sp.count[k]; i++) { term.push_back(sp.ip_base[p0] + (size_t)i * E); pidx.push_back(slot_of(k, i, true, k / 2)); }
+    } else {
+      for (uint32_t p : {p0, p1}) {
+        if (p == 0xFFFFFFFFu) continue;
+        const uint32_t k = sp.ip_vec[p];
+        for (uint32_t i = 0; i < sp.count[k]; i++) {
+          const uint8_t kd = sp.kind[k] ? sp.kind[k][sp.lo[k] + i] : (uint8_t)RSG_AUX_POLY;
+          term.push_back(sp.ip_base[p] + (size_t)i * E);
+          pidx.push_back(kd == RSG_TERM_ONE ? 0xFFFFFFFFu : slot_of(k, i, false, 0));   // a SKIP tag is honoured through slot_skip
+        }
+      }
+    }
+    if (sp.grp_extra[g]) { term.push_back(sp.grp_extra[g]); pidx.push_back(0xFFFFFFFFu); }
+    grp_t.push_back((uint32_t)term.size());
   }
-  grp_t.push_back((uint32_t)term.size());
   fp->n_terms = (uint32_t)term.size();
-  // near-equal term chunks that never straddle a group: ~ 148 x 8 CTAs of k_crs_lincomb in one launch
+  fp->n_out = sp.n_out;
+  // near-equal term chunks that never straddle a group: ~ 148 x 8 x 4 CTAs of k_crs_lincomb in one launch
   const uint32_t base_blocks = (uint32_t)std::max<size_t>(1, (c->N_E / 512) * c->L_R * c->L_E);
   uint32_t want = c->fast_splits > 0 ? (uint32_t)c->fast_splits : std::max(4u, (148u * 8 * 4 + base_blocks - 1) / base_blocks);
   uint32_t chunk = std::max(8u, (fp->n_terms + want - 1) / std::max(1u, want));
   if (c->overlap_mode && c->fast_splits <= 0) chunk = std::min(chunk, 128u);   // phases are built from whole chunks
-  std::vector<uint32_t> zoff{0};
-  for (int g = 0; g < 4; g++) {
-    const uint32_t t0 = grp_t[g], t1 = grp_t[g + 1], len = t1 - t0;
-    fp->grp_z[g] = (uint32_t)zoff.size() - 1;
-    if (!len) continue;
-    const uint32_t pieces = (len + chunk - 1) / chunk, per = (len + pieces - 1) / pieces;
-    for (uint32_t a = t0; a < t1; a += per) zoff.push_back(std::min(t1, a + per));
+  std::vector<uint32_t> zoff{0}, zr(sp.n_out + 1, 0);
+  {
+    uint32_t g = 0;
+    for (uint32_t o = 0; o < sp.n_out; o++) {
+      zr[o] = (uint32_t)zoff.size() - 1;
+      for (; g < sp.n_grp && sp.grp_out[g] == o; g++) {
+        const uint32_t t0 = grp_t[g], t1 = grp_t[g + 1], len = t1 - t0;
+        if (!len) continue;
+        const uint32_t pieces = (len + chunk - 1) / chunk, per = (len + pieces - 1) / pieces;
+        for (uint32_t a = t0; a < t1; a += per) zoff.push_back(std::min(t1, a + per));
+      }
+    }
+    zr[sp.n_out] = (uint32_t)zoff.size() - 1;
   }
   fp->Z = (uint32_t)zoff.size() - 1;
-  fp->grp_z[4] = fp->Z;
   for (uint32_t z = 0; z < fp->Z; z++) {
     uint32_t a = 0xFFFFFFFFu, b = 0;
     for (uint32_t t = zoff[z]; t < zoff[z + 1]; t++)
@@ -2265,32 +2289,83 @@ static int fast_get_plan(rsg_context *c, const rsg_groth16_layout *L, size_t n, 
     fp->zs0.push_back(a == 0xFFFFFFFFu ? 0 : a);
     fp->zs1.push_back(a == 0xFFFFFFFFu ? 0 : b);
   }
-  const uint32_t zr[4] = {fp->grp_z[0], fp->grp_z[1], fp->grp_z[2], fp->grp_z[4]};   // outputs A, B, C
-  std::vector<uint32_t> idx;
-  idx.insert(idx.end(), term.begin(), term.end());
+  std::vector<uint32_t> idx(fp->n_terms, 0);
   idx.insert(idx.end(), pidx.begin(), pidx.end());
   idx.insert(idx.end(), zoff.begin(), zoff.end());
-  idx.insert(idx.end(), zr, zr + 4);
+  idx.insert(idx.end(), zr.begin(), zr.end());
   void *v = nullptr;
   cudaError_t e = cudaMalloc(&v, idx.size() * 4);
   if (e != cudaSuccess) { delete fp; return fail(RSG_ERR_CUDA, cudaGetErrorString(e)); }
   fp->d_idx = (uint32_t *)v;
   e = cudaMemcpy(fp->d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && h_aux_kind && n_aux) {
-    // the device copy is indexed by ABSOLUTE auxiliary index like the host array
-    e = cudaMalloc(&v, n_aux);
+  if (e == cudaSuccess) e = cudaMalloc(&v, std::max<size_t>(1, term.size()) * 8);
+  if (e == cudaSuccess) {
+    fp->d_tptr = (const uint64_t **)v;
+    e = cudaMemcpy((void *)fp->d_tptr, term.data(), term.size() * 8, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess && kind_bytes) {
+    e = cudaMalloc(&v, kind_bytes);
     if (e == cudaSuccess) {
       fp->d_kind = (uint8_t *)v;
-      std::vector<uint8_t> all(n_aux, (uint8_t)RSG_AUX_POLY);
-      memcpy(all.data() + m_lo, h_aux_kind + m_lo, nM);
-      e = cudaMemcpy(fp->d_kind, all.data(), n_aux, cudaMemcpyHostToDevice);
+      size_t at = 0;
+      for (uint32_t k = 0; k < sp.n_vec && e == cudaSuccess; k++)
+        if (sp.kind[k]) {
+          e = cudaMemcpy(fp->d_kind + at, sp.kind[k], sp.kind_len[k], cudaMemcpyHostToDevice);
+          T.kind[k] = fp->d_kind + at;
+          at += sp.kind_len[k];
+        }
     }
   }
-  if (e != cudaSuccess) { cudaFree(fp->d_idx); cudaFree(fp->d_kind); delete fp; return fail(RSG_ERR_CUDA, cudaGetErrorString(e)); }
-  T.aux_kind = fp->d_kind;
+  if (e != cudaSuccess) { fast_free_plan(fp); return fail(RSG_ERR_CUDA, cudaGetErrorString(e)); }
   c->fplan = fp;
   *out = fp;
   return RSG_OK;
+}
+static void key_put(std::vector<uint8_t> &key, const void *p, size_t n) { key.insert(key.end(), (const uint8_t *)p, (const uint8_t *)p + n); }
+
+// CRS references of a ringGroth16 key: contiguous encodings s_pows / delta_ts / delta_mid (element `lo` of each range first) and
+// the two bare encodings (nullable) -- one arena with a layout (rsg_groth16_prove) or one arena per vector (rsg_groth16_prove_refs)
+struct G16Ptrs { const uint64_t *s_pows, *delta_ts, *delta_mid, *alpha, *beta; };
+static G16Ptrs g16_ptrs(const rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L) {
+  const size_t NONE = (size_t)-1, E = c->enc_words();
+  return G16Ptrs{crs->d + L->s_pows_off * E, crs->d + L->delta_ts_off * E, crs->d + L->delta_mid_off * E,
+                 L->alpha_idx == NONE ? nullptr : crs->d + L->alpha_idx * E, L->beta_idx == NONE ? nullptr : crs->d + L->beta_idx * E};
+}
+static int fast_get_plan(rsg_context *c, const G16Ptrs &G, const rsg_groth16_layout *L, size_t n, size_t n_aux, const uint8_t *h_aux_kind,
+                         FastPlan **out) {
+  const size_t s_lo = L->s_pows_lo, s_hi = std::min(L->s_pows_hi, n), t_lo = L->delta_ts_lo, t_hi = std::min(L->delta_ts_hi, n + 1);
+  const size_t m_lo = L->delta_mid_lo, m_hi = std::min(L->delta_mid_hi, n_aux);
+  const uint32_t nS = (uint32_t)(s_hi > s_lo ? s_hi - s_lo : 0), nH = (uint32_t)(t_hi > t_lo ? t_hi - t_lo : 0),
+                 nM = (uint32_t)(m_hi > m_lo ? m_hi - m_lo : 0);
+  std::vector<uint8_t> key;
+  const uint32_t tagk = 0x67313600u | (uint32_t)c->overlap_mode;
+  key_put(key, &tagk, 4); key_put(key, L, sizeof(*L)); key_put(key, &n, sizeof(n)); key_put(key, &n_aux, sizeof(n_aux));
+  key_put(key, &G, sizeof(G));
+  if (h_aux_kind) key_put(key, h_aux_kind + m_lo, nM);
+  if (c->fplan && c->fplan->key == key) { *out = c->fplan; return RSG_OK; }
+  FastSpec sp;
+  sp.n_vec = 6; sp.nS = nS;
+  const uint32_t lo[6] = {(uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)s_lo, (uint32_t)t_lo, (uint32_t)m_lo};
+  const uint32_t cnt[6] = {nS, nS, nS, nS, nH, nM};
+  const uint64_t *base[6] = {G.s_pows, G.s_pows, G.s_pows, G.s_pows, G.delta_ts, G.delta_mid};
+  sp.n_ip = 6;
+  for (int k = 0; k < 6; k++) { sp.lo[k] = lo[k]; sp.count[k] = cnt[k]; sp.ip_vec[k] = k; sp.ip_base[k] = base[k]; }
+  std::vector<uint8_t> all;
+  if (h_aux_kind && n_aux) {   // indexed by ABSOLUTE auxiliary index like the host array
+    all.assign(n_aux, (uint8_t)RSG_AUX_POLY);
+    memcpy(all.data() + m_lo, h_aux_kind + m_lo, nM);
+    sp.kind[5] = all.data();
+    sp.kind_len[5] = n_aux;
+  }
+  sp.alpha = G.alpha;
+  sp.beta = G.beta;
+  // groups A (merged io + mid, + alpha) | B (merged, + beta) | H | aux; outputs A, B, C = H + aux
+  sp.n_grp = 4; sp.n_out = 3;
+  sp.grp_ip[0][0] = 0; sp.grp_ip[0][1] = 1; sp.grp_merged[0] = true; sp.grp_extra[0] = sp.alpha; sp.grp_out[0] = 0;
+  sp.grp_ip[1][0] = 2; sp.grp_ip[1][1] = 3; sp.grp_merged[1] = true; sp.grp_extra[1] = sp.beta; sp.grp_out[1] = 1;
+  sp.grp_ip[2][0] = 4; sp.grp_ip[2][1] = 0xFFFFFFFFu; sp.grp_out[2] = 2;
+  sp.grp_ip[3][0] = 5; sp.grp_ip[3][1] = 0xFFFFFFFFu; sp.grp_out[3] = 2;
+  return fast_build_plan(c, sp, key, out);
 }
 
 static bool fast_applies(const rsg_context *c, const rsg_groth16_layout *L, size_t n, size_t n_aux) {
@@ -2353,8 +2428,9 @@ static int fast_launch_ntt(rsg_context *c, const uint64_t *nttsrc, uint32_t s0, 
 }
 
 // splits [z0, z1) of the plan's term chunks -> partial[z]
-static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, const uint64_t *d_crs, uint32_t z0, uint32_t z1, const uint8_t *slot_skip,
+static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, uint32_t z0, uint32_t z1, const uint8_t *slot_skip,
                                cudaStream_t st, bool lowreg = false) {
+  const uint64_t *d_crs = nullptr;   // every term carries its own pointer
   if (z1 <= z0) return RSG_OK;
   const uint32_t *d_term = fp->d_idx, *d_pidx = fp->d_idx + fp->n_terms, *d_zoff = fp->d_idx + 2 * fp->n_terms;
   uint64_t *partial = c->d_partial + (size_t)z0 * c->enc_words();
@@ -2371,26 +2447,23 @@ static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, const uint64_
     }
     const size_t items = (size_t)(z1 - z0) * c->L_R * c->L_E * (c->N_E / LT_XC);
     const unsigned grid = (unsigned)std::min<size_t>(items, (size_t)148 * c->lt_ctas);
-    k_crs_lincomb_tma<<<grid, LT_THREADS, LT_SMEM, st>>>(c->d_params, d_crs, d_term, d_pidx, d_zoff + z0, z1 - z0, slot_skip, c->d_pntt, partial);
+    k_crs_lincomb_tma<<<grid, LT_THREADS, LT_SMEM, st>>>(c->d_params, fp->d_tptr, d_pidx, d_zoff + z0, z1 - z0, slot_skip, c->d_pntt, partial);
   } else {
     const unsigned th = (unsigned)std::min<size_t>(c->lin_threads > 0 ? c->lin_threads : 256, c->N_E / 2);
     const dim3 grid((unsigned)(c->N_E / 2 / th), (unsigned)(c->L_R * c->L_E), z1 - z0);
-    if (lowreg) k_crs_lincomb_r64<<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip);
-    else k_crs_lincomb<2><<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip);
+    if (lowreg) k_crs_lincomb_r64<<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip,
+                                                       fp->d_tptr);
+    else k_crs_lincomb<2><<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip,
+                                               fp->d_tptr);
   }
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
 
-// Returns RSG_OK with *candidate = 1 when a probe sum vanished (the caller then runs the exact path).  Synchronises once.
-static int groth16_lincombs_fast(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
-                                 const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *out,
-                                 size_t *n_used, int *candidate) {
+// Everything up to the probes for one plan: flags -> batch encode -> (merged pairs) -> forward NTTs -> the one-launch lincomb ->
+// per-output sums into `out` (fp->n_out encodings) -> probe totals.  No synchronisation.
+static int fast_run(rsg_context *c, FastPlan *fp, const FastTable &T, uint64_t *out) {
   int rc;
-  FastPlan *fp;
-  if ((rc = fast_get_plan(c, L, n, n_aux, h_aux_kind, &fp))) return rc;
-  FastTable T = fp->T;
-  for (int k = 0; k < 6; k++) T.vec[k].base = vec[k];
   const size_t poly = c->L_R * c->N_E, per_general = poly * c->L_E, E = c->enc_words();
   if ((rc = ensure(c, &c->d_fp_flags, &c->cap_fp_flags, (size_t)T.n_elems + T.n_slots + 64))) return rc;
   if ((rc = ensure(c, &c->d_fp_parts, &c->cap_fp_parts, std::max<size_t>(1, (size_t)T.n_parts * poly)))) return rc;
@@ -2402,7 +2475,7 @@ static int groth16_lincombs_fast(rsg_context *c, const rsg_crs *crs, const rsg_g
     void *v = nullptr;
     CUDA_TRY(cudaMalloc(&v, FPS_WORDS * 4));
     c->d_fp_status = (uint32_t *)v;
-    CUDA_TRY(cudaMalloc(&v, 6 * MAX_LR * 8));
+    CUDA_TRY(cudaMalloc(&v, FP_MAXIP * MAX_LR * 8));
     c->d_fp_totals = (uint64_t *)v;
     CUDA_TRY(cudaHostAlloc(&v, FPS_WORDS * 4, cudaHostAllocDefault));
     c->h_fp_status = (uint32_t *)v;
@@ -2429,7 +2502,8 @@ static int groth16_lincombs_fast(rsg_context *c, const rsg_crs *crs, const rsg_g
     if (T.n_parts && (rc = launch_intt_finish(c, c->d_fp_parts, (size_t)T.n_parts * c->L_R, c->d_modq, c->d_invN_q, c->d_invNw_q, (uint32_t)c->L_R,
                                              0xFFFFFFFFu, 1u)))
       return rc;
-    if (T.nH + T.nM && (rc = launch_intt_finish(c, c->d_fp_nttsrc + (size_t)2 * T.nS * poly, (size_t)(T.nH + T.nM) * c->L_R, c->d_modq, c->d_invN_q,
+    const uint32_t plain_slots = T.n_slots - 2 * T.nS;
+    if (plain_slots && (rc = launch_intt_finish(c, c->d_fp_nttsrc + (size_t)2 * T.nS * poly, (size_t)plain_slots * c->L_R, c->d_modq, c->d_invN_q,
                                                c->d_invNw_q, (uint32_t)c->L_R, 0xFFFFFFFFu, 1u)))
       return rc;
   }
@@ -2443,9 +2517,10 @@ static int groth16_lincombs_fast(rsg_context *c, const rsg_crs *crs, const rsg_g
   c->st_lin_plain += T.n_slots;
   c->st_merged += T.nS ? 2 : 0;
   if (c->overlap_mode) {
-    // Phases of ~overlap_terms terms (whole term chunks): the transforms of phase p+1 run on the main stream while the
-    // HBM-bound lincomb of phase p streams on the second one.  The register-capped kernel pair (96 x 512 + 64 x 256 = 64 Ki
-    // registers) lets one lincomb CTA sit on each SM next to the transform CTA; the last phase's lincomb runs alone.
+    // Phases of whole term chunks: the transforms of phase p+1 run on the main stream while the HBM-bound lincomb of phase p
+    // streams on the second one.  RSG_OVERLAP=1 uses the register-capped kernel pair (96 x 512 + 64 x 256 = 64 Ki registers:
+    // one lincomb CTA fits next to the transform CTA on an SM), RSG_OVERLAP=2 the full-register kernels.  Measured on B200
+    // (C4): neither shortens the proof -- kept as an experiment, not the default.
     if (!c->stream2) {
       CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
       for (auto &e : c->ev_phase) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2464,42 +2539,59 @@ static int groth16_lincombs_fast(rsg_context *c, const rsg_crs *crs, const rsg_g
       ntt_done = s_end;
       CUDA_TRY(cudaEventRecord(c->ev_phase[pe], st));
       CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_phase[pe], 0));
-      if ((rc = fast_launch_lincomb(c, fp, crs->d, z0, z1, slot_skip, c->stream2, lowreg))) return rc;
+      if ((rc = fast_launch_lincomb(c, fp, z0, z1, slot_skip, c->stream2, lowreg))) return rc;
     }
     CUDA_TRY(cudaEventRecord(c->ev_join, c->stream2));
     CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
   } else {
     if ((rc = fast_launch_ntt(c, c->d_fp_nttsrc, 0, T.n_slots, slot_skip))) return rc;
-    if ((rc = fast_launch_lincomb(c, fp, crs->d, 0, fp->Z, slot_skip, st))) return rc;
+    if ((rc = fast_launch_lincomb(c, fp, 0, fp->Z, slot_skip, st))) return rc;
   }
   {
     LaunchScope ls(c, "k_enc_sum");
     const size_t pairs = E / 2;
-    k_enc_sum_ranges<<<dim3((unsigned)((pairs + 255) / 256), 3), 256, 0, st>>>(c->d_params, c->d_partial, fp->d_idx + 2 * fp->n_terms + fp->Z + 1, out);
+    k_enc_sum_ranges<<<dim3((unsigned)((pairs + 255) / 256), fp->n_out), 256, 0, st>>>(c->d_params, c->d_partial,
+                                                                                      fp->d_idx + 2 * fp->n_terms + fp->Z + 1, out);
   }
   {
     LaunchScope ls(c, "k_probe");
-    k_probe_fast<<<dim3(6, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, crs->d, elem_flag, c->d_pval, c->d_pntt, c->d_fp_totals, nullptr, 0u,
-                                                            c->d_fp_status);
+    k_probe_fast<<<dim3(T.n_ip, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, elem_flag, c->d_pval, c->d_pntt, c->d_fp_totals, nullptr, 0u,
+                                                                 c->d_fp_status);
   }
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+
+// Returns RSG_OK with *candidate = 1 when a probe sum vanished (the caller then runs the exact path).  Synchronises once.
+static int groth16_lincombs_fast(rsg_context *c, const G16Ptrs &G, const rsg_groth16_layout *L, size_t n, size_t n_aux,
+                                 const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *out,
+                                 size_t *n_used, int *candidate) {
+  int rc;
+  FastPlan *fp;
+  if ((rc = fast_get_plan(c, G, L, n, n_aux, h_aux_kind, &fp))) return rc;
+  FastTable T = fp->T;
+  for (int k = 0; k < 6; k++) T.vec[k].base = vec[k];
+  if ((rc = fast_run(c, fp, T, out))) return rc;
+  cudaStream_t st = c->stream;
   {
     LaunchScope ls(c, "k_probe");
-    k_probe_chain<<<1, 32, 0, st>>>(c->d_params, T, crs->d, c->d_fp_totals, c->d_fp_status);
+    k_probe_chain<<<1, 32, 0, st>>>(c->d_params, T, c->d_fp_totals, c->d_fp_status);
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(c->h_fp_status, c->d_fp_status, FPS_WORDS * 4, cudaMemcpyDeviceToHost, st));
-  if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 3 * E * 8, cudaMemcpyDeviceToHost, st));
+  if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 3 * c->enc_words() * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   const uint32_t *hs = c->h_fp_status;
   *candidate = hs[FPS_CANDIDATE] != 0;
   if (n_used) {
-    n_used[0] = (size_t)hs[FPS_COUNT0 + 0] + hs[FPS_COUNT0 + 1] + (T.alpha_idx != 0xFFFFFFFFu);
-    n_used[1] = (size_t)hs[FPS_COUNT0 + 2] + hs[FPS_COUNT0 + 3] + (T.beta_idx != 0xFFFFFFFFu);
+    n_used[0] = (size_t)hs[FPS_COUNT0 + 0] + hs[FPS_COUNT0 + 1] + (T.alpha != nullptr);
+    n_used[1] = (size_t)hs[FPS_COUNT0 + 2] + hs[FPS_COUNT0 + 3] + (T.beta != nullptr);
     n_used[2] = (size_t)hs[FPS_COUNT0 + 4] + hs[FPS_COUNT0 + 5];
   }
   c->st_fast++;
   return RSG_OK;
 }
+
 // ------------------------------------------------------------------------------------------------------------
 // groth16::prover (groth16.tcc:69-115): the witness map, then the reference's own sequence of six inner products combined
 // with operator+= (kept separate, not fused into three, because the transparent-ciphertext rule is order-dependent).
@@ -2650,7 +2742,7 @@ static int groth16_lincombs_dev(rsg_context *c, const rsg_crs *crs, const rsg_gr
       out = c->d_out_scratch;
     }
     int candidate = 0;
-    if ((rc = groth16_lincombs_fast(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, out, n_used, &candidate))) return rc;
+    if ((rc = groth16_lincombs_fast(c, g16_ptrs(c, crs, L), L, n, n_aux, vec, h_aux_kind, h_proof, out, n_used, &candidate))) return rc;
     if (!candidate) return RSG_OK;
     c->st_fast_fallback++;
   }
@@ -2692,5 +2784,167 @@ extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg
   // coeffs order in HBM: A_io, B_io, C_io, A_mid, B_mid, C_mid
   const uint64_t *vec[6] = {coeffs, coeffs + 3 * n * W, coeffs + n * W, coeffs + 4 * n * W, H, assignment->d + n_io * W};
   return groth16_lincombs_dev(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, d_proof, n_used);
+}
+// ------------------------------------------------------------------------------------------------------------
+// Provers over CRS vectors that live in DIFFERENT arenas (one per EncodingElem::encode call of the generator templates).
+static int ref_ptr(const rsg_context *c, const rsg_crs_ref &r, size_t count, const uint64_t **out) {
+  if (!r.crs) { *out = nullptr; return count ? fail(RSG_ERR_ARG, "null CRS reference") : RSG_OK; }
+  if (r.crs->ctx != c || r.first + count > r.crs->n) return fail(RSG_ERR_ARG, "CRS reference out of range or of another context");
+  *out = r.crs->d + r.first * c->enc_words();
+  return RSG_OK;
+}
+
+extern "C" int rsg_groth16_prove_refs(rsg_context *c, const rsg_r1cs *r1cs, const rsg_crs_ref refs[5], rsg_ringvec *assignment,
+                                      const uint64_t *h_assignment, const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
+                                      size_t *n_used) {
+  RSG_TRACE_CALL();
+  if (!c || !r1cs || !refs || !assignment) return fail(RSG_ERR_ARG, "null argument");
+  const size_t n = r1cs->n, n_io = r1cs->n_io, n_aux = r1cs->n_aux, W = c->ring_words();
+  if (assignment->n < n_io + n_aux) return fail(RSG_ERR_ARG, "assignment too short");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc;
+  G16Ptrs G;
+  if ((rc = ref_ptr(c, refs[0], n + 1, &G.s_pows)) || (rc = ref_ptr(c, refs[1], n + 1, &G.delta_ts)) ||
+      (rc = ref_ptr(c, refs[2], n_aux, &G.delta_mid)) || (rc = ref_ptr(c, refs[3], 1, &G.alpha)) || (rc = ref_ptr(c, refs[4], 1, &G.beta)))
+    return rc;
+  rsg_groth16_layout L;
+  memset(&L, 0, sizeof(L));
+  L.s_pows_hi = n + 1; L.delta_ts_hi = n + 1; L.delta_mid_hi = n_aux;   // whole vectors; the offsets are carried by G
+  if (!fast_applies(c, &L, n, n_aux)) return fail(RSG_ERR_UNSUPPORTED, "term set above the NTT-plaintext budget: use the per-inner-product entry points");
+  if (h_assignment)
+    CUDA_TRY(cudaMemcpyAsync(assignment->d, h_assignment, (n_io + n_aux) * W * 8, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = ensure(c, &c->d_evals, &c->cap_evals, 9 * n * W))) return rc;
+  if ((rc = ensure(c, &c->d_wit, &c->cap_wit, (7 * n + 1) * W))) return rc;
+  uint64_t *coeffs = c->d_wit, *H = c->d_wit + 6 * n * W;
+  if ((rc = r1cs_eval_dev(c, r1cs, assignment->d, c->d_evals))) return rc;
+  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H, nullptr, const_cast<rsg_r1cs *>(r1cs), /*need_C=*/false))) return rc;
+  const uint64_t *vec[6] = {coeffs, coeffs + 3 * n * W, coeffs + n * W, coeffs + 4 * n * W, H, assignment->d + n_io * W};
+  uint64_t *out = d_proof;
+  if (!out) {
+    if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 3 * c->enc_words()))) return rc;
+    out = c->d_out_scratch;
+  }
+  int candidate = 0;
+  if ((rc = groth16_lincombs_fast(c, G, &L, n, n_aux, vec, h_aux_kind, h_proof, out, n_used, &candidate))) return rc;
+  if (candidate) {
+    c->st_fast_fallback++;
+    return fail(RSG_ERR_TRANSPARENT, "transparent-ciphertext candidate: resolve with the per-inner-product entry points");
+  }
+  return RSG_OK;
+}
+
+// rinocchio::prover (zk_proof_systems/rinocchio/rinocchio.tcc:74-190) in one call: zero-knowledge witness map, the eleven inner
+// products with ONE batch encoding and ONE set of forward NTTs per coefficient (the reference, and the template path, transform
+// a_mid / b_mid / c_mid / h / z twice: once for s_pows, once for alpha_s_pows), and the nine shifts.
+extern "C" int rsg_rinocchio_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg_crs_ref refs[6], rsg_ringvec *assignment,
+                                   const uint64_t *h_assignment, const uint8_t *h_aux_kind, const uint64_t *h_d, uint64_t *h_proof,
+                                   uint64_t *d_proof, size_t *n_used) {
+  RSG_TRACE_CALL();
+  if (!c || !r1cs || !refs || !assignment) return fail(RSG_ERR_ARG, "null argument");
+  const size_t n = r1cs->n, n_io = r1cs->n_io, n_aux = r1cs->n_aux, W = c->ring_words(), E = c->enc_words();
+  if (assignment->n < n_io + n_aux) return fail(RSG_ERR_ARG, "assignment too short");
+  if (!c->fast_mode) return fail(RSG_ERR_UNSUPPORTED, "RSG_FAST=0: use the per-inner-product entry points");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc;
+  const bool zk = h_d != nullptr;
+  const uint64_t *p_s, *p_as, *p_bp, *p_bt[3] = {nullptr, nullptr, nullptr};
+  if ((rc = ref_ptr(c, refs[0], n + 1, &p_s)) || (rc = ref_ptr(c, refs[1], n + 1, &p_as)) || (rc = ref_ptr(c, refs[2], n_aux, &p_bp))) return rc;
+  if (zk && n_aux)
+    for (int k = 0; k < 3; k++)
+      if ((rc = ref_ptr(c, refs[3 + k], 1, &p_bt[k]))) return rc;
+  const size_t slots = 3 * n + 2 * (n + 1) + n_aux + (zk ? 3 : 0);
+  if (slots * c->L_R * c->L_E * c->N_E > c->pntt_budget_words)
+    return fail(RSG_ERR_UNSUPPORTED, "term set above the NTT-plaintext budget: use the per-inner-product entry points");
+  if (h_assignment)
+    CUDA_TRY(cudaMemcpyAsync(assignment->d, h_assignment, (n_io + n_aux) * W * 8, cudaMemcpyHostToDevice, c->stream));
+  const uint64_t *d_zk = nullptr;
+  if (zk) {
+    if ((rc = ensure(c, &c->d_zk, &c->cap_zk, 3 * W))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->d_zk, h_d, 3 * W * 8, cudaMemcpyHostToDevice, c->stream));
+    d_zk = c->d_zk;
+  }
+  if ((rc = ensure(c, &c->d_evals, &c->cap_evals, 9 * n * W))) return rc;
+  if ((rc = ensure(c, &c->d_wit, &c->cap_wit, (7 * n + 1) * W))) return rc;
+  uint64_t *coeffs = c->d_wit, *H = c->d_wit + 6 * n * W;
+  if ((rc = r1cs_eval_dev(c, r1cs, assignment->d, c->d_evals))) return rc;
+  if ((rc = witness_map_dev(c, n, c->d_evals, coeffs, H, d_zk, const_cast<rsg_r1cs *>(r1cs)))) return rc;
+  // coefficients_for_Z as ring elements: every coefficient below the leading one has been through a negation in the reference
+  // (evaluation_domain.tcc:53-60) and is a polynomial with the constant in every slot; the leading one is the scalar 1
+  WitnessTables *wt;
+  if ((rc = get_witness_tables(c, n, &wt))) return rc;
+  if (!wt->d_Zvec) {
+    std::vector<uint64_t> zv((n + 1) * W);
+    for (size_t k = 0; k <= n; k++)
+      for (size_t j = 0; j < c->L_R; j++) std::fill(zv.begin() + k * W + j * c->N_R, zv.begin() + k * W + (j + 1) * c->N_R, wt->h_Z[j * (n + 1) + k]);
+    void *v = nullptr;
+    CUDA_TRY(cudaMalloc(&v, zv.size() * 8));
+    wt->d_Zvec = (uint64_t *)v;
+    CUDA_TRY(cudaMemcpy(wt->d_Zvec, zv.data(), zv.size() * 8, cudaMemcpyHostToDevice));
+  }
+  // plan: vectors A_mid, B_mid, C_mid, H, Z, aux, D; inner products in the proof's order + z, alpha_z, f
+  std::vector<uint8_t> key, zkind(n + 1, (uint8_t)RSG_AUX_POLY), all;
+  zkind[n] = RSG_TERM_ONE;
+  const uint32_t tagk = 0x72696E6Fu;
+  key_put(key, &tagk, 4); key_put(key, &n, sizeof(n)); key_put(key, &n_aux, sizeof(n_aux)); key_put(key, &zk, sizeof(zk));
+  key_put(key, &p_s, 8); key_put(key, &p_as, 8); key_put(key, &p_bp, 8); key_put(key, p_bt, sizeof(p_bt));
+  if (h_aux_kind) key_put(key, h_aux_kind, n_aux);
+  FastPlan *fp;
+  {
+    FastSpec sp;
+    sp.n_vec = zk ? 7 : 6; sp.nS = 0;
+    const uint32_t cnt[7] = {(uint32_t)n, (uint32_t)n, (uint32_t)n, (uint32_t)(n + 1), (uint32_t)(n + 1), (uint32_t)n_aux, 3};
+    for (uint32_t k = 0; k < sp.n_vec; k++) { sp.lo[k] = 0; sp.count[k] = cnt[k]; }
+    sp.kind[4] = zkind.data(); sp.kind_len[4] = n + 1;
+    if (h_aux_kind && n_aux) { sp.kind[5] = h_aux_kind; sp.kind_len[5] = n_aux; }
+    sp.n_ip = n_aux ? 11 : 10;
+    const uint32_t ipv[11] = {0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5};
+    for (uint32_t p = 0; p < sp.n_ip; p++) { sp.ip_vec[p] = ipv[p]; sp.ip_base[p] = p == 10 ? p_bp : ((p & 1) ? p_as : p_s); }
+    sp.n_grp = sp.n_out = sp.n_ip;
+    for (uint32_t p = 0; p < sp.n_ip; p++) { sp.grp_ip[p][0] = p; sp.grp_ip[p][1] = 0xFFFFFFFFu; sp.grp_out[p] = p; }
+    // the D vector has no inner product of its own: its slots are only transformed (the shift plaintexts)
+    if ((rc = fast_build_plan(c, sp, key, &fp))) return rc;
+  }
+  FastTable T = fp->T;
+  const uint64_t *bases[7] = {coeffs + 3 * n * W, coeffs + 4 * n * W, coeffs + 5 * n * W, H, wt->d_Zvec, assignment->d + n_io * W, c->d_zk};
+  for (uint32_t k = 0; k < T.n_vec; k++) T.vec[k].base = bases[k];
+  if ((rc = ensure(c, &c->d_ip, &c->cap_ip, 11 * E))) return rc;
+  CUDA_TRY(cudaMemsetAsync(c->d_ip + 10 * E, 0, E * 8, c->stream));   // f stays the empty encoding without auxiliary inputs
+  if ((rc = fast_run(c, fp, T, c->d_ip))) return rc;
+  uint64_t *out = d_proof;
+  if (!out) {
+    if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 9 * E))) return rc;
+    out = c->d_out_scratch;
+  }
+  cudaStream_t st = c->stream;
+  RinoShift R;
+  for (int k = 0; k < 3; k++) R.beta_ts[k] = p_bt[k];
+  const uint32_t d_slot0 = (uint32_t)(T.vec[6].eid0);   // nS = 0: slot = element id
+  const uint32_t shifts = zk ? (n_aux ? 2u : 1u) : 0u;     // 2: also the three beta_r?_ts shifts of f
+  if (zk) {
+    LaunchScope ls(c, "k_probe");
+    k_probe_chain_rino<<<1, 32, 0, st>>>(c->d_params, R, c->d_pntt, d_slot0, c->d_fp_totals, c->d_fp_status, shifts);
+  }
+  {
+    LaunchScope ls(c, "k_rino_combine");
+    k_rino_combine<<<dim3((unsigned)((E / 2 + 255) / 256), 9), 256, 0, st>>>(c->d_params, c->d_ip, R, c->d_pntt, d_slot0, shifts, out);
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(c->h_fp_status, c->d_fp_status, FPS_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 9 * E * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const uint32_t *hs = c->h_fp_status;
+  if (n_used) {
+    const int v[9] = {0, 0, 1, 1, 2, 2, 3, 3, 5};
+    for (int e = 0; e < 9; e++) n_used[e] = hs[FPS_COUNT0 + v[e]] + ((zk && e != 6 && e != 7 && (e < 8 || n_aux)) ? 1 : 0);
+    if (!n_aux) n_used[8] = 0;
+  }
+  c->st_fast++;
+  if (hs[FPS_CANDIDATE]) {
+    c->st_fast_fallback++;
+    return fail(RSG_ERR_TRANSPARENT, "transparent-ciphertext candidate: resolve with the per-inner-product entry points");
+  }
+  return RSG_OK;
 }
 #include "serialize.inl"

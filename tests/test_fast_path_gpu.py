@@ -312,3 +312,94 @@ def test_encode_round_trip_full_size():
         del vec, crs
     finally:
         ctx.close()
+
+
+def _ip_exact(ctx, crs, first, vec, vfirst, count, tags=None):
+    """one EncodingElem::inner_product through the exact per-inner-product entry point"""
+    if tags is None:
+        tags = ctx.term_tags(vec, first=vfirst, count=count)
+    return ctx.inner_product(crs, vec, tags, crs_first=first, coeff_first=vfirst)
+
+
+@pytest.mark.parametrize("cfg_name,zk", [("c4m", True), ("c1", True), ("c4m", False)])
+def test_fused_rinocchio_equals_per_inner_product_sequence(cfg_name, zk):
+    """rsg_rinocchio_prove (one transform per coefficient, shared by the s_pows and alpha_s_pows streams, shifts fused) against
+    the reference's own sequence rinocchio.tcc:74-190 assembled from the exact per-inner-product entry points: ten / eleven
+    rsg_inner_product calls, d_k * z_enc as a one-term inner product over the intermediate encoding, rsg_enc_add."""
+    import torch
+    import ringsnark_b200 as rs
+    from ringsnark_b200.backend import rinocchio_prove, groth16_prove_refs
+    from ringsnark_b200.capi import check
+    from ringsnark_b200.params import CONFIGS, synthetic_r1cs
+    cfg = CONFIGS[cfg_name]
+    n, io, aux = cfg["n"], cfg["io"], cfg["aux"]
+    row_ptr, col, coeff = synthetic_r1cs(n, io, aux, seed=5)
+    ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"])
+    try:
+        W, E = ctx.ring_words, ctx.enc_words
+        r1cs = rs.R1cs(ctx, n, io, aux, row_ptr, col, coeff)
+        s_pows, alpha_s = ctx.crs(n + 1), ctx.crs(n + 1)
+        beta_prods, beta_ts = ctx.crs(aux), ctx.crs(3)
+        for k, a in enumerate((s_pows, alpha_s, beta_prods, beta_ts)):
+            a.fill_uniform(100 + k)
+        assignment = ctx.ringvec(io + aux)
+        assignment.fill_uniform(7)
+        dvec = ctx.ringvec(3)
+        dvec.fill_uniform(8)
+        h_d = dvec.download() if zk else None
+        refs = [(s_pows, 0), (alpha_s, 0), (beta_prods, 0), (beta_ts, 0), (beta_ts, 1), (beta_ts, 2)]
+        got, used = rinocchio_prove(ctx, r1cs, refs, assignment, h_d)
+        assert ctx.stat("fast_fallbacks") == 0
+        # ---- the reference's sequence, exact entry points
+        evals = r1cs.evaluate(assignment)
+        coeffs, H = ctx.ringvec(6 * n), ctx.ringvec(n + 1)
+        import ctypes as C
+        check(ctx.lib.rsg_witness_map_r1cs(ctx.h, r1cs.h, evals.h, h_d.ctypes.data_as(C.c_void_p) if zk else None, coeffs.h, H.h))
+        Zc = ctx.vanishing(n)                                   # [L_R][n+1]
+        zw = np.repeat(Zc.T.reshape(n + 1, ctx.L_R, 1), ctx.N_R, axis=2).reshape(n + 1, W)
+        Z = ctx.ringvec_from(zw)
+        ztags = ctx.term_tags(Z)
+        ztags[n] = 1                                            # the leading coefficient is the scalar 1
+        want = []
+        for vfirst in (3 * n, 4 * n, 5 * n):                   # a_mid, b_mid, c_mid
+            for crs in (s_pows, alpha_s):
+                want.append(_ip_exact(ctx, crs, 0, coeffs, vfirst, n)[0])
+        for crs in (s_pows, alpha_s):
+            want.append(_ip_exact(ctx, crs, 0, H, 0, n + 1)[0])
+        z_enc = [_ip_exact(ctx, crs, 0, Z, 0, n + 1, ztags)[0] for crs in (s_pows, alpha_s)]
+        aux_vec = ctx.ringvec_from(assignment.download(io, aux))
+        want.append(_ip_exact(ctx, beta_prods, 0, aux_vec, 0, aux)[0])
+
+        def shifted(acc_words, enc_words_list, ks):
+            acc = torch.from_numpy(acc_words.view(np.int64)).cuda()
+            for words, k in zip(enc_words_list, ks):
+                one = ctx.crs_from(words.reshape(1, E))
+                prod, _ = ctx.inner_product(one, dvec, np.array([2], dtype=np.uint8), coeff_first=k)
+                t = torch.from_numpy(prod.view(np.int64)).cuda()
+                assert ctx.lib.rsg_enc_add(ctx.h, acc.data_ptr(), t.data_ptr()) == 0
+                ctx.sync()
+                del one
+            torch.cuda.synchronize()
+            return acc.cpu().numpy().view(np.uint64)
+
+        if zk:
+            for e in range(6):
+                want[e] = shifted(want[e], [z_enc[e & 1]], [e // 2])
+            bt = beta_ts.download()
+            want[8] = shifted(want[8], [bt[0], bt[1], bt[2]], [0, 1, 2])
+        for e in range(9):
+            assert np.array_equal(got[e], want[e]), e
+        # ringGroth16 over separate arenas == over one arena
+        pk = rs.Groth16ProvingKey(ctx, r1cs)
+        pk.fill_synthetic(9)
+        pk.assignment.upload(assignment.download())
+        one_arena, used1 = pk.prove()
+        L = pk.layout
+        parts = [ctx.crs_from(pk.crs.download(L.s_pows_off, n + 1)), ctx.crs_from(pk.crs.download(L.delta_ts_off, n + 1)),
+                 ctx.crs_from(pk.crs.download(L.delta_mid_off, aux)), ctx.crs_from(pk.crs.download(L.alpha_idx, 2))]
+        refs5 = [(parts[0], 0), (parts[1], 0), (parts[2], 0), (parts[3], 0), (parts[3], 1)]
+        many, used5 = groth16_prove_refs(ctx, r1cs, refs5, assignment)
+        assert np.array_equal(many, one_arena) and used5 == used1
+        del pk, parts, r1cs, s_pows, alpha_s, beta_prods, beta_ts, assignment, dvec, evals, coeffs, H, Z, aux_vec
+    finally:
+        ctx.close()
