@@ -139,8 +139,8 @@ class RingElem {
     if (!host_valid_) {
       std::lock_guard<std::mutex> g(detail::host_mutex());
       if (!host_valid_) {
-        auto &b = detail::backend();
-        std::vector<uint64_t> w(b.ring_words);
+        auto rp = Host::get_context().first_context_data()->parms();
+        std::vector<uint64_t> w(rp.poly_modulus_degree() * rp.coeff_modulus().size());
         detail::check(rsg_ringvec_download(dev_->v, dev_idx_, 1, w.data()));
         host_ = Host(polytools::SealPoly(Host::get_context(), w, &Host::get_context().first_parms_id()));
         host_valid_ = true;
@@ -248,6 +248,31 @@ inline RingElem operator/(const RingElem &l, const RingElem &r) { RingElem x(l);
 inline bool operator==(const RingElem &l, const RingElem &r) { return l.host() == r.host(); }
 inline bool operator!=(const RingElem &l, const RingElem &r) { return !(l == r); }
 inline std::ostream &operator<<(std::ostream &out, const RingElem &e) { return out << e.host(); }
+
+namespace detail {
+// The backend ring-only callers use (interpolate<RingElem> before any EncodingElem::set_context, as in the reference's
+// util/interpolation_test.cpp:87-91): the full backend when it exists, else a device context built from the ring parameters
+// alone (N_E = N_R, one stand-in encoding limb) -- the witness kernels only touch the ring primes.
+inline Backend &ring_backend() {
+  Backend &full = backend_storage();
+  if (full.ctx) return full;
+  static Backend rb;
+  std::lock_guard<std::mutex> g(host_mutex());
+  if (!rb.ctx) {
+    auto rp = RingElem::get_context().first_context_data()->parms();
+    rb.N_R = rb.N_E = rp.poly_modulus_degree();
+    rb.L_R = rp.coeff_modulus().size();
+    rb.L_E = 1;
+    for (auto &m : rp.coeff_modulus()) rb.q.push_back(m.value());
+    rb.Q.push_back(rb.q[0]);
+    rb.ring_words = rb.N_R * rb.L_R;
+    rb.enc_words = rb.L_R * 2 * rb.N_E;
+    const char *dev = std::getenv("RSG_DEVICE");
+    check(rsg_context_create(&rb.ctx, rb.N_R, rb.L_R, rb.q.data(), rb.N_E, rb.L_E, rb.Q.data(), dev ? std::atoi(dev) : 0));
+  }
+  return rb;
+}
+}  // namespace detail
 
 // =====================================================================================================================
 class EncodingElem {
@@ -810,7 +835,7 @@ inline std::vector<ringsnark::seal_gpu::RingElem> interpolate<ringsnark::seal_gp
     const auto hc = interpolate<R::Host>(hx, hy);
     return std::vector<R>(hc.begin(), hc.end());
   }
-  auto &b = D::backend();
+  auto &b = D::ring_backend();
   auto make_vec = [&](size_t count) {
     auto v = std::make_shared<D::DevRing>();
     D::check(rsg_ringvec_create(b.ctx, count, &v->v));
