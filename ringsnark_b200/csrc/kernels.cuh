@@ -182,6 +182,13 @@ struct LiftIoF64 {
   ModConst m;
   uint64_t thr, tm;
   double pd, pinv;
+  __device__ __forceinline__ void init(const DevParams *__restrict__ P, uint32_t j, uint32_t l) {
+    m = P->Q[l];
+    pd = (double)m.p;
+    pinv = P->Qinv_f64[l];
+    thr = P->thr[j];
+    tm = P->tmodQ[j][l];
+  }
   __device__ __forceinline__ Raw load_raw(uint32_t i) const { return __ldg(src + i); }
   __device__ __forceinline__ double lift(Raw v) const {
     if constexpr (SIGNED) {   // sum of two centred plaintexts (k_centre_add), |v| < 2^61
@@ -194,6 +201,7 @@ struct LiftIoF64 {
       return centre_to_f64(r, m.p);
     }
   }
+  __device__ __forceinline__ uint64_t canon(double x) const { return canon_f64(x, pd, pinv, m.p); }
   template <int R>
   __device__ __forceinline__ void store(uint32_t base, const double (&v)[R]) const {
     static_assert(R % 2 == 0, "pairs");
@@ -203,7 +211,55 @@ struct LiftIoF64 {
   }
 };
 
-template <int LOGN, int LVL0, bool SIGNED>
+// The same lift with a SMALL QUOTIENT (context flag lift_smallq: t < 2^54 and t / min Q_l < 2^11, true for every reference
+// configuration): |v| < 2^55 fits 31 bits after a shift by 24, one float multiply estimates v / Q_l to within 1/2 + 2^-12, and
+// x = v - q Q_l is one 32 x 64 product: |x| <= (1/2 + 2^-12) Q_l, the same residue class as the Barrett lift above and, after the
+// transform, the same canonical words.  About twenty instructions per coefficient instead of about forty; measured on B200
+// (tools/ntt_lab.cu, C4): 5.05 -> 4.43 ms per proof -- the kernel is bound by instruction issue (FP64 instructions hold the
+// issue port two cycles, every other instruction about one: tools/fp64_lab.cu), not by the FP64 pipe alone.
+// Integer <-> double conversions add the bit pattern of 1.5 * 2^52 (exact for |x| < 2^51) instead of using the XU pipe.
+constexpr long long F64_MAGIC_BITS = 0x4338000000000000LL;   // bit pattern of F64_MAGIC
+__device__ __forceinline__ double ll2double_magic(long long x) { return __dadd_rn(__longlong_as_double(x + F64_MAGIC_BITS), -F64_MAGIC); }
+__device__ __forceinline__ long long double2ll_magic(double x) { return __double_as_longlong(__dadd_rn(x, F64_MAGIC)) - F64_MAGIC_BITS; }
+
+template <bool SIGNED>
+struct LiftIoSmallQ {
+  using Raw = uint64_t;
+  const uint64_t *src;
+  uint64_t *dst;
+  uint64_t p, thr, t;
+  float qinv24;        // 2^24 / Q_l
+  double pd, pinv;
+  __device__ __forceinline__ void init(const DevParams *__restrict__ P, uint32_t j, uint32_t l) {
+    p = P->Q[l].p;
+    pd = (double)p;
+    pinv = P->Qinv_f64[l];
+    qinv24 = (float)(16777216.0 * pinv);
+    thr = P->thr[j];
+    t = P->q[j].p;
+  }
+  __device__ __forceinline__ Raw load_raw(uint32_t i) const { return __ldg(src + i); }
+  __device__ __forceinline__ double lift(Raw raw) const {
+    long long v = (long long)raw;
+    if constexpr (!SIGNED) v = raw >= thr ? (long long)(raw - t) : (long long)raw;   // context.cpp:329, evaluator.cpp:2243-2259
+    const int vh = (int)(v >> 24);
+    const float qf = __fadd_rn(__fmul_rn(__int2float_rn(vh), qinv24), 12582912.0f);   // 1.5 * 2^23: mantissa = round(quotient)
+    const int q = __float_as_int(qf) - 0x4B400000;
+    return ll2double_magic(v - (long long)q * (long long)p);
+  }
+  __device__ __forceinline__ uint64_t canon(double x) const {
+    const long long r = double2ll_magic(recentre_f64(x, pd, pinv));
+    return (uint64_t)(r + ((r >> 63) & (long long)p));
+  }
+  template <int R>
+  __device__ __forceinline__ void store(uint32_t base, const double (&v)[R]) const {
+    static_assert(R % 2 == 0, "pairs");
+#pragma unroll
+    for (int k = 0; k < R; k += 2) *reinterpret_cast<ulonglong2 *>(dst + base + k) = make_ulonglong2(canon(v[k]), canon(v[k + 1]));
+  }
+};
+
+template <int LOGN, int LVL0, bool SIGNED, bool SMALLQ>
 __device__ __forceinline__ void lift_fwd_ntt_f64_body(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
                                                       uint64_t *__restrict__ out, const uint8_t *__restrict__ slot_skip) {
   extern __shared__ double smf[];
@@ -212,12 +268,8 @@ __device__ __forceinline__ void lift_fwd_ntt_f64_body(const DevParams *__restric
   const uint32_t h = blockIdx.x & ((1u << LVL0) - 1), el = blockIdx.x >> LVL0;
   const uint32_t e = el / L_E, l = el - e * L_E, j = blockIdx.y;
   if (slot_skip && slot_skip[e]) return;   // term skipped on the device (prover_fast.cuh): nothing reads this slot
-  LiftIoF64<SIGNED> io;
-  io.m = P->Q[l];
-  io.pd = (double)io.m.p;
-  io.pinv = P->Qinv_f64[l];
-  io.thr = P->thr[j];
-  io.tm = P->tmodQ[j][l];
+  std::conditional_t<SMALLQ, LiftIoSmallQ<SIGNED>, LiftIoF64<SIGNED>> io;
+  io.init(P, j, l);
   io.src = plain + (((size_t)e * L_R + j) << (LOGN + LVL0));
   io.dst = out + (((((size_t)e * L_R + j) * L_E + l)) << (LOGN + LVL0)) + (size_t)h * n;
   const double *tab = P->fwdQ_f64[l];
@@ -234,19 +286,167 @@ __device__ __forceinline__ void lift_fwd_ntt_f64_body(const DevParams *__restric
   }
   PassChainF<LOGN, 0, LVL0 == 0>::fwd(smf, tab, io.pd, io.pinv, LVL0, h, tw0, io);
 }
-template <int LOGN, int LVL0, bool SIGNED>
+template <int LOGN, int LVL0, bool SIGNED, bool SMALLQ = false>
 __global__ void __launch_bounds__(512) k_lift_fwd_ntt_f64(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
                                                           uint64_t *__restrict__ out,
                                                           const uint8_t *__restrict__ slot_skip = nullptr) {
-  lift_fwd_ntt_f64_body<LOGN, LVL0, SIGNED>(P, plain, out, slot_skip);
+  lift_fwd_ntt_f64_body<LOGN, LVL0, SIGNED, SMALLQ>(P, plain, out, slot_skip);
 }
+// ---- N_E = 2^14 on thread-block clusters (what ships for the C4 / C3' shape) ------------------------------------------------
+// Measured on B200 (tools/ntt_lab.cu): the single-CTA kernel above spends 39 % of its time with the FP64
+// pipe idle behind its own global traffic -- 128 KiB of coefficients in before the first butterfly, 128 KiB of results out
+// after the last, one CTA per SM (a 2^14-point polynomial fills the shared memory) and therefore nothing to overlap them
+// with -- while its radix-16 passes themselves run at 91 % of the pipe's peak.  This kernel removes that:
+//   * one polynomial per CLUSTER of four 128-thread CTAs; CTA r keeps rows 4r..4r+3 of the 16 x 1024 matrix (34 KiB), so five
+//     CTAs of different clusters share an SM and one polynomial's loads / stores run under another's butterflies;
+//   * pass 1 (levels 0-3, column-wise): CTA r transforms columns [256 r, 256 r + 256) and sends each of the 16 rows to its
+//     owner through distributed shared memory (st.shared::cluster, 128 bit); one cluster barrier;
+//   * passes 2-4 stay inside a row of 1024: one WARP per row, __syncwarp only (no CTA barrier after the first pass);
+//   * every radix-16 pass handles two adjacent columns per thread: one LDS.128 / STS.128 moves both, the fifteen twiddles
+//     serve 64 butterflies; padding of four words per 64 (pad2) keeps pairs 16-byte aligned and the passes conflict-free;
+//   * results leave as one 256-bit store per four words (a whole 32-byte sector per lane: 128-bit stores at 32-byte stride
+//     wrote half sectors and cost 0.4 ms per proof).
+// Same butterflies in the same order as ntt_pass_f64: identical words (tools/ntt_lab.cu compares them).  5.05 -> 3.46 ms per
+// C4 proof for the 37 056 transforms.
+__device__ __forceinline__ uint32_t pad2(uint32_t i) { return i + ((i >> 6) << 2); }
+
+__device__ __forceinline__ void radix16_pair(double (&a)[16], double (&b)[16], const double (&w)[15], double p, double pinv) {
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const int half = 16 >> (u + 1);
+#pragma unroll
+    for (int grp = 0; grp < (1 << u); grp++) {
+      const double ww = w[(1 << u) - 1 + grp], wp = __dmul_rn(ww, pinv);
+#pragma unroll
+      for (int k = 0; k < half; k++) {
+        bfly_fwd_f64(a[grp * 2 * half + k], a[grp * 2 * half + k + half], ww, wp, p);
+        bfly_fwd_f64(b[grp * 2 * half + k], b[grp * 2 * half + k + half], ww, wp, p);
+      }
+    }
+  }
+}
+// the fifteen twiddles of levels lvl..lvl+3 for block b of level lvl: entries (1 << (lvl + u)) + (b << u) + grp, grp < 2^u --
+// contiguous and 16-byte aligned for u >= 1
+__device__ __forceinline__ void ld_tw15(double (&w)[15], const double *tab, uint32_t lvl, uint32_t b) {
+  w[0] = ldg_f64_here(tab + (1u << lvl) + b);
+#pragma unroll
+  for (int u = 1; u < 4; u++) {
+    const double *q = tab + (1u << (lvl + u)) + (b << u);
+#pragma unroll
+    for (int g2 = 0; g2 < (1 << u); g2 += 2)
+      asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(w[(1 << u) - 1 + g2]), "=d"(w[(1 << u) + g2]) : "l"(q + g2));
+  }
+}
+
+constexpr int NTT_CL = 4;                        // CTAs per cluster
+constexpr int NTT_CL_THREADS = 512 / NTT_CL;     // 128
+constexpr uint32_t NTT_CL_ROWW = 1024 + 64;      // one padded row
+constexpr size_t NTT_CL_SMEM = (size_t)(16 / NTT_CL) * NTT_CL_ROWW * 8;
+
+template <bool SIGNED, bool SMALLQ>
+__global__ void __cluster_dims__(NTT_CL, 1, 1) __launch_bounds__(NTT_CL_THREADS, 5)
+    k_lift_fwd_ntt_f64_cl(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain, uint64_t *__restrict__ out,
+                          const uint8_t *__restrict__ slot_skip) {
+  constexpr int LOGN = 14;
+  constexpr uint32_t RPC = 16 / NTT_CL;   // rows per CTA
+  extern __shared__ double smf[];
+  uint32_t r;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  const uint32_t L_R = P->L_R, L_E = P->L_E;
+  const uint32_t el = blockIdx.x / NTT_CL, e = el / L_E, l = el - e * L_E, j = blockIdx.y;
+  if (slot_skip && slot_skip[e]) return;   // all CTAs of the cluster together
+  // the peers' shared memory may be written once they run: arrive now, wait just before the first remote store
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  std::conditional_t<SMALLQ, LiftIoSmallQ<SIGNED>, LiftIoF64<SIGNED>> io;
+  io.init(P, j, l);
+  io.src = plain + (((size_t)e * L_R + j) << LOGN);
+  io.dst = out + (((((size_t)e * L_R + j) * L_E + l)) << LOGN);
+  const double *tab = P->fwdQ_f64[l];
+  const double pd = io.pd, pinv = io.pinv;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  double a[16], b[16], w[15];
+  {   // pass 1: column pair o of all 16 rows
+    const uint32_t o = 2 * (NTT_CL_THREADS * r + tid);
+    ulonglong2 raw[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) raw[k] = __ldg(reinterpret_cast<const ulonglong2 *>(io.src + o + 1024 * k));
+    ld_tw15(w, tab, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 16; k++) { a[k] = io.lift(raw[k].x); b[k] = io.lift(raw[k].y); }
+    radix16_pair(a, b, w, pd, pinv);
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(smf) + pad2(o) * 8;
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      uint32_t dstaddr;
+      asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dstaddr) : "r"(local + (uint32_t)(k % RPC) * NTT_CL_ROWW * 8), "r"((uint32_t)(k / RPC)));
+      asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(dstaddr), "d"(recentre_f64(a[k], pd, pinv)), "d"(recentre_f64(b[k], pd, pinv)) : "memory");
+    }
+  }
+  const uint32_t row = RPC * r + wrp;   // the row (block of 1024) this warp owns from here on
+  double *rp = smf + wrp * NTT_CL_ROWW;
+  ld_tw15(w, tab, 4, row);
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  {   // pass 2: levels 4..7, elements 64 apart
+    double *ptr = rp + 2 * lane;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const double2 t = *reinterpret_cast<const double2 *>(ptr + 68 * k);
+      a[k] = t.x; b[k] = t.y;
+    }
+    radix16_pair(a, b, w, pd, pinv);
+#pragma unroll
+    for (int k = 0; k < 16; k++) *reinterpret_cast<double2 *>(ptr + 68 * k) = make_double2(recentre_f64(a[k], pd, pinv), recentre_f64(b[k], pd, pinv));
+  }
+  {   // pass 3: levels 8..11, elements 4 apart inside block bb of 64
+    const uint32_t bb = lane >> 1, o = 2 * (lane & 1);
+    ld_tw15(w, tab, 8, row * 16 + bb);
+    __syncwarp();
+    double *ptr = rp + bb * 68 + o;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const double2 t = *reinterpret_cast<const double2 *>(ptr + 4 * k);
+      a[k] = t.x; b[k] = t.y;
+    }
+    radix16_pair(a, b, w, pd, pinv);
+#pragma unroll
+    for (int k = 0; k < 16; k++) *reinterpret_cast<double2 *>(ptr + 4 * k) = make_double2(recentre_f64(a[k], pd, pinv), recentre_f64(b[k], pd, pinv));
+  }
+  {   // pass 4: levels 12, 13 on four consecutive elements; items lane + 32 m of the row's 256
+    double w12[8], w13a[8], w13b[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const uint32_t i = row * 256 + lane + 32 * m;
+      w12[m] = ldg_f64_here(tab + 4096 + i);
+      asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(w13a[m]), "=d"(w13b[m]) : "l"(tab + 8192 + 2 * i));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const uint32_t il = lane + 32 * m;
+      const double *ptr = rp + pad2(4 * il);
+      const double2 t0 = *reinterpret_cast<const double2 *>(ptr), t1 = *reinterpret_cast<const double2 *>(ptr + 2);
+      double v0 = t0.x, v1 = t0.y, v2 = t1.x, v3 = t1.y;
+      const double wa = w12[m], wap = __dmul_rn(wa, pinv);
+      bfly_fwd_f64(v0, v2, wa, wap, pd);
+      bfly_fwd_f64(v1, v3, wa, wap, pd);
+      bfly_fwd_f64(v0, v1, w13a[m], __dmul_rn(w13a[m], pinv), pd);
+      bfly_fwd_f64(v2, v3, w13b[m], __dmul_rn(w13b[m], pinv), pd);
+      asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(io.dst + 1024 * row + 4 * il), "l"(io.canon(v0)), "l"(io.canon(v1)),
+                   "l"(io.canon(v2)), "l"(io.canon(v3))
+                   : "memory");
+    }
+  }
+}
+
 // The same transform capped at 96 registers (a few twiddles spill to L1): 512 x 96 = 48 Ki registers leave room for one
 // 256-thread CTA of k_crs_lincomb_r64 on the same SM, so the HBM-bound stream of one term group runs UNDER the FP64-bound
 // transforms of the next (prover_fast.cuh, RSG_OVERLAP).
-template <int LOGN, int LVL0, bool SIGNED>
+template <int LOGN, int LVL0, bool SIGNED, bool SMALLQ = false>
 __global__ void __maxnreg__(96) k_lift_fwd_ntt_f64_r96(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain,
                                                        uint64_t *__restrict__ out, const uint8_t *__restrict__ slot_skip) {
-  lift_fwd_ntt_f64_body<LOGN, LVL0, SIGNED>(P, plain, out, slot_skip);
+  lift_fwd_ntt_f64_body<LOGN, LVL0, SIGNED, SMALLQ>(P, plain, out, slot_skip);
 }
 
 // Raw NTT of `batch` polynomials; grid (batch << LVL0).  In place for LVL0 = 0.  For LVL0 = 1 the forward transform reads

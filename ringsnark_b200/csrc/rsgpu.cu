@@ -267,6 +267,8 @@ struct rsg_context {
   int overlap_mode = 0;             // RSG_OVERLAP=1: lincomb of one term group on a second stream under the next group's NTTs
   int fast_splits = 0;              // RSG_FAST_SPLITS: number of term chunks of the one-launch lincomb (0 = auto)
   int ntt_half = 0;                 // RSG_NTT_HALF=1 (experiment, see fast_launch_ntt)
+  int ntt_cluster = 1;              // N_E = 2^14, FP64 path: k_lift_fwd_ntt_f64_cl (4-CTA clusters); RSG_NTT_CLUSTER=0 -> single-CTA kernel
+  bool lift_smallq = false;         // LiftIoSmallQ applies (kernels.cuh): t < 2^54 and t / min Q_l < 2^11; RSG_LIFT=barrett turns it off
   int overlap_chunks = 4;           // RSG_OVERLAP_CHUNKS: term chunks (<= 128 terms each) per overlap phase
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_phase[8] = {};     // NTT group done (stream -> stream2)
@@ -479,6 +481,14 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (const char *m = getenv("RSG_OVERLAP")) c->overlap_mode = atoi(m);
   if (const char *m = getenv("RSG_FAST_SPLITS")) c->fast_splits = atoi(m);
   if (const char *m = getenv("RSG_NTT_HALF")) c->ntt_half = atoi(m);
+  if (const char *m = getenv("RSG_NTT_CLUSTER")) c->ntt_cluster = atoi(m);
+  {
+    uint64_t tmax = 0, Qmin = ~0ull;
+    for (uint64_t p : c->q) tmax = std::max(tmax, p);
+    for (uint64_t p : c->Q) Qmin = std::min(Qmin, p);
+    const char *m = getenv("RSG_LIFT");
+    c->lift_smallq = c->f64_ntt && tmax < (1ull << 54) && tmax / Qmin < 2048 && !(m && !strcmp(m, "barrett"));
+  }
   if (const char *m = getenv("RSG_OVERLAP_CHUNKS")) c->overlap_chunks = std::max(1, atoi(m));
   if (const char *m = getenv("RSG_WITNESS")) c->witness_mode = !strcmp(m, "dense") ? 1 : (!strcmp(m, "fast") ? 2 : 0);
   if (const char *m = getenv("RSG_WF_SL")) c->wf_sl = atoi(m);
@@ -803,6 +813,9 @@ static int set_smem_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_r96<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64<LOGN, LV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_r96<LOGN, LV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_TRY(cudaFuncSetAttribute(k_ntt<LOGN, LV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done[dev] = true;
@@ -861,9 +874,22 @@ static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count
   bool lazy = true;   // correction-free butterflies need (4 * log2 N + 1) * Q_l < 2^64
   for (uint64_t p : c->Q) lazy = lazy && p < (1ull << 58);
   LaunchScope ls(c, "k_lift_fwd_ntt");
+  if (c->f64_ntt && c->ntt_mode != 1 && c->logN == 14 && c->ntt_cluster) {
+    const dim3 cgrid((unsigned)(count * c->L_E * NTT_CL), (unsigned)c->L_R);
+    if (c->lift_smallq) {
+      if (is_signed) k_lift_fwd_ntt_f64_cl<true, true><<<cgrid, NTT_CL_THREADS, NTT_CL_SMEM, c->stream>>>(c->d_params, d_plain, d_pntt, nullptr);
+      else k_lift_fwd_ntt_f64_cl<false, true><<<cgrid, NTT_CL_THREADS, NTT_CL_SMEM, c->stream>>>(c->d_params, d_plain, d_pntt, nullptr);
+    } else if (is_signed) k_lift_fwd_ntt_f64_cl<true, false><<<cgrid, NTT_CL_THREADS, NTT_CL_SMEM, c->stream>>>(c->d_params, d_plain, d_pntt, nullptr);
+    else k_lift_fwd_ntt_f64_cl<false, false><<<cgrid, NTT_CL_THREADS, NTT_CL_SMEM, c->stream>>>(c->d_params, d_plain, d_pntt, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   if (c->f64_ntt && c->ntt_mode != 1) {
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
-                             if (is_signed) k_lift_fwd_ntt_f64<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
+                             if (c->lift_smallq) {
+                               if (is_signed) k_lift_fwd_ntt_f64<LG, LV, true, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
+                               else k_lift_fwd_ntt_f64<LG, LV, false, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
+                             } else if (is_signed) k_lift_fwd_ntt_f64<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt);
                              else k_lift_fwd_ntt_f64<LG, LV, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, d_pntt); });
     CUDA_TRY(cudaGetLastError());
     return RSG_OK;
@@ -2414,9 +2440,19 @@ static int fast_launch_ntt(rsg_context *c, const uint64_t *nttsrc, uint32_t s0, 
     CUDA_TRY(cudaGetLastError());
     return RSG_OK;
   }
+  if (c->f64_ntt && c->ntt_mode != 1 && c->logN == 14 && c->ntt_cluster && !lowreg) {
+    const dim3 cgrid((unsigned)(count * c->L_E * NTT_CL), (unsigned)c->L_R);
+    if (c->lift_smallq) k_lift_fwd_ntt_f64_cl<true, true><<<cgrid, NTT_CL_THREADS, NTT_CL_SMEM, c->stream>>>(c->d_params, src, dst, sk);
+    else k_lift_fwd_ntt_f64_cl<true, false><<<cgrid, NTT_CL_THREADS, NTT_CL_SMEM, c->stream>>>(c->d_params, src, dst, sk);
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   if (c->f64_ntt && c->ntt_mode != 1) {
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
-                             if (lowreg) k_lift_fwd_ntt_f64_r96<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk);
+                             if (c->lift_smallq) {
+                               if (lowreg) k_lift_fwd_ntt_f64_r96<LG, LV, true, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk);
+                               else k_lift_fwd_ntt_f64<LG, LV, true, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk);
+                             } else if (lowreg) k_lift_fwd_ntt_f64_r96<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk);
                              else k_lift_fwd_ntt_f64<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk); });
   } else {
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
@@ -2449,6 +2485,18 @@ static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, uint32_t z0, 
     const unsigned grid = (unsigned)std::min<size_t>(items, (size_t)148 * c->lt_ctas);
     k_crs_lincomb_tma<<<grid, LT_THREADS, LT_SMEM, st>>>(c->d_params, fp->d_tptr, d_pidx, d_zoff + z0, z1 - z0, slot_skip, c->d_pntt, partial);
   } else {
+    if (c->overlap_mode) {
+      // the transform kernel needs the maximum shared-memory carve-out; a kernel that prefers another split of the L1/shared
+      // array cannot become resident on the same SM at the same time -- ask for the same carve-out
+      static bool carve_done[64] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!carve_done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(k_crs_lincomb_r64, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUDA_TRY(cudaFuncSetAttribute(k_crs_lincomb<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        carve_done[dev] = true;
+      }
+    }
     const unsigned th = (unsigned)std::min<size_t>(c->lin_threads > 0 ? c->lin_threads : 256, c->N_E / 2);
     const dim3 grid((unsigned)(c->N_E / 2 / th), (unsigned)(c->L_R * c->L_E), z1 - z0);
     if (lowreg) k_crs_lincomb_r64<<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip,
