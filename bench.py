@@ -366,7 +366,7 @@ def run_gpu_arm(args, cfg_name, cfg):
         h_aux = torch.from_numpy(np.ascontiguousarray(h_assign_np[io + sp.m_lo:io + sp.m_hi]).view(np.int64)).pin_memory()
         h_proof = torch.empty(3 * ctx.enc_words, dtype=torch.int64).pin_memory()
         sp.load_assignment_shards(h_shard, h_aux, non_blocking=False)
-        d_all = torch.zeros(world * 3 * ctx.enc_words, dtype=torch.int64, device="cuda")
+        d_all = torch.zeros(world * sp.part_words, dtype=torch.int64, device="cuda")
         h2d_bytes = int((h_shard.numel() + h_aux.numel()) * 8)
 
         def prove(host_io):
@@ -378,7 +378,9 @@ def run_gpu_arm(args, cfg_name, cfg):
                 dist.all_to_all_single(recv, send)
                 used = sp.lincomb_phase(recv)
                 dist.all_gather_into_tensor(d_all, sp.t_part)
-                sp.combine(d_all)
+                if sp.combine(d_all):    # a global prefix vanished at the probe slot (never with uniform CRS words): exact chain
+                    from ringsnark_b200.distributed import run_chain
+                    run_chain(sp, dist)
                 if host_io:
                     h_proof.copy_(sp.t_final, non_blocking=True)
                 return used

@@ -127,6 +127,10 @@ int rsg_crs_copy(rsg_crs *dst, size_t dst_first, const rsg_crs *src, size_t src_
 /* out = sum of `parts` blocks stored back to back, each block = n_enc encodings (n_enc = 3: a whole proof):
  * the modular-add kernel that follows the NCCL all-gather (modular addition is not an NCCL reduction). */
 int rsg_enc_sum(rsg_context *ctx, const uint64_t *d_parts, size_t parts, size_t n_enc, uint64_t *d_out);
+/* The same over parts that lie part_stride_words apart (0 = back to back): the all-gathered [partial proof | probe block]
+ * records of rsg_groth16_lincombs_shard. */
+int rsg_enc_sum_strided(rsg_context *ctx, const uint64_t *d_parts, size_t parts, size_t n_enc, size_t part_stride_words,
+                        uint64_t *d_out);
 
 /* ---- hot path (a): r1cs_to_qrp_witness_map (reductions/r1cs_to_qrp/r1cs_to_qrp.tcc:148-259) ----
  * evals: 9*n ring elements, order A_mid,B_mid,C_mid,A_io,B_io,C_io,A_full,B_full,C_full (the outputs of
@@ -268,6 +272,34 @@ int rsg_rinocchio_prove(rsg_context *ctx, const rsg_r1cs *r1cs, const rsg_crs_re
 int rsg_groth16_lincombs(rsg_context *ctx, const rsg_crs *crs, const rsg_groth16_layout *layout, size_t n, size_t n_aux,
                          const uint64_t *const d_vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
                          size_t *n_used);
+/* ---- the same on G term shards with the reference's ORDER-DEPENDENT rule kept exact (seal_ring.tcc:493-504: a running sum
+ * whose c1 vanishes is dropped) ----
+ * rsg_groth16_lincombs_shard: this rank's partial proof (3 encodings, the plain modular sums over its term ranges) into d_part
+ * and, behind it, a PROBE BLOCK of rsg_groth16_shard_block_words(L_R, pstride) words: the running sums of every inner product
+ * at one fixed NTT slot (c1, limb 0, x = 0) over this rank's live terms, their totals, the live-term counts and rank 0's
+ * alpha / beta words.  pstride >= the largest term range of any rank.  No local fallback: the ranks all-gather
+ * [d_part | block] and EVERY rank calls rsg_groth16_shard_check on the gathered blocks (host words): it shifts each rank's
+ * running sums by the totals of the ranks before it -- the global prefix sums -- and replays the operator+= chains of
+ * groth16.tcc:89-112 at that slot.  *verdict = 0: no prefix vanished anywhere, the modular sum of the G partial proofs IS the
+ * reference's proof.  *verdict = 1 (structured CRS only, e.g. the tiny_transp golden case): the ranks run the exact CHAIN instead:
+ *   rank 0 .. G-1 in order:  rsg_groth16_lincombs_chain(carry from the rank before) -> carry for the next rank
+ *   rank 0 (holds alpha, beta):  rsg_groth16_chain_finish(last carry) -> the proof
+ * carry = the six inner products <s_pows,A_io>, <s_pows,A_mid>, <s_pows,B_io>, <s_pows,B_mid>, <delta_ts,H>, <delta_mid,aux> over
+ * all terms so far (6 encodings, device) + present[6] (0 = still the empty EncodingElem).  A rank enters its carry as the first
+ * term of each inner product (coefficient 1, seal_ring.tcc:525-528), so prefixes and drops are the global ones.  The arena
+ * must hold 6 spare encodings from index carry_first on (the carry is staged there). */
+#define RSG_SHARD_BLOCK_HEADER 8   /* words: [0] flags (bit 0: static plan not applicable -> chain), [1..6] live terms per inner product, [7] pstride */
+size_t rsg_groth16_shard_block_words(size_t L_R, size_t pstride);
+int rsg_groth16_lincombs_shard(rsg_context *ctx, const rsg_crs *crs, const rsg_groth16_layout *layout, size_t n, size_t n_aux,
+                               const uint64_t *const d_vec[6], const uint8_t *h_aux_kind, uint64_t *d_part, size_t pstride,
+                               size_t *n_used);
+/* Pure host arithmetic (no device, no context): h_blocks = world blocks back to back, Q0 = first encoding prime. */
+int rsg_groth16_shard_check(const uint64_t *h_blocks, size_t world, size_t L_R, size_t pstride, uint64_t Q0, int *verdict);
+int rsg_groth16_lincombs_chain(rsg_context *ctx, rsg_crs *crs, size_t carry_first, const rsg_groth16_layout *layout, size_t n,
+                               size_t n_aux, const uint64_t *const d_vec[6], const uint8_t *h_aux_kind, uint64_t *d_carry,
+                               uint8_t *h_present);
+int rsg_groth16_chain_finish(rsg_context *ctx, const rsg_crs *crs, const rsg_groth16_layout *layout, const uint64_t *d_carry,
+                             const uint8_t *h_present, uint64_t *d_proof);
 /* A non-owning rsg_ringvec over caller-owned device memory (e.g. a torch tensor): n_elems ring elements at d_words. */
 int rsg_ringvec_wrap(rsg_context *ctx, uint64_t *d_words, size_t n_elems, rsg_ringvec **out);
 

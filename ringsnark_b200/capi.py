@@ -52,6 +52,7 @@ SIGNATURES = {
     "rsg_enc_add": (_int, [_vp, _vp, _vp]),
     "rsg_crs_copy": (_int, [_vp, _sz, _vp, _sz, _sz]),
     "rsg_enc_sum": (_int, [_vp, _vp, _sz, _sz, _vp]),
+    "rsg_enc_sum_strided": (_int, [_vp, _vp, _sz, _sz, _sz, _vp]),
     "rsg_witness_map": (_int, [_vp, _sz, _vp, _vp, _vp]),
     "rsg_witness_map_zk": (_int, [_vp, _sz, _vp, _vp, _vp, _vp]),
     "rsg_witness_map_r1cs": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -73,6 +74,11 @@ SIGNATURES = {
     "rsg_groth16_prove_refs": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rsg_rinocchio_prove": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rsg_groth16_lincombs": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "rsg_groth16_shard_block_words": (_sz, [_sz, _sz]),
+    "rsg_groth16_lincombs_shard": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "rsg_groth16_shard_check": (_int, [_vp, _sz, _sz, _sz, _u64, C.POINTER(_int)]),
+    "rsg_groth16_lincombs_chain": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "rsg_groth16_chain_finish": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "rsg_ringvec_wrap": (_int, [_vp, _vp, _sz, _pp]),
     "rsg_batch_encode": (_int, [_vp, _vp, _sz, _vp]),
     "rsg_plain_to_ntt": (_int, [_vp, _vp, _sz, _vp]),

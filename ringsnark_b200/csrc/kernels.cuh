@@ -589,17 +589,19 @@ __global__ void __maxnreg__(64) k_crs_lincomb_r64(const DevParams *__restrict__ 
 
 // out[w] = sum_s parts[s][w] mod Q_l(w): the modular-add kernel (after split-K or after the NCCL all-gather).
 // `n_enc` encodings per part (a whole proof = 3), parts stored back to back.
+// part_stride (words, 0 = back to back): distance between consecutive parts.
 __global__ void __launch_bounds__(256) k_enc_sum(const DevParams *__restrict__ P, const uint64_t *__restrict__ parts,
-                                                 uint32_t n_parts, uint32_t n_enc, uint64_t *__restrict__ out) {
+                                                 uint32_t n_parts, uint32_t n_enc, uint64_t *__restrict__ out, size_t part_stride = 0) {
   const uint32_t N_E = P->N_E, L_E = P->L_E;
   const size_t enc_words = (size_t)n_enc * P->L_R * 2 * L_E * N_E;
+  if (!part_stride) part_stride = enc_words;
   const size_t w = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (w >= enc_words) return;
   const uint32_t l = (uint32_t)((w / N_E) % L_E);
   const uint64_t p = P->Q[l].p;
   ulonglong2 acc = *reinterpret_cast<const ulonglong2 *>(parts + w);
   for (uint32_t s = 1; s < n_parts; s++) {
-    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(parts + (size_t)s * enc_words + w);
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(parts + (size_t)s * part_stride + w);
     acc.x = add_mod(acc.x, v.x, p);
     acc.y = add_mod(acc.y, v.y, p);
   }

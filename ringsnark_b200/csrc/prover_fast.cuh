@@ -225,6 +225,25 @@ __global__ void k_probe_chain(const DevParams *__restrict__ P, FastTable T,
   }
 }
 
+// Header, totals and alpha / beta words of a shard's probe block (include/rsgpu.h, rsg_groth16_lincombs_shard): one block of
+// 32 threads.  block = [8 header | 6 L_R totals | 2 L_R alpha, beta words (~0: not on this rank) | 6 L_R pstride running sums].
+__global__ void k_probe_block_header(const DevParams *__restrict__ P, FastTable T, const uint64_t *__restrict__ totals,
+                                     const uint32_t *__restrict__ status, uint32_t pstride, uint64_t *__restrict__ block) {
+  const uint32_t L_R = P->L_R, L_E = P->L_E, N_E = P->N_E;
+  const size_t ct_words = 2 * (size_t)L_E * N_E;
+  if (threadIdx.x == 0) {
+    block[0] = 0;
+    for (int k = 0; k < 6; k++) block[1 + k] = status[FPS_COUNT0 + k];
+    block[7] = pstride;
+  }
+  for (uint32_t w = threadIdx.x; w < 6 * L_R; w += blockDim.x) block[8 + w] = totals[w];
+  for (uint32_t w = threadIdx.x; w < 2 * L_R; w += blockDim.x) {
+    const uint64_t *extra = w < L_R ? T.alpha : T.beta;
+    const uint32_t j = w < L_R ? w : w - L_R;
+    block[8 + 6 * L_R + w] = extra ? extra[(size_t)j * ct_words + (size_t)L_E * N_E] : ~0ull;
+  }
+}
+
 // rinocchio::prover's shifts at the probe slot (rinocchio.tcc:166-186).  Inner products: 0 a, 1 alpha_a, 2 b, 3 alpha_b, 4 c,
 // 5 alpha_c, 6 d, 7 alpha_d, 8 z, 9 alpha_z, 10 f.  X += d_k * Y: candidate when the NTT-domain sum vanishes at the slot.
 // dhat[k][j]: NTT-domain plaintext of d_k at (l = 0, x = 0) = pntt of D's slots.  One block of 32 threads.

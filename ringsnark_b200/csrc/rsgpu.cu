@@ -279,6 +279,8 @@ struct rsg_context {
   uint64_t *d_fp_parts = nullptr, *d_fp_nttsrc = nullptr;
   size_t cap_fp_parts = 0, cap_fp_nttsrc = 0;
   uint64_t *d_fp_totals = nullptr;  // [6][MAX_LR] probe totals
+  uint64_t *fp_block = nullptr;     // rsg_groth16_lincombs_shard: probe block of this call (device), see include/rsgpu.h
+  uint32_t fp_pstride = 0;
   uint32_t *d_fp_status = nullptr, *h_fp_status = nullptr;   // FPS_WORDS device words + pinned host mirror
   uint64_t st_fast = 0, st_fast_fallback = 0;
   bool f64_ntt = false;             // every Q_l < 2^49: forward NTTs of the plaintext pipeline run on the FP64 pipe
@@ -1341,14 +1343,21 @@ extern "C" int rsg_inner_product_idx(rsg_context *c, const rsg_crs *crs, const u
   return inner_product_impl(c, crs, 0, h_crs_idx, coeffs, 0, h_coeff_idx, count, h_tags, h_out, d_out, n_used);
 }
 
-extern "C" int rsg_enc_sum(rsg_context *c, const uint64_t *d_parts, size_t parts, size_t n_enc, uint64_t *d_out) {
+extern "C" int rsg_enc_sum_strided(rsg_context *c, const uint64_t *d_parts, size_t parts, size_t n_enc, size_t part_stride_words,
+                                   uint64_t *d_out) {
   if (!c || !d_parts || !d_out || !parts || !n_enc) return fail(RSG_ERR_ARG, "null argument");
+  if (part_stride_words && (part_stride_words < n_enc * c->enc_words() || (part_stride_words & 1))) return fail(RSG_ERR_ARG, "part stride");
   std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   LaunchScope ls(c, "k_enc_sum");
   const size_t pairs = n_enc * c->enc_words() / 2;
-  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_parts, (uint32_t)parts, (uint32_t)n_enc, d_out);
+  k_enc_sum<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, d_parts, (uint32_t)parts, (uint32_t)n_enc, d_out,
+                                                                     part_stride_words);
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
+}
+extern "C" int rsg_enc_sum(rsg_context *c, const uint64_t *d_parts, size_t parts, size_t n_enc, uint64_t *d_out) {
+  return rsg_enc_sum_strided(c, d_parts, parts, n_enc, 0, d_out);
 }
 extern "C" int rsg_enc_add(rsg_context *c, uint64_t *d_acc, const uint64_t *d_other) {
   RSG_TRACE_CALL();
@@ -2603,7 +2612,8 @@ static int fast_run(rsg_context *c, FastPlan *fp, const FastTable &T, uint64_t *
   }
   {
     LaunchScope ls(c, "k_probe");
-    k_probe_fast<<<dim3(T.n_ip, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, elem_flag, c->d_pval, c->d_pntt, c->d_fp_totals, nullptr, 0u,
+    k_probe_fast<<<dim3(T.n_ip, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, elem_flag, c->d_pval, c->d_pntt, c->d_fp_totals,
+                                                                 c->fp_block ? c->fp_block + RSG_SHARD_BLOCK_HEADER + 8 * c->L_R : nullptr, c->fp_pstride,
                                                                  c->d_fp_status);
   }
   CUDA_TRY(cudaGetLastError());
@@ -2625,6 +2635,10 @@ static int groth16_lincombs_fast(rsg_context *c, const G16Ptrs &G, const rsg_gro
     LaunchScope ls(c, "k_probe");
     k_probe_chain<<<1, 32, 0, st>>>(c->d_params, T, c->d_fp_totals, c->d_fp_status);
   }
+  if (c->fp_block) {
+    LaunchScope ls(c, "k_probe");
+    k_probe_block_header<<<1, 32, 0, st>>>(c->d_params, T, c->d_fp_totals, c->d_fp_status, c->fp_pstride, c->fp_block);
+  }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(c->h_fp_status, c->d_fp_status, FPS_WORDS * 4, cudaMemcpyDeviceToHost, st));
   if (h_proof) CUDA_TRY(cudaMemcpyAsync(h_proof, out, 3 * c->enc_words() * 8, cudaMemcpyDeviceToHost, st));
@@ -2640,19 +2654,12 @@ static int groth16_lincombs_fast(rsg_context *c, const G16Ptrs &G, const rsg_gro
   return RSG_OK;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// groth16::prover (groth16.tcc:69-115): the witness map, then the reference's own sequence of six inner products combined
-// with operator+= (kept separate, not fused into three, because the transparent-ciphertext rule is order-dependent).
-// The six inner products + operator+= chain of groth16.tcc:89-112 over this shard's term ranges.  vec[k] (k = A_io, A_mid,
-// B_io, B_mid, H, aux) is the address element 0 of that coefficient vector WOULD have: only the elements of the shard's
-// ranges ([s_lo, min(s_hi, n)) for the first four, [t_lo, min(t_hi, n+1)) for H, [m_lo, min(m_hi, n_aux)) for aux) are read.
-static int groth16_lincombs_exact(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
-                                  const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
-                                  size_t *n_used) {
+// The six term lists of groth16.tcc:89-112 over this shard's ranges: which coefficients SealPoly::is_zero skips (one flag
+// kernel per vector range, one copy; synchronises), scalar auxiliary inputs by kind.
+static int g16_term_lists(rsg_context *c, const rsg_groth16_layout *L, size_t n, size_t n_aux, const uint64_t *const vec[6],
+                          const uint8_t *h_aux_kind, std::vector<TermSpec> (&ip)[6]) {
   int rc;
   const size_t W = c->ring_words();
-  const size_t NONE = (size_t)-1;
-  // SealPoly::is_zero prefix flags of every coefficient fed to inner_product (one launch per vector range, one copy)
   struct Range { size_t lo, hi; };
   const Range rg[6] = {{L->s_pows_lo, std::min(L->s_pows_hi, n)}, {L->s_pows_lo, std::min(L->s_pows_hi, n)},
                        {L->s_pows_lo, std::min(L->s_pows_hi, n)}, {L->s_pows_lo, std::min(L->s_pows_hi, n)},
@@ -2669,13 +2676,6 @@ static int groth16_lincombs_exact(rsg_context *c, const rsg_crs *crs, const rsg_
   std::vector<uint8_t> flags(std::max<size_t>(foff[6], 1));
   if (foff[6]) CUDA_TRY(cudaMemcpyAsync(flags.data(), c->d_flags, foff[6], cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-
-  uint64_t *out = d_proof;
-  if (!out) {
-    if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 3 * c->enc_words()))) return rc;
-    out = c->d_out_scratch;
-  }
-  std::vector<TermSpec> ip[6];
   const size_t crs_off[6] = {L->s_pows_off, L->s_pows_off, L->s_pows_off, L->s_pows_off, L->delta_ts_off, L->delta_mid_off};
   for (int k = 0; k < 5; k++)
     for (size_t i = rg[k].lo; i < rg[k].hi; i++)
@@ -2690,6 +2690,27 @@ static int groth16_lincombs_exact(rsg_context *c, const rsg_crs *crs, const rsg_
     } else if (kind == RSG_TERM_GENERAL) {
       ip[5].push_back({ci, vec[5], (uint32_t)i});
     }
+  }
+  return RSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// groth16::prover (groth16.tcc:69-115): the witness map, then the reference's own sequence of six inner products combined
+// with operator+= (kept separate, not fused into three, because the transparent-ciphertext rule is order-dependent).
+// The six inner products + operator+= chain of groth16.tcc:89-112 over this shard's term ranges.  vec[k] (k = A_io, A_mid,
+// B_io, B_mid, H, aux) is the address element 0 of that coefficient vector WOULD have: only the elements of the shard's
+// ranges ([s_lo, min(s_hi, n)) for the first four, [t_lo, min(t_hi, n+1)) for H, [m_lo, min(m_hi, n_aux)) for aux) are read.
+static int groth16_lincombs_exact(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
+                                  const uint64_t *const vec[6], const uint8_t *h_aux_kind, uint64_t *h_proof, uint64_t *d_proof,
+                                  size_t *n_used) {
+  int rc;
+  const size_t NONE = (size_t)-1;
+  std::vector<TermSpec> ip[6];
+  if ((rc = g16_term_lists(c, L, n, n_aux, vec, h_aux_kind, ip))) return rc;
+  uint64_t *out = d_proof;
+  if (!out) {
+    if ((rc = ensure(c, &c->d_out_scratch, &c->cap_out_scratch, 3 * c->enc_words()))) return rc;
+    out = c->d_out_scratch;
   }
   const size_t E = c->enc_words();
   if (n_used) {
@@ -2810,6 +2831,156 @@ extern "C" int rsg_groth16_lincombs(rsg_context *c, const rsg_crs *crs, const rs
   const size_t lo[6] = {L->s_pows_lo, L->s_pows_lo, L->s_pows_lo, L->s_pows_lo, L->delta_ts_lo, L->delta_mid_lo};
   for (int k = 0; k < 6; k++) vec[k] = d_vec[k] ? d_vec[k] - lo[k] * W : nullptr;
   return groth16_lincombs_dev(c, crs, L, n, n_aux, vec, h_aux_kind, h_proof, d_proof, n_used);
+}
+
+// ---- term shards with the order-dependent transparent-ciphertext rule kept exact (include/rsgpu.h) ----------------------
+extern "C" size_t rsg_groth16_shard_block_words(size_t L_R, size_t pstride) { return RSG_SHARD_BLOCK_HEADER + 8 * L_R + 6 * L_R * pstride; }
+
+static void g16_rebase(const rsg_context *c, const rsg_groth16_layout *L, const uint64_t *const d_vec[6], const uint64_t *vec[6]) {
+  const size_t W = c->ring_words();
+  const size_t lo[6] = {L->s_pows_lo, L->s_pows_lo, L->s_pows_lo, L->s_pows_lo, L->delta_ts_lo, L->delta_mid_lo};
+  for (int k = 0; k < 6; k++) vec[k] = d_vec[k] ? d_vec[k] - lo[k] * W : nullptr;
+}
+
+extern "C" int rsg_groth16_lincombs_shard(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, size_t n, size_t n_aux,
+                                          const uint64_t *const d_vec[6], const uint8_t *h_aux_kind, uint64_t *d_part, size_t pstride,
+                                          size_t *n_used) {
+  RSG_TRACE_CALL();
+  if (!c || !crs || !L || !d_vec || !d_part) return fail(RSG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t cnt[3] = {std::min(L->s_pows_hi, n) > L->s_pows_lo ? std::min(L->s_pows_hi, n) - L->s_pows_lo : 0,
+                         std::min(L->delta_ts_hi, n + 1) > L->delta_ts_lo ? std::min(L->delta_ts_hi, n + 1) - L->delta_ts_lo : 0,
+                         std::min(L->delta_mid_hi, n_aux) > L->delta_mid_lo ? std::min(L->delta_mid_hi, n_aux) - L->delta_mid_lo : 0};
+  if (cnt[0] > pstride || cnt[1] > pstride || cnt[2] > pstride || pstride > 0xFFFFFFFFull) return fail(RSG_ERR_ARG, "pstride below a term range");
+  const uint64_t *vec[6];
+  g16_rebase(c, L, d_vec, vec);
+  const size_t E = c->enc_words(), bw = rsg_groth16_shard_block_words(c->L_R, pstride);
+  uint64_t *block = d_part + 3 * E;
+  CUDA_TRY(cudaMemsetAsync(block, 0xFF, bw * 8, c->stream));   // ~0: no term at this position
+  if (n_used) n_used[0] = n_used[1] = n_used[2] = 0;
+  const bool no_terms = !cnt[0] && !cnt[1] && !cnt[2] && L->alpha_idx == (size_t)-1 && L->beta_idx == (size_t)-1;
+  if (no_terms || !fast_applies(c, L, n, n_aux)) {
+    // a rank without terms (more ranks than terms) contributes nothing; without a static plan (RSG_FAST=0, term set above the
+    // NTT-plaintext budget) the block asks for the chain
+    const uint64_t hdr[RSG_SHARD_BLOCK_HEADER] = {no_terms ? 0ull : 1ull, 0, 0, 0, 0, 0, 0, (uint64_t)pstride};
+    CUDA_TRY(cudaMemsetAsync(d_part, 0, 3 * E * 8, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(block, hdr, sizeof(hdr), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RSG_OK;
+  }
+  c->fp_block = block;
+  c->fp_pstride = (uint32_t)pstride;
+  int candidate = 0;   // local only: the global check (rsg_groth16_shard_check) decides
+  const int rc = groth16_lincombs_fast(c, g16_ptrs(c, crs, L), L, n, n_aux, vec, h_aux_kind, nullptr, d_part, n_used, &candidate);
+  c->fp_block = nullptr;
+  c->fp_pstride = 0;
+  return rc;
+}
+
+extern "C" int rsg_groth16_shard_check(const uint64_t *h_blocks, size_t world, size_t L_R, size_t pstride, uint64_t Q0, int *verdict) {
+  if (!h_blocks || !verdict || !world || !L_R || L_R > (size_t)MAX_LR || Q0 < 2) return fail(RSG_ERR_ARG, "bad argument");
+  const size_t bw = rsg_groth16_shard_block_words(L_R, pstride);
+  bool cand = false;
+  uint64_t gtot[6][MAX_LR] = {}, gcount[6] = {};
+  for (size_t r = 0; r < world; r++) {
+    const uint64_t *b = h_blocks + r * bw;
+    if (b[7] != pstride) return fail(RSG_ERR_ARG, "probe block of another pstride");
+    cand = cand || (b[0] & 1);
+    for (int k = 0; k < 6; k++) gcount[k] += b[1 + k];
+  }
+  // global prefix sums: rank r's running sums shifted by the totals of ranks 0..r-1 (term ranges are in rank order)
+  for (int ip = 0; ip < 6 && !cand; ip++)
+    for (size_t j = 0; j < L_R; j++) {
+      uint64_t off = 0;
+      for (size_t r = 0; r < world; r++) {
+        const uint64_t *b = h_blocks + r * bw;
+        const uint64_t *pre = b + RSG_SHARD_BLOCK_HEADER + 8 * L_R + ((size_t)ip * L_R + j) * pstride;
+        for (size_t t = 0; t < pstride; t++)
+          if (pre[t] != ~0ull && (pre[t] + off) % Q0 == 0) cand = true;
+        if (b[1 + ip]) off = (off + b[RSG_SHARD_BLOCK_HEADER + ip * L_R + j]) % Q0;
+      }
+      gtot[ip][j] = off;
+    }
+  // the operator+= chains of groth16.tcc:89-112 at the probe slot, on the global totals (k_probe_chain on one GPU)
+  for (int e = 0; e < 3 && !cand; e++) {
+    const int a = 2 * e, b2 = a + 1;
+    if (gcount[a] + gcount[b2] == 0) continue;
+    for (size_t j = 0; j < L_R; j++) {
+      uint64_t sum = (gtot[a][j] + gtot[b2][j]) % Q0;
+      cand = cand || sum == 0;
+      if (e < 2)
+        for (size_t r = 0; r < world; r++) {
+          const uint64_t x = h_blocks[r * bw + RSG_SHARD_BLOCK_HEADER + 6 * L_R + (size_t)e * L_R + j];
+          if (x == ~0ull) continue;
+          sum = (sum + x) % Q0;
+          cand = cand || sum == 0;
+        }
+    }
+  }
+  *verdict = cand ? 1 : 0;
+  return RSG_OK;
+}
+
+extern "C" int rsg_groth16_lincombs_chain(rsg_context *c, rsg_crs *crs, size_t carry_first, const rsg_groth16_layout *L, size_t n,
+                                          size_t n_aux, const uint64_t *const d_vec[6], const uint8_t *h_aux_kind, uint64_t *d_carry,
+                                          uint8_t *h_present) {
+  RSG_TRACE_CALL();
+  if (!c || !crs || !L || !d_vec || !d_carry || !h_present) return fail(RSG_ERR_ARG, "null argument");
+  if (carry_first + 6 > crs->n) return fail(RSG_ERR_ARG, "the arena needs six spare encodings from carry_first on");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc;
+  const uint64_t *vec[6];
+  g16_rebase(c, L, d_vec, vec);
+  std::vector<TermSpec> ip[6];
+  if ((rc = g16_term_lists(c, L, n, n_aux, vec, h_aux_kind, ip))) return rc;
+  const size_t E = c->enc_words();
+  if ((rc = ensure(c, &c->d_ip, &c->cap_ip, 6 * E))) return rc;
+  for (int k = 0; k < 6; k++) {
+    std::vector<TermSpec> terms;
+    if (h_present[k]) {   // everything before this rank's range enters as ONE term with coefficient 1 (seal_ring.tcc:525-528)
+      CUDA_TRY(cudaMemcpyAsync(crs->d + (carry_first + k) * E, d_carry + k * E, E * 8, cudaMemcpyDeviceToDevice, c->stream));
+      terms.push_back({(uint32_t)(carry_first + k), nullptr, 0});
+    }
+    terms.insert(terms.end(), ip[k].begin(), ip[k].end());
+    if (terms.empty()) continue;   // still the empty EncodingElem
+    if ((rc = inner_product_terms(c, crs->d, terms, c->d_ip + k * E))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_carry + k * E, c->d_ip + k * E, E * 8, cudaMemcpyDeviceToDevice, c->stream));
+    h_present[k] = 1;
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
+}
+
+extern "C" int rsg_groth16_chain_finish(rsg_context *c, const rsg_crs *crs, const rsg_groth16_layout *L, const uint64_t *d_carry,
+                                        const uint8_t *h_present, uint64_t *d_proof) {
+  RSG_TRACE_CALL();
+  if (!c || !crs || !L || !d_carry || !h_present || !d_proof) return fail(RSG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t E = c->enc_words(), NONE = (size_t)-1;
+  for (int e = 0; e < 3; e++) {   // EncodingElem::operator+= chain of groth16.tcc:89-112
+    const int a = 2 * e, b = a + 1;
+    const size_t extra = e == 0 ? L->alpha_idx : (e == 1 ? L->beta_idx : NONE);
+    const uint64_t *src[3] = {h_present[a] ? d_carry + a * E : nullptr, h_present[b] ? d_carry + b * E : nullptr,
+                              extra != NONE ? crs->d + extra * E : nullptr};
+    uint64_t *acc = d_proof + e * E;
+    bool have = false;
+    for (int k = 0; k < 3; k++) {
+      if (!src[k]) continue;
+      if (!have) {
+        CUDA_TRY(cudaMemcpyAsync(acc, src[k], E * 8, cudaMemcpyDeviceToDevice, c->stream));
+        have = true;
+      } else {
+        const int r = enc_add_fix(c, acc, src[k]);
+        if (r) return r;
+      }
+    }
+    if (!have) CUDA_TRY(cudaMemsetAsync(acc, 0, E * 8, c->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
 }
 
 extern "C" int rsg_groth16_prove(rsg_context *c, const rsg_r1cs *r1cs, const rsg_crs *crs, const rsg_groth16_layout *L,

@@ -9,7 +9,15 @@ range; one all-gather of the partials and the modular-add kernel (modular additi
     phase 1  rsg_r1cs_evaluate + rsg_witness_map_groth16  on a context with N_R/G slots      (sharded by slot)
     phase 2  all_to_all_single                                                             (slots <-> terms)
     phase 3  rsg_groth16_lincombs                        on the full context, term shard of the CRS
-    phase 4  all_gather_into_tensor + rsg_enc_sum
+    phase 4  all_gather_into_tensor + rsg_enc_sum_strided, then rsg_groth16_shard_check on the gathered probe blocks
+
+The reference's inner product DROPS a running sum whose c1 polynomial vanishes (seal_ring.tcc:493-504): an order-dependent
+rule over the GLOBAL term order.  Every rank therefore ships, behind its partial proof, the running sums of its inner products
+at one NTT slot; after the all-gather each rank shifts them by the totals of the ranks before it and checks that no global
+prefix (and no operator+= of groth16.tcc:89-112) vanished there -- then the modular sum of the partials IS the reference's
+proof.  Otherwise (a structured CRS, e.g. the tiny_transp golden case; never for real encryptions) the ranks run the exact
+chain: rank 0 .. G-1 in order extend the six inner products (`chain_step`, the carry travels rank to rank), rank 0 -- which
+holds alpha and beta -- applies the operator+= chain (`chain_finish`).
 
 The index bookkeeping (`send_rows`, `unpack`) is pure host logic and is exercised on CPU with gloo in
 tests/test_multi_rank_cpu.py; tests/test_gpu_parity.py runs all phases for G simulated ranks on one GPU.
@@ -83,7 +91,11 @@ class ShardedGroth16Prover:
         self.layout = Groth16Layout()
         for k, _ in Groth16Layout._fields_:
             setattr(self.layout, k, d[k])
-        self.crs = self.ctxP.crs(d["n_elems"])
+        self.carry_first = d["n_elems"]
+        self.crs = self.ctxP.crs(d["n_elems"] + 6)   # six spare encodings: the chain's carry is staged there
+        self.pstride = max(rows_per_rank(n, world), (self.aux + world - 1) // world, 1)
+        self.block_words = int(self.ctxP.lib.rsg_groth16_shard_block_words(self.L_R, self.pstride))
+        self.part_words = 3 * self.ctxP.enc_words + self.block_words   # what one rank contributes to the all-gather
         dev = torch.device("cuda", device)
         Ws = self.L_R * self.S
         # witness tensor of this slot block: [6n coefficients | n+1 H | zero row]; the library writes into it through wraps
@@ -94,9 +106,10 @@ class ShardedGroth16Prover:
         self.idx = torch.from_numpy(idx).to(dev)
         self.m_lo, self.m_hi = d["delta_mid_lo"], d["delta_mid_hi"]
         self.t_aux = torch.zeros(max(self.m_hi - self.m_lo, 1), self.L_R * self.N_R, dtype=torch.int64, device=dev)
-        self.t_part = torch.zeros(3 * self.ctxP.enc_words, dtype=torch.int64, device=dev)
+        self.t_part = torch.zeros(self.part_words, dtype=torch.int64, device=dev)
         self.t_final = torch.zeros(3 * self.ctxP.enc_words, dtype=torch.int64, device=dev)
         self._wraps = []
+        self._h_blocks = None
         self.rv_assign = self._wrap(self.ctxW, self.t_assign, self.io + self.aux)
         self.rv_evals = self._wrap(self.ctxW, self.t_evals, 9 * n)
         self.rv_coeffs = self._wrap(self.ctxW, self.t_wit, 6 * n)
@@ -149,15 +162,45 @@ class ShardedGroth16Prover:
             aux_kind = np.ascontiguousarray(aux_kind, dtype=np.uint8)
             assert aux_kind.size == self.aux
         self._aux_kind = aux_kind
-        check(self.ctxP.lib.rsg_groth16_lincombs(self.ctxP.h, self.crs.h, C.byref(self.layout), self.n, self.aux, ptrs,
-                                                 aux_kind.ctypes.data_as(C.c_void_p) if aux_kind is not None else None,
-                                                 C.c_void_p(h_proof_ptr) if h_proof_ptr else None,
-                                                 C.c_void_p(self.t_part.data_ptr()), used))
+        self._ptrs = ptrs
+        check(self.ctxP.lib.rsg_groth16_lincombs_shard(self.ctxP.h, self.crs.h, C.byref(self.layout), self.n, self.aux, ptrs,
+                                                       aux_kind.ctypes.data_as(C.c_void_p) if aux_kind is not None else None,
+                                                       C.c_void_p(self.t_part.data_ptr()), self.pstride, used))
         return [int(u) for u in used]
 
     def combine(self, all_parts):
-        """Phase 4 after the all-gather: modular sum of the `world` partial proofs."""
-        self.ctxP.enc_sum(all_parts.data_ptr(), self.world, 3, self.t_final.data_ptr())
+        """Phase 4 after the all-gather of the `world` records [partial proof | probe block]: modular sum of the partial
+        proofs into t_final (asynchronous), then the global transparent-prefix check on the probe blocks.  Returns the
+        verdict: 0 = t_final is the proof; 1 = run the chain (chain_step on ranks 0..G-1 in order, chain_finish on rank 0)."""
+        E3 = 3 * self.ctxP.enc_words
+        check(self.ctxP.lib.rsg_enc_sum_strided(self.ctxP.h, C.c_void_p(all_parts.data_ptr()), self.world, 3, self.part_words,
+                                                C.c_void_p(self.t_final.data_ptr())))
+        if self._h_blocks is None:
+            self._h_blocks = self.torch.empty(self.world, self.block_words, dtype=self.torch.int64).pin_memory()
+        self._h_blocks.copy_(all_parts.view(self.world, self.part_words)[:, E3:], non_blocking=True)   # one strided D2H copy
+        self.torch.cuda.current_stream().synchronize()
+        blocks = self._h_blocks.numpy().view(np.uint64)
+        verdict = C.c_int(0)
+        check(self.ctxP.lib.rsg_groth16_shard_check(blocks.ctypes.data_as(C.c_void_p), self.world, self.L_R, self.pstride,
+                                                    int(self.ctxP.Q[0]), C.byref(verdict)))
+        return verdict.value
+
+    def new_carry(self):
+        """The chain's state before rank 0: six empty inner products."""
+        return self.torch.zeros(6 * self.ctxP.enc_words, dtype=self.torch.int64, device=self.t_part.device), np.zeros(6, dtype=np.uint8)
+
+    def chain_step(self, carry, present):
+        """Exact continuation of the six inner products over this rank's terms (after lincomb_phase of the same proof);
+        carry / present are updated in place and travel to the next rank."""
+        ak = self._aux_kind
+        check(self.ctxP.lib.rsg_groth16_lincombs_chain(self.ctxP.h, self.crs.h, self.carry_first, C.byref(self.layout), self.n,
+                                                       self.aux, self._ptrs, ak.ctypes.data_as(C.c_void_p) if ak is not None else None,
+                                                       C.c_void_p(carry.data_ptr()), present.ctypes.data_as(C.c_void_p)))
+
+    def chain_finish(self, carry, present):
+        """Rank 0 (holds alpha and beta): operator+= chain of groth16.tcc:89-112 over the complete inner products -> t_final."""
+        check(self.ctxP.lib.rsg_groth16_chain_finish(self.ctxP.h, self.crs.h, C.byref(self.layout), C.c_void_p(carry.data_ptr()),
+                                                     present.ctypes.data_as(C.c_void_p), C.c_void_p(self.t_final.data_ptr())))
 
     def close(self):
         for ctx, h in self._wraps:
@@ -168,3 +211,31 @@ class ShardedGroth16Prover:
             obj.__del__()
         self.ctxW.close()
         self.ctxP.close()
+
+
+def run_chain(sp, dist):
+    """The exact chain over NCCL ranks (torch.distributed point-to-point): the carry visits rank 0 .. G-1 and returns to
+    rank 0, which finishes and broadcasts the proof.  Collective: every rank calls it after combine() returned 1."""
+    torch = sp.torch
+    carry, present = sp.new_carry()
+    flags = torch.zeros(6, dtype=torch.uint8, device=carry.device)
+    if sp.rank > 0:
+        dist.recv(carry, src=sp.rank - 1)
+        dist.recv(flags, src=sp.rank - 1)
+        present[:] = flags.cpu().numpy()
+    sp.chain_step(carry, present)
+    flags.copy_(torch.from_numpy(present))
+    if sp.world > 1:
+        dst = sp.rank + 1 if sp.rank + 1 < sp.world else 0
+        if sp.rank == 0:
+            dist.send(carry, dst=dst)
+            dist.send(flags, dst=dst)
+            dist.recv(carry, src=sp.world - 1)
+            dist.recv(flags, src=sp.world - 1)
+            present[:] = flags.cpu().numpy()
+        else:
+            dist.send(carry, dst=dst)
+            dist.send(flags, dst=dst)
+    if sp.rank == 0:
+        sp.chain_finish(carry, present)
+    dist.broadcast(sp.t_final, src=0)

@@ -267,26 +267,79 @@ def test_groth16_prove(gold):
 
 
 def test_groth16_prove_sharded(gold):
-    """Term-sharded proving keys (what each rank of an N-GPU run holds): partial proofs sum to the proof."""
+    """Term-sharded proving keys (what each rank of an N-GPU run holds): partial proofs sum to the proof -- unless a global
+    prefix of an inner product is a transparent ciphertext, which the reference DROPS (seal_ring.tcc:493-504): the probe
+    blocks of the three shards must then say so (rsg_groth16_shard_check) and the exact chain must give the proof."""
     import ctypes as C
+    import torch
+    import ringsnark_b200 as rs
+    from ringsnark_b200.backend import Groth16Layout, groth16_shard_layout
     case, ctx = gold
-    if int(case.seed) == 11:
-        pytest.skip("tiny_transp: a prefix of <s_pows, A_io> is a transparent ciphertext, which the reference DROPS "
-                    "(seal_ring.tcc:493-504); that rule is order-dependent and is resolved exactly on one GPU only "
-                    "(DESIGN.md section 5)")
-    parts = []
     world = 3
-    for rank in range(world):
-        pk = _pk(case, ctx, rank, world)
-        p, _ = pk.prove(_assignment(case), _aux_kind(case))
-        parts.append(p)
     want = case.enc("proof")[0]
-    for e in range(3):
-        stack = _torch_dev(np.stack([p[e] for p in parts]))
-        out = _torch_dev(np.zeros(case.enc_words, dtype=np.uint64))
-        assert ctx.lib.rsg_enc_sum(ctx.h, C.c_void_p(stack.data_ptr()), world, 1, C.c_void_p(out.data_ptr())) == 0
-        ctx.sync()
-        assert np.array_equal(_host(out), want[e])
+    if int(case.seed) != 11:
+        parts = []
+        for rank in range(world):
+            pk = _pk(case, ctx, rank, world)
+            p, _ = pk.prove(_assignment(case), _aux_kind(case))
+            parts.append(p)
+        for e in range(3):
+            stack = _torch_dev(np.stack([p[e] for p in parts]))
+            out = _torch_dev(np.zeros(case.enc_words, dtype=np.uint64))
+            assert ctx.lib.rsg_enc_sum(ctx.h, C.c_void_p(stack.data_ptr()), world, 1, C.c_void_p(out.data_ptr())) == 0
+            ctx.sync()
+            assert np.array_equal(_host(out), want[e])
+        return
+    # tiny_transp: witness map once, then the sharded protocol on three term shards through the C ABI
+    n, io, aux, W, E = case.n, case.io, case.aux, case.N_R * case.L_R, case.enc_words
+    pk0 = _pk(case, ctx)
+    pk0.assignment.upload(_assignment(case))
+    coeffs, H = ctx.witness_map(n, pk0.r1cs.evaluate(pk0.assignment))          # A_io, B_io, C_io, A_mid, B_mid, C_mid | H
+    ctx.sync()
+    base = {0: coeffs.device_ptr(), 1: coeffs.device_ptr() + 3 * n * W * 8, 2: coeffs.device_ptr() + n * W * 8,
+            3: coeffs.device_ptr() + 4 * n * W * 8, 4: H.device_ptr(), 5: pk0.assignment.device_ptr() + io * W * 8}
+    pstride = max((n + 1 + world - 1) // world, (aux + world - 1) // world, 1)
+    bw = int(ctx.lib.rsg_groth16_shard_block_words(case.L_R, pstride))
+    s_pows, delta_ts, delta_mid = case.enc("crs_s_pows")[0], case.enc("crs_delta_ts")[0], case.enc("crs_delta_mid")[0]
+    shards, records = [], []
+    for rank in range(world):
+        d = groth16_shard_layout(n, aux, rank, world)
+        L = Groth16Layout()
+        for k, _ in Groth16Layout._fields_:
+            setattr(L, k, d[k])
+        crs = ctx.crs(d["n_elems"] + 6)
+        crs.upload(s_pows[L.s_pows_lo:L.s_pows_hi], L.s_pows_off)
+        crs.upload(delta_ts[L.delta_ts_lo:L.delta_ts_hi], L.delta_ts_off)
+        if L.delta_mid_hi > L.delta_mid_lo:
+            crs.upload(delta_mid[L.delta_mid_lo:L.delta_mid_hi], L.delta_mid_off)
+        if rank == 0:
+            crs.upload(case.enc("crs_alpha")[0], L.alpha_idx)
+            crs.upload(case.enc("crs_beta")[0], L.beta_idx)
+        lo = [L.s_pows_lo] * 4 + [L.delta_ts_lo, L.delta_mid_lo]
+        ptrs = (C.c_void_p * 6)(*[base[k] + lo[k] * W * 8 for k in range(6)])
+        rec = torch.zeros(3 * E + bw, dtype=torch.int64, device="cuda")
+        used = (C.c_size_t * 3)()
+        kind = _aux_kind(case)
+        rs.capi.check(ctx.lib.rsg_groth16_lincombs_shard(ctx.h, crs.h, C.byref(L), n, aux, ptrs, kind.ctypes.data_as(C.c_void_p),
+                                                         C.c_void_p(rec.data_ptr()), pstride, used))
+        shards.append((crs, L, ptrs, kind, d["n_elems"]))
+        records.append(rec)
+    torch.cuda.synchronize()
+    blocks = np.stack([_host(r)[3 * E:] for r in records])
+    verdict = C.c_int(-1)
+    rs.capi.check(ctx.lib.rsg_groth16_shard_check(blocks.ctypes.data_as(C.c_void_p), world, case.L_R, pstride, int(case.Q[0]), C.byref(verdict)))
+    assert verdict.value == 1
+    carry = torch.zeros(6 * E, dtype=torch.int64, device="cuda")
+    present = np.zeros(6, dtype=np.uint8)
+    for crs, L, ptrs, kind, first in shards:
+        rs.capi.check(ctx.lib.rsg_groth16_lincombs_chain(ctx.h, crs.h, first, C.byref(L), n, aux, ptrs, kind.ctypes.data_as(C.c_void_p),
+                                                         C.c_void_p(carry.data_ptr()), present.ctypes.data_as(C.c_void_p)))
+    out = torch.zeros(3 * E, dtype=torch.int64, device="cuda")
+    crs0, L0 = shards[0][0], shards[0][1]
+    rs.capi.check(ctx.lib.rsg_groth16_chain_finish(ctx.h, crs0.h, C.byref(L0), C.c_void_p(carry.data_ptr()),
+                                                   present.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr())))
+    torch.cuda.synchronize()
+    assert np.array_equal(_host(out).reshape(3, -1), want)
 
 
 @pytest.mark.parametrize("name", ["c4s", "c1"])
@@ -345,10 +398,6 @@ def test_slot_and_term_sharded_prover(gold, world):
     import torch
     from ringsnark_b200.distributed import ShardedGroth16Prover
     case, _ = gold
-    if int(case.seed) == 11:
-        pytest.skip("tiny_transp: order-dependent transparent-ciphertext rule, single-GPU only (DESIGN.md section 5)")
-    if bool(case.quirks):
-        pytest.skip("scalar auxiliary inputs need h_aux_kind, which the sharded driver does not take")
     cfg = dict(N_R=case.N_R, q=case.q, N_E=case.N_E, Q=case.Q, n=case.n, io=case.io, aux=case.aux)
     csr = (case.d["r1cs_row_ptr"], case.d["r1cs_col"], case.d["r1cs_coeff"])
     provers = [ShardedGroth16Prover(cfg, csr, r, world, stream=torch.cuda.current_stream().cuda_stream) for r in range(world)]
@@ -371,10 +420,17 @@ def test_slot_and_term_sharded_prover(gold, world):
         parts = []
         for p in provers:
             recv = torch.stack([s[p.rank * blk:(p.rank + 1) * blk] for s in sends])     # what all_to_all_single delivers
-            p.lincomb_phase(recv)
+            p.lincomb_phase(recv, aux_kind=_aux_kind(case))
             parts.append(p.t_part)
         allp = torch.cat(parts)                                                          # what all_gather delivers
-        provers[0].combine(allp)
+        verdicts = [p.combine(allp) for p in provers]
+        assert len(set(verdicts)) == 1                                                   # every rank reaches the same verdict
+        assert verdicts[0] == (1 if int(case.seed) == 11 else 0)                         # tiny_transp: a global prefix is transparent
+        if verdicts[0]:                                                                  # the exact chain, rank by rank
+            carry, present = provers[0].new_carry()
+            for p in provers:
+                p.chain_step(carry, present)
+            provers[0].chain_finish(carry, present)
         torch.cuda.synchronize()
         assert np.array_equal(_host(provers[0].t_final).reshape(3, -1), case.enc("proof")[0])
     finally:

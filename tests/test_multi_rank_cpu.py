@@ -143,3 +143,82 @@ def test_slot_to_term_exchange_gloo(world):
         assert p.exitcode == 0
     res = sorted(q.get(timeout=10) for _ in range(world))
     assert res == [(r, True) for r in range(world)]
+
+
+def _probe_worker(rank, world, port, golden, q):
+    """The global transparent-prefix check of the N-GPU path (include/rsgpu.h, rsg_groth16_shard_check) on CPU: every rank
+    builds the probe block its GPU would ship -- the running sums of its inner products at NTT slot (c1, limb 0, x = 0), here from
+    the C oracle's per-term products --, the blocks are all-gathered with gloo and every rank must reach the same verdict."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import ctypes as C
+    import torch
+    import oracle_lib as O
+    from rsgv import Case
+    import ringsnark_b200 as rs
+    from ringsnark_b200.backend import NONE, groth16_shard_layout
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = Case(golden)
+        n, aux, L_R, Q0 = case.n, case.aux, case.L_R, int(case.Q[0])
+        lib = rs.load_library()
+        L = groth16_shard_layout(n, aux, rank, world)
+        pstride = max((n + 1 + world - 1) // world, (aux + world - 1) // world, 1)
+        bw = int(lib.rsg_groth16_shard_block_words(L_R, pstride))
+        block = np.full(bw, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+        block[0:8] = 0
+        block[7] = pstride
+        ct_words = 2 * case.L_E * case.N_E
+        probe = lambda enc, j: int(enc[j * ct_words + case.L_E * case.N_E])          # c1, limb 0, x = 0 of ring limb j
+        vecs = [("crs_s_pows", "wit_A_io", L["s_pows_lo"], min(L["s_pows_hi"], n)), ("crs_s_pows", "wit_A_mid", L["s_pows_lo"], min(L["s_pows_hi"], n)),
+                ("crs_s_pows", "wit_B_io", L["s_pows_lo"], min(L["s_pows_hi"], n)), ("crs_s_pows", "wit_B_mid", L["s_pows_lo"], min(L["s_pows_hi"], n)),
+                ("crs_delta_ts", "wit_H", L["delta_ts_lo"], min(L["delta_ts_hi"], n + 1)),
+                ("crs_delta_mid", "auxiliary_input", L["delta_mid_lo"], min(L["delta_mid_hi"], aux))]
+        for ip, (cname, vname, lo, hi) in enumerate(vecs):
+            crs = case.enc(cname)[0]
+            words, tag, scalar = case.ring(vname)
+            tags = O.term_tags(words, tag, scalar)
+            run = [0] * L_R
+            live = 0
+            for t in range(lo, hi):
+                if tags[t] == 0:
+                    continue
+                live += 1
+                term, _ = O.inner_product(crs[t:t + 1], words[t:t + 1], tags[t:t + 1], case.N_R, L_R, case.q, case.N_E, case.L_E, case.Q)
+                for j in range(L_R):
+                    run[j] = (run[j] + probe(term, j)) % Q0
+                    block[8 + 8 * L_R + (ip * L_R + j) * pstride + (t - lo)] = run[j]
+            block[1 + ip] = live
+            for j in range(L_R):
+                block[8 + ip * L_R + j] = run[j]
+        if L["alpha_idx"] != NONE:
+            for e, name in enumerate(("crs_alpha", "crs_beta")):
+                for j in range(L_R):
+                    block[8 + 6 * L_R + e * L_R + j] = probe(case.enc(name)[0][0], j)
+        mine = torch.from_numpy(block.view(np.int64))
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        blocks = np.ascontiguousarray(torch.stack(gathered).numpy().view(np.uint64))
+        verdict = C.c_int(-1)
+        rc = lib.rsg_groth16_shard_check(blocks.ctypes.data_as(C.c_void_p), world, L_R, pstride, Q0, C.byref(verdict))
+        q.put((rank, rc, verdict.value))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("golden,want", [("tiny_fast", 0), ("tiny_quirks", 0), ("tiny_transp", 1)])
+def test_global_transparent_prefix_check_gloo(golden, want):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + want + len(golden)
+    procs = [ctx.Process(target=_probe_worker, args=(r, world, port, os.path.join(HERE, "golden", golden + ".rsgv"), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(world))
+    assert res == [(r, 0, want) for r in range(world)]

@@ -108,6 +108,8 @@ int main(int argc, char **argv) {
   CK(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_v6<true, 2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 + 64) * 8));
   CK(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_v6<true, 2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 + 64) * 8));
   CK(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_v6<true, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 + 64) * 8));
+  CK(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_v6<true, 2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 + 64) * 8));
+  CK(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_v6<true, 2, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 + 64) * 8));
   CK(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_v6<true, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 + 64) * 8));
   CK(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_v6<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (1024 + 64) * 8));
   CK(cudaFuncSetAttribute(k_lift_fwd_ntt_f64_v6<true, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (1024 + 64) * 8));
@@ -137,6 +139,8 @@ int main(int argc, char **argv) {
     else if (variant == 21) k_lift_fwd_ntt_f64_v6<true, 2, 2, 1><<<dim3((unsigned)(terms * L_E * 2), 1), 256, 8 * (1024 + 64) * 8>>>(dP, src, out, nullptr);
     else if (variant == 22) k_lift_fwd_ntt_f64_v6<true, 2, 2, 2><<<dim3((unsigned)(terms * L_E * 2), 1), 256, 8 * (1024 + 64) * 8>>>(dP, src, out, nullptr);
     else if (variant == 23) k_lift_fwd_ntt_f64_v6<true, 2, 2, 3><<<dim3((unsigned)(terms * L_E * 2), 1), 256, 8 * (1024 + 64) * 8>>>(dP, src, out, nullptr);
+    else if (variant == 25) k_lift_fwd_ntt_f64_v6<true, 2, 2, 4><<<dim3((unsigned)(terms * L_E * 2), 1), 256, 8 * (1024 + 64) * 8>>>(dP, src, out, nullptr);
+    else if (variant == 26) k_lift_fwd_ntt_f64_v6<true, 2, 2, 5><<<dim3((unsigned)(terms * L_E * 2), 1), 256, 8 * (1024 + 64) * 8>>>(dP, src, out, nullptr);
     else if (variant == 17) k_lift_fwd_ntt_f64_v6<true, 2, 3><<<dim3((unsigned)(terms * L_E * 2), 1), 256, 8 * (1024 + 64) * 8>>>(dP, src, out, nullptr);
     else if (variant == 18) k_lift_fwd_ntt_f64_v6<true, 4, 4><<<dim3((unsigned)(terms * L_E * 4), 1), 128, 4 * (1024 + 64) * 8>>>(dP, src, out, nullptr);
     else if (variant == 19) k_lift_fwd_ntt_f64_v6<true, 4, 5><<<dim3((unsigned)(terms * L_E * 4), 1), 128, 4 * (1024 + 64) * 8>>>(dP, src, out, nullptr);
@@ -152,10 +156,11 @@ int main(int argc, char **argv) {
                          "v5 diag: L1 source + no stores", "v5 + 256-bit result stores", "v5 diag: L1 source + no stores + hot twiddles",
                          "v5 diag: 256-bit stores + hot twiddles", "v6 cluster of 2 x 256 thr, warp per row, 2 CTAs/SM",
                          "v6 cluster 2 x 256, 3 CTAs/SM (85 regs)", "v6 cluster 4 x 128, 4 CTAs/SM", "v6 cluster 4 x 128, 5 CTAs/SM (102 regs)",
-                         "v6 cluster 8 x 64, 8 CTAs/SM", "v6 diag: L1 source", "v6 diag: no stores", "v6 diag: L1 source + no stores", "SHIPPED k_lift_fwd_ntt_f64_cl (kernels.cuh)"};
+                         "v6 cluster 8 x 64, 8 CTAs/SM", "v6 diag: L1 source", "v6 diag: no stores", "v6 diag: L1 source + no stores", "SHIPPED k_lift_fwd_ntt_f64_cl (kernels.cuh)",
+                         "v6 diag: results into an 8 MiB window (L2-resident)", "v6 diag: L1 source + results into 8 MiB window"};
   run(0, out0);
   CK(cudaDeviceSynchronize());
-  for (int v = 0; v < 25; v++) {
+  for (int v = 0; v < 27; v++) {
     run(v, out1);   // warm-up
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());

@@ -348,7 +348,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512 / CS, MINB)
   LiftIoSmallQ<SIGNED> io;
   io.init(P, j, l);
   io.src = plain + (((size_t)e * L_R + j) << LOGN);
-  io.dst = out + (((((size_t)e * L_R + j) * L_E + l)) << LOGN);
+  io.dst = out + ((((((size_t)e * L_R + j) * L_E + l)) % ((MODE & 4) ? 64 : 0x7FFFFFFF)) << LOGN);   // MODE 4: results into an 8 MiB window (L2)
   const double *tab = P->fwdQ_f64[l];
   const double pd = io.pd, pinv = io.pinv;
   const uint32_t tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
