@@ -357,7 +357,25 @@ def run_gpu_arm(args, cfg_name, cfg):
     else:
         # slot-sharded witness map -> all-to-all -> term-sharded lincombs -> all-gather + modular add (distributed.py)
         from ringsnark_b200.distributed import ShardedGroth16Prover, slot_shard
-        sp = ShardedGroth16Prover(cfg, (row_ptr, col, coeff), rank, world, device=local, stream=stream.cuda_stream)
+        # peer memory (torch symmetric memory: CUDA IPC mappings + device-side barriers) turns the two exchange steps into single
+        # kernels over NVLink (csrc/p2p.cuh); RSG_P2P=0 or an unavailable symmetric-memory backend falls back to NCCL collectives
+        symm = None
+        if os.environ.get("RSG_P2P", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm
+            except Exception:
+                symm = None
+        alloc = (lambda numel: symm.empty(numel, dtype=torch.int64, device=f"cuda:{local}")) if symm else None
+        sp = ShardedGroth16Prover(cfg, (row_ptr, col, coeff), rank, world, device=local, stream=stream.cuda_stream, alloc=alloc)
+        p2p = False
+        if symm:
+            try:
+                hd = [symm.rendezvous(t, dist.group.WORLD.group_name) for t in (sp.t_full_raw, sp.t_part, sp.t_final)]
+                sp.set_peers(list(hd[0].buffer_ptrs), list(hd[1].buffer_ptrs), list(hd[2].buffer_ptrs), lambda: hd[0].barrier())
+                sp.t_part.zero_(); sp.t_final.zero_(); sp.t_full_raw.zero_()
+                p2p = True
+            except Exception as ex:
+                sys.stderr.write(f"bench.py: symmetric memory unavailable ({ex!r}); NCCL collectives\n")
         ctx = sp.ctxP
         ctxs = [sp.ctxP, sp.ctxW]
         sp.fill_synthetic(SEED)
@@ -373,6 +391,15 @@ def run_gpu_arm(args, cfg_name, cfg):
             with torch.cuda.stream(stream):
                 if host_io:
                     sp.load_assignment_shards(h_shard, h_aux)
+                if p2p:
+                    sp.witness_phase_p2p()
+                    used = sp.lincomb_phase()
+                    if sp.combine_p2p():
+                        from ringsnark_b200.distributed import run_chain
+                        run_chain(sp, dist)
+                    if host_io:
+                        h_proof.copy_(sp.t_final, non_blocking=True)
+                    return used
                 send = sp.witness_phase()
                 recv = torch.empty_like(send)
                 dist.all_to_all_single(recv, send)
@@ -384,6 +411,46 @@ def run_gpu_arm(args, cfg_name, cfg):
                 if host_io:
                     h_proof.copy_(sp.t_final, non_blocking=True)
                 return used
+
+        def prove_phases(reps=5):
+            """GPU-timeline share of each phase of the sharded proof (CUDA events on the launching stream, separate pass)."""
+            names = ("witness_map", "all_to_all", "lincombs", "all_gather", "sum_and_check")
+            acc = dict.fromkeys(names, 0.0)
+            for _ in range(reps if p2p else 0):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                with torch.cuda.stream(stream):
+                    ev[0].record(stream)
+                    sp.witness_phase_p2p()
+                    ev[1].record(stream)
+                    sp.lincomb_phase()
+                    ev[2].record(stream)
+                    sp.combine_p2p()
+                    ev[3].record(stream)
+                torch.cuda.synchronize()
+                for k, nm in enumerate(("witness_map", "lincombs", "sum_and_check")):
+                    acc[nm] += ev[k].elapsed_time(ev[k + 1]) / reps
+            if p2p:
+                acc["all_to_all"] = acc["all_gather"] = None     # folded into the neighbouring phases (one kernel + barrier each)
+                return acc
+            for _ in range(reps):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+                with torch.cuda.stream(stream):
+                    ev[0].record(stream)
+                    send = sp.witness_phase()
+                    recv = torch.empty_like(send)
+                    ev[1].record(stream)
+                    dist.all_to_all_single(recv, send)
+                    ev[2].record(stream)
+                    sp.lincomb_phase(recv)
+                    ev[3].record(stream)
+                    dist.all_gather_into_tensor(d_all, sp.t_part)
+                    ev[4].record(stream)
+                    sp.combine(d_all)
+                    ev[5].record(stream)
+                torch.cuda.synchronize()
+                for k, nm in enumerate(names):
+                    acc[nm] += ev[k].elapsed_time(ev[k + 1]) / reps
+            return acc
 
         def final_words():
             torch.cuda.synchronize()
@@ -457,6 +524,12 @@ def run_gpu_arm(args, cfg_name, cfg):
         kern[name] = {"ms_per_step": ms / psteps, "launches_per_step": cnt / psteps}
     for cx in ctxs:
         cx.enable_timing(False)
+
+    phases = None
+    if not single:
+        barrier()
+        phases = prove_phases()
+        barrier()
 
     # ---- parity, outside every timed region
     proof_words = final_words()
@@ -543,6 +616,8 @@ def run_gpu_arm(args, cfg_name, cfg):
                              "butterflies_per_step": fwd_bfly, "kernel_ms_per_step": fwd_ms,
                              "peak_source": f"148 SM x 64 lanes x {sm_max:.0f} MHz (maximum SM clock)"},
             "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()},
+            "phases_ms": {k: (round(v, 4) if v is not None else None) for k, v in phases.items()} if phases else None,
+            "exchange": ("peer memory (NVLink loads/stores, csrc/p2p.cuh)" if p2p else "NCCL collectives") if not single else None,
             "ntt": {"forward_butterflies_per_step": fwd_bfly, "inverse_butterflies_per_step": inv_bfly,
                     "forward_gbutterflies_per_s": fwd_bfly / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
                     "inverse_gbutterflies_per_s": inv_bfly / (inv_ms * 1e-3) / 1e9 if inv_ms else None},

@@ -300,6 +300,19 @@ int rsg_groth16_lincombs_chain(rsg_context *ctx, rsg_crs *crs, size_t carry_firs
                                uint8_t *h_present);
 int rsg_groth16_chain_finish(rsg_context *ctx, const rsg_crs *crs, const rsg_groth16_layout *layout, const uint64_t *d_carry,
                              const uint8_t *h_present, uint64_t *d_proof);
+/* ---- the N-GPU driver's two exchange steps over NVLink peer memory (csrc/p2p.cuh): the host driver maps every rank's buffers
+ * into every process (CUDA IPC / symmetric memory) and orders the launches with device-side barriers; h_peer_* are `world` device
+ * pointers (rank order).
+ * rsg_exchange_p2p (on the rank's WITNESS context, N_R = slots per rank): this rank's slot block of the witness rows d_wit
+ *   ([7n+2][L_R*S]: A_io|B_io|C_io|A_mid|B_mid|C_mid (n each) | H (n+1) | a zero row) goes straight into the term owners'
+ *   coefficient buffers h_peer_full[d] = [5 (A_io, A_mid, B_io, B_mid, H)][per][L_R][world*S] -- the slots<->terms all-to-all.
+ * rsg_enc_sum_p2p: rank `rank` sums slice `rank` of the world records [n_enc encodings | block_words] at h_peer_parts and stores it
+ *   into every rank's h_peer_final (reduce-scatter + all-gather of the modular sum in one launch); the probe blocks are copied
+ *   to d_blocks ([world][block_words]) for rsg_groth16_shard_check. */
+int rsg_exchange_p2p(rsg_context *ctx, const uint64_t *d_wit, size_t n, size_t world, size_t rank, size_t per,
+                     uint64_t *const *h_peer_full);
+int rsg_enc_sum_p2p(rsg_context *ctx, uint64_t *const *h_peer_parts, uint64_t *const *h_peer_final, size_t world, size_t rank,
+                    size_t n_enc, size_t block_words, uint64_t *d_blocks);
 /* A non-owning rsg_ringvec over caller-owned device memory (e.g. a torch tensor): n_elems ring elements at d_words. */
 int rsg_ringvec_wrap(rsg_context *ctx, uint64_t *d_words, size_t n_elems, rsg_ringvec **out);
 

@@ -79,6 +79,8 @@ SIGNATURES = {
     "rsg_groth16_shard_check": (_int, [_vp, _sz, _sz, _sz, _u64, C.POINTER(_int)]),
     "rsg_groth16_lincombs_chain": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _vp, _vp, _vp, _vp]),
     "rsg_groth16_chain_finish": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "rsg_exchange_p2p": (_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp]),
+    "rsg_enc_sum_p2p": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _sz, _vp]),
     "rsg_ringvec_wrap": (_int, [_vp, _vp, _sz, _pp]),
     "rsg_batch_encode": (_int, [_vp, _vp, _sz, _vp]),
     "rsg_plain_to_ntt": (_int, [_vp, _vp, _sz, _vp]),

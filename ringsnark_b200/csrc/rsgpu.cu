@@ -20,6 +20,7 @@
 #include "ringops.cuh"
 #include "prover_fast.cuh"
 #include "encode.cuh"
+#include "p2p.cuh"
 
 using namespace rsg;
 typedef unsigned __int128 u128;
@@ -2980,6 +2981,42 @@ extern "C" int rsg_groth16_chain_finish(rsg_context *c, const rsg_crs *crs, cons
     if (!have) CUDA_TRY(cudaMemsetAsync(acc, 0, E * 8, c->stream));
   }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return RSG_OK;
+}
+
+// ---- the two exchange steps over NVLink peer memory (p2p.cuh) -----------------------------------------------------------
+extern "C" int rsg_exchange_p2p(rsg_context *c, const uint64_t *d_wit, size_t n, size_t world, size_t rank, size_t per,
+                                uint64_t *const *h_peer_full) {
+  RSG_TRACE_CALL();
+  if (!c || !d_wit || !h_peer_full || !world || world > (size_t)P2P_MAX || rank >= world || !per) return fail(RSG_ERR_ARG, "bad argument");
+  if (c->N_R & 1) return fail(RSG_ERR_ARG, "the slot block of a rank must hold an even number of slots");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  PeerPtrs pp;
+  for (size_t d = 0; d < world; d++) pp.p[d] = h_peer_full[d];
+  LaunchScope ls(c, "k_exchange_p2p");
+  // c is the WITNESS context of the rank: its N_R is the slot block S
+  k_exchange_p2p<<<dim3((unsigned)(5 * per), (unsigned)world, (unsigned)c->L_R), 128, 0, c->stream>>>(d_wit, pp, (uint32_t)n, (uint32_t)per, (uint32_t)c->N_R,
+                                                                                                  (uint32_t)c->L_R, (uint32_t)world, (uint32_t)rank);
+  CUDA_TRY(cudaGetLastError());
+  return RSG_OK;
+}
+extern "C" int rsg_enc_sum_p2p(rsg_context *c, uint64_t *const *h_peer_parts, uint64_t *const *h_peer_final, size_t world, size_t rank,
+                               size_t n_enc, size_t block_words, uint64_t *d_blocks) {
+  RSG_TRACE_CALL();
+  if (!c || !h_peer_parts || !h_peer_final || !world || world > (size_t)P2P_MAX || rank >= world || !n_enc) return fail(RSG_ERR_ARG, "bad argument");
+  if (block_words && !d_blocks) return fail(RSG_ERR_ARG, "null block buffer");
+  const size_t words3 = n_enc * c->enc_words();
+  if (words3 % (2 * world)) return fail(RSG_ERR_ARG, "the proof does not split into `world` even slices");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
+  PeerPtrs pa, pf;
+  for (size_t d = 0; d < world; d++) { pa.p[d] = h_peer_parts[d]; pf.p[d] = h_peer_final[d]; }
+  LaunchScope ls(c, "k_enc_sum");
+  const size_t pairs = words3 / world / 2;
+  k_enc_sum_p2p<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(c->d_params, pa, pf, (uint32_t)world, (uint32_t)rank, words3,
+                                                                       (uint32_t)block_words, d_blocks);
+  CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
 

@@ -19,6 +19,11 @@ proof.  Otherwise (a structured CRS, e.g. the tiny_transp golden case; never for
 chain: rank 0 .. G-1 in order extend the six inner products (`chain_step`, the carry travels rank to rank), rank 0 -- which
 holds alpha and beta -- applies the operator+= chain (`chain_finish`).
 
+With peer memory (`set_peers`: every rank maps the others' buffers -- torch symmetric memory in bench.py) phases 2 and 4 are
+single kernels over NVLink instead of NCCL collectives (csrc/p2p.cuh): `exchange_p2p` writes this rank's slot block of every
+coefficient straight into the term owner's buffer, `combine_p2p` is reduce-scatter + all-gather of the modular sum in one
+launch; device-side barriers order them.  The NCCL form stays as the fallback and as the reference the tests compare with.
+
 The index bookkeeping (`send_rows`, `unpack`) is pure host logic and is exercised on CPU with gloo in
 tests/test_multi_rank_cpu.py; tests/test_gpu_parity.py runs all phases for G simulated ranks on one GPU.
 """
@@ -71,7 +76,9 @@ class ShardedGroth16Prover:
     """One rank of the G-GPU prover.  `exchange(send) -> recv` and `gather(part) -> all_parts` are injected so that the
     same code runs under NCCL (bench.py), and rank-by-rank on one GPU in the tests."""
 
-    def __init__(self, cfg, r1cs_csr, rank, world, device=0, stream=None):
+    def __init__(self, cfg, r1cs_csr, rank, world, device=0, stream=None, alloc=None):
+        """alloc (optional): callable(numel) -> int64 CUDA tensor for the three buffers other ranks touch in the peer-memory
+        form (coefficients of this rank's terms, partial-proof record, proof) -- e.g. torch symmetric memory."""
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
@@ -106,8 +113,13 @@ class ShardedGroth16Prover:
         self.idx = torch.from_numpy(idx).to(dev)
         self.m_lo, self.m_hi = d["delta_mid_lo"], d["delta_mid_hi"]
         self.t_aux = torch.zeros(max(self.m_hi - self.m_lo, 1), self.L_R * self.N_R, dtype=torch.int64, device=dev)
-        self.t_part = torch.zeros(self.part_words, dtype=torch.int64, device=dev)
-        self.t_final = torch.zeros(3 * self.ctxP.enc_words, dtype=torch.int64, device=dev)
+        alloc = alloc or (lambda numel: torch.zeros(numel, dtype=torch.int64, device=dev))
+        self.t_part = alloc(self.part_words)
+        self.t_final = alloc(3 * self.ctxP.enc_words)
+        self.t_full_raw = alloc(len(VEC_ROWS) * self.per * self.L_R * self.N_R)
+        self.t_full = self.t_full_raw.view(len(VEC_ROWS), self.per, self.L_R * self.N_R)
+        self.t_blocks = torch.zeros(world * self.block_words, dtype=torch.int64, device=dev)
+        self._peers = None
         self._wraps = []
         self._h_blocks = None
         self.rv_assign = self._wrap(self.ctxW, self.t_assign, self.io + self.aux)
@@ -151,10 +163,44 @@ class ShardedGroth16Prover:
             self.crs.fill_uniform_at(L.alpha_idx, 1, 2 * n + 2 + aux, seed)
             self.crs.fill_uniform_at(L.beta_idx, 1, 2 * n + 3 + aux, seed)
 
-    def lincomb_phase(self, recv, h_proof_ptr=None, aux_kind=None):
-        """Phase 3 from the received buffer [world, 5, per, L_R, S]; leaves the partial proof in t_part.
+    # ---- peer-memory form of phases 2 and 4
+    def set_peers(self, full_ptrs, part_ptrs, final_ptrs, barrier):
+        """Device pointers (rank order) of every rank's t_full / t_part / t_final as mapped into THIS process, and a callable
+        that enqueues a device-side barrier over all ranks on the current stream."""
+        G = self.world
+        assert len(full_ptrs) == len(part_ptrs) == len(final_ptrs) == G
+        self._peers = ((C.c_void_p * G)(*full_ptrs), (C.c_void_p * G)(*part_ptrs), (C.c_void_p * G)(*final_ptrs), barrier)
+
+    def witness_phase_p2p(self):
+        """Phase 1, then phase 2 as ONE kernel: this rank's slots of every coefficient go straight into the term owners' t_full."""
+        lib, ctx = self.ctxW.lib, self.ctxW
+        check(lib.rsg_r1cs_evaluate(ctx.h, self.r1csW.h, self.rv_assign, self.rv_evals))
+        check(lib.rsg_witness_map_groth16(ctx.h, self.r1csW.h, self.rv_evals, self.rv_coeffs, self.rv_H))
+        check(lib.rsg_exchange_p2p(ctx.h, C.c_void_p(self.t_wit.data_ptr()), self.n, self.world, self.rank, self.per, self._peers[0]))
+        self._peers[3]()     # every rank's coefficients have arrived
+
+    def combine_p2p(self):
+        """Phase 4 as ONE kernel (after lincomb_phase): slice sums over peer loads, stored into every rank's t_final; the probe
+        blocks come along for the global transparent-prefix check.  Returns the verdict (see combine)."""
+        _, parts, finals, barrier = self._peers
+        barrier()            # every rank's partial proof is complete
+        check(self.ctxP.lib.rsg_enc_sum_p2p(self.ctxP.h, parts, finals, self.world, self.rank, 3, self.block_words,
+                                            C.c_void_p(self.t_blocks.data_ptr())))
+        barrier()            # every slice has landed everywhere (and nobody still reads the partials / coefficient buffers)
+        if self._h_blocks is None:
+            self._h_blocks = self.torch.empty(self.world, self.block_words, dtype=self.torch.int64).pin_memory()
+        self._h_blocks.view(-1).copy_(self.t_blocks, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        verdict = C.c_int(0)
+        check(self.ctxP.lib.rsg_groth16_shard_check(self._h_blocks.numpy().view(np.uint64).ctypes.data_as(C.c_void_p), self.world,
+                                                    self.L_R, self.pstride, int(self.ctxP.Q[0]), C.byref(verdict)))
+        return verdict.value
+
+    def lincomb_phase(self, recv=None, h_proof_ptr=None, aux_kind=None):
+        """Phase 3 from the received buffer [world, 5, per, L_R, S] (NCCL form) or, with recv=None, from t_full (peer-memory
+        form); leaves the partial proof and its probe block in t_part.
         aux_kind (nullable): RSG_TERM_* / RSG_AUX_POLY per ABSOLUTE auxiliary index, as rsg_groth16_prove takes it."""
-        full = unpack(recv, self.world, self.per, self.L_R, self.S).contiguous()
+        full = unpack(recv, self.world, self.per, self.L_R, self.S).contiguous() if recv is not None else self.t_full
         self._full = full   # keep alive until the kernels have run
         ptrs = (C.c_void_p * 6)(*[full[v].data_ptr() for v in range(5)], self.t_aux.data_ptr())
         used = (C.c_size_t * 3)()

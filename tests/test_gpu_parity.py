@@ -433,6 +433,26 @@ def test_slot_and_term_sharded_prover(gold, world):
             provers[0].chain_finish(carry, present)
         torch.cuda.synchronize()
         assert np.array_equal(_host(provers[0].t_final).reshape(3, -1), case.enc("proof")[0])
+        # the same proof with the two exchange steps as kernels over peer memory (csrc/p2p.cuh); here every "peer" buffer is on
+        # this GPU and the ranks run one after the other, so the barrier is a no-op
+        want_full = [p._full.clone() for p in provers]
+        for p in provers:
+            p.t_final.zero_()
+            p.set_peers([q.t_full_raw.data_ptr() for q in provers], [q.t_part.data_ptr() for q in provers],
+                        [q.t_final.data_ptr() for q in provers], lambda: None)
+        for p in provers:
+            p.witness_phase_p2p()
+        torch.cuda.synchronize()
+        for p, w in zip(provers, want_full):
+            assert torch.equal(p.t_full, w)                                              # slots <-> terms: same as the all-to-all
+        for p in provers:
+            p.lincomb_phase(None, aux_kind=_aux_kind(case))
+        v2 = [p.combine_p2p() for p in provers]
+        assert v2 == verdicts
+        if not verdicts[0]:
+            torch.cuda.synchronize()
+            for p in provers:
+                assert np.array_equal(_host(p.t_final).reshape(3, -1), case.enc("proof")[0])
     finally:
         for p in provers:
             p.close()
