@@ -268,7 +268,8 @@ def parity_single(ctx, r1cs, pk, cfg, proof, rs, seed=7):
         ptrs = [d_c + (base[k] + s[0]) * W * 8 for k in range(4)] + [d_h + t[0] * W * 8, d_a + m[0] * W * 8]
         return ctx.groth16_lincombs(pk.crs, L, n, aux, ptrs)[0]
 
-    T, a = min(32, n - 2, aux), min(100, max(0, n - 2 - 32))
+    T = max(1, min(32, n - 2, aux))                      # tiny circuits (C1: n = 2): one term
+    a = min(100, max(0, n - 2 - 32))
     part = lincombs((a, a + T), (a, a + T), (a, a + T), False)
     tags = np.full(T, 2, dtype=np.uint8)
     ipk = lambda crs_first, words: O.inner_product(pk.crs.download(crs_first, T), words, tags, N_R, L_R, q, ctx.N_E, ctx.L_E, Q)[0]

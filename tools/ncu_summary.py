@@ -120,7 +120,7 @@ def main():
         per_step = int(round(bench["work_per_step"]["lincomb_launches"]))
         first = lincomb[:per_step]                     # the launches of one proof, in order
         traffic = sum(x["dram_read_bytes"] + x["dram_write_bytes"] for x in first)
-        out = {"kernel": "k_crs_lincomb<4>", "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full --clock-control none, "
+        out = {"kernel": "k_crs_lincomb<2>", "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full --clock-control none, "
                "bench.py --steps 1 --warmup 1, C4, 1x B200)", "per_launch": first, "launches_per_step": per_step,
                "dram_bytes_per_step": traffic, "algorithmic_bytes_per_step": bench["roofline"]["algorithmic_bytes_per_step"],
                "ratio": traffic / bench["roofline"]["algorithmic_bytes_per_step"]}
