@@ -32,9 +32,15 @@ typedef ringsnark::seal_gpu::RingElem GR;
 typedef ringsnark::seal_gpu::EncodingElem GE;
 using std::vector;
 
+struct GRingAccess : GR {   // the GPU backend's ring type keeps its own generator (same protected hook as the reference's)
+  static void seed(uint64_t s) {
+    prng = seal::Blake2xbPRNGFactory(seal::prng_seed_type{s, 0x52494e47, 0, 0, 0, 0, 0, 0}).create();
+  }
+};
 struct RingAccess : R {
   static void seed(uint64_t s) {
     prng = seal::Blake2xbPRNGFactory(seal::prng_seed_type{s, 0x52494e47, 0, 0, 0, 0, 0, 0}).create();
+    GRingAccess::seed(s);   // both backends draw the same stream from the same point
   }
 };
 struct EncAccess : E {

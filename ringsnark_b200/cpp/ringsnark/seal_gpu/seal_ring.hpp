@@ -13,12 +13,12 @@
 //         linear_combination::evaluate pass in front of it (relations/variable.tcc:246-254), and
 //         r1cs_to_qrp_instance_map_with_evaluation (r1cs_to_qrp.tcc:75-116: the O(m^2) step of setup and of every
 //         verification).  There is no CPU fallback for these: without librsgpu.so and a CUDA device they throw.
-//   host: ring elements that drivers build (circuits, assignments) are host values exactly as in the reference --
-//         this class keeps a ringsnark::seal::RingElem inside and forwards the element-wise operators to it, so the
-//         scalar/polynomial variant rules (seal_ring.tcc:105-263) and SealPoly::is_zero's prefix quirk
-//         (depends/SEAL-Polytools/src/poly_arith.cpp:147-153) are the reference's own code, not a re-statement.
-//         Setup (keygen, encode) delegates to ringsnark::seal::EncodingElem: SURVEY.md section 8 keeps it on the SEAL
-//         path.  EncodingElem::decode (the verifier's front half) runs on the GPU (rsg_decode).
+//   host: ring elements that drivers build (circuits, assignments) are host values; RingElem is this backend's OWN class -- the
+//         scalar / polynomial variant rules (seal_ring.tcc:105-263), SEAL's modular routines and SealPoly::is_zero / is_equal's
+//         byte-count quirks (depends/SEAL-Polytools/src/poly_arith.cpp:147-162) restated, checked operator by operator against
+//         the reference's class (oracle/ringelem_check.cpp, tests/test_ringelem.py).  Operators on two HBM-resident operands run
+//         on the GPU (rsg_ring_*).  EncodingElem::keygen and the decode of EMPTY encodings still call the reference's SEAL path;
+//         EncodingElem::encode (rsg_encode) and decode (rsg_decode) run on the GPU.
 //   Ring elements PRODUCED by the GPU witness map stay in HBM (a RingElem then holds a ref-counted slice of a device
 //   vector plus its is_zero flag) and are fed to inner_product without a round trip; they are downloaded lazily only
 //   if host code looks at them.  Encodings live in HBM arenas: one arena per encode() call, so a proving-key vector
@@ -26,8 +26,11 @@
 #ifndef RINGSNARK_SEAL_GPU_RING_HPP
 #define RINGSNARK_SEAL_GPU_RING_HPP
 
+#include <atomic>
+#include <cmath>
 #include <cstring>
 #include <memory>
+#include <variant>
 #include <mutex>
 #include <stdexcept>
 #include <tuple>
@@ -75,6 +78,7 @@ inline std::mutex &host_mutex() {
 
 struct DevRing {   // a vector<RingElem> resident in HBM
   rsg_ringvec *v = nullptr;
+  rsg_context *ctx = nullptr;   // the device context the vector belongs to
   std::vector<uint8_t> zero;   // SealPoly::is_zero (prefix semantics) of every element, computed on the device
   ~DevRing() { rsg_ringvec_destroy(v); }
 };
@@ -99,113 +103,243 @@ struct SealEncAccess : ::ringsnark::seal::EncodingElem {
 }  // namespace detail
 
 // =====================================================================================================================
+// RingElem: the ring R_q = prod_j Z_{q_j}^{N_R} in slot (double-CRT) form, with the reference's value semantics
+// (ringsnark/seal/seal_ring.hpp:18-214, seal_ring.tcc:5-302) restated over this backend's own storage -- no
+// ringsnark::seal::RingElem, no polytools arithmetic:
+//   * a SCALAR (uint64, "the same value in every slot", kept scalar while its bit length stays below q_1's,
+//     seal_ring.tcc:126-147,220-239), or
+//   * a POLYNOMIAL of L_R x N_R residues that lives on the host (copy-on-write word vector), in HBM (a slice of a device
+//     vector the witness / instance map produced) or both.
+// Element-wise operators on two HBM-resident operands run on the GPU (rsg_ring_binop / rsg_ring_scalar_op / rsg_ring_negate /
+// rsg_ring_invert, csrc/ringops.cuh) and leave their result there; anything else runs on the host words with the same
+// modular routines SEAL applies (util/uintarithsmallmod.h: add_uint_mod / sub_uint_mod take the scalar operand UNREDUCED with
+// one conditional correction, multiply reduces it first; poly_arith.cpp:164-350).  SealPoly::is_zero / is_equal keep their
+// byte-count quirks (poly_arith.cpp:147-162): only bytes [0, W + 7) resp. [0, W) of the W words are looked at.
+namespace detail {
+struct RingParams {
+  ::seal::SEALContext *ctx = nullptr;
+  size_t N = 0, L = 0;
+  std::vector<uint64_t> q;
+  std::vector<int> q_bits;
+};
+inline RingParams &ring_params_storage() {
+  static RingParams p;
+  return p;
+}
+inline const RingParams &ring_params() {
+  const RingParams &p = ring_params_storage();
+  if (!p.ctx) throw std::invalid_argument("context not set");
+  return p;
+}
+inline uint64_t mulmod(uint64_t a, uint64_t b, uint64_t p) { return (uint64_t)(((unsigned __int128)a * b) % p); }
+// 1 + floor(log2(x)) exactly as seal_ring.tcc:127-128,221-222 evaluates it (double arithmetic, then converted to size_t)
+inline size_t bitsize_like_reference(uint64_t x) { return 1 + std::floor(std::log2(x)); }
+}  // namespace detail
+
 class RingElem {
  public:
-  using Host = ::ringsnark::seal::RingElem;
+  using Host = ::ringsnark::seal::RingElem;   // the reference's type: conversions only (harnesses, RSG_ENCODE=seal)
+  using Words = std::vector<uint64_t>;
+
+ protected:
+  inline static std::shared_ptr<::seal::UniformRandomGenerator> prng = nullptr;   // random_element (seal_ring.hpp:27,90-102)
 
  private:
-  mutable Host host_;                      // valid iff host_valid_
-  mutable bool host_valid_ = true;
-  std::shared_ptr<detail::DevRing> dev_;   // non-null: the value lives in HBM at element dev_idx_ of *dev_
+  bool poly_ = false;
+  uint64_t scalar_ = 0;
+  mutable std::shared_ptr<const Words> host_;   // polynomial words [L_R][N_R] once they exist on the host
+  std::shared_ptr<detail::DevRing> dev_;        // non-null: the polynomial lives in HBM at element dev_idx_ of *dev_
   size_t dev_idx_ = 0;
-  inline static bool bound_ = false;
 
-  Host &mut() {                            // about to be modified on the host: materialise, then detach from HBM
-    host();
+  static std::shared_ptr<const Words> make_words(Words &&w) { return std::make_shared<const Words>(std::move(w)); }
+  void set_poly(Words &&w) {
+    poly_ = true;
+    scalar_ = 0;
     dev_.reset();
-    return host_;
+    std::atomic_store(&host_, make_words(std::move(w)));
   }
+  void set_scalar(uint64_t v) {
+    poly_ = false;
+    scalar_ = v;
+    dev_.reset();
+    std::atomic_store(&host_, std::shared_ptr<const Words>());
+  }
+  bool device_only() const { return poly_ && dev_ && !std::atomic_load(&host_); }
+  // words of the polynomial "scalar in every slot" as SealPoly(context).add_scalar_inplace(scalar) leaves them (seal_ring.tcc:265-277)
+  static Words scalar_words(uint64_t v) {
+    const auto &rp = detail::ring_params();
+    Words w(rp.N * rp.L, 0);
+    if (v)
+      for (size_t j = 0; j < rp.L; j++) std::fill(w.begin() + j * rp.N, w.begin() + (j + 1) * rp.N, v >= rp.q[j] ? v - rp.q[j] : v);
+    return w;
+  }
+  template <class F>
+  void map_words(F f) {   // w[j][i] <- f(w[j][i], q_j), copy-on-write
+    const auto &rp = detail::ring_params();
+    Words w(words());
+    for (size_t j = 0; j < rp.L; j++)
+      for (size_t i = 0; i < rp.N; i++) w[j * rp.N + i] = f(w[j * rp.N + i], rp.q[j]);
+    set_poly(std::move(w));
+  }
+  template <class F>
+  void zip_words(const Words &o, F f) {
+    const auto &rp = detail::ring_params();
+    Words w(words());
+    for (size_t j = 0; j < rp.L; j++)
+      for (size_t i = 0; i < rp.N; i++) w[j * rp.N + i] = f(w[j * rp.N + i], o[j * rp.N + i], rp.q[j]);
+    set_poly(std::move(w));
+  }
+  // device-side operators (defined after detail::ring_backend): true when the operation ran in HBM
+  bool dev_binop(int op, const RingElem &o);
+  bool dev_scalar_op(int op, uint64_t v);
+  bool dev_negate();
+  bool dev_invert();
 
  public:
   RingElem() = default;
-  RingElem(const RingElem &) = default;
-  RingElem(RingElem &&) = default;
-  RingElem &operator=(const RingElem &) = default;
-  RingElem &operator=(RingElem &&) = default;
+  RingElem(const RingElem &o) : poly_(o.poly_), scalar_(o.scalar_), host_(std::atomic_load(&o.host_)), dev_(o.dev_), dev_idx_(o.dev_idx_) {}
+  RingElem(RingElem &&o) noexcept : poly_(o.poly_), scalar_(o.scalar_), host_(std::atomic_load(&o.host_)), dev_(std::move(o.dev_)), dev_idx_(o.dev_idx_) {}
+  RingElem &operator=(const RingElem &o) {
+    if (this != &o) {
+      poly_ = o.poly_;
+      scalar_ = o.scalar_;
+      std::atomic_store(&host_, std::atomic_load(&o.host_));
+      dev_ = o.dev_;
+      dev_idx_ = o.dev_idx_;
+    }
+    return *this;
+  }
+  RingElem &operator=(RingElem &&o) noexcept { return *this = static_cast<const RingElem &>(o); }
   virtual ~RingElem() = default;
-  RingElem(uint64_t value) : host_(value) {}
-  explicit RingElem(const polytools::SealPoly &poly) : host_(poly) {}
-  RingElem(const Host &h) : host_(h) {}
+  RingElem(uint64_t value) : scalar_(value) {}
+  explicit RingElem(const polytools::SealPoly &poly) : poly_(true) {
+    polytools::SealPoly p(poly);   // get_limb is not const upstream
+    Words w;
+    for (size_t j = 0; j < p.get_coeff_modulus_count(); j++) {
+      auto limb = p.get_limb(j);
+      w.insert(w.end(), limb.begin(), limb.end());
+    }
+    host_ = make_words(std::move(w));
+  }
+  RingElem(const Host &h) {   // from the reference's type (harnesses that run both backends side by side)
+    if (h.is_scalar()) scalar_ = h.get_scalar();
+    else *this = RingElem(h.get_poly());
+  }
+  static RingElem from_words(Words &&w) {
+    RingElem r;
+    r.set_poly(std::move(w));
+    return r;
+  }
   static RingElem from_device(std::shared_ptr<detail::DevRing> dev, size_t idx) {
     RingElem r;
-    r.host_valid_ = false;
+    r.poly_ = true;
     r.dev_ = std::move(dev);
     r.dev_idx_ = idx;
     return r;
   }
 
-  // The host value (downloads once if the element was produced on the GPU).
-  const Host &host() const {
-    if (!host_valid_) {
+  // The polynomial's words (downloads once if the element was produced on the GPU; safe under concurrent readers).
+  const Words &words() const {
+    auto h = std::atomic_load(&host_);
+    if (!h) {
       std::lock_guard<std::mutex> g(detail::host_mutex());
-      if (!host_valid_) {
-        auto rp = Host::get_context().first_context_data()->parms();
-        std::vector<uint64_t> w(rp.poly_modulus_degree() * rp.coeff_modulus().size());
+      h = std::atomic_load(&host_);
+      if (!h) {
+        const auto &rp = detail::ring_params();
+        Words w(rp.N * rp.L);
         detail::check(rsg_ringvec_download(dev_->v, dev_idx_, 1, w.data()));
-        host_ = Host(polytools::SealPoly(Host::get_context(), w, &Host::get_context().first_parms_id()));
-        host_valid_ = true;
+        h = make_words(std::move(w));
+        std::atomic_store(&host_, h);
       }
     }
-    return host_;
+    return *h;
+  }
+  // The reference's representation of this value.
+  Host host() const {
+    if (!poly_) return Host(scalar_);
+    auto &ctx = get_context();
+    return Host(polytools::SealPoly(ctx, words(), &ctx.first_parms_id()));
   }
   const std::shared_ptr<detail::DevRing> &device_vector() const { return dev_; }
   size_t device_index() const { return dev_idx_; }
 
   // [L_R][N_R] words of the element as to_poly() would give them (seal_ring.tcc:265-277), appended to `out`.
   void append_words(std::vector<uint64_t> &out) const {
-    const Host &h = host();
-    if (h.is_scalar()) {
-      Host tmp(h);
-      tmp.to_poly_inplace();
-      auto &p = tmp.get_poly();
-      for (size_t j = 0; j < p.get_coeff_modulus_count(); j++) {
-        auto limb = p.get_limb(j);
-        out.insert(out.end(), limb.begin(), limb.end());
-      }
+    if (poly_) {
+      const Words &w = words();
+      out.insert(out.end(), w.begin(), w.end());
     } else {
-      auto p = h.get_poly();
-      for (size_t j = 0; j < p.get_coeff_modulus_count(); j++) {
-        auto limb = p.get_limb(j);
-        out.insert(out.end(), limb.begin(), limb.end());
-      }
+      const Words w = scalar_words(scalar_);
+      out.insert(out.end(), w.begin(), w.end());
     }
   }
 
   /* Static (seal_ring.hpp:52-118) */
   static void set_context(::seal::SEALContext &context_) {
-    if (bound_) throw std::invalid_argument("cannot re-set context once set");
-    try {
+    auto &rp = detail::ring_params_storage();
+    if (rp.ctx) throw std::invalid_argument("cannot re-set context once set");
+    rp.ctx = new ::seal::SEALContext(context_);
+    const auto parms = rp.ctx->first_context_data()->parms();
+    rp.N = parms.poly_modulus_degree();
+    rp.L = parms.coeff_modulus().size();
+    for (const auto &m : parms.coeff_modulus()) {
+      rp.q.push_back(m.value());
+      rp.q_bits.push_back(m.bit_count());
+    }
+    try {   // harnesses that also instantiate the reference backend in this process share the ring
       Host::set_context(context_);
     } catch (const std::invalid_argument &) {
-      // the SEAL backend of this process already holds a ring context: share it
     }
-    bound_ = true;
   }
-  static ::seal::SEALContext &get_context() {
-    if (!bound_) throw std::invalid_argument("context not set");
-    return Host::get_context();
-  }
+  static ::seal::SEALContext &get_context() { return *detail::ring_params().ctx; }
   static RingElem one() { return RingElem(1); }
   static RingElem zero() { return RingElem(0); }
+  // seal_ring.hpp:70-88: rejection sampling of a scalar below q_1 (and above the domain) under the reference's mask
   static RingElem random_exceptional_element(const std::shared_ptr<evaluation_domain<RingElem>> domain = nullptr) {
-    std::shared_ptr<evaluation_domain<Host>> hd;
-    if (domain) hd = std::make_shared<evaluation_domain<Host>>(domain->m);
-    return RingElem(Host::random_exceptional_element(hd));
+    const uint64_t q1 = detail::ring_params().q[0];
+    const uint64_t bit_width = 1ULL + (uint64_t)std::floor(std::log2l(q1));
+    const uint64_t mask = (1 << (bit_width + 1)) - 1;   // an int shift, as upstream: the effective width is (bit_width + 1) mod 32
+    uint64_t rand = ::seal::random_uint64() & mask;
+    while (rand >= q1 || (domain && rand <= domain->m)) rand = ::seal::random_uint64() & mask;
+    return RingElem(rand);
   }
-  static RingElem random_element() { return RingElem(Host::random_element()); }
-  static RingElem random_invertible_element() { return RingElem(Host::random_invertible_element()); }
-  static RingElem random_nonzero_element() { return RingElem(Host::random_nonzero_element()); }
+  static RingElem random_element() {   // seal_ring.hpp:90-102: uniform residues from SEAL's sampler
+    if (prng == nullptr) prng = ::seal::UniformRandomGeneratorFactory::DefaultFactory()->create();
+    const auto &rp = detail::ring_params();
+    Words w(rp.N * rp.L);
+    ::seal::util::sample_poly_uniform(prng, rp.ctx->first_context_data()->parms(), w.data());
+    return from_words(std::move(w));
+  }
+  static RingElem random_invertible_element() {
+    RingElem res;
+    do res = random_element();
+    while (!res.is_invertible());
+    return res;
+  }
+  static RingElem random_nonzero_element() {
+    RingElem res;
+    do res = random_element();
+    while (res.is_zero());
+    return res;
+  }
 
   /* Members (seal_ring.hpp:123-182) */
-  [[nodiscard]] size_t size_in_bits() const { return host().size_in_bits(); }
-  [[nodiscard]] bool is_zero() const {
-    if (!host_valid_ && dev_) return dev_->zero[dev_idx_] != 0;   // same prefix test, done on the device
-    return host().is_zero();
+  [[nodiscard]] size_t size_in_bits() const {
+    if (!poly_) return 8 * sizeof(uint64_t);
+    const auto &rp = detail::ring_params();
+    size_t size = 0;
+    for (int b : rp.q_bits) size += (size_t)b * rp.N;
+    return size;
   }
-  [[nodiscard]] bool fast_is_zero() const { return host_valid_ ? host_.fast_is_zero() : false; }
-  [[nodiscard]] bool is_poly() const { return host_valid_ ? host_.is_poly() : true; }
-  [[nodiscard]] bool is_scalar() const { return host_valid_ ? host_.is_scalar() : false; }
-  void negate_inplace() { mut().negate_inplace(); }
+  [[nodiscard]] bool is_zero() const;   // after detail::dev_zero_flag
+  [[nodiscard]] bool fast_is_zero() const { return !poly_ && scalar_ == 0; }
+  [[nodiscard]] bool is_poly() const { return poly_; }
+  [[nodiscard]] bool is_scalar() const { return !poly_; }
+  void negate_inplace() {   // seal_ring.tcc:58-69: a scalar becomes a polynomial first
+    to_poly_inplace();
+    if (dev_negate()) return;
+    map_words([](uint64_t x, uint64_t p) { return x ? p - x : 0; });
+  }
   RingElem operator-() const {
     RingElem res(*this);
     res.negate_inplace();
@@ -213,41 +347,158 @@ class RingElem {
   }
   [[nodiscard]] bool is_invertible() const noexcept {
     try {
-      return host().is_invertible();
+      RingElem tmp(*this);
+      tmp.invert_inplace();
+      return true;
     } catch (...) {
       return false;
     }
   }
-  void invert_inplace() { mut().invert_inplace(); }
+  void invert_inplace() {   // seal_ring.tcc:87-103 over poly_arith.cpp:304-340: every slot must be invertible
+    to_poly_inplace();
+    if (dev_invert()) return;
+    const auto &rp = detail::ring_params();
+    Words w(words());
+    for (size_t j = 0; j < rp.L; j++)
+      for (size_t i = 0; i < rp.N; i++) {
+        const uint64_t x = w[j * rp.N + i], p = rp.q[j];
+        if (x % p == 0) throw std::invalid_argument("element is not invertible in ring");
+        uint64_t r = 1, base = x % p, e = p - 2;   // q_j prime: x^(p-2), the unique inverse in [1, p) that try_invert_uint_mod returns
+        while (e) {
+          if (e & 1) r = detail::mulmod(r, base, p);
+          base = detail::mulmod(base, base, p);
+          e >>= 1;
+        }
+        w[j * rp.N + i] = r;
+      }
+    set_poly(std::move(w));
+  }
   [[nodiscard]] RingElem inverse() const {
     RingElem res(*this);
     res.invert_inplace();
     return res;
   }
-  RingElem &operator+=(const RingElem &o) { mut() += o.host(); return *this; }
-  RingElem &operator-=(const RingElem &o) { mut() -= o.host(); return *this; }
-  RingElem &operator*=(const RingElem &o) { mut() *= o.host(); return *this; }
-  RingElem &operator/=(const RingElem &o) { mut() /= o.host(); return *this; }
-  RingElem &to_poly_inplace() { mut().to_poly_inplace(); return *this; }
+  RingElem &operator+=(const RingElem &o) {   // seal_ring.tcc:105-152
+    if (poly_) {
+      if (o.poly_) {
+        if (!dev_binop(0, o)) zip_words(o.words(), [](uint64_t a, uint64_t b, uint64_t p) { const uint64_t s = a + b; return s >= p ? s - p : s; });
+      } else if (o.scalar_ != 0) {
+        const uint64_t v = o.scalar_;
+        if (!dev_scalar_op(0, v)) map_words([v](uint64_t a, uint64_t p) { const uint64_t s = a + v; return s >= p ? s - p : s; });
+      }
+    } else {
+      if (scalar_ == 0) return *this = o;
+      if (o.poly_) {
+        const uint64_t v = scalar_;
+        *this = o;
+        return *this += RingElem(v);
+      }
+      const size_t a = detail::bitsize_like_reference(scalar_), b = detail::bitsize_like_reference(o.scalar_);
+      const size_t res = a == b ? a + 1 : std::max(a, b);
+      if (res < detail::bitsize_like_reference(detail::ring_params().q[0])) scalar_ += o.scalar_;
+      else {
+        to_poly_inplace();
+        return *this += o;
+      }
+    }
+    return *this;
+  }
+  RingElem &operator-=(const RingElem &o) {   // seal_ring.tcc:154-185
+    if (poly_) {
+      if (o.poly_) {
+        if (!dev_binop(1, o)) zip_words(o.words(), [](uint64_t a, uint64_t b, uint64_t p) { return a >= b ? a - b : a - b + p; });
+      } else if (o.scalar_ != 0) {
+        const uint64_t v = o.scalar_;
+        if (!dev_scalar_op(1, v)) map_words([v](uint64_t a, uint64_t p) { return a >= v ? a - v : a - v + p; });
+      }
+    } else if (o.poly_) {   // scalar - poly = -poly + scalar
+      const uint64_t v = scalar_;
+      *this = o;
+      negate_inplace();
+      if (v) *this += RingElem(v);
+    } else {                // scalar - scalar always becomes a polynomial (seal_ring.tcc:175-178)
+      to_poly_inplace();
+      if (o.scalar_ != 0) *this -= o;
+    }
+    return *this;
+  }
+  RingElem &operator*=(const RingElem &o) {   // seal_ring.tcc:187-247
+    if (poly_) {
+      if (o.poly_) {
+        if (!dev_binop(2, o)) zip_words(o.words(), [](uint64_t a, uint64_t b, uint64_t p) { return detail::mulmod(a, b, p); });
+      } else {
+        if (o.scalar_ == 1) return *this;
+        if (o.scalar_ == 0) {
+          set_scalar(0);
+          return *this;
+        }
+        const uint64_t v = o.scalar_;
+        if (!dev_scalar_op(2, v)) map_words([v](uint64_t a, uint64_t p) { return detail::mulmod(a, v % p, p); });
+      }
+    } else {
+      if (scalar_ == 1) return *this = o;
+      if (scalar_ == 0) return *this;
+      if (o.fast_is_zero()) {
+        set_scalar(0);
+        return *this;
+      }
+      if (o.poly_) {
+        const uint64_t v = scalar_;
+        *this = o;
+        return *this *= RingElem(v);
+      }
+      const size_t res = detail::bitsize_like_reference(scalar_) + detail::bitsize_like_reference(o.scalar_);
+      if (res < detail::bitsize_like_reference(detail::ring_params().q[0])) scalar_ *= o.scalar_;
+      else {
+        to_poly_inplace();
+        return *this *= o;
+      }
+    }
+    return *this;
+  }
+  RingElem &operator/=(const RingElem &o) { return *this *= o.inverse(); }
+  RingElem &to_poly_inplace() {
+    if (!poly_) set_poly(scalar_words(scalar_));
+    return *this;
+  }
   [[nodiscard]] RingElem to_poly() const {
     RingElem res(*this);
     res.to_poly_inplace();
     return res;
   }
-  [[nodiscard]] size_t hash() const { return host().hash(); }
+  [[nodiscard]] size_t hash() const {
+    if (!poly_) return scalar_;
+    size_t h = 0;
+    for (uint64_t v : words()) h ^= v;
+    return h;
+  }
   using invalid_ring_elem_types = Host::invalid_ring_elem_types;
-  [[nodiscard]] uint64_t get_scalar() const { return host().get_scalar(); }
-  [[nodiscard]] polytools::SealPoly get_poly() const { return host().get_poly(); }
-  [[nodiscard]] polytools::SealPoly &get_poly() { return mut().get_poly(); }
+  [[nodiscard]] uint64_t get_scalar() const {
+    if (poly_) throw std::bad_variant_access();
+    return scalar_;
+  }
+  [[nodiscard]] polytools::SealPoly get_poly() const {
+    if (!poly_) throw std::bad_variant_access();
+    auto &ctx = get_context();
+    return polytools::SealPoly(ctx, words(), &ctx.first_parms_id());
+  }
+  // SealPoly::is_equal (poly_arith.cpp:155-162): memcmp over data.size() BYTES, i.e. the first W / 8 words
+  static bool prefix_equal(const Words &a, const Words &b) { return a.size() == b.size() && !std::memcmp(a.data(), b.data(), a.size()); }
 };
 
 inline RingElem operator+(const RingElem &l, const RingElem &r) { RingElem x(l); x += r; return x; }
 inline RingElem operator-(const RingElem &l, const RingElem &r) { RingElem x(l); x -= r; return x; }
 inline RingElem operator*(const RingElem &l, const RingElem &r) { RingElem x(l); x *= r; return x; }
 inline RingElem operator/(const RingElem &l, const RingElem &r) { RingElem x(l); x /= r; return x; }
-inline bool operator==(const RingElem &l, const RingElem &r) { return l.host() == r.host(); }
+inline bool operator==(const RingElem &l, const RingElem &r) {   // seal_ring.tcc:249-263
+  if (l.is_scalar() && r.is_scalar()) return l.get_scalar() == r.get_scalar();
+  return RingElem::prefix_equal(l.to_poly().words(), r.to_poly().words());
+}
 inline bool operator!=(const RingElem &l, const RingElem &r) { return !(l == r); }
-inline std::ostream &operator<<(std::ostream &out, const RingElem &e) { return out << e.host(); }
+inline std::ostream &operator<<(std::ostream &out, const RingElem &e) {
+  if (e.is_scalar()) return out << e.get_scalar();
+  return out << e.get_poly().to_json();
+}
 
 namespace detail {
 // The backend ring-only callers use (interpolate<RingElem> before any EncodingElem::set_context, as in the reference's
@@ -272,7 +523,67 @@ inline Backend &ring_backend() {
   }
   return rb;
 }
+// SealPoly::is_zero (poly_arith.cpp:147-153) of element idx of a device vector: the flags are computed on the device, once
+inline bool dev_zero_flag(const std::shared_ptr<DevRing> &d, size_t idx) {
+  std::lock_guard<std::mutex> g(host_mutex());
+  if (d->zero.empty()) {
+    const size_t cnt = rsg_ringvec_size(d->v);
+    d->zero.resize(cnt);
+    check(rsg_ringvec_is_zero_prefix(d->v, 0, cnt, d->zero.data()));
+  }
+  return d->zero[idx] != 0;
+}
+inline std::shared_ptr<DevRing> new_dev_elem(rsg_context *ctx) {
+  auto v = std::make_shared<DevRing>();
+  check(rsg_ringvec_create(ctx, 1, &v->v));
+  v->ctx = ctx;
+  return v;
+}
 }  // namespace detail
+
+inline bool RingElem::is_zero() const {
+  if (!poly_) return scalar_ == 0;
+  if (device_only()) return detail::dev_zero_flag(dev_, dev_idx_);
+  const Words &w = words();   // bytes [0, W + 7) of the W words
+  const size_t W = w.size(), bytes = W + 7, full = std::min(bytes / 8, W), rem = bytes % 8;
+  for (size_t i = 0; i < full; i++)
+    if (w[i]) return false;
+  return !(rem && full < W && (w[full] & ((1ull << (8 * rem)) - 1)));
+}
+// Both operands in HBM (same device context), no host copy yet: the operator runs there and the result stays there.
+inline bool RingElem::dev_binop(int op, const RingElem &o) {
+  if (!device_only() || !o.device_only() || !dev_->ctx || dev_->ctx != o.dev_->ctx) return false;
+  auto out = detail::new_dev_elem(dev_->ctx);
+  detail::check(rsg_ring_binop(dev_->ctx, op, dev_->v, dev_idx_, o.dev_->v, o.dev_idx_, out->v, 0, 1));
+  dev_ = out;
+  dev_idx_ = 0;
+  return true;
+}
+inline bool RingElem::dev_scalar_op(int op, uint64_t v) {
+  if (!device_only() || !dev_->ctx) return false;
+  auto out = detail::new_dev_elem(dev_->ctx);
+  detail::check(rsg_ring_scalar_op(dev_->ctx, op, dev_->v, dev_idx_, v, out->v, 0, 1));
+  dev_ = out;
+  dev_idx_ = 0;
+  return true;
+}
+inline bool RingElem::dev_negate() {
+  if (!device_only() || !dev_->ctx) return false;
+  auto out = detail::new_dev_elem(dev_->ctx);
+  detail::check(rsg_ring_negate(dev_->ctx, dev_->v, dev_idx_, out->v, 0, 1));
+  dev_ = out;
+  dev_idx_ = 0;
+  return true;
+}
+inline bool RingElem::dev_invert() {
+  if (!device_only() || !dev_->ctx) return false;
+  auto out = detail::new_dev_elem(dev_->ctx);
+  uint8_t ok = 0;
+  detail::check(rsg_ring_invert(dev_->ctx, dev_->v, dev_idx_, out->v, 0, 1, &ok));   // RSG_ERR_NOTINV -> std::invalid_argument
+  dev_ = out;
+  dev_idx_ = 0;
+  return true;
+}
 
 // =====================================================================================================================
 class EncodingElem {
@@ -635,6 +946,7 @@ inline qrp_witness<seal_gpu::RingElem> r1cs_to_qrp_witness_map<seal_gpu::RingEle
   auto make_vec = [&](size_t count) {
     auto v = std::make_shared<D::DevRing>();
     D::check(rsg_ringvec_create(b.ctx, count ? count : 1, &v->v));
+    v->ctx = b.ctx;
     return v;
   };
   auto evals = make_vec(9 * n);
@@ -780,6 +1092,7 @@ inline qrp_instance_evaluation<seal_gpu::RingElem> r1cs_to_qrp_instance_map_with
   auto make_vec = [&](size_t count) {
     auto v = std::make_shared<D::DevRing>();
     D::check(rsg_ringvec_create(b.ctx, count ? count : 1, &v->v));
+    v->ctx = b.ctx;
     return v;
   };
   rsg_r1cs *r1cs = nullptr;
@@ -839,6 +1152,7 @@ inline std::vector<ringsnark::seal_gpu::RingElem> interpolate<ringsnark::seal_gp
   auto make_vec = [&](size_t count) {
     auto v = std::make_shared<D::DevRing>();
     D::check(rsg_ringvec_create(b.ctx, count, &v->v));
+    v->ctx = b.ctx;
     return v;
   };
   std::vector<uint64_t> w;
