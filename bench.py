@@ -611,7 +611,7 @@ def run_gpu_arm(args, cfg_name, cfg):
                          "launch_ms": lin_ms / lin_launches if lin_launches else None, "launches_per_step": lin_launches,
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": lin_ms,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"},
-            "roofline_ntt": {"kernel": "k_lift_fwd_ntt_f64" if f64 else "k_lift_fwd_ntt", "bound": "fp64 pipe" if f64 else "int32 pipe",
+            "roofline_ntt": {"kernel": ("k_lift_fwd_ntt_f64_cl" if logN == 14 and os.environ.get("RSG_NTT_CLUSTER", "1") != "0" else "k_lift_fwd_ntt_f64") if f64 else "k_lift_fwd_ntt", "bound": "fp64 pipe" if f64 else "int32 pipe",
                              "achieved": ntt_ach / 1e12, "peak": pipe_peak / 1e12, "unit": "T lane-instr/s",
                              "frac": ntt_ach / pipe_peak if pipe_peak else None, "instr_per_butterfly_model": per_bfly,
                              "butterflies_per_step": fwd_bfly, "kernel_ms_per_step": fwd_ms,
