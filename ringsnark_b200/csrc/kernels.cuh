@@ -94,6 +94,114 @@ __global__ void __launch_bounds__(512) k_encode_intt(const DevParams *__restrict
   encode_body<LOGN, LVL0, false>(P, src, dst, j, h);
 }
 
+// ---- Batch encode at N_E = 2^14 when the slot vector uses the first matrix row only (N_R <= N_E / 2): compact rows ----------
+// The index map leaves quarters 1 and 3 of the transform's input empty (ntt.cuh, ntt_inverse_smem_q02), i.e. rows 4-7 and 12-15 of
+// the 16 x 1024 matrix: only the EIGHT non-zero rows are kept in shared memory (68 KiB instead of 136: two 256-thread CTAs per SM,
+// so one polynomial's 128 KiB of stores drain under the butterflies of another -- the lesson of k_lift_fwd_ntt_f64_cl).  The inverse
+// transform runs small strides first: levels 13..4 stay inside a row, one WARP per row with __syncwarp only; one CTA barrier; the
+// last pass (levels 3..0, column-wise) reads the eight rows, produces all sixteen output rows in registers -- levels 3, 2 on the
+// non-zero groups only, level 1 as products (x, 0) -> (x, x w), level 0 with N^-1 folded into its two multiplications, the way
+// SEAL merges the scaling into its last stage (util/dwthandler.h:60-73) -- centres them and writes them straight to global memory
+// (no scaling pass over shared memory).  Same residues as encode_body.
+constexpr uint32_t ENC_ROWW = 1024 + 64;
+constexpr size_t ENC_ROWS_SMEM = 8 * (size_t)ENC_ROWW * 8;
+
+template <int RL, int S>
+__device__ __forceinline__ void enc_row_pass(uint64_t *rp, const Twiddle *__restrict__ tab, uint64_t p, uint32_t row16, uint32_t lane) {
+  constexpr int LS = S - 4, R = 1 << RL;            // the row is the block of 1024 at level 4
+  constexpr uint32_t g = 1024u >> (LS + RL), items = 1024u >> RL;
+  const uint64_t four_p = p << 2;
+  for (uint32_t item = lane; item < items; item += 32) {
+    const uint32_t o = item & (g - 1), lb = item / g;
+    const uint32_t b = (row16 << LS) + lb;           // block index at level S
+    uint64_t *ptr = rp + pad_idx(lb * (1024u >> LS) + o);
+    uint64_t v[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) v[k] = ptr[k * g + ((k * g) >> 4)];
+#pragma unroll
+    for (int u = RL - 1; u >= 0; u--) {
+      const int half = R >> (u + 1);
+      const uint32_t tbase = (1u << (S + u)) + (b << u);
+#pragma unroll
+      for (int grp = 0; grp < (1 << u); grp++) {
+        const Twiddle t = load_tw(tab, tbase + grp);
+#pragma unroll
+        for (int k = 0; k < half; k++) bfly_inv_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, four_p);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) ptr[k * g + ((k * g) >> 4)] = v[k];
+  }
+}
+
+template <bool CENTRE>
+__device__ __forceinline__ void encode_rows_body(const DevParams *__restrict__ P, const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
+                                                 uint32_t j) {
+  extern __shared__ uint64_t sm[];
+  const uint32_t N_R = P->N_R, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const uint64_t p = P->q[j].p, four_p = p << 2;
+  const Twiddle *tab = P->invq[j];
+  for (uint32_t i = tid; i < 8 * ENC_ROWW / 2; i += blockDim.x) reinterpret_cast<ulonglong2 *>(sm)[i] = make_ulonglong2(0, 0);
+  __syncthreads();
+  const uint32_t *map = P->index_map;
+  for (uint32_t k = tid; k < N_R; k += blockDim.x) {
+    const uint32_t pos = __ldg(map + k), row16 = pos >> 10;              // rows 0-3 and 8-11 only
+    sm[((row16 & 3) | ((row16 >> 3) << 2)) * ENC_ROWW + pad_idx(pos & 1023)] = src[k];
+  }
+  __syncthreads();
+  {   // levels 13..4 inside the rows: warp `wrp` owns compact row `wrp`
+    const uint32_t row16 = (wrp & 3) | ((wrp >> 2) << 3);
+    uint64_t *rp = sm + wrp * ENC_ROWW;
+    enc_row_pass<2, 12>(rp, tab, p, row16, lane);
+    __syncwarp();
+    enc_row_pass<4, 8>(rp, tab, p, row16, lane);
+    __syncwarp();
+    enc_row_pass<4, 4>(rp, tab, p, row16, lane);
+  }
+  __syncthreads();
+  // levels 3..0 across the rows: v[k] = row k at this column; rows 4-7 and 12-15 are zero on entry
+  Twiddle t3[4], t2[2], t1[2];
+  t3[0] = load_tw(tab, 8 + 0); t3[1] = load_tw(tab, 8 + 1); t3[2] = load_tw(tab, 8 + 4); t3[3] = load_tw(tab, 8 + 5);
+  t2[0] = load_tw(tab, 4 + 0); t2[1] = load_tw(tab, 4 + 2);
+  t1[0] = load_tw(tab, 2 + 0); t1[1] = load_tw(tab, 2 + 1);
+  const Twiddle invn = P->invN_q[j], invnw = P->invNw_q[j];
+  const uint64_t thr = P->thr[j];
+  for (uint32_t col = tid; col < 1024; col += blockDim.x) {
+    const uint64_t *cp = sm + pad_idx(col);
+    uint64_t v[16];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[8 * h + k] = cp[(4 * h + k) * ENC_ROWW];
+      bfly_inv_lazy(v[8 * h + 0], v[8 * h + 1], t3[2 * h + 0], p, four_p);     // level 3: rows (0,1), (2,3) | (8,9), (10,11)
+      bfly_inv_lazy(v[8 * h + 2], v[8 * h + 3], t3[2 * h + 1], p, four_p);
+      bfly_inv_lazy(v[8 * h + 0], v[8 * h + 2], t2[h], p, four_p);             // level 2: rows (0,2), (1,3) | (8,10), (9,11)
+      bfly_inv_lazy(v[8 * h + 1], v[8 * h + 3], t2[h], p, four_p);
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[8 * h + 4 + k] = mul_shoup_approx(v[8 * h + k], t1[h], p);   // level 1: (x, 0) -> (x, x w)
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {   // level 0 with N^-1 folded in: exact Shoup products of any 64-bit word, canonical
+      const uint64_t x = v[k], y = v[k + 8];
+      uint64_t a = mul_shoup(x + y, invn, p), b = mul_shoup(x - y + four_p, invnw, p);
+      if (CENTRE) {
+        a = a >= thr ? a - p : a;
+        b = b >= thr ? b - p : b;
+      }
+      dst[col + 1024 * k] = a;
+      dst[col + 1024 * (k + 8)] = b;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) k_encode_intt_rows(const DevParams *__restrict__ P, const uint64_t *__restrict__ ring,
+                                                             const uint32_t *__restrict__ elem_idx, uint64_t *__restrict__ plain) {
+  const uint32_t j = blockIdx.y, e = blockIdx.x;
+  const uint32_t N_R = P->N_R, L_R = P->L_R;
+  const uint32_t src_e = elem_idx ? elem_idx[e] : e;
+  encode_rows_body<false>(P, ring + ((size_t)src_e * L_R + j) * N_R, plain + (((size_t)e * L_R + j) << 14), j);
+}
+
 // Last Gentleman-Sande level of a split inverse transform + scaling: (x, y) -> ((x + y) N^-1, (x - y) w N^-1), canonical.
 // data: `polys` polynomials of 2*half words, values < 2p.  which_q: per-polynomial modulus index = poly % n_mod.
 __global__ void __launch_bounds__(256) k_intt_finish(uint64_t *__restrict__ data, uint32_t half, size_t polys,

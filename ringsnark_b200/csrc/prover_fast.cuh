@@ -95,6 +95,19 @@ __global__ void __launch_bounds__(512) k_encode_fast(const DevParams *__restrict
   encode_body<LOGN, LVL0, true>(P, src, poly + ((size_t)h << LOGN), j, h);
 }
 
+// The same for N_E = 2^14 with N_R <= N_E / 2 (compact rows, two CTAs per SM: encode_rows_body in kernels.cuh).  grid (n_elems, L_R).
+__global__ void __launch_bounds__(256, 2) k_encode_fast_rows(const DevParams *__restrict__ P, FastTable T, const uint8_t *__restrict__ elem_flag,
+                                                             uint64_t *__restrict__ parts, uint64_t *__restrict__ nttsrc) {
+  const uint32_t eid = blockIdx.x, j = blockIdx.y;
+  if (elem_flag[eid]) return;
+  uint32_t k, i;
+  fast_locate(T, eid, k, i);
+  const uint32_t N_R = P->N_R, L_R = P->L_R;
+  const uint64_t *src = T.vec[k].base + ((size_t)i * L_R + j) * N_R;
+  uint64_t *poly = eid < T.n_parts ? parts + (((size_t)eid * L_R + j) << 14) : nttsrc + (((size_t)(2 * T.nS + eid - T.n_parts) * L_R + j) << 14);
+  encode_rows_body<true>(P, src, poly, j);
+}
+
 // Merged slots: nttsrc[m] = parts[X] + parts[Y] (int64), a skipped part counts as absent; slot_skip[m] = both skipped.
 // While both parts stream through, the one NTT-domain word the probe needs of EACH part is evaluated directly:
 // pval[eid][j] = NTT_{Q_0}(lift(part))[0] = sum_i part_i psi^i mod Q_0 (the parts' own transforms are never formed).

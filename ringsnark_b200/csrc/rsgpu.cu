@@ -268,6 +268,7 @@ struct rsg_context {
   int overlap_mode = 0;             // RSG_OVERLAP=1: lincomb of one term group on a second stream under the next group's NTTs
   int fast_splits = 0;              // RSG_FAST_SPLITS: number of term chunks of the one-launch lincomb (0 = auto)
   int ntt_half = 0;                 // RSG_NTT_HALF=1 (experiment, see fast_launch_ntt)
+  int enc_rows = 1;                 // N_E = 2^14, N_R <= N_E / 2: compact-row batch encode (k_encode_*_rows); RSG_ENC_ROWS=0 -> encode_body
   int ntt_cluster = 1;              // N_E = 2^14, FP64 path: k_lift_fwd_ntt_f64_cl (4-CTA clusters); RSG_NTT_CLUSTER=0 -> single-CTA kernel
   bool lift_smallq = false;         // LiftIoSmallQ applies (kernels.cuh): t < 2^54 and t / min Q_l < 2^11; RSG_LIFT=barrett turns it off
   int overlap_chunks = 4;           // RSG_OVERLAP_CHUNKS: term chunks (<= 128 terms each) per overlap phase
@@ -485,6 +486,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (const char *m = getenv("RSG_FAST_SPLITS")) c->fast_splits = atoi(m);
   if (const char *m = getenv("RSG_NTT_HALF")) c->ntt_half = atoi(m);
   if (const char *m = getenv("RSG_NTT_CLUSTER")) c->ntt_cluster = atoi(m);
+  if (const char *m = getenv("RSG_ENC_ROWS")) c->enc_rows = atoi(m);
   {
     uint64_t tmax = 0, Qmin = ~0ull;
     for (uint64_t p : c->q) tmax = std::max(tmax, p);
@@ -855,6 +857,17 @@ static int launch_encode(rsg_context *c, const uint64_t *d_ring, const uint32_t 
   const size_t sm = ntt_smem(c->logN);
   const unsigned split = c->logN > 14 ? 2 : 1;
   dim3 grid((unsigned)count * split, (unsigned)c->L_R);
+  if (c->enc_rows && c->logN == 14 && 2 * c->N_R <= c->N_E) {
+    LaunchScope ls(c, "k_encode_intt");
+    static bool attr_done[64] = {};
+    if (!attr_done[c->device]) {
+      CUDA_TRY(cudaFuncSetAttribute(k_encode_intt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_ROWS_SMEM));
+      attr_done[c->device] = true;
+    }
+    k_encode_intt_rows<<<dim3((unsigned)count, (unsigned)c->L_R), 256, ENC_ROWS_SMEM, c->stream>>>(c->d_params, d_ring, d_eidx, d_plain);
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   {
     LaunchScope ls(c, "k_encode_intt");
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
@@ -2549,7 +2562,15 @@ static int fast_run(rsg_context *c, FastPlan *fp, const FastTable &T, uint64_t *
   const size_t sm = ntt_smem(c->logN);
   const unsigned split = c->logN > 14 ? 2 : 1;
   c->st_inv_polys += (uint64_t)T.n_elems * c->L_R;
-  {
+  if (c->enc_rows && c->logN == 14 && 2 * c->N_R <= c->N_E) {
+    LaunchScope ls(c, "k_encode_intt");
+    static bool attr_done[64] = {};
+    if (!attr_done[c->device]) {
+      CUDA_TRY(cudaFuncSetAttribute(k_encode_fast_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_ROWS_SMEM));
+      attr_done[c->device] = true;
+    }
+    k_encode_fast_rows<<<dim3(T.n_elems, (unsigned)c->L_R), 256, ENC_ROWS_SMEM, st>>>(c->d_params, T, elem_flag, c->d_fp_parts, c->d_fp_nttsrc);
+  } else {
     LaunchScope ls(c, "k_encode_intt");
     DISPATCH_LOGN(c->logN, { if ((rc = fast_set_attr<LG, LV>())) return rc;
                              k_encode_fast<LG, LV><<<dim3(T.n_elems * split, (unsigned)c->L_R), th, sm, st>>>(c->d_params, T, elem_flag, c->d_fp_parts,
