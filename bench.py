@@ -172,7 +172,7 @@ class ClockSampler(threading.Thread):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled_over": "warm-up proofs (>= 0.5 s, same load) + both timed regions, 20 ms period"}
 
 
 def make_assignment(cfg, row_ptr, col, coeff, seed):
@@ -470,16 +470,26 @@ def run_gpu_arm(args, cfg_name, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # clocks are sampled from here to the end of the second timed region: nvidia-smi needs ~0.1 s to deliver its first line and
+    # a timed region at 8 GPUs lasts ~30 ms, so the warm-up (the same proofs under the same load) is stretched to >= 0.5 s
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_warm = time.perf_counter()
     used = None
     for _ in range(max(3, args.warmup)):
         used = prove(False)
         prove(True)
+    while True:
+        torch.cuda.synchronize()
+        go = torch.tensor([1.0 if time.perf_counter() - t_warm < 0.5 else 0.0], device="cuda")
+        if dist:
+            dist.all_reduce(go, op=dist.ReduceOp.MAX)      # every rank runs the same number of (collective) warm-up proofs
+        if go.item() == 0.0:
+            break
+        used = prove(False)
     barrier()
 
     # ---- timed region 1: device-resident inputs ("value"); NO per-launch instrumentation inside it
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.05)
     l0 = sum(cx.launch_count() for cx in ctxs)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
