@@ -548,6 +548,126 @@ __global__ void __cluster_dims__(NTT_CL, 1, 1) __launch_bounds__(NTT_CL_THREADS,
   }
 }
 
+// ---- the integer transform on clusters (every Q_l < 2^58; what C5's 55-bit limbs run) ---------------------------------------
+// k_lift_fwd_ntt_f64_cl's structure with Shoup butterflies: one polynomial of 2^(10 + LOGR) coefficients = 2^LOGR rows of 1024 per
+// cluster of 2^LOGR / 4 CTAs (128 threads, four rows = 34 KiB each, so four CTAs of different clusters share an SM).  Pass 1:
+// every thread owns ONE column, loads its 2^LOGR coefficients (coalesced across the warp), lifts them, runs levels 0..LOGR-1 in
+// registers (radix-32 at N_E = 2^15) and sends each row's value to the row's owner through distributed shared memory; one cluster
+// barrier; levels LOGR.. stay inside a row -- one warp per row, __syncwarp only (radix 16, 16, 4) -- and the last pass writes
+// canonical words with 256-bit stores.  Correction-free butterflies (bfly_fwd_lazy: values grow by 4p per level, 61p < 2^64 after 15
+// levels), one Barrett reduction per word at the store: the same residues as k_lift_fwd_ntt.
+template <int RL, int LS>   // levels [LS, LS + RL) of the row-local transform of 1024; gl0 = global level of row-local level 0
+__device__ __forceinline__ void int_row_pass_fwd(uint64_t *rp, const Twiddle *__restrict__ tab, uint64_t p, uint32_t gl0, uint32_t row, uint32_t lane) {
+  constexpr int R = 1 << RL;
+  constexpr uint32_t g = 1024u >> (LS + RL), items = 1024u >> RL;
+  const uint64_t four_p = p << 2;
+  for (uint32_t item = lane; item < items; item += 32) {
+    const uint32_t o = item & (g - 1), lb = item / g;
+    const uint32_t b = (row << LS) + lb;   // block index at global level gl0 + LS
+    uint64_t *ptr = rp + pad_idx(lb * (1024u >> LS) + o);
+    uint64_t v[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) v[k] = ptr[k * g + ((k * g) >> 4)];
+#pragma unroll
+    for (int u = 0; u < RL; u++) {
+      const int half = R >> (u + 1);
+      const uint32_t tbase = (1u << (gl0 + LS + u)) + (b << u);
+#pragma unroll
+      for (int grp = 0; grp < (1 << u); grp++) {
+        const Twiddle t = load_tw(tab, tbase + grp);
+#pragma unroll
+        for (int k = 0; k < half; k++) bfly_fwd_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, four_p);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) ptr[k * g + ((k * g) >> 4)] = v[k];
+  }
+}
+
+template <int LOGR, bool SIGNED>
+__global__ void __cluster_dims__((1 << LOGR) / 4, 1, 1) __launch_bounds__(128, 4)
+    k_lift_fwd_ntt_int_cl(const DevParams *__restrict__ P, const uint64_t *__restrict__ plain, uint64_t *__restrict__ out,
+                          const uint8_t *__restrict__ slot_skip) {
+  constexpr int ROWS = 1 << LOGR, CS = ROWS / 4, LOGN = 10 + LOGR;
+  constexpr uint32_t ROWW = 1024 + 64;
+  extern __shared__ uint64_t smi[];
+  uint32_t r;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  const uint32_t L_R = P->L_R, L_E = P->L_E;
+  const uint32_t el = blockIdx.x / CS, e = el / L_E, l = el - e * L_E, j = blockIdx.y;
+  if (slot_skip && slot_skip[e]) return;   // all CTAs of the cluster together
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  const ModConst m = P->Q[l];
+  const uint64_t p = m.p, four_p = p << 2;
+  const uint64_t thr = P->thr[j], tm = P->tmodQ[j][l];
+  const Twiddle *tab = P->fwdQ[l];
+  const uint64_t *src = plain + (((size_t)e * L_R + j) << LOGN);
+  uint64_t *dst = out + (((((size_t)e * L_R + j) * L_E + l)) << LOGN);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+#pragma unroll 1
+  for (uint32_t it = 0; it < 1024 / CS / 128; it++) {   // pass 1: column `col` of all rows, levels 0..LOGR-1 (1024 / CS columns per CTA)
+    const uint32_t col = (1024 / CS) * r + 128 * it + tid;
+    uint64_t v[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) v[k] = __ldg(src + col + 1024 * k);
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      if (SIGNED) {   // sum of two centred plaintexts (k_centre_add)
+        const long long sv = (long long)v[k];
+        const uint64_t x = reduce64((uint64_t)(sv < 0 ? -sv : sv), m);
+        v[k] = sv < 0 ? neg_mod(x, p) : x;
+      } else {
+        uint64_t x = reduce64(v[k], m);
+        if (v[k] >= thr) x = sub_mod(x, tm, p);   // v + (Q - t)  ==  v - t  (mod Q_l)
+        v[k] = x;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LOGR; u++) {
+      const int half = ROWS >> (u + 1);
+#pragma unroll
+      for (int grp = 0; grp < (1 << u); grp++) {
+        const Twiddle t = load_tw(tab, (1u << u) + grp);
+#pragma unroll
+        for (int k = 0; k < half; k++) bfly_fwd_lazy(v[grp * 2 * half + k], v[grp * 2 * half + k + half], t, p, four_p);
+      }
+    }
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(smi) + pad_idx(col) * 8;
+    if (it == 0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // the peers run: their shared memory exists
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      uint32_t dstaddr;
+      asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dstaddr) : "r"(local + (uint32_t)(k & 3) * ROWW * 8), "r"((uint32_t)(k >> 2)));
+      asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dstaddr), "l"(v[k]) : "memory");
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const uint32_t row = 4 * r + wrp;   // block of 1024 at level LOGR
+  uint64_t *rp = smi + wrp * ROWW;
+  int_row_pass_fwd<4, 0>(rp, tab, p, LOGR, row, lane);
+  __syncwarp();
+  int_row_pass_fwd<4, 4>(rp, tab, p, LOGR, row, lane);
+  __syncwarp();
+  {   // row-local levels 8, 9 on four consecutive elements, straight to global memory
+    const uint32_t lvl8 = 1u << (LOGR + 8), lvl9 = 1u << (LOGR + 9);
+#pragma unroll 2
+    for (uint32_t it = lane; it < 256; it += 32) {
+      const uint32_t b = row * 256 + it;
+      const uint64_t *ptr = rp + pad_idx(4 * it);
+      uint64_t v0 = ptr[0], v1 = ptr[1], v2 = ptr[2], v3 = ptr[3];
+      const Twiddle ta = load_tw(tab, lvl8 + b), tb = load_tw(tab, lvl9 + 2 * b), tc = load_tw(tab, lvl9 + 2 * b + 1);
+      bfly_fwd_lazy(v0, v2, ta, p, four_p);
+      bfly_fwd_lazy(v1, v3, ta, p, four_p);
+      bfly_fwd_lazy(v0, v1, tb, p, four_p);
+      bfly_fwd_lazy(v2, v3, tc, p, four_p);
+      asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 1024 * row + 4 * it), "l"(reduce64(v0, m)), "l"(reduce64(v1, m)),
+                   "l"(reduce64(v2, m)), "l"(reduce64(v3, m))
+                   : "memory");
+    }
+  }
+}
+
 // The same transform capped at 96 registers (a few twiddles spill to L1): 512 x 96 = 48 Ki registers leave room for one
 // 256-thread CTA of k_crs_lincomb_r64 on the same SM, so the HBM-bound stream of one term group runs UNDER the FP64-bound
 // transforms of the next (prover_fast.cuh, RSG_OVERLAP).

@@ -910,6 +910,20 @@ static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count
     CUDA_TRY(cudaGetLastError());
     return RSG_OK;
   }
+  if (lazy && c->ntt_cluster && (c->logN == 15 || c->logN == 14)) {   // integer transform on clusters (kernels.cuh)
+    const size_t smc = 4 * (1024 + 64) * 8;
+    const unsigned cs = c->logN == 15 ? 8 : 4;
+    const dim3 cgrid((unsigned)(count * c->L_E * cs), (unsigned)c->L_R);
+    if (c->logN == 15) {
+      if (is_signed) k_lift_fwd_ntt_int_cl<5, true><<<cgrid, 128, smc, c->stream>>>(c->d_params, d_plain, d_pntt, nullptr);
+      else k_lift_fwd_ntt_int_cl<5, false><<<cgrid, 128, smc, c->stream>>>(c->d_params, d_plain, d_pntt, nullptr);
+    } else {
+      if (is_signed) k_lift_fwd_ntt_int_cl<4, true><<<cgrid, 128, smc, c->stream>>>(c->d_params, d_plain, d_pntt, nullptr);
+      else k_lift_fwd_ntt_int_cl<4, false><<<cgrid, 128, smc, c->stream>>>(c->d_params, d_plain, d_pntt, nullptr);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
                            if (lazy) k_lift_fwd_ntt<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, is_signed, d_pntt);
                            else k_lift_fwd_ntt<LG, LV, false><<<grid, th, sm, c->stream>>>(c->d_params, d_plain, is_signed, d_pntt); });
@@ -2477,6 +2491,11 @@ static int fast_launch_ntt(rsg_context *c, const uint64_t *nttsrc, uint32_t s0, 
                                else k_lift_fwd_ntt_f64<LG, LV, true, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk);
                              } else if (lowreg) k_lift_fwd_ntt_f64_r96<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk);
                              else k_lift_fwd_ntt_f64<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, dst, sk); });
+  } else if (lazy && c->ntt_cluster && !lowreg && (c->logN == 15 || c->logN == 14)) {
+    const size_t smc = 4 * (1024 + 64) * 8;
+    const dim3 cgrid((unsigned)(count * c->L_E * (c->logN == 15 ? 8 : 4)), (unsigned)c->L_R);
+    if (c->logN == 15) k_lift_fwd_ntt_int_cl<5, true><<<cgrid, 128, smc, c->stream>>>(c->d_params, src, dst, sk);
+    else k_lift_fwd_ntt_int_cl<4, true><<<cgrid, 128, smc, c->stream>>>(c->d_params, src, dst, sk);
   } else {
     DISPATCH_LOGN(c->logN, { int rc = set_smem_attrs<LG, LV>(); if (rc) return rc;
                              if (lazy) k_lift_fwd_ntt<LG, LV, true><<<grid, th, sm, c->stream>>>(c->d_params, src, 1u, dst, sk);
