@@ -286,9 +286,14 @@ class RingElem {
       rp.q.push_back(m.value());
       rp.q_bits.push_back(m.bit_count());
     }
-    try {   // harnesses that also instantiate the reference backend in this process share the ring
+    try {   // harnesses that also instantiate the reference backend in this process share the ring ...
       Host::set_context(context_);
-    } catch (const std::invalid_argument &) {
+    } catch (const std::invalid_argument &) {   // ... which must then be the SAME ring
+      if (Host::get_context().first_parms_id() != context_.first_parms_id()) {
+        delete rp.ctx;
+        rp = detail::RingParams();
+        throw std::invalid_argument("the reference backend of this process is bound to another ring context");
+      }
     }
   }
   static ::seal::SEALContext &get_context() { return *detail::ring_params().ctx; }
@@ -666,6 +671,8 @@ class EncodingElem {
       have = false;
     }
     if (!have) SealEnc::set_context(N);
+    else if (N && SealEnc::get_contexts()[0].first_context_data()->parms().poly_modulus_degree() != N)
+      throw std::invalid_argument("the encoding contexts of this process were set for another N");
     init_backend();
   }
   static void set_contexts(const std::vector<::seal::SEALContext> &contexts_) {
@@ -676,6 +683,13 @@ class EncodingElem {
       have = false;
     }
     if (!have) SealEnc::set_contexts(contexts_);
+    else {
+      auto &held = SealEnc::get_contexts();
+      if (held.size() != contexts_.size()) throw std::invalid_argument("the encoding contexts of this process differ from the ones supplied");
+      for (size_t i = 0; i < held.size(); i++)
+        if (held[i].first_parms_id() != contexts_[i].first_parms_id())
+          throw std::invalid_argument("the encoding contexts of this process differ from the ones supplied");
+    }
     init_backend();
   }
   static std::vector<::seal::SEALContext> &get_contexts() {
@@ -881,11 +895,12 @@ class EncodingElem {
 
   // seal_ring.tcc:479-507 (SEAL's add_inplace treats the size-0 zero ciphertext as the identity as well)
   EncodingElem &operator+=(const EncodingElem &other) {
-    if (other.is_empty() || other.zero_) return *this;
-    if (!arena_) {
-      *this = other;
+    if (other.is_empty()) return *this;
+    if (!arena_) {   // empty += anything non-empty (also the size-0 zero ciphertexts: the result is then NOT empty); zero += encoding
+      if (is_empty() || other.arena_) *this = other;
       return *this;
     }
+    if (other.zero_) return *this;   // SEAL's add_inplace with a size-0 ciphertext adds nothing
     make_unique();
     detail::check(rsg_enc_add(detail::backend().ctx, dptr(), other.dptr()));
     return *this;

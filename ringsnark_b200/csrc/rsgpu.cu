@@ -526,11 +526,14 @@ extern "C" void rsg_context_destroy(rsg_context *c) {
 }
 extern "C" int rsg_context_sync(rsg_context *c) {
   if (!c) return fail(RSG_ERR_STATE, "context not set");
+  CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
 }
 extern "C" int rsg_context_set_stream(rsg_context *c, void *s) {
   if (!c) return fail(RSG_ERR_STATE, "context not set");
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (c->own_stream) cudaStreamDestroy(c->stream);
   c->stream = (cudaStream_t)s;
@@ -604,6 +607,8 @@ extern "C" int rsg_crs_upload(rsg_crs *r, size_t first, size_t count, const uint
   RSG_TRACE_CALL();
   if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "CRS range");
   rsg_context *c = r->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaMemcpyAsync(r->d + first * c->enc_words(), h, count * c->enc_words() * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
@@ -612,6 +617,8 @@ extern "C" int rsg_crs_download(const rsg_crs *r, size_t first, size_t count, ui
   RSG_TRACE_CALL();
   if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "CRS range");
   rsg_context *c = r->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaMemcpyAsync(h, r->d + first * c->enc_words(), count * c->enc_words() * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
@@ -663,6 +670,8 @@ extern "C" int rsg_ringvec_upload(rsg_ringvec *r, size_t first, size_t count, co
   RSG_TRACE_CALL();
   if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "ringvec range");
   rsg_context *c = r->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaMemcpyAsync(r->d + first * c->ring_words(), h, count * c->ring_words() * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
@@ -671,6 +680,8 @@ extern "C" int rsg_ringvec_download(const rsg_ringvec *r, size_t first, size_t c
   RSG_TRACE_CALL();
   if (!r || first + count > r->n) return fail(RSG_ERR_ARG, "ringvec range");
   rsg_context *c = r->ctx;
+  std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaMemcpyAsync(h, r->d + first * c->ring_words(), count * c->ring_words() * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return RSG_OK;
@@ -703,6 +714,7 @@ extern "C" int rsg_ringvec_is_zero_prefix(const rsg_ringvec *r, size_t first, si
   if (!count) return RSG_OK;
   rsg_context *c = r->ctx;
   std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   int rc = ensure(c, &c->d_flags, &c->cap_flags, count);
   if (rc) return rc;
   {
@@ -934,11 +946,13 @@ static int launch_lift_ntt(rsg_context *c, const uint64_t *d_plain, size_t count
 extern "C" int rsg_batch_encode(rsg_context *c, const uint64_t *d_ring, size_t count, uint64_t *d_plain) {
   if (!c) return fail(RSG_ERR_STATE, "context not set");
   std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   return launch_encode(c, d_ring, nullptr, count, d_plain);
 }
 extern "C" int rsg_plain_to_ntt(rsg_context *c, const uint64_t *d_plain, size_t count, uint64_t *d_pntt) {
   if (!c) return fail(RSG_ERR_STATE, "context not set");
   std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   return launch_lift_ntt(c, d_plain, count, d_pntt);
 }
 static int ntt_dev(rsg_context *c, uint64_t *d, size_t batch, int which, size_t idx, int inverse);
@@ -947,6 +961,7 @@ extern "C" int rsg_ntt(rsg_context *c, uint64_t *d, size_t batch, int which, siz
   if ((which == 0 && idx >= c->L_E) || (which == 1 && idx >= c->L_R) || which < 0 || which > 1) return fail(RSG_ERR_ARG, "bad modulus index");
   if (!batch) return RSG_OK;
   std::lock_guard<std::mutex> g(c->mu);
+  CUDA_TRY(cudaSetDevice(c->device));
   return ntt_dev(c, d, batch, which, idx, inverse);
 }
 // `batch` contiguous N_E-point polynomials, in place, canonical in and out; which = 0: mod Q_idx, 1: mod q_idx.  Caller holds c->mu.

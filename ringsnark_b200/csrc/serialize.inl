@@ -23,6 +23,14 @@ constexpr uint64_t kFnvInit = 0xcbf29ce484222325ull;
 struct FileCloser {
   FILE *f;
   ~FileCloser() { if (f) fclose(f); }
+  // writers: a buffered write can fail as late as here (ENOSPC); report it instead of returning RSG_OK
+  int finish() {
+    FILE *g = f;
+    f = nullptr;
+    if (!g) return RSG_OK;
+    const bool bad = fflush(g) != 0;
+    return (fclose(g) != 0 || bad) ? fail(RSG_ERR_ARG, "write failed (flush / close)") : RSG_OK;
+  }
 };
 // header of an open file -> info[0..5] = kind, N_R, L_R, N_E, L_E, n_elems; primes appended to q / Q
 int read_header(FILE *f, uint64_t *info, std::vector<uint64_t> &q, std::vector<uint64_t> &Q) {
@@ -79,6 +87,7 @@ extern "C" int rsg_enc_file_write(const char *path, uint64_t kind, size_t N_R, s
   if (rc) return rc;
   const uint64_t tail[2] = {fnv_words(kFnvInit, h_words, words), kFileEnd};
   if (fwrite(h_words, 8, words, fc.f) != words || fwrite(tail, 8, 2, fc.f) != 2) return fail(RSG_ERR_ARG, "write failed");
+  if (int frc = fc.finish()) return frc;
   return RSG_OK;
 }
 
@@ -134,7 +143,7 @@ extern "C" int rsg_crs_save(const rsg_crs *r, size_t first, size_t count, const 
   if (rc) return rc;
   const uint64_t tail[2] = {h, kFileEnd};
   if (fwrite(tail, 8, 2, fc.f) != 2) return fail(RSG_ERR_ARG, "write failed");
-  return RSG_OK;
+  return fc.finish();
 }
 
 extern "C" int rsg_crs_load(rsg_crs *r, size_t first, const char *path, size_t *count_out) {
@@ -155,24 +164,31 @@ extern "C" int rsg_crs_load(rsg_crs *r, size_t first, const char *path, size_t *
   const size_t ew = c->enc_words(), chunk = std::max<size_t>(1, ((size_t)64 << 20) / (ew * 8));
   uint64_t *stage = nullptr;
   CUDA_TRY(cudaMallocHost((void **)&stage, chunk * ew * 8));
-  uint64_t h = kFnvInit;
-  for (size_t i = 0; i < count && rc == RSG_OK; i += chunk) {
-    const size_t k = std::min(chunk, count - i);
-    if (fread(stage, 8, k * ew, fc.f) != k * ew)
-      rc = fail(RSG_ERR_ARG, "short file");
-    else if (!words_in_range(stage, k, c->L_R, c->L_E, c->N_E, c->Q.data()))
-      rc = fail(RSG_ERR_ARG, "a word is not a canonical residue");
-    else if (cudaMemcpyAsync(r->d + (first + i) * ew, stage, k * ew * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
-             cudaStreamSynchronize(c->stream) != cudaSuccess)
-      rc = fail(RSG_ERR_CUDA, "host to device copy failed");
-    else
-      h = fnv_words(h, stage, k * ew);
+  // pass 0 verifies the whole payload (ranges, checksum, end mark) WITHOUT touching the arena; pass 1 copies.  A corrupt or
+  // truncated file therefore leaves the proving key as it was.
+  const long payload = ftell(fc.f);
+  for (int pass = 0; pass < 2 && rc == RSG_OK; pass++) {
+    if (fseek(fc.f, payload, SEEK_SET) != 0) { rc = fail(RSG_ERR_ARG, "seek failed"); break; }
+    uint64_t h = kFnvInit;
+    for (size_t i = 0; i < count && rc == RSG_OK; i += chunk) {
+      const size_t k = std::min(chunk, count - i);
+      if (fread(stage, 8, k * ew, fc.f) != k * ew)
+        rc = fail(RSG_ERR_ARG, "short file");
+      else if (pass == 0 && !words_in_range(stage, k, c->L_R, c->L_E, c->N_E, c->Q.data()))
+        rc = fail(RSG_ERR_ARG, "a word is not a canonical residue");
+      else if (pass == 1 && (cudaMemcpyAsync(r->d + (first + i) * ew, stage, k * ew * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                             cudaStreamSynchronize(c->stream) != cudaSuccess))
+        rc = fail(RSG_ERR_CUDA, "host to device copy failed");
+      else
+        h = fnv_words(h, stage, k * ew);
+    }
+    if (rc) break;
+    uint64_t tail[2];
+    if (fread(tail, 8, 2, fc.f) != 2 || tail[1] != kFileEnd) rc = fail(RSG_ERR_ARG, "end mark missing");
+    else if (tail[0] != h) rc = fail(RSG_ERR_ARG, pass == 0 ? "checksum mismatch (arena untouched)" : "file changed between the two passes");
   }
   cudaFreeHost(stage);
   if (rc) return rc;
-  uint64_t tail[2];
-  if (fread(tail, 8, 2, fc.f) != 2 || tail[1] != kFileEnd) return fail(RSG_ERR_ARG, "end mark missing");
-  if (tail[0] != h) return fail(RSG_ERR_ARG, "checksum mismatch (arena range now holds the corrupt payload)");
   if (count_out) *count_out = count;
   return RSG_OK;
 }

@@ -106,6 +106,16 @@ def test_crs_and_proof_through_hbm(tmp_path):
         assert kind == S.FILE_CRS and np.array_equal(host, crs.download(1, 3))
         with pytest.raises(RsgError, match="too small"):
             S.load_crs(ctx.crs(2), tmp_path / "range.rsgk")
+        # a corrupt payload is detected BEFORE anything is written: the arena keeps what it held
+        raw = bytearray((tmp_path / "range.rsgk").read_bytes())
+        raw[len(raw) // 2] ^= 0x01
+        (tmp_path / "flip.rsgk").write_bytes(raw)
+        keep = ctx.crs(4)
+        keep.fill_uniform(13)
+        before = keep.download(0, 4).copy()
+        with pytest.raises(RsgError, match="arena untouched|canonical"):
+            S.load_crs(keep, tmp_path / "flip.rsgk", first=1)
+        assert np.array_equal(keep.download(0, 4), before)
         # a proving key saved and reloaded proves the same proof (= the reference's)
         sys.path.insert(0, os.path.join(root, "tests"))
         r1cs = rs.R1cs(ctx, case.n, case.io, case.aux, case.d["r1cs_row_ptr"], case.d["r1cs_col"], case.d["r1cs_coeff"])
