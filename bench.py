@@ -542,6 +542,50 @@ def run_gpu_arm(args, cfg_name, cfg):
         phases = prove_phases()
         barrier()
 
+    # ---- the other proof system on the same shape (single GPU): rinocchio::prover (rinocchio.tcc:74-190) in zero-knowledge
+    # mode through rsg_rinocchio_prove -- eleven inner products over s_pows / alpha_s_pows / beta_prods with every coefficient
+    # encoded and transformed once, nine proof elements.  Reported beside the headline, not instead of it.
+    rino = None
+    if single and os.environ.get("RSG_BENCH_RINOCCHIO", "1") != "0":
+        try:
+            from ringsnark_b200.backend import CrsRef
+            arenas = [ctx.crs(n + 1), ctx.crs(n + 1), ctx.crs(max(aux, 1)), ctx.crs(3)]
+            for k_, a_ in enumerate(arenas):
+                a_.fill_uniform(SEED + 100 + k_)
+            refs = (CrsRef * 6)()
+            for k_, (a_, f_) in enumerate(((arenas[0], 0), (arenas[1], 0), (arenas[2], 0), (arenas[3], 0), (arenas[3], 1), (arenas[3], 2))):
+                refs[k_].crs, refs[k_].first = a_.h, f_
+            dvec = ctx.ringvec(3)
+            dvec.fill_uniform(SEED + 200)
+            h_d = dvec.download()
+            d_rino = torch.zeros(9 * ctx.enc_words, dtype=torch.int64, device="cuda")
+            used9 = (C.c_size_t * 9)()
+
+            def prove_rino():
+                with torch.cuda.stream(stream):
+                    check(ctx.lib.rsg_rinocchio_prove(ctx.h, r1cs.h, refs, pk.assignment.h, None, None, C.c_void_p(h_d.ctypes.data), None,
+                                                      C.c_void_p(d_rino.data_ptr()), used9))
+            for _ in range(3):
+                prove_rino()
+            torch.cuda.synchronize()
+            rsteps = max(3, min(args.steps, 10))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(rsteps):
+                prove_rino()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            rms = e0.elapsed_time(e1) / rsteps
+            rino = {"metric": "Rinocchio prove time (zero-knowledge)", "value": rms, "unit": UNIT, "steps": rsteps, "proof_elements": 9,
+                    "ratio_to_ringGroth16": rms / ms_dev if ms_dev else None, "terms": [int(u) for u in used9],
+                    "fast_fallbacks": int(ctx.stat("fast_fallbacks")),
+                    "proof_checksum": proof_checksum(d_rino.cpu().numpy().view(np.uint64)),
+                    "parity": "tests/test_fast_path_gpu.py::test_fused_rinocchio_equals_per_inner_product_sequence (c1, c4m); full C4 against "
+                              "the reference's prover: profiles/r2_dropin_c4_full_rinocchio.json"}
+            del arenas, dvec, d_rino
+        except Exception as ex:
+            rino = {"error": repr(ex)[:300]}
+
     # ---- parity, outside every timed region
     proof_words = final_words()
     checksum = proof_checksum(proof_words)
@@ -628,6 +672,7 @@ def run_gpu_arm(args, cfg_name, cfg):
                              "peak_source": f"148 SM x 64 lanes x {sm_max:.0f} MHz (maximum SM clock)"},
             "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()},
             "phases_ms": {k: (round(v, 4) if v is not None else None) for k, v in phases.items()} if phases else None,
+            "rinocchio": rino,
             "exchange": ("peer memory (NVLink loads/stores, csrc/p2p.cuh)" if p2p else "NCCL collectives") if not single else None,
             "ntt": {"forward_butterflies_per_step": fwd_bfly, "inverse_butterflies_per_step": inv_bfly,
                     "forward_gbutterflies_per_s": fwd_bfly / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
