@@ -658,7 +658,7 @@ def run_gpu_arm(args, cfg_name, cfg):
             "parity_checked": bool(parity and parity.get("ok")), "parity": parity, "proof_checksum": checksum,
             # per launch: algorithmic bytes / average launch duration, both from the separate profiled pass (CUDA events on
             # the launching stream); traffic = DRAM bytes per launch from the committed ncu --set full capture
-            "roofline": {"kernel": "k_crs_lincomb", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_crs_lincomb" if os.environ.get("RSG_LIN") == "narrow" else "k_crs_lincomb_wide", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None,
                          "traffic": traffic / lin_launches if traffic and lin_launches and world == 1 else None,
                          "algorithmic_bytes_per_launch": alg_bytes / lin_launches if lin_launches else None,

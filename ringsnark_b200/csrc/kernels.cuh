@@ -805,6 +805,68 @@ __global__ void __launch_bounds__(256) k_crs_lincomb(const DevParams *__restrict
                                                      const uint64_t *const *__restrict__ term_ptr = nullptr) {
   crs_lincomb_body<UNROLL>(P, crs, term, pidx, n_terms, terms_per_split, pntt, partial, zoff, slot_skip, term_ptr);
 }
+// The same stream with FOUR adjacent x per thread: 256-bit loads (one whole 32-byte sector per lane and instruction), eight 192-bit
+// accumulators, 256-bit stores.  grid (N_E / (4*blockDim), L_R*L_E, splits).  What the static plan launches (RSG_LIN=narrow: the
+// two-x kernel above): 5.5 -> 6.45 TB/s inside the C4 proof = 98.6 % of the measured copy peak.
+struct u64x4 {
+  uint64_t a, b, c, d;
+};
+__device__ __forceinline__ u64x4 ld_stream4(const uint64_t *p) {
+  u64x4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+  return v;
+}
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_crs_lincomb_wide(const DevParams *__restrict__ P, const uint32_t *__restrict__ pidx,
+                                                          const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
+                                                          const uint32_t *__restrict__ zoff, const uint8_t *__restrict__ slot_skip,
+                                                          const uint64_t *const *__restrict__ term_ptr) {
+  const uint32_t N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
+  const uint32_t x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const uint32_t j = blockIdx.y / L_E, l = blockIdx.y - j * L_E;
+  const uint32_t t0 = zoff[blockIdx.z], t1 = zoff[blockIdx.z + 1];
+  const size_t poly = (size_t)N_E, ct_words = 2 * (size_t)L_E * poly, enc_words = (size_t)L_R * ct_words;
+  const size_t c_off = (size_t)j * ct_words + (size_t)l * poly + x, k_stride = (size_t)L_E * poly;
+  const size_t p_off = ((size_t)j * L_E + l) * poly + x, p_stride = (size_t)L_R * L_E * poly;
+  Acc192 a0[4], a1[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { a0[i].clear(); a1[i].clear(); }
+  auto mac4 = [&](const u64x4 &c0, const u64x4 &c1, const u64x4 &pp) {
+    a0[0].mac(c0.a, pp.a); a0[1].mac(c0.b, pp.b); a0[2].mac(c0.c, pp.c); a0[3].mac(c0.d, pp.d);
+    a1[0].mac(c1.a, pp.a); a1[1].mac(c1.b, pp.b); a1[2].mac(c1.c, pp.c); a1[3].mac(c1.d, pp.d);
+  };
+  const u64x4 ones = {1, 1, 1, 1}, zeros = {0, 0, 0, 0};
+  uint32_t t = t0;
+  for (; t + UNROLL <= t1; t += UNROLL) {
+    u64x4 c0[UNROLL], c1[UNROLL], pp[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const uint32_t pi = __ldg(pidx + t + u);
+      const uint64_t *c = term_ptr[t + u] + c_off;
+      if (slot_skip && pi != 0xFFFFFFFFu && slot_skip[pi]) {
+        c0[u] = c1[u] = pp[u] = zeros;
+        continue;
+      }
+      c0[u] = ld_stream4(c);
+      c1[u] = ld_stream4(c + k_stride);
+      pp[u] = pi != 0xFFFFFFFFu ? ld_stream4(pntt + (size_t)pi * p_stride + p_off) : ones;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) mac4(c0[u], c1[u], pp[u]);
+  }
+  for (; t < t1; t++) {
+    const uint32_t pi = __ldg(pidx + t);
+    if (slot_skip && pi != 0xFFFFFFFFu && slot_skip[pi]) continue;
+    const uint64_t *c = term_ptr[t] + c_off;
+    const u64x4 c0 = ld_stream4(c), c1 = ld_stream4(c + k_stride);
+    mac4(c0, c1, pi != 0xFFFFFFFFu ? ld_stream4(pntt + (size_t)pi * p_stride + p_off) : ones);
+  }
+  const ModConst m = P->Q[l];
+  uint64_t *o = partial + (size_t)blockIdx.z * enc_words + c_off;
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(a0[0].reduce(m)), "l"(a0[1].reduce(m)), "l"(a0[2].reduce(m)), "l"(a0[3].reduce(m)) : "memory");
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o + k_stride), "l"(a1[0].reduce(m)), "l"(a1[1].reduce(m)), "l"(a1[2].reduce(m)), "l"(a1[3].reduce(m)) : "memory");
+}
+
 // 64 registers x 256 threads = 16 Ki registers: the CTA that fits next to k_lift_fwd_ntt_f64_r96 on one SM.
 __global__ void __maxnreg__(64) k_crs_lincomb_r64(const DevParams *__restrict__ P, const uint64_t *__restrict__ crs,
                                                   const uint32_t *__restrict__ term, const uint32_t *__restrict__ pidx,

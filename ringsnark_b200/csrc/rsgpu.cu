@@ -263,7 +263,7 @@ struct rsg_context {
   uint64_t st_lin_terms = 0, st_lin_plain = 0, st_lin_launches = 0, st_fwd_polys = 0, st_inv_polys = 0, st_merged = 0;
   // ---- static-plan prover (prover_fast.cuh)
   int fast_mode = 1;                // RSG_FAST=0: always the host-driven exact path
-  int lin_mode = 0;                 // RSG_LIN=tma: k_crs_lincomb_tma instead of k_crs_lincomb (0 = ldg, 1 = tma)
+  int lin_mode = 2;                 // static-plan lincomb: 2 = k_crs_lincomb_wide (default), 0 = k_crs_lincomb (RSG_LIN=narrow), 1 = TMA-fed (RSG_LIN=tma)
   int lt_ctas = 2;                  // RSG_LT_CTAS: persistent CTAs per SM of k_crs_lincomb_tma
   int overlap_mode = 0;             // RSG_OVERLAP=1: lincomb of one term group on a second stream under the next group's NTTs
   int fast_splits = 0;              // RSG_FAST_SPLITS: number of term chunks of the one-launch lincomb (0 = auto)
@@ -480,7 +480,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   }
   if (const char *m = getenv("RSG_MERGE")) c->merge_mode = atoi(m);
   if (const char *m = getenv("RSG_FAST")) c->fast_mode = atoi(m);
-  if (const char *m = getenv("RSG_LIN")) c->lin_mode = !strcmp(m, "tma") ? 1 : 0;
+  if (const char *m = getenv("RSG_LIN")) c->lin_mode = !strcmp(m, "tma") ? 1 : (!strcmp(m, "narrow") ? 0 : 2);
   if (const char *m = getenv("RSG_LT_CTAS")) c->lt_ctas = std::max(1, atoi(m));
   if (const char *m = getenv("RSG_OVERLAP")) c->overlap_mode = atoi(m);
   if (const char *m = getenv("RSG_FAST_SPLITS")) c->fast_splits = atoi(m);
@@ -2556,7 +2556,12 @@ static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, uint32_t z0, 
     }
     const unsigned th = (unsigned)std::min<size_t>(c->lin_threads > 0 ? c->lin_threads : 256, c->N_E / 2);
     const dim3 grid((unsigned)(c->N_E / 2 / th), (unsigned)(c->L_R * c->L_E), z1 - z0);
-    if (lowreg) k_crs_lincomb_r64<<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip,
+    if (c->lin_mode == 2 && c->N_E % 1024 == 0) {   // four x per thread, 256-bit loads (default)
+      const dim3 gw((unsigned)(c->N_E / 4 / 256), (unsigned)(c->L_R * c->L_E), z1 - z0);
+      if (c->lin_unroll == 1) k_crs_lincomb_wide<1><<<gw, 256, 0, st>>>(c->d_params, d_pidx, c->d_pntt, partial, d_zoff + z0, slot_skip, fp->d_tptr);
+      else if (c->lin_unroll == 3) k_crs_lincomb_wide<3><<<gw, 256, 0, st>>>(c->d_params, d_pidx, c->d_pntt, partial, d_zoff + z0, slot_skip, fp->d_tptr);
+      else k_crs_lincomb_wide<2><<<gw, 256, 0, st>>>(c->d_params, d_pidx, c->d_pntt, partial, d_zoff + z0, slot_skip, fp->d_tptr);
+    } else if (lowreg) k_crs_lincomb_r64<<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip,
                                                        fp->d_tptr);
     else k_crs_lincomb<2><<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip,
                                                fp->d_tptr);
