@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256, 2) k_encode_fast_rows(const DevParams *__
 __global__ void __launch_bounds__(256) k_centre_add_fast(const DevParams *__restrict__ P, FastTable T, const uint8_t *__restrict__ elem_flag,
                                                          const uint64_t *__restrict__ parts, uint64_t *__restrict__ nttsrc,
                                                          uint8_t *__restrict__ slot_skip, const uint64_t *__restrict__ psi_pow,
-                                                         uint64_t *__restrict__ pval) {
+                                                         uint64_t *__restrict__ pval, uint32_t s128) {
   __shared__ uint64_t red[2][8];
   const uint32_t m = blockIdx.x, j = blockIdx.y, N_E = P->N_E, L_R = P->L_R, nS = T.nS;
   const uint32_t ex = m < nS ? m : 2 * nS + (m - nS), ey = ex + nS;
@@ -127,30 +127,76 @@ __global__ void __launch_bounds__(256) k_centre_add_fast(const DevParams *__rest
   const ulonglong2 *b = reinterpret_cast<const ulonglong2 *>(parts + ((size_t)ey * L_R + j) * N_E);
   const ulonglong2 *pw = reinterpret_cast<const ulonglong2 *>(psi_pow);
   ulonglong2 *o = reinterpret_cast<ulonglong2 *>(nttsrc + ((size_t)m * L_R + j) * N_E);
-  auto lift0 = [&](uint64_t v) {   // centred int64 -> residue mod Q_0
-    const long long sv = (long long)v;
-    const uint64_t r = reduce64((uint64_t)(sv < 0 ? -sv : sv), m0);
-    return sv < 0 ? neg_mod(r, m0.p) : r;
+  // sum_i part_i psi^i with the centred coefficients taken as SIGNED integers: |part_i| < 2^53, psi^i < 2^49, N_E <= 2^15 terms --
+  // the exact sum fits a signed 128-bit accumulator, so there is no per-coefficient reduction, only one at the end
+  struct AccS128 {
+    uint64_t lo;
+    long long hi;
+    __device__ __forceinline__ void mac(long long v, uint64_t w) {
+      asm("mad.lo.cc.u64 %0, %2, %3, %0;\n\t"
+          "madc.hi.s64 %1, %2, %3, %1;"
+          : "+l"(lo), "+l"(hi)
+          : "l"(v), "l"(w));
+    }
+    __device__ __forceinline__ uint64_t reduce(const ModConst &m) const {
+      const bool neg = hi < 0;
+      uint64_t l = lo, h = (uint64_t)hi;
+      if (neg) {   // two's complement negation of (h : l)
+        l = ~l + 1;
+        h = ~h + (l == 0);
+      }
+      const uint64_t r = reduce128(l, h, m);
+      return neg ? neg_mod(r, m.p) : r;
+    }
   };
-  Acc192 ax, ay;
-  ax.clear(); ay.clear();
-  for (uint32_t i = threadIdx.x; i < N_E / 2; i += blockDim.x) {
-    const ulonglong2 w = __ldg(pw + i);
-    ulonglong2 x = make_ulonglong2(0, 0);
-    if (!sx) {
-      x = a[i];
-      ax.mac(lift0(x.x), w.x);
-      ax.mac(lift0(x.y), w.y);
+  uint64_t s0, s1;
+  if (s128) {   // host: bits(t) + bits(Q_0) + log2 N_E <= 126 (every reference configuration)
+    AccS128 ax{0, 0}, ay{0, 0};
+    for (uint32_t i = threadIdx.x; i < N_E / 2; i += blockDim.x) {
+      const ulonglong2 w = __ldg(pw + i);
+      ulonglong2 x = make_ulonglong2(0, 0);
+      if (!sx) {
+        x = a[i];
+        ax.mac((long long)x.x, w.x);
+        ax.mac((long long)x.y, w.y);
+      }
+      if (!sy) {
+        const ulonglong2 y = b[i];
+        ay.mac((long long)y.x, w.x);
+        ay.mac((long long)y.y, w.y);
+        x.x += y.x; x.y += y.y;
+      }
+      o[i] = x;
     }
-    if (!sy) {
-      const ulonglong2 y = b[i];
-      ay.mac(lift0(y.x), w.x);
-      ay.mac(lift0(y.y), w.y);
-      x.x += y.x; x.y += y.y;
+    s0 = ax.reduce(m0);
+    s1 = ay.reduce(m0);
+  } else {
+    auto lift0 = [&](uint64_t v) {   // centred int64 -> residue mod Q_0
+      const long long sv = (long long)v;
+      const uint64_t r = reduce64((uint64_t)(sv < 0 ? -sv : sv), m0);
+      return sv < 0 ? neg_mod(r, m0.p) : r;
+    };
+    Acc192 ax, ay;
+    ax.clear(); ay.clear();
+    for (uint32_t i = threadIdx.x; i < N_E / 2; i += blockDim.x) {
+      const ulonglong2 w = __ldg(pw + i);
+      ulonglong2 x = make_ulonglong2(0, 0);
+      if (!sx) {
+        x = a[i];
+        ax.mac(lift0(x.x), w.x);
+        ax.mac(lift0(x.y), w.y);
+      }
+      if (!sy) {
+        const ulonglong2 y = b[i];
+        ay.mac(lift0(y.x), w.x);
+        ay.mac(lift0(y.y), w.y);
+        x.x += y.x; x.y += y.y;
+      }
+      o[i] = x;
     }
-    o[i] = x;
+    s0 = ax.reduce(m0);
+    s1 = ay.reduce(m0);
   }
-  uint64_t s0 = ax.reduce(m0), s1 = ay.reduce(m0);
 #pragma unroll
   for (int off = 16; off; off >>= 1) {
     s0 = add_mod(s0, __shfl_xor_sync(0xFFFFFFFFu, s0, off), m0.p);

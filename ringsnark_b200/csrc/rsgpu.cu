@@ -2627,8 +2627,13 @@ static int fast_run(rsg_context *c, FastPlan *fp, const FastTable &T, uint64_t *
   }
   if (T.nS) {
     LaunchScope ls(c, "k_centre_add");
+    // the probe sums fit a signed 128-bit accumulator when bits(t) + bits(Q_0) + log2 N_E <= 126
+    uint64_t tmax = 0;
+    for (uint64_t p : c->q) tmax = std::max(tmax, p);
+    const int tb = 64 - __builtin_clzll(tmax), qb = 64 - __builtin_clzll(c->Q[0]);
+    const uint32_t s128 = tb + qb + c->logN <= 126 ? 1u : 0u;
     k_centre_add_fast<<<dim3(2 * T.nS, (unsigned)c->L_R), 256, 0, st>>>(c->d_params, T, elem_flag, c->d_fp_parts, c->d_fp_nttsrc, slot_skip,
-                                                                        c->d_psi_pow, c->d_pval);
+                                                                        c->d_psi_pow, c->d_pval, s128);
     CUDA_TRY(cudaGetLastError());
   }
   c->st_lin_terms += fp->n_terms;
