@@ -28,11 +28,19 @@ MODES = {
     "fast_tma_1cta": {"RSG_LIN": "tma", "RSG_LT_CTAS": "1", "RSG_FAST_SPLITS": "3"},
     "fast_overlap_fullreg": {"RSG_OVERLAP": "2", "RSG_OVERLAP_CHUNKS": "1"},
     "fast_ntt_half": {"RSG_NTT_HALF": "1"},
+    # round-2 kernels against the ones they replaced
+    "fast_lin_narrow": {"RSG_LIN": "narrow"},                              # k_crs_lincomb<2> instead of k_crs_lincomb_wide
+    "fast_ntt_single_cta": {"RSG_NTT_CLUSTER": "0"},                       # k_lift_fwd_ntt_f64 / k_lift_fwd_ntt instead of the cluster kernels
+    "fast_lift_barrett": {"RSG_NTT_CLUSTER": "0", "RSG_LIFT": "barrett"},  # LiftIoF64 instead of LiftIoSmallQ
+    "fast_ntt_int": {"RSG_NTT": "int"},                                    # integer cluster transform also where the FP64 one applies
+    "fast_ntt_int_single_cta": {"RSG_NTT": "int", "RSG_NTT_CLUSTER": "0"},
+    "fast_enc_full": {"RSG_ENC_ROWS": "0"},                                # encode_body instead of the compact-row batch encode
 }
 
 
 def _set_mode(monkeypatch, mode):
-    for k in ("RSG_FAST", "RSG_LIN", "RSG_OVERLAP", "RSG_LT_CTAS", "RSG_FAST_SPLITS", "RSG_OVERLAP_CHUNKS", "RSG_NTT_HALF"):
+    for k in ("RSG_FAST", "RSG_LIN", "RSG_OVERLAP", "RSG_LT_CTAS", "RSG_FAST_SPLITS", "RSG_OVERLAP_CHUNKS", "RSG_NTT_HALF", "RSG_NTT_CLUSTER",
+              "RSG_LIFT", "RSG_NTT", "RSG_ENC_ROWS"):
         monkeypatch.delenv(k, raising=False)
     for k, v in MODES[mode].items():
         monkeypatch.setenv(k, v)
