@@ -471,6 +471,11 @@ __global__ void __cluster_dims__(NTT_CL, 1, 1) __launch_bounds__(NTT_CL_THREADS,
   io.dst = out + (((((size_t)e * L_R + j) * L_E + l)) << LOGN);
   const double *tab = P->fwdQ_f64[l];
   const double pd = io.pd, pinv = io.pinv;
+  // Q_l < 2^48: the re-centring after passes 1 and 3 is skipped.  With |v| <= (1/2 + |y| 2^-52) p per butterfly and p < 2^48 a
+  // bound of b p grows to (b + 1/2 + b/16) p per level: 0.501 -> 2.84 p after four levels, 5.81 p after eight -- below 2^51 = 8 p,
+  // the limit on a multiplied operand, and far below 2^53; pass 2 re-centres, passes 3 + 4 end at 4.3 p and the store canonicalises.
+  // (49-bit primes: 3.22 p after four levels, the fifth would pass 4 p = 2^51: every pass re-centres.)
+  const bool lazy48 = P->Q[l].p < (1ull << 48);
   const uint32_t tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   double a[16], b[16], w[15];
   {   // pass 1: column pair o of all 16 rows
@@ -484,11 +489,15 @@ __global__ void __cluster_dims__(NTT_CL, 1, 1) __launch_bounds__(NTT_CL_THREADS,
     radix16_pair(a, b, w, pd, pinv);
     const uint32_t local = (uint32_t)__cvta_generic_to_shared(smf) + pad2(o) * 8;
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (!lazy48) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) { a[k] = recentre_f64(a[k], pd, pinv); b[k] = recentre_f64(b[k], pd, pinv); }
+    }
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       uint32_t dstaddr;
       asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dstaddr) : "r"(local + (uint32_t)(k % RPC) * NTT_CL_ROWW * 8), "r"((uint32_t)(k / RPC)));
-      asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(dstaddr), "d"(recentre_f64(a[k], pd, pinv)), "d"(recentre_f64(b[k], pd, pinv)) : "memory");
+      asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(dstaddr), "d"(a[k]), "d"(b[k]) : "memory");
     }
   }
   const uint32_t row = RPC * r + wrp;   // the row (block of 1024) this warp owns from here on
@@ -518,8 +527,12 @@ __global__ void __cluster_dims__(NTT_CL, 1, 1) __launch_bounds__(NTT_CL_THREADS,
       a[k] = t.x; b[k] = t.y;
     }
     radix16_pair(a, b, w, pd, pinv);
+    if (!lazy48) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) *reinterpret_cast<double2 *>(ptr + 4 * k) = make_double2(recentre_f64(a[k], pd, pinv), recentre_f64(b[k], pd, pinv));
+      for (int k = 0; k < 16; k++) { a[k] = recentre_f64(a[k], pd, pinv); b[k] = recentre_f64(b[k], pd, pinv); }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) *reinterpret_cast<double2 *>(ptr + 4 * k) = make_double2(a[k], b[k]);
   }
   {   // pass 4: levels 12, 13 on four consecutive elements; items lane + 32 m of the row's 256
     double w12[8], w13a[8], w13b[8];
