@@ -213,6 +213,56 @@ def proof_checksum(words):
         return "%016x" % int(np.bitwise_xor.reduce(w * k))
 
 
+def make_assignment_gpu(cfg, row_ptr, col, coeff, seed, device):
+    """The same satisfying assignment built on the device (setup, untimed) for shapes where the host loop of make_assignment
+    is hopeless (C5: 8193 variables x 32768 slots): free variables uniform (k_fill_uniform), every constraint's output
+    variable = <A_i, x> * <B_i, x> through the library's element-wise ring operators (rsg_ring_binop / rsg_ring_scalar_op).
+    Returns the host words [io+aux][L_R*N_R]."""
+    import ctypes as C
+    import ringsnark_b200 as rs
+    from ringsnark_b200.capi import check
+    n, io, aux = cfg["n"], cfg["io"], cfg["aux"]
+    nv, nfree = io + aux, io + aux - n
+    ctx = rs.Context(cfg["N_R"], cfg["q"], cfg["N_E"], cfg["Q"], device=device)
+    try:
+        x = ctx.ringvec(nv)
+        x.fill_uniform(seed)
+        tmp = ctx.ringvec(3)     # 0: <A_i, x>, 1: <B_i, x>, 2: one scaled term
+        lib = ctx.lib
+
+        def lc(m, i, dst):
+            r = m * n + i
+            first = True
+            const = 0
+            for t in range(row_ptr[r], row_ptr[r + 1]):
+                v, k = int(col[t]), int(coeff[t])
+                if v == 0:
+                    const += k
+                    continue
+                if k == 1:
+                    src, sidx = x, v - 1
+                else:
+                    check(lib.rsg_ring_scalar_op(ctx.h, 2, x.h, v - 1, k, tmp.h, 2, 1))
+                    src, sidx = tmp, 2
+                if first:
+                    check(lib.rsg_ring_scalar_op(ctx.h, 0, src.h, sidx, 0, tmp.h, dst, 1))      # copy (add the scalar 0)
+                    first = False
+                else:
+                    check(lib.rsg_ring_binop(ctx.h, 0, tmp.h, dst, src.h, sidx, tmp.h, dst, 1))
+            assert not first
+            if const:
+                check(lib.rsg_ring_scalar_op(ctx.h, 0, tmp.h, dst, const, tmp.h, dst, 1))
+
+        for i in range(n):
+            lc(0, i, 0)
+            lc(1, i, 1)
+            check(lib.rsg_ring_binop(ctx.h, 2, tmp.h, 0, tmp.h, 1, x.h, nfree + i, 1))
+        ctx.sync()
+        return x.download()
+    finally:
+        ctx.close()
+
+
 def parity_single(ctx, r1cs, pk, cfg, proof, rs, seed=7):
     """Outside every timed region: is the proof the bench just timed the reference's proof?
       witness_identity        A(r) B(r) - C(r) = H(r) Z(r) at a random point, on the device's witness-map output
@@ -316,7 +366,14 @@ def run_gpu_arm(args, cfg_name, cfg):
     SEED = 0xB200
     stream = torch.cuda.Stream()
     row_ptr, col, coeff = synthetic_r1cs(n, io, aux, seed=1)
-    h_assign_np = make_assignment(cfg, row_ptr, col, coeff, seed=SEED)
+    big = (io + aux) * cfg["N_R"] * len(cfg["q"]) > (1 << 25)
+    h_assign_np = make_assignment_gpu(cfg, row_ptr, col, coeff, SEED, local) if big else make_assignment(cfg, row_ptr, col, coeff, seed=SEED)
+    # NTT-domain plaintexts of one rank's term shard beyond the library's default 8 GiB scratch: raise the budget so that the
+    # static plan (one launch sequence per proof) still applies -- the shape must then fit HBM, which c5m on one B200 does
+    slots = 2 * n + (n + 1) + aux
+    need = (slots + world - 1) // world * len(cfg["q"]) * len(cfg["Q"]) * cfg["N_E"]
+    if need > (8 << 27) and "RSG_PNTT_BUDGET_WORDS" not in os.environ:
+        os.environ["RSG_PNTT_BUDGET_WORDS"] = str(int(need * 1.05))
     import ctypes as C
     from ringsnark_b200.capi import check
     single = world == 1
@@ -546,7 +603,8 @@ def run_gpu_arm(args, cfg_name, cfg):
     # mode through rsg_rinocchio_prove -- eleven inner products over s_pows / alpha_s_pows / beta_prods with every coefficient
     # encoded and transformed once, nine proof elements.  Reported beside the headline, not instead of it.
     rino = None
-    if single and os.environ.get("RSG_BENCH_RINOCCHIO", "1") != "0":
+    rino_key_bytes = (2 * (n + 1) + aux + 3) * ctx.enc_words * 8
+    if single and os.environ.get("RSG_BENCH_RINOCCHIO", "1") != "0" and rino_key_bytes < (24 << 30):   # a second key must fit beside the first
         try:
             from ringsnark_b200.backend import CrsRef
             arenas = [ctx.crs(n + 1), ctx.crs(n + 1), ctx.crs(max(aux, 1)), ctx.crs(3)]

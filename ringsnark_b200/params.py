@@ -25,6 +25,9 @@ CONFIGS = {
     # SURVEY.md 8(d) C5 parameters (N_R = N_E = 2^15, one 54-bit ring prime = 1 mod 2^16, 8 x 55-bit limbs) with a circuit
     # small enough for the O(n^2) witness map; the n = 2^16 circuit itself needs the fast interpolation that is not built yet
     "c5s": dict(N_R=32768, q=[18014398506729473], N_E=32768, Q=Q_32768_8, n=257, io=129, aux=384),
+    # C5 parameters with the largest circuit whose proving key (57 GiB), witness vectors and NTT-domain plaintexts fit ONE B200
+    # (n = 2^16 needs the witness map beyond n = 16400 and a key of 1.3 TiB: DESIGN.md section 8)
+    "c5m": dict(N_R=32768, q=[18014398506729473], N_E=32768, Q=Q_32768_8, n=4096, io=2049, aux=6144),
     "c4s": dict(N_R=2048, q=[18014398508400641], N_E=16384, Q=Q_16384, n=33, io=17, aux=48),
 }
 
