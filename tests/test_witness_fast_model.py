@@ -228,3 +228,166 @@ def test_model_matches_oracle(n):
     col = lambda v: np.array(v, dtype=np.uint64).reshape(n, 1)
     Hw, hl = O.witness_H(col(a), col(b), col([0] * n), 1, 1, [p])
     assert hl == n - 1 and H == [int(x) for x in Hw[:, 0]]
+
+
+# ---- blocked products (witness_fast.cuh, k_interp_big / k_quotient_big): n beyond what one transform of size TS <= N_E serves ----
+# Polynomials are cut into blocks of h = TS/2 coefficients; a block product (< 2h coefficients) fits one negacyclic transform
+# of size TS without wrapping, the blocks of a constant are held transformed, and the partial products of one output block are
+# summed in the transform domain before its single inverse transform.  n <= 4h = 2*TS.
+def blocks_fwd(src, nblk, h, lgT):
+    """[nblk][TS] transformed copies of the h-coefficient blocks of src (zero-padded)"""
+    TS = 2 * h
+    X = [0] * (nblk * TS)
+    for j in range(nblk):
+        for i in range(h):
+            if j * h + i < len(src): X[j * TS + i] = src[j * h + i]
+    ntt_fwd(X, nblk, lgT, 0)
+    return X
+def block_out(X, nx, C, nc, k, TS, lgT, scale=1):
+    """inverse transform of sum_{i+j=k, i<nx, j<nc} X_i * C_j (coefficients k*h .. k*h+2h-1 of that part of the product)"""
+    T = [0] * TS
+    for i in range(nx):
+        j = k - i
+        if 0 <= j < nc:
+            for e in range(TS): T[e] = (T[e] + X[i * TS + e] * C[j * TS + e]) % p
+    if scale != 1: T = [x * scale % p for x in T]
+    ntt_inv(T, 1, lgT)
+    return T
+def polymul_big(a, b):   # any product; the model's tables use the schoolbook one (the host code: blocked transforms)
+    return polymul(a, b)
+
+def tables_big(n, TS):
+    h = TS // 2; lgT = TS.bit_length() - 1
+    Sb = 2 * h if n <= 2 * h else 4 * h
+    assert h + B <= n <= 4 * h
+    nx = (n + h - 1) // h
+    fact = [1] * (n + 1)
+    for i in range(1, n + 1): fact[i] = fact[i - 1] * i % p
+    ifact = [inv(f) for f in fact]
+    g = [(p - ifact[i]) % p if i & 1 else ifact[i] for i in range(n)]
+    invT = inv(TS)
+    Gblk = [x * invT % p for x in blocks_fwd(g, nx, h, lgT)]
+    npad = (n + B - 1) // B * B
+    tree = []
+    for r in range(npad // B):
+        f = [1]
+        for x in range(r * B, (r + 1) * B): f = polymul(f, [(-x) % p, 1])
+        tree.append(f)
+    Phat, Pnat, Ptop = [], [], None
+    m = B
+    while m < n:
+        two_m = 2 * m
+        if two_m <= TS:
+            nb_active = (n - m + two_m - 1) // two_m; lg = two_m.bit_length() - 1
+            ph = [0] * Sb
+            for b in range(nb_active):
+                a = h_ntt_fwd(tree[2 * b] + [0] * (two_m - m - 1), lg)
+                for i in range(two_m): ph[b * two_m + i] = a[i] * inv(two_m) % p
+            Phat.append(ph); Pnat.append(tree[2 * (nb_active - 1)])
+        else:     # m = TS: P = x^m + (two blocks), the blocks held transformed
+            assert m == TS and len(tree[0]) == m + 1
+            Ptop = [x * invT % p for x in blocks_fwd(tree[0][:m], 2, h, lgT)]
+        tree = [polymul(tree[2 * r], tree[2 * r + 1]) for r in range(len(tree) // 2)]
+        m <<= 1
+    Z = [1]
+    for x in range(n): Z = polymul(Z, [(-x) % p, 1])
+    lu = n - 1
+    u = [0] * max(lu, 1); u[0] = 1
+    for i in range(1, lu):
+        acc = sum(Z[n - t] * u[i - t] for t in range(1, i + 1)) % p
+        u[i] = (-acc) % p
+    Vblk = [x * invT % p for x in blocks_fwd(u[:lu], (lu + h - 1) // h, h, lgT)]
+    return dict(TS=TS, h=h, lgT=lgT, Sb=Sb, nx=nx, ifact=ifact, Gblk=Gblk, Phat=Phat, Pnat=Pnat, Ptop=Ptop, Vblk=Vblk, invT=invT)
+
+def interp_big(y, n, T):
+    TS, h, lgT, Sb, nx = T['TS'], T['h'], T['lgT'], T['Sb'], T['nx']
+    A = [y[i] * T['ifact'][i] % p if i < n else 0 for i in range(Sb)]
+    X = blocks_fwd(A, nx, h, lgT)
+    for k in range(nx):                       # Newton coefficients: low n of u * g
+        Tk = block_out(X, nx, T['Gblk'], nx, k, TS, lgT)
+        for i in range(TS):
+            pos = k * h + i
+            if pos >= Sb: continue
+            if pos >= n: A[pos] = 0
+            elif i >= h or k == 0: A[pos] = Tk[i]
+            else: A[pos] = (A[pos] + Tk[i]) % p
+    npad = (n + B - 1) // B * B
+    for blk in range(npad // B):
+        c = A[blk * B:(blk + 1) * B]
+        for k in range(B - 2, -1, -1):
+            pt = blk * B + k
+            for j in range(k, B - 1): c[j] = (c[j] - c[j + 1] * pt) % p
+        A[blk * B:(blk + 1) * B] = c
+    m = B; lvl = 0
+    Bf = [0] * Sb
+    while m < n and 2 * m <= TS:
+        lg = (2 * m).bit_length() - 1; two_m = 2 * m
+        nb_active = (n - m + two_m - 1) // two_m; last = nb_active - 1
+        h_last = min(m, n - (last * two_m + m)); shortp = h_last <= HMAX; nbN = nb_active - (1 if shortp else 0)
+        for b in range(nbN):
+            for i in range(m):
+                v = A[b * two_m + m + i]; Bf[b * two_m + i] = v; Bf[b * two_m + m + i] = v
+        hs = [A[last * two_m + m + i] for i in range(h_last)] if shortp else []
+        if nbN:
+            ntt_fwd(Bf, nbN, lg, 1)
+            for idx in range(nbN * two_m): Bf[idx] = Bf[idx] * T['Phat'][lvl][idx] % p
+            ntt_inv(Bf, nbN, lg)
+            for idx in range(nbN * two_m):
+                x = Bf[idx]
+                if (idx & (two_m - 1)) < m: x = (x + A[idx]) % p
+                A[idx] = x
+        if shortp:
+            Pn = T['Pnat'][lvl]
+            for j in range(two_m):
+                acc = 0; i = j - m if j > m else 0
+                while i < h_last and i <= j: acc += hs[i] * Pn[j - i]; i += 1
+                x = acc % p
+                if j < m: x = (x + A[last * two_m + j]) % p
+                A[last * two_m + j] = x
+        m <<= 1; lvl += 1
+    if m < n:                                  # the one level above TS: F = F_lo + x^m F_hi + p * F_hi, m = TS = 2h
+        assert m == TS
+        nf = (n - m + h - 1) // h
+        X = blocks_fwd(A[m:], nf, h, lgT)
+        for k in range(nf + 1):
+            Tk = block_out(X, nf, T['Ptop'], 2, k, TS, lgT)
+            for i in range(TS): A[k * h + i] = (A[k * h + i] + Tk[i]) % p
+    return A[:n]
+
+def quotient_big(a, b, n, T):
+    TS, h, lgT, Sb, nx = T['TS'], T['h'], T['lgT'], T['Sb'], T['nx']
+    X = blocks_fwd(a, nx, h, lgT); Y = blocks_fwd(b, nx, h, lgT)
+    lu = n - 1
+    U = [0] * Sb
+    for k in range(2 * nx - 1):
+        if k * h + TS <= n: continue
+        Tk = block_out(X, nx, Y, nx, k, TS, lgT, T['invT'])
+        for i in range(TS):
+            pos = k * h + i
+            if n <= pos <= 2 * n - 2: U[2 * n - 2 - pos] = (U[2 * n - 2 - pos] + Tk[i]) % p
+    nu = (lu + h - 1) // h
+    X = blocks_fwd(U[:lu], nu, h, lgT)
+    R = [0] * Sb
+    for k in range(nu):
+        Tk = block_out(X, nu, T['Vblk'], nu, k, TS, lgT)
+        for i in range(TS):
+            pos = k * h + i
+            if pos < lu: R[pos] = (R[pos] + Tk[i]) % p
+    return [R[lu - 1 - i] for i in range(lu)]
+
+
+@pytest.mark.parametrize("n,TS", [(48, 64), (50, 64), (64, 64), (65, 64), (80, 64), (81, 64), (97, 64), (127, 64), (128, 64),
+                                  (150, 128), (256, 128), (300, 256)])
+def test_blocked_model_matches_oracle(n, TS):
+    random.seed(n * 7 + TS)
+    T = tables_big(n, TS)
+    y = [random.randrange(p) for _ in range(n)]
+    got = interp_big(y, n, T)
+    want = O.interpolate(np.array(y, dtype=np.uint64).reshape(n, 1), 1, 1, [p])[:, 0]
+    assert got == [int(x) for x in want]
+    a = [random.randrange(p) for _ in range(n)]
+    b = [random.randrange(p) for _ in range(n)]
+    H = quotient_big(a, b, n, T)
+    col = lambda v: np.array(v, dtype=np.uint64).reshape(n, 1)
+    Hw, hl = O.witness_H(col(a), col(b), col([0] * n), 1, 1, [p])
+    assert hl == n - 1 and H == [int(x) for x in Hw[:, 0]]
