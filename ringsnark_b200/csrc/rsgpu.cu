@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/rsgpu.h"
+#include "host_poly.hpp"
 #include "kernels.cuh"
 #include "witness.cuh"
 #include "witness_fast.cuh"
@@ -211,6 +212,8 @@ struct rsg_context {
   size_t n_recs = 0;
   std::map<size_t, WitnessTables> wit;
   std::vector<std::vector<uint64_t>> h_fwdq;   // host copy of the forward twiddles mod q_j (witness_fast tables)
+  std::vector<rsg_host::NttTables> h_ntt;       // the same with their inverses, built on first use (host_poly.hpp)
+  uint32_t wf_ts = 0;               // RSG_WF_TS: cap on the witness kernels' transform size (tests: blocked mode at small n)
   int witness_mode = 0;             // 0 = auto, 1 = dense (RSG_WITNESS=dense), 2 = quasi-linear wherever it applies (RSG_WITNESS=fast)
   int wf_sl = 0;                    // RSG_WF_SL: slots per CTA of the quasi-linear kernels (0 = auto)
   int lin_threads = 0;
@@ -497,6 +500,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (const char *m = getenv("RSG_OVERLAP_CHUNKS")) c->overlap_chunks = std::max(1, atoi(m));
   if (const char *m = getenv("RSG_WITNESS")) c->witness_mode = !strcmp(m, "dense") ? 1 : (!strcmp(m, "fast") ? 2 : 0);
   if (const char *m = getenv("RSG_WF_SL")) c->wf_sl = atoi(m);
+  if (const char *m = getenv("RSG_WF_TS")) c->wf_ts = (uint32_t)atoi(m);
   if (const char *m = getenv("RSG_LIN_SPLITS")) c->lin_splits = atoi(m);
   if (const char *m = getenv("RSG_LIN_THREADS")) c->lin_threads = atoi(m);
   if (const char *m = getenv("RSG_LIN_UNROLL")) c->lin_unroll = atoi(m);
@@ -1426,6 +1430,11 @@ extern "C" int rsg_crs_copy(rsg_crs *dst, size_t dst_first, const rsg_crs *src, 
 // Per-prime constants for the domain {0..n-1}: Z, V^-1 (column j = coefficients of the j-th Lagrange basis
 // polynomial, i.e. what interpolate() accumulates for y = e_j, polynomials.tcc:26-41) and the Toeplitz matrix of
 // rev(Z)^-1 mod x^(n-1) that turns "top half of the dividend" into the quotient of the long division by Z.
+static const rsg_host::NttTables &host_ntt(rsg_context *c, size_t j) {
+  if (c->h_ntt.size() != c->L_R) c->h_ntt.assign(c->L_R, rsg_host::NttTables());
+  if (!c->h_ntt[j].p) c->h_ntt[j].set(c->q[j], c->h_fwdq[j]);
+  return c->h_ntt[j];
+}
 static int get_witness_tables(rsg_context *c, size_t n, WitnessTables **out) {
   auto it = c->wit.find(n);
   if (it != c->wit.end()) { *out = &it->second; return RSG_OK; }
@@ -1439,6 +1448,18 @@ static int get_witness_tables(rsg_context *c, size_t n, WitnessTables **out) {
   for (size_t j = 0; j < L_R; j++) {
     const uint64_t p = c->q[j];
     uint64_t *Z = wt.h_Z.data() + j * (n + 1);
+    if (n >= 2048) {   // divide and conquer + Newton iteration over transform products: the same residues in O(n log^2 n)
+      const rsg_host::NttTables &t = host_ntt(c, j);
+      const rsg_host::Poly z = rsg_host::node_product(0, n, t);
+      std::copy(z.begin(), z.end(), Z);
+      if (m) {
+        rsg_host::Poly rz(n + 1);
+        for (size_t i = 0; i <= n; i++) rz[i] = z[n - i];
+        const rsg_host::Poly u = rsg_host::series_inverse(rz, m, t);
+        std::copy(u.begin(), u.begin() + m, wt.h_u.data() + j * m);
+      }
+      continue;
+    }
     Z[0] = 1;
     for (size_t i = 0; i < n; i++) {   // multiply by (x - i)
       const uint64_t neg = (p - i % p) % p;
@@ -1519,12 +1540,24 @@ static void wf_shape(size_t n, uint32_t *S, uint32_t *logS, uint32_t *wc) {
   *logS = lg;
   *wc = 2 * n - 1 > s ? (uint32_t)(2 * n - 1 - s) : 0;
 }
+// the largest transform the witness kernels take: no 2S-th root of unity is guaranteed beyond N_E, buffers are laid out to 32768
+static uint32_t wf_max_ts(const rsg_context *c) {
+  uint32_t ts = (uint32_t)std::min<size_t>(c->N_E, 32768);
+  if (c->wf_ts >= 64 && !(c->wf_ts & (c->wf_ts - 1))) ts = std::min(ts, c->wf_ts);
+  return ts;
+}
+// blocked mode (witness_fast.cuh, k_interp_big / k_quotient_big): products assembled from blocks of TS/2 coefficients, n <= 2*TS
+static bool wf_big(const rsg_context *c, size_t n) {
+  uint32_t S, logS, wc;
+  wf_shape(n, &S, &logS, &wc);
+  const uint32_t ts = wf_max_ts(c);
+  return S > ts && n <= 2 * (size_t)ts && n >= ts / 2 + WF_B;
+}
 static bool wf_supported(const rsg_context *c, size_t n) {
   if (n < 2) return false;
   uint32_t S, logS, wc;
   wf_shape(n, &S, &logS, &wc);
-  if (S > c->N_E) return false;                                // no 2S-th root of unity guaranteed beyond N_E
-  if (S > 32768) return false;
+  if (S > wf_max_ts(c) && !wf_big(c, n)) return false;
   for (uint64_t p : c->q)
     if (p >= (1ull << 61)) return false;
   return true;
@@ -1558,8 +1591,10 @@ static std::vector<uint64_t> h_polymul(const std::vector<uint64_t> &a, const std
   }
   return r;
 }
+static int ensure_big_tables(rsg_context *c, size_t n, WitnessTables *wt);
 static int ensure_fast_tables(rsg_context *c, size_t n, WitnessTables *wt) {
   if (wt->fast_ready) return RSG_OK;
+  if (wf_big(c, n)) return ensure_big_tables(c, n, wt);
   FastTables &ft = wt->ft;
   memset(&ft, 0, sizeof(ft));
   uint32_t S, logS, wc;
@@ -1648,6 +1683,98 @@ static int ensure_fast_tables(rsg_context *c, size_t n, WitnessTables *wt) {
   wt->fast_ready = true;
   return RSG_OK;
 }
+// Blocked mode: the same constants cut into blocks of h = TS/2 coefficients, each transformed at size TS and scaled by 1/TS;
+// the tree levels with 2m <= TS keep the layout above (S = the coefficient-buffer size), the level m = TS is P - x^TS as two blocks.
+static int ensure_big_tables(rsg_context *c, size_t n, WitnessTables *wt) {
+  FastTables &ft = wt->ft;
+  memset(&ft, 0, sizeof(ft));
+  const uint32_t TS = wf_max_ts(c), h = TS / 2;
+  uint32_t lgT = 0;
+  while ((1u << lgT) < TS) lgT++;
+  const uint32_t Sb = n <= 2 * (size_t)h ? 2 * h : 4 * h, nx = (uint32_t)((n + h - 1) / h);
+  ft.n = (uint32_t)n; ft.S = Sb; ft.wc = 0; ft.big = 1; ft.TS = TS; ft.logTS = lgT; ft.nx = nx;
+  while ((1u << ft.logS) < Sb) ft.logS++;
+  uint32_t levels = 0;
+  for (size_t m = WF_B; m < n && 2 * m <= TS; m <<= 1) levels++;
+  ft.levels = std::max<uint32_t>(levels, 1);
+  const size_t L_R = c->L_R, npad = (n + WF_B - 1) / WF_B * WF_B, lu = n - 1;
+  std::vector<Twiddle> invfact(L_R * n), pts(L_R * npad), Phat(L_R * ft.levels * Sb, Twiddle{0, 0});
+  std::vector<uint64_t> Pnat(L_R * ft.levels * (Sb / 2 + 1), 0), Gblk(L_R * nx * TS, 0), Vblk(L_R * nx * TS, 0), Ptop(L_R * 2 * TS, 0);
+  for (size_t j = 0; j < L_R; j++) {
+    const uint64_t p = c->q[j];
+    const rsg_host::NttTables &t = host_ntt(c, j);
+    const uint64_t invT = h_inv(TS % p, p);
+    ft.invTS[j] = h_twiddle(invT, p);
+    ft.invS[j] = ft.invTS[j];
+    std::vector<uint64_t> fact(n + 1, 1), ifact(n + 1), g(n);
+    for (size_t i = 1; i <= n; i++) fact[i] = h_mulmod(fact[i - 1], i % p, p);
+    ifact[n] = h_inv(fact[n], p);
+    for (size_t i = n; i > 0; i--) ifact[i - 1] = h_mulmod(ifact[i], i % p, p);
+    for (size_t i = 0; i < n; i++) {
+      invfact[j * n + i] = h_twiddle(ifact[i], p);
+      g[i] = (i & 1) ? (p - ifact[i]) % p : ifact[i];
+    }
+    for (size_t i = 0; i < npad; i++) pts[j * npad + i] = h_twiddle(i % p, p);
+    auto put_blocks = [&](const std::vector<uint64_t> &src, size_t len, uint64_t *dst) {   // transformed, scaled blocks of src[0..len)
+      const rsg_host::Poly a(src.begin(), src.begin() + len);
+      const std::vector<rsg_host::Poly> blk = rsg_host::blocks_fwd(a, h, (int)lgT, t);
+      for (size_t b = 0; b < blk.size(); b++)
+        for (size_t i = 0; i < TS; i++) dst[b * TS + i] = h_mulmod(blk[b][i], invT, p);
+    };
+    put_blocks(g, n, Gblk.data() + j * nx * TS);
+    {
+      std::vector<uint64_t> u(wt->h_u.begin() + j * std::max<size_t>(lu, 1), wt->h_u.begin() + j * std::max<size_t>(lu, 1) + lu);
+      put_blocks(u, lu, Vblk.data() + j * nx * TS);
+    }
+    std::vector<rsg_host::Poly> tree(npad / WF_B);
+    for (size_t r = 0; r < tree.size(); r++) tree[r] = rsg_host::node_product(r * WF_B, (r + 1) * WF_B, t);
+    size_t lvl = 0;
+    for (size_t m = WF_B; m < n; m <<= 1, lvl++) {
+      const size_t two_m = 2 * m;
+      if (two_m <= TS) {
+        const size_t nb_active = (n - m + two_m - 1) / two_m;
+        int lg = 0;
+        while (((size_t)1 << lg) < two_m) lg++;
+        const uint64_t inv2m = h_inv(two_m % p, p);
+        for (size_t b = 0; b < nb_active; b++) {
+          rsg_host::Poly a(two_m, 0);
+          const rsg_host::Poly &Pb = tree[2 * b];
+          for (size_t i = 0; i <= m; i++) a[i] = Pb[i];
+          rsg_host::ntt_fwd(a, lg, t);
+          Twiddle *dst = Phat.data() + (j * ft.levels + lvl) * Sb + b * two_m;
+          for (size_t i = 0; i < two_m; i++) dst[i] = h_twiddle(h_mulmod(a[i], inv2m, p), p);
+        }
+        const rsg_host::Poly &Pl = tree[2 * (nb_active - 1)];
+        std::copy(Pl.begin(), Pl.end(), Pnat.begin() + (j * ft.levels + lvl) * (Sb / 2 + 1));
+      } else {   // m = TS: tree[0] = prod_{x < TS} (X - x), monic of degree TS
+        put_blocks(tree[0], m, Ptop.data() + j * 2 * TS);
+      }
+      std::vector<rsg_host::Poly> next;
+      if (2 * m < n)   // the root itself is Z: not needed again
+        for (size_t r = 0; 2 * r + 1 < tree.size(); r++) next.push_back(rsg_host::polymul(tree[2 * r], tree[2 * r + 1], t));
+      tree.swap(next);
+    }
+  }
+  int rc;
+  Twiddle *dt;
+  uint64_t *du;
+  if ((rc = upload_vec(c, invfact, &dt))) return rc;
+  ft.invfact = dt;
+  if ((rc = upload_vec(c, pts, &dt))) return rc;
+  ft.pts = dt;
+  if ((rc = upload_vec(c, Phat, &dt))) return rc;
+  ft.Phat = dt;
+  if ((rc = upload_vec(c, Pnat, &du))) return rc;
+  ft.Pnat = du;
+  if ((rc = upload_vec(c, Gblk, &du))) return rc;
+  ft.Gblk = du;
+  if ((rc = upload_vec(c, Vblk, &du))) return rc;
+  ft.Vblk = du;
+  if ((rc = upload_vec(c, Ptop, &du))) return rc;
+  ft.Ptop = du;
+  wt->fast_ready = true;
+  return RSG_OK;
+}
 // slots per CTA: a power of two dividing the slot count; both polynomial buffers of a CTA stay below ~100 KiB (2 CTAs/SM)
 // S = 16384: two S-word buffers per slot exceed an SM's shared memory; the scratch buffer then lives in global memory (L2)
 static int wf_n_global(uint32_t S) { return wf_smem_bytes(S, 1, 0) <= 227 * 1024 ? 0 : (wf_smem_bytes(S, 1, 1) <= 227 * 1024 ? 1 : 2); }
@@ -1697,11 +1824,34 @@ static int wf_launch_interp(rsg_context *c, const FastTables &ft, const uint64_t
   CUDA_TRY(cudaGetLastError());
   return RSG_OK;
 }
+// blocked mode: a persistent grid, a few CTAs per SM, each with a private range of global scratch
+static int wf_big_grid(rsg_context *c, const FastTables &ft, size_t items, unsigned *grid, uint64_t **scratch) {
+  int per_sm = 4;
+  if (const char *m = getenv("RSG_WF_BIG_CTAS")) per_sm = std::max(1, std::min(8, atoi(m)));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  *grid = (unsigned)std::min<size_t>(items, (size_t)sms * per_sm);
+  int rc = ensure(c, &c->d_wfB, &c->cap_wfB, (size_t)*grid * wf_big_words(ft.S, ft.TS));
+  if (rc) return rc;
+  *scratch = c->d_wfB;
+  return RSG_OK;
+}
 static int launch_interp_fast(rsg_context *c, WitnessTables *wt, const uint64_t *Y, uint64_t *C, size_t batch, size_t nslots,
                               size_t coef_stride, size_t limb_stride, size_t vec_stride, const char *name = "k_interp_fast") {
   if (!batch) return RSG_OK;
   LaunchScope ls(c, name);
   c->st_wf++;
+  if (wt->ft.big) {
+    const size_t items = nslots * batch * c->L_R;
+    unsigned grid;
+    uint64_t *scratch;
+    int rc = wf_big_grid(c, wt->ft, items, &grid, &scratch);
+    if (rc) return rc;
+    auto kern = wf_lazy(c) ? k_interp_big<true> : k_interp_big<false>;
+    kern<<<grid, 256, 0, c->stream>>>(c->d_params, wt->ft, Y, C, coef_stride, limb_stride, vec_stride, (uint32_t)nslots, (uint32_t)items, scratch);
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   switch (wf_pick_sl(c, wt->ft.S, nslots, batch * c->L_R)) {
     case 8: return wf_launch_interp<8>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
     case 4: return wf_launch_interp<4>(c, wt->ft, Y, C, batch, nslots, coef_stride, limb_stride, vec_stride);
@@ -1731,6 +1881,17 @@ static int wf_launch_quotient(rsg_context *c, const FastTables &ft, const uint64
 static int launch_quotient_fast(rsg_context *c, WitnessTables *wt, const uint64_t *A, const uint64_t *B, uint64_t *H) {
   LaunchScope ls(c, "k_quotient_fast");
   c->st_wf++;
+  if (wt->ft.big) {
+    const size_t items = c->N_R * c->L_R;
+    unsigned grid;
+    uint64_t *scratch;
+    int rc = wf_big_grid(c, wt->ft, items, &grid, &scratch);
+    if (rc) return rc;
+    auto kern = wf_lazy(c) ? k_quotient_big<true> : k_quotient_big<false>;
+    kern<<<grid, 256, 0, c->stream>>>(c->d_params, wt->ft, A, B, H, (uint32_t)items, scratch);
+    CUDA_TRY(cudaGetLastError());
+    return RSG_OK;
+  }
   switch (wf_pick_sl(c, wt->ft.S, c->N_R, c->L_R)) {
     case 8: return wf_launch_quotient<8>(c, wt->ft, A, B, H);
     case 4: return wf_launch_quotient<4>(c, wt->ft, A, B, H);

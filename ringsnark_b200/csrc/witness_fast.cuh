@@ -44,6 +44,14 @@ struct FastTables {              // device pointers; [L_R] major
   const uint64_t *v_nat;         // [L_R][n]      rev(Z)^-1 mod x^(n-1)
   Twiddle invS[MAX_LR];          // 1 / S
   uint32_t n, S, logS, wc, levels;
+  // blocked mode (`big`): n beyond what one transform of size TS <= N_E serves (n <= 2*TS).  Polynomials are cut into blocks
+  // of h = TS/2 coefficients; S is then the coefficient-buffer size (2h or 4h) and only the tree levels with 2m <= TS have a
+  // Phat / Pnat entry.  Constants as plain residues: the partial products of an output block are summed before one reduction.
+  const uint64_t *Gblk;          // [L_R][nx][TS]  NTT_TS(block j of (-1)^k / k!) / TS
+  const uint64_t *Ptop;          // [L_R][2][TS]   NTT_TS(block j of prod_{x<TS}(X - x) - X^TS) / TS   (n > TS)
+  const uint64_t *Vblk;          // [L_R][nx][TS]  NTT_TS(block j of rev(Z)^-1 mod x^(n-1)) / TS
+  Twiddle invTS[MAX_LR];         // 1 / TS
+  uint32_t big, TS, logTS, nx;
 };
 
 // One radix-2^RL pass (levels [s, s+RL) of the forward transform, or the same levels of the inverse) over a batch of
@@ -309,7 +317,7 @@ __device__ __forceinline__ void wf_leaf(uint64_t *f /* WF_B words in shared memo
 template <bool LAZY>
 __device__ __forceinline__ void wf_newton_to_monomial(uint64_t *A, uint64_t *B, uint64_t *hs, const FastTables &T, uint32_t limb,
                                                       uint32_t nsl, uint32_t stride, const Twiddle *fw, const Twiddle *iv,
-                                                      uint64_t p, const ModConst &mc) {
+                                                      uint64_t p, const ModConst &mc, uint32_t max_tr = 0xffffffffu) {
   const uint32_t n = T.n, S = T.S;
   const uint32_t npad = (n + WF_B - 1) / WF_B * WF_B;
   {   // leaves: one thread per (slot, 16-coefficient block); a leaf never straddles a pad word (16-aligned)
@@ -322,7 +330,7 @@ __device__ __forceinline__ void wf_newton_to_monomial(uint64_t *A, uint64_t *B, 
     __syncthreads();
   }
   uint32_t lvl = 0;
-  for (uint32_t m = WF_B; m < n; m <<= 1, lvl++) {
+  for (uint32_t m = WF_B; m < n && 2 * m <= max_tr; m <<= 1, lvl++) {   // max_tr: the largest transform (blocked mode stops early)
     const uint32_t lg = 32 - __clz(m), two_m = 2 * m;          // log2(2m)
     const uint32_t nb_active = (n - m + two_m - 1) / two_m;
     const uint32_t last = nb_active - 1;
@@ -493,6 +501,186 @@ __global__ void __launch_bounds__(512) k_quotient_fast(const DevParams *__restri
     uint64_t x = canon4(B[s * stride + pad_idx(k)], p);
     if (k < wc2) x = add_mod(x, wr2[s * WF_WC_MAX + k], p);
     H[goff + (size_t)i * W + s] = x;
+  }
+}
+
+
+// ---- blocked mode: n beyond one transform (FastTables::big) ---------------------------------------------------------
+// A product whose length exceeds TS (the largest transform the ring primes support, or the largest the buffers are laid out
+// for) is assembled from block products: operands cut into blocks of h = TS/2 coefficients, each block transformed once at
+// size TS (a block product has < 2h coefficients: nothing wraps), the partial products of output block k summed in the
+// transform domain (192-bit accumulator, one reduction) and inverse-transformed once; output block k covers coefficients
+// [k*h, k*h + 2h).  C5's headline n = 2^16 at N_E = 2^15 is four blocks of 16384.  The tree levels with 2m <= TS are the ones
+// above (wf_newton_to_monomial); the one level beyond, m = TS, is F_lo + x^m F_hi + (P - x^m) F_hi with P - x^m as two blocks.
+// One CTA walks slots (persistent grid); its buffers are a private range of global memory: A (coefficients), X / Y
+// (transformed blocks; X doubles as the tree's scratch), U, Tb.  tests/test_witness_fast_model.py holds the same steps in Python.
+__host__ __device__ constexpr size_t wf_big_words(uint32_t Sb, uint32_t TS) {
+  return 2 * ((size_t)padded_words(Sb) + 16) + 2 * ((size_t)padded_words(2 * Sb) + 16) + (size_t)padded_words(TS) + 16;
+}
+struct WfBig {
+  uint64_t *A, *X, *Y, *U, *Tb;
+  __device__ __forceinline__ WfBig(uint64_t *base, uint32_t Sb, uint32_t TS) {
+    A = base;
+    U = A + padded_words(Sb) + 16;
+    X = U + padded_words(Sb) + 16;
+    Y = X + padded_words(2 * Sb) + 16;
+    Tb = Y + padded_words(2 * Sb) + 16;
+  }
+};
+// X[j*TS + i] = src[off + j*h + i] for i < h while j*h + i < len, zero elsewhere (j < nblk).  Ends with a barrier.
+__device__ __forceinline__ void wf_blk_spread(uint64_t *X, const uint64_t *src, uint32_t off, uint32_t len, uint32_t nblk, uint32_t lgT) {
+  const uint32_t TS = 1u << lgT, h = TS >> 1;
+  for (uint32_t t = threadIdx.x; t < (nblk << lgT); t += blockDim.x) {
+    const uint32_t j = t >> lgT, i = t & (TS - 1), pos = j * h + i;
+    X[pad_idx(t)] = (i < h && pos < len) ? src[pad_idx(off + pos)] : 0;
+  }
+  __syncthreads();
+}
+// Tb = sum_{i+j=k, i<nx, j<nc} X_i * C_j (canonical; times *scale when given).  C: plain residues in global memory
+// ([nc][TS], CONSTC) or a second buffer of transformed blocks.  Ends with a barrier.
+template <bool LAZY, bool CONSTC>
+__device__ __forceinline__ void wf_blk_mac(uint64_t *Tb, const uint64_t *X, uint32_t nx, const uint64_t *Cc, uint32_t nc, uint32_t k,
+                                           uint32_t lgT, const ModConst &mc, const Twiddle *scale) {
+  const uint32_t TS = 1u << lgT;
+  const uint32_t i_lo = k >= nc ? k - nc + 1 : 0, i_hi = min(k, nx - 1);
+  for (uint32_t e = threadIdx.x; e < TS; e += blockDim.x) {
+    Acc192 acc;
+    acc.clear();
+    for (uint32_t i = i_lo; i <= i_hi; i++) {
+      const uint64_t xv = X[pad_idx((i << lgT) + e)];
+      const uint64_t a = LAZY ? reduce64(xv, mc) : canon4(xv, mc.p);
+      uint64_t b;
+      if (CONSTC) {
+        b = __ldg(Cc + ((size_t)(k - i) << lgT) + e);
+      } else {
+        const uint64_t yv = Cc[pad_idx(((k - i) << lgT) + e)];
+        b = LAZY ? reduce64(yv, mc) : canon4(yv, mc.p);
+      }
+      acc.mac(a, b);
+    }
+    uint64_t r = acc.reduce(mc);
+    if (scale) r = mul_shoup(r, *scale, mc.p);
+    Tb[pad_idx(e)] = r;
+  }
+  __syncthreads();
+}
+
+// Interpolation, blocked mode: same arguments as k_interp_fast; `items` = nslots * batch * L_R, grid-stride over them.
+template <bool LAZY>
+__global__ void __launch_bounds__(256) k_interp_big(const DevParams *__restrict__ P, FastTables T, const uint64_t *__restrict__ Y,
+                                                    uint64_t *__restrict__ C, size_t coef_stride, size_t limb_stride, size_t vec_stride,
+                                                    uint32_t nslots, uint32_t items, uint64_t *scratch) {
+  __shared__ uint64_t hs[WF_HMAX];
+  const uint32_t L_R = P->L_R, n = T.n, Sb = T.S, TS = T.TS, lgT = T.logTS, h = TS >> 1, nx = T.nx;
+  const WfBig W((uint64_t *)scratch + (size_t)blockIdx.x * wf_big_words(Sb, TS), Sb, TS);
+  for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const uint32_t slot = item % nslots, vl = item / nslots, v = vl / L_R, limb = vl - v * L_R;
+    const ModConst mc = P->q[limb];
+    const uint64_t p = mc.p;
+    const Twiddle *fw = P->fwdq[limb], *iv = P->invq[limb];
+    const size_t goff = (size_t)v * vec_stride + (size_t)limb * limb_stride + slot;
+    const Twiddle *invfact = T.invfact + (size_t)limb * n;
+    for (uint32_t t = threadIdx.x; t < Sb; t += blockDim.x)
+      W.A[pad_idx(t)] = t < n ? mul_shoup(Y[goff + (size_t)t * coef_stride], load_tw(invfact, t), p) : 0;
+    __syncthreads();
+    // Newton coefficients: the low n coefficients of (y_i / i!) * ((-1)^k / k!)
+    wf_blk_spread(W.X, W.A, 0, n, nx, lgT);
+    wf_ntt_fwd<LAZY>(W.X, 0, 1, nx, lgT, 0, fw, p);
+    const uint64_t *G = T.Gblk + ((size_t)limb * nx << lgT);
+    for (uint32_t k = 0; k < nx; k++) {
+      wf_blk_mac<LAZY, true>(W.Tb, W.X, nx, G, nx, k, lgT, mc, nullptr);
+      wf_ntt_inv<LAZY>(W.Tb, 0, 1, 1, lgT, iv, p);
+      for (uint32_t i = threadIdx.x; i < TS; i += blockDim.x) {
+        const uint32_t pos = k * h + i;
+        if (pos >= Sb) continue;
+        uint64_t x = 0;
+        if (pos < n) {
+          x = canon4(W.Tb[pad_idx(i)], p);
+          if (i < h && k) x = add_mod(x, W.A[pad_idx(pos)], p);     // the lower half overlaps the previous block's upper half
+        }
+        W.A[pad_idx(pos)] = x;
+      }
+      __syncthreads();
+    }
+    wf_newton_to_monomial<LAZY>(W.A, W.X, hs, T, limb, 1, 0, fw, iv, p, mc, TS);
+    if (n > TS) {   // the level m = TS: F_lo + x^m F_hi + (P - x^m) * F_hi
+      const uint32_t nf = (n - TS + h - 1) / h;
+      wf_blk_spread(W.X, W.A, TS, n - TS, nf, lgT);
+      wf_ntt_fwd<LAZY>(W.X, 0, 1, nf, lgT, 0, fw, p);
+      const uint64_t *Pt = T.Ptop + ((size_t)limb * 2 << lgT);
+      for (uint32_t k = 0; k <= nf; k++) {
+        wf_blk_mac<LAZY, true>(W.Tb, W.X, nf, Pt, 2, k, lgT, mc, nullptr);
+        wf_ntt_inv<LAZY>(W.Tb, 0, 1, 1, lgT, iv, p);
+        for (uint32_t i = threadIdx.x; i < TS; i += blockDim.x) {
+          uint64_t *a = W.A + pad_idx(k * h + i);
+          *a = add_mod(canon4(W.Tb[pad_idx(i)], p), *a, p);
+        }
+        __syncthreads();
+      }
+    }
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) C[goff + (size_t)t * coef_stride] = W.A[pad_idx(t)];
+    __syncthreads();
+  }
+}
+
+// Quotient, blocked mode: H[i] (i < n-1) as k_quotient_fast.  items = N_R * L_R.
+template <bool LAZY>
+__global__ void __launch_bounds__(256) k_quotient_big(const DevParams *__restrict__ P, FastTables T, const uint64_t *__restrict__ Ac,
+                                                      const uint64_t *__restrict__ Bc, uint64_t *__restrict__ H, uint32_t items,
+                                                      uint64_t *scratch) {
+  const uint32_t N_R = P->N_R, L_R = P->L_R, n = T.n, Sb = T.S, TS = T.TS, lgT = T.logTS, h = TS >> 1, nx = T.nx;
+  const size_t Wd = (size_t)N_R * L_R;
+  const WfBig W((uint64_t *)scratch + (size_t)blockIdx.x * wf_big_words(Sb, TS), Sb, TS);
+  const uint32_t lu = n - 1, nu = (lu + h - 1) / h;
+  for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const uint32_t slot = item % N_R, limb = item / N_R;
+    const ModConst mc = P->q[limb];
+    const uint64_t p = mc.p;
+    const Twiddle *fw = P->fwdq[limb], *iv = P->invq[limb];
+    const size_t goff = (size_t)limb * N_R + slot;
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+      W.A[pad_idx(t)] = Ac[goff + (size_t)t * Wd];
+      W.U[pad_idx(t)] = Bc[goff + (size_t)t * Wd];
+    }
+    __syncthreads();
+    wf_blk_spread(W.X, W.A, 0, n, nx, lgT);
+    wf_blk_spread(W.Y, W.U, 0, n, nx, lgT);
+    for (uint32_t t = threadIdx.x; t < Sb; t += blockDim.x) { W.U[pad_idx(t)] = 0; W.A[pad_idx(t)] = 0; }
+    wf_ntt_fwd<LAZY>(W.X, 0, 1, nx, lgT, 0, fw, p);
+    wf_ntt_fwd<LAZY>(W.Y, 0, 1, nx, lgT, 0, fw, p);
+    // u_i = coefficient 2n-2-i of A*B (i < n-1): the output blocks that reach position n and beyond
+    const Twiddle invTS = T.invTS[limb];
+    for (uint32_t k = 0; k + 1 < 2 * nx; k++) {
+      if (k * h + TS <= n) continue;
+      wf_blk_mac<LAZY, false>(W.Tb, W.X, nx, W.Y, nx, k, lgT, mc, &invTS);
+      wf_ntt_inv<LAZY>(W.Tb, 0, 1, 1, lgT, iv, p);
+      for (uint32_t i = threadIdx.x; i < TS; i += blockDim.x) {
+        const uint32_t pos = k * h + i;
+        if (pos >= n && pos <= 2 * n - 2) {
+          uint64_t *u = W.U + pad_idx(2 * n - 2 - pos);
+          *u = add_mod(canon4(W.Tb[pad_idx(i)], p), *u, p);
+        }
+      }
+      __syncthreads();
+    }
+    // rq = u * rev(Z)^-1 mod x^(n-1), accumulated into A
+    wf_blk_spread(W.X, W.U, 0, lu, nu, lgT);
+    wf_ntt_fwd<LAZY>(W.X, 0, 1, nu, lgT, 0, fw, p);
+    const uint64_t *V = T.Vblk + ((size_t)limb * nx << lgT);
+    for (uint32_t k = 0; k < nu; k++) {
+      wf_blk_mac<LAZY, true>(W.Tb, W.X, nu, V, nu, k, lgT, mc, nullptr);
+      wf_ntt_inv<LAZY>(W.Tb, 0, 1, 1, lgT, iv, p);
+      for (uint32_t i = threadIdx.x; i < TS; i += blockDim.x) {
+        const uint32_t pos = k * h + i;
+        if (pos < lu) {
+          uint64_t *a = W.A + pad_idx(pos);
+          *a = add_mod(canon4(W.Tb[pad_idx(i)], p), *a, p);
+        }
+      }
+      __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < lu; i += blockDim.x) H[goff + (size_t)i * Wd] = W.A[pad_idx(lu - 1 - i)];   // H_i = rq_(n-2-i)
+    __syncthreads();
   }
 }
 

@@ -794,3 +794,69 @@ def test_fast_witness_map_all_global(monkeypatch):
     res = _witness_both_modes(monkeypatch, 16, cfg["q"], cfg["N_E"], cfg["Q"], 8300, seed=43)
     assert np.array_equal(res["dense"][0], res["fast"][0]), "interpolants differ"
     assert np.array_equal(res["dense"][1], res["fast"][1]), "quotient differs"
+
+
+@pytest.mark.parametrize("name,N_R,n,ts,lazy", [
+    ("c3p", 64, 50, 64, "1"), ("c3p", 64, 64, 64, "1"), ("c3p", 64, 65, 64, "0"), ("c3p", 64, 81, 64, "1"), ("c3p", 64, 97, 64, "1"),
+    ("c3p", 64, 127, 64, "1"), ("c3p", 64, 128, 64, "0"), ("c3p", 32, 150, 128, "1"), ("c3p", 32, 256, 128, "1"),
+    ("c3p", 32, 300, 256, "1"), ("c4", 16, 1031, 1024, "1"), ("c4", 16, 2048, 1024, "1"), ("c4", 8, 4200, 4096, "1")])
+def test_blocked_witness_map_equals_dense(name, N_R, n, ts, lazy, monkeypatch):
+    """witness_fast.cuh's blocked mode (k_interp_big / k_quotient_big: products assembled from blocks of TS/2 coefficients, the
+    tree level above TS as two blocks) with the transform size capped by RSG_WF_TS so that small n reach it: two, three and
+    four blocks, ragged last blocks, short trailing tree blocks, with and without the level above TS, lazy and corrected
+    butterflies, and (n >= 2048) the host's divide-and-conquer Z / Newton-iteration rev(Z)^-1.  Same residues as the dense path."""
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS[name]
+    monkeypatch.setenv("RSG_WF_TS", str(ts))
+    monkeypatch.setenv("RSG_WF_LAZY", lazy)
+    res = _witness_both_modes(monkeypatch, N_R, cfg["q"], cfg["N_E"], cfg["Q"], n, seed=7 * n + ts)
+    assert np.array_equal(res["dense"][2], res["fast"][2])
+    assert np.array_equal(res["dense"][0], res["fast"][0]), "interpolants differ"
+    assert np.array_equal(res["dense"][1], res["fast"][1]), "quotient differs"
+
+
+def test_witness_map_c5_headline_n65536(monkeypatch):
+    """C5's headline constraint count n = 2^16 on C5's ring prime (54 bit, N_E = 2^15): four blocks of 16384 coefficients,
+    transforms of size 32768, the tree level m = 32768 as two blocks.  No dense path exists at this size (V^-1 alone would be
+    34 GB), so the result is checked by what defines it: the interpolants reproduce their evaluations at sampled nodes, and
+    A(r) B(r) - C(r) = H(r) Z(r) at a random point for evaluations with C = A o B on the domain (two slots)."""
+    import random
+    import ringsnark_b200 as rs
+    from ringsnark_b200.params import CONFIGS
+    cfg = CONFIGS["c5s"]
+    N_R, n, p = 8, 65536, int(cfg["q"][0])
+    monkeypatch.setenv("RSG_WITNESS", "fast")
+    ctx = rs.Context(N_R, cfg["q"], cfg["N_E"], cfg["Q"])
+    try:
+        ev = ctx.ringvec(9 * n)
+        ev.fill_uniform(65536)
+        e = ev.download()                                          # [9n][N_R] words
+        a, b = e[6 * n:7 * n].astype(object), e[7 * n:8 * n].astype(object)
+        e[8 * n:9 * n] = ((a * b) % p).astype(np.uint64)           # C_full = A_full o B_full on the domain
+        ev.upload(e)
+        coeffs, H = ctx.witness_map(n, ev)
+        full = ctx.interpolate(n, ev, batch=3, y_first=6 * n).download()
+        assert ctx.stat("witness_fast_launches") > 0 and ctx.stat("witness_dense_launches") == 0
+        got, Hg = coeffs.download(), H.download()
+        assert not Hg[n - 1:].any()
+
+        def horner(col, x):
+            acc = 0
+            for c in reversed(col):
+                acc = (acc * x + int(c)) % p
+            return acc
+        rnd = random.Random(5)
+        for slot in (0, N_R - 1):
+            # interpolants at sampled nodes: A_io (vector 0 of coeffs <- evals vector 3) and B_mid (vector 4 <- evals vector 1)
+            for vec, src in ((0, 3), (4, 1)):
+                col = got[vec * n:(vec + 1) * n, slot]
+                for node in (0, 1, 16383, 16384, 32768, 49152, 65535, rnd.randrange(n)):
+                    assert horner(col, node) == int(e[src * n + node, slot]), (slot, vec, node)
+            r = rnd.randrange(n, p)
+            A, B, Cc = (horner(full[k * n:(k + 1) * n, slot], r) for k in range(3))
+            Z = 1
+            for i in range(n):
+                Z = Z * (r - i) % p
+            assert (A * B - Cc) % p == horner(Hg[:n - 1, slot], r) * Z % p, slot
+    finally:
+        ctx.close()
