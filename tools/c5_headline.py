@@ -19,6 +19,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--slots", type=int, default=4096)
 ap.add_argument("--full", type=int, default=1)
 ap.add_argument("--n", type=int, default=65536)
+ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--sweep-ctas", type=int, default=0)
 args = ap.parse_args()
 cfg = CONFIGS["c5s"]
 n, p = args.n, int(cfg["q"][0])
@@ -55,6 +57,23 @@ if args.full:
 
 N_R = args.slots
 ctx = rs.Context(N_R, cfg["q"], cfg["N_E"], cfg["Q"])
+if args.sweep_ctas:
+    import os
+    y, c = ctx.ringvec(n), ctx.ringvec(n)
+    y.fill_uniform(3)
+    ctx.interpolate(n, y, out=c)
+    ctx.sync()
+    out["ctas_per_sm_sweep"] = {"N_R": N_R, "ms_one_vector": {}}
+    for k in (1, 2, 3, 4, 6, 8):
+        os.environ["RSG_WF_BIG_CTAS"] = str(k)
+        ctx.interpolate(n, y, out=c)
+        ctx.sync()
+        t0 = time.time()
+        ctx.interpolate(n, y, out=c)
+        ctx.sync()
+        out["ctas_per_sm_sweep"]["ms_one_vector"][k] = round((time.time() - t0) * 1e3, 1)
+    del os.environ["RSG_WF_BIG_CTAS"]
+    del y, c
 ev = ctx.ringvec(9 * n)
 ev.fill_uniform(2)
 e = ev.download(6 * n, 3 * n)
@@ -72,6 +91,9 @@ ctx.sync()
 wall = time.time() - t0
 out["witness_map"] = {"N_R": N_R, "wall_s": round(wall, 3), "kernels_ms": kernel_ms(ctx),
                       "full_ring_estimate_s": round(wall * cfg["N_R"] / N_R, 2)}
+if not args.check:
+    print(json.dumps(out))
+    sys.exit(0)
 full = ctx.interpolate(n, ev, batch=3, y_first=6 * n).download()
 Hg = H.download()
 rnd = random.Random(9)
