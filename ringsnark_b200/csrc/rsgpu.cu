@@ -395,6 +395,10 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (device < 0 || device >= ndev) return fail(RSG_ERR_ARG, "bad device index");
   CUDA_TRY(cudaSetDevice(device));
   rsg_context *c = new rsg_context();
+  struct Guard {   // an error on the way out releases what was allocated so far
+    rsg_context *c;
+    ~Guard() { if (c) rsg_context_destroy(c); }
+  } guard{c};
   c->device = device;
   c->N_R = N_R; c->L_R = L_R; c->N_E = N_E; c->L_E = L_E;
   while (((size_t)1 << c->logN) < N_E) c->logN++;
@@ -507,6 +511,7 @@ extern "C" int rsg_context_create(rsg_context **out, size_t N_R, size_t L_R, con
   if (const char *m = getenv("RSG_WF_THREADS")) c->wf_threads = atoi(m);
   if (const char *m = getenv("RSG_PNTT_BUDGET_WORDS")) c->pntt_budget_words = std::max<size_t>(1, strtoull(m, nullptr, 10));   // tests: force chunking
   if ((rc = dev_alloc(c, &c->d_nz, MAX_LR, false))) return rc;
+  guard.c = nullptr;
   *out = c;
   return RSG_OK;
 }
@@ -1983,6 +1988,10 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
       void *v = nullptr;
       CUDA_TRY(cudaMalloc(&v, r1cs->h_const.size() * 8));
       d_const = (uint64_t *)v;
+      struct DevFree {   // staging buffer: released on every way out
+        void *p;
+        ~DevFree() { cudaFree(p); }
+      } staging{d_const};
       CUDA_TRY(cudaMalloc(&v, r1cs->h_const.size() * 8));
       r1cs->d_cc = (uint64_t *)v;
       CUDA_TRY(cudaMemcpyAsync(d_const, r1cs->h_const.data(), r1cs->h_const.size() * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1997,7 +2006,6 @@ static int witness_map_dev(rsg_context *c, size_t n, const uint64_t *d_evals, ui
       }
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(c->stream));
-      cudaFree(d_const);
     }
     LaunchScope ls(c, "k_full_from_parts");
     k_full_from_parts<<<dim3((unsigned)n, (unsigned)((W + 255) / 256), 2), 256, 0, c->stream>>>(c->d_modq, d_coeffs, r1cs->d_cc, aA, (uint32_t)n,
