@@ -140,8 +140,11 @@ int rsg_enc_sum_strided(rsg_context *ctx, const uint64_t *d_parts, size_t parts,
  * Interpolation on the domain {0..n-1} (util/polynomials.tcc:9-43), product and exact division by the monic
  * Z (util/polynomials.tcc:61-81, util/evaluation_domain.tcc:53-84); all slot-parallel on the GPU.
  * Two implementations with identical (canonical) results: dense constant-matrix products for small n, and for
- * n >= 320 with transform size <= min(N_E, 32768) (n <= 8208 at N_E = 2^14, <= 16400 at 2^15) the quasi-linear path of csrc/witness_fast.cuh (Newton coefficients by one negacyclic product,
- * Newton -> monomial on the subproduct tree, quotient by two products).  RSG_WITNESS=dense|fast overrides the choice;
+ * n >= 320 the quasi-linear path of csrc/witness_fast.cuh (Newton coefficients by one negacyclic product, Newton -> monomial
+ * on the subproduct tree, quotient by two products): one transform per product while its size stays <= min(N_E, 32768)
+ * (n <= 8208 at N_E = 2^14, <= 16400 at 2^15), products assembled from blocks of N_E/2 coefficients beyond that, up to
+ * n = 2*N_E (n = 2^16 at N_E = 2^15); larger n takes the dense path.  RSG_WITNESS=dense|fast overrides the choice
+ * (RSG_WF_TS=<power of two> caps the transform size: tests reach the blocked mode at small n with it);
  * rsg_context_stat("witness_fast_launches" / "witness_dense_launches") says which one ran. */
 int rsg_witness_map(rsg_context *ctx, size_t n, const rsg_ringvec *evals, rsg_ringvec *coeffs, rsg_ringvec *H);
 /* The zero-knowledge variant rinocchio::prover calls (rinocchio.tcc:88-93, r1cs_to_qrp.tcc:225-235):
