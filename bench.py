@@ -570,8 +570,8 @@ def run_gpu_arm(args, cfg_name, cfg):
 
     # ---- separate profiled pass (per-launch CUDA events on the launching streams): kernel breakdown + roofline inputs
     psteps = max(1, min(args.steps, 5))
-    stat_names = ("lincomb_terms", "lincomb_plain_terms", "lincomb_launches", "ntt_forward_polys", "ntt_inverse_polys",
-                  "merged_lincombs", "exact_fallbacks", "fast_proofs", "fast_fallbacks")
+    stat_names = ("lincomb_terms", "lincomb_plain_terms", "lincomb_shared_terms", "lincomb_launches", "ntt_forward_polys",
+                  "ntt_inverse_polys", "merged_lincombs", "exact_fallbacks", "fast_proofs", "fast_fallbacks")
     for cx in ctxs:
         cx.enable_timing(True)
     st0 = {k: sum(cx.stat(k) for cx in ctxs) for k in stat_names}
@@ -677,7 +677,9 @@ def run_gpu_arm(args, cfg_name, cfg):
     # beta / scalar-1 inputs), + one 2-word output per output encoding; counted by the library
     lin_launches = stats["lincomb_launches"]
     n_outputs = 3 if stats["fast_proofs"] else lin_launches
-    alg_bytes = row * (2 * stats["lincomb_terms"] + stats["lincomb_plain_terms"] + 2 * n_outputs)
+    # A CRS element that two paired splits both multiply (ringGroth16's A and B inner products run over the same s_pows; their
+    # CTAs are launched side by side so that the second read is an L2 hit) has to come from HBM once: it is counted once.
+    alg_bytes = row * (2 * (stats["lincomb_terms"] - stats["lincomb_shared_terms"]) + stats["lincomb_plain_terms"] + 2 * n_outputs)
     lin_ms = kern["k_crs_lincomb"]["ms_per_step"]
     peaks = {}
     try:

@@ -833,11 +833,28 @@ template <int UNROLL>
 __global__ void __launch_bounds__(256) k_crs_lincomb_wide(const DevParams *__restrict__ P, const uint32_t *__restrict__ pidx,
                                                           const uint64_t *__restrict__ pntt, uint64_t *__restrict__ partial,
                                                           const uint32_t *__restrict__ zoff, const uint8_t *__restrict__ slot_skip,
-                                                          const uint64_t *const *__restrict__ term_ptr) {
+                                                          const uint64_t *const *__restrict__ term_ptr,
+                                                          const uint32_t *__restrict__ zorder = nullptr, uint32_t n_paired = 0) {
+  // zorder: launch position -> split.  Two splits that stream the SAME CRS encodings with different plaintexts (the ringGroth16 A
+  // and B inner products both run over s_pows, groth16.tcc:89-104) come first, pair by pair, and their CTAs alternate in launch
+  // order -- CTA 2i works on the first split of the pair and CTA 2i+1 on the same (x, limb) tile of the second -- so the two run
+  // side by side and the second read of every encoding is an L2 hit instead of a second trip to HBM.
+  uint32_t z = blockIdx.z, bx = blockIdx.x, by = blockIdx.y;
+  if (zorder) {
+    const uint32_t per = gridDim.x * gridDim.y, b = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (b < n_paired * per) {
+      const uint32_t q = b / (2 * per), r = b - q * 2 * per, xy = r >> 1;
+      by = xy / gridDim.x;
+      bx = xy - by * gridDim.x;
+      z = zorder[2 * q + (r & 1)];
+    } else {
+      z = zorder[blockIdx.z];
+    }
+  }
   const uint32_t N_E = P->N_E, L_E = P->L_E, L_R = P->L_R;
-  const uint32_t x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const uint32_t j = blockIdx.y / L_E, l = blockIdx.y - j * L_E;
-  const uint32_t t0 = zoff[blockIdx.z], t1 = zoff[blockIdx.z + 1];
+  const uint32_t x = 4 * (bx * blockDim.x + threadIdx.x);
+  const uint32_t j = by / L_E, l = by - j * L_E;
+  const uint32_t t0 = zoff[z], t1 = zoff[z + 1];
   const size_t poly = (size_t)N_E, ct_words = 2 * (size_t)L_E * poly, enc_words = (size_t)L_R * ct_words;
   const size_t c_off = (size_t)j * ct_words + (size_t)l * poly + x, k_stride = (size_t)L_E * poly;
   const size_t p_off = ((size_t)j * L_E + l) * poly + x, p_stride = (size_t)L_R * L_E * poly;
@@ -875,7 +892,7 @@ __global__ void __launch_bounds__(256) k_crs_lincomb_wide(const DevParams *__res
     mac4(c0, c1, pi != 0xFFFFFFFFu ? ld_stream4(pntt + (size_t)pi * p_stride + p_off) : ones);
   }
   const ModConst m = P->Q[l];
-  uint64_t *o = partial + (size_t)blockIdx.z * enc_words + c_off;
+  uint64_t *o = partial + (size_t)z * enc_words + c_off;
   asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o), "l"(a0[0].reduce(m)), "l"(a0[1].reduce(m)), "l"(a0[2].reduce(m)), "l"(a0[3].reduce(m)) : "memory");
   asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(o + k_stride), "l"(a1[0].reduce(m)), "l"(a1[1].reduce(m)), "l"(a1[2].reduce(m)), "l"(a1[3].reduce(m)) : "memory");
 }

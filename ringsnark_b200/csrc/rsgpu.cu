@@ -264,6 +264,7 @@ struct rsg_context {
   size_t cap_encode = 0;
   uint64_t st_wf = 0, st_wd = 0;
   uint64_t st_lin_terms = 0, st_lin_plain = 0, st_lin_launches = 0, st_fwd_polys = 0, st_inv_polys = 0, st_merged = 0;
+  uint64_t st_lin_shared = 0;       // CRS elements of paired splits that a neighbouring CTA streams too (counted once in the byte floor)
   // ---- static-plan prover (prover_fast.cuh)
   int fast_mode = 1;                // RSG_FAST=0: always the host-driven exact path
   int lin_mode = 2;                 // static-plan lincomb: 2 = k_crs_lincomb_wide (default), 0 = k_crs_lincomb (RSG_LIN=narrow), 1 = TMA-fed (RSG_LIN=tma)
@@ -555,6 +556,7 @@ extern "C" uint64_t rsg_context_stat(const rsg_context *c, const char *name) {
   const std::string n(name);
   if (n == "lincomb_terms") return c->st_lin_terms;       // CRS elements streamed by k_crs_lincomb
   if (n == "lincomb_plain_terms") return c->st_lin_plain; // of which multiplied by an NTT-domain plaintext
+  if (n == "lincomb_shared_terms") return c->st_lin_shared;   // CRS elements read by both splits of a pair (second read: L2)
   if (n == "lincomb_launches") return c->st_lin_launches;
   if (n == "ntt_forward_polys") return c->st_fwd_polys;   // N_E-point forward transforms (k_lift_fwd_ntt)
   if (n == "ntt_inverse_polys") return c->st_inv_polys;   // N_E-point inverse transforms (k_encode_intt)
@@ -2416,7 +2418,9 @@ struct FastPlan {
   FastTable T;                 // vec[].base filled per call
   uint32_t n_terms = 0, Z = 0, n_out = 0;
   std::vector<uint32_t> zs0, zs1;   // NTT slots [zs0[z], zs1[z]) feed the terms of split z
-  uint32_t *d_idx = nullptr;   // [(unused) n_terms | pidx n_terms | zoff Z+1 | zr n_out+1]
+  uint32_t n_paired = 0;            // splits placed next to a split over the same CRS encodings (0: d_idx has no zorder)
+  uint32_t shared_terms = 0;        // terms whose CRS encoding a neighbouring split reads too
+  uint32_t *d_idx = nullptr;   // [(unused) n_terms | pidx n_terms | zoff Z+1 | zr n_out+1 | zorder Z]
   const uint64_t **d_tptr = nullptr;   // device pointer of every term's encoding
   uint8_t *d_kind = nullptr;   // device copies of the per-vector kind arrays
 };
@@ -2514,21 +2518,63 @@ static int fast_build_plan(rsg_context *c, const FastSpec &sp, const std::vector
   uint32_t want = c->fast_splits > 0 ? (uint32_t)c->fast_splits : std::max(4u, (148u * 8 * 4 + base_blocks - 1) / base_blocks);
   uint32_t chunk = std::max(8u, (fp->n_terms + want - 1) / std::max(1u, want));
   if (c->overlap_mode && c->fast_splits <= 0) chunk = std::min(chunk, 128u);   // phases are built from whole chunks
-  std::vector<uint32_t> zoff{0}, zr(sp.n_out + 1, 0);
+  std::vector<uint32_t> zoff{0}, zr(sp.n_out + 1, 0), grp_z(sp.n_grp + 1, 0);
   {
     uint32_t g = 0;
     for (uint32_t o = 0; o < sp.n_out; o++) {
       zr[o] = (uint32_t)zoff.size() - 1;
       for (; g < sp.n_grp && sp.grp_out[g] == o; g++) {
         const uint32_t t0 = grp_t[g], t1 = grp_t[g + 1], len = t1 - t0;
+        grp_z[g] = (uint32_t)zoff.size() - 1;
         if (!len) continue;
         const uint32_t pieces = (len + chunk - 1) / chunk, per = (len + pieces - 1) / pieces;
         for (uint32_t a = t0; a < t1; a += per) zoff.push_back(std::min(t1, a + per));
       }
     }
     zr[sp.n_out] = (uint32_t)zoff.size() - 1;
+    for (; g <= sp.n_grp; g++) grp_z[g] = (uint32_t)zoff.size() - 1;
   }
   fp->Z = (uint32_t)zoff.size() - 1;
+  // Launch order of the splits: two groups of equal length and equal cuts whose terms point at the same CRS encodings (the A and B
+  // inner products over s_pows; a trailing bare element may differ) are interleaved split by split -- their CTAs then run side
+  // by side and the second read of an encoding hits the L2 (k_crs_lincomb_wide, zorder).  RSG_LIN_PAIR=0: plan order.
+  std::vector<uint32_t> zorder;
+  {
+    bool allow = c->lin_mode == 2 && c->N_E % 1024 == 0 && !c->overlap_mode;
+    if (const char *m = getenv("RSG_LIN_PAIR")) allow = allow && atoi(m) != 0;
+    std::vector<uint32_t> partner(sp.n_grp, 0xFFFFFFFFu);
+    for (uint32_t g = 0; allow && g < sp.n_grp; g++) {
+      if (partner[g] != 0xFFFFFFFFu || grp_z[g + 1] == grp_z[g]) continue;
+      const uint32_t len = grp_t[g + 1] - grp_t[g], nz = grp_z[g + 1] - grp_z[g];
+      for (uint32_t h = g + 1; h < sp.n_grp; h++) {
+        if (partner[h] != 0xFFFFFFFFu || grp_t[h + 1] - grp_t[h] != len || grp_z[h + 1] - grp_z[h] != nz) continue;
+        uint32_t shared = 0;
+        for (uint32_t i = 0; i < len; i++) shared += term[grp_t[g] + i] == term[grp_t[h] + i];
+        bool same_cuts = true;
+        for (uint32_t k = 0; k < nz; k++)
+          same_cuts = same_cuts && zoff[grp_z[g] + k + 1] - zoff[grp_z[g] + k] == zoff[grp_z[h] + k + 1] - zoff[grp_z[h] + k];
+        if (!same_cuts || 2 * shared < len) continue;
+        partner[g] = h;
+        partner[h] = g;
+        fp->shared_terms += shared;
+        fp->n_paired += 2 * nz;
+        break;
+      }
+    }
+    if (fp->n_paired) {   // the pairs first (first, second, first, second, ..), then every other split in plan order
+      for (uint32_t g = 0; g < sp.n_grp; g++) {
+        const uint32_t h = partner[g];
+        if (h == 0xFFFFFFFFu || h < g) continue;
+        for (uint32_t k = 0; k < grp_z[g + 1] - grp_z[g]; k++) {
+          zorder.push_back(grp_z[g] + k);
+          zorder.push_back(grp_z[h] + k);
+        }
+      }
+      for (uint32_t g = 0; g < sp.n_grp; g++)
+        if (partner[g] == 0xFFFFFFFFu)
+          for (uint32_t k = grp_z[g]; k < grp_z[g + 1]; k++) zorder.push_back(k);
+    }
+  }
   for (uint32_t z = 0; z < fp->Z; z++) {
     uint32_t a = 0xFFFFFFFFu, b = 0;
     for (uint32_t t = zoff[z]; t < zoff[z + 1]; t++)
@@ -2540,6 +2586,7 @@ static int fast_build_plan(rsg_context *c, const FastSpec &sp, const std::vector
   idx.insert(idx.end(), pidx.begin(), pidx.end());
   idx.insert(idx.end(), zoff.begin(), zoff.end());
   idx.insert(idx.end(), zr.begin(), zr.end());
+  idx.insert(idx.end(), zorder.begin(), zorder.end());
   void *v = nullptr;
   cudaError_t e = cudaMalloc(&v, idx.size() * 4);
   if (e != cudaSuccess) { delete fp; return fail(RSG_ERR_CUDA, cudaGetErrorString(e)); }
@@ -2729,6 +2776,10 @@ static int fast_launch_lincomb(rsg_context *c, const FastPlan *fp, uint32_t z0, 
       const dim3 gw((unsigned)(c->N_E / 4 / 256), (unsigned)(c->L_R * c->L_E), z1 - z0);
       if (c->lin_unroll == 1) k_crs_lincomb_wide<1><<<gw, 256, 0, st>>>(c->d_params, d_pidx, c->d_pntt, partial, d_zoff + z0, slot_skip, fp->d_tptr);
       else if (c->lin_unroll == 3) k_crs_lincomb_wide<3><<<gw, 256, 0, st>>>(c->d_params, d_pidx, c->d_pntt, partial, d_zoff + z0, slot_skip, fp->d_tptr);
+      else if (fp->n_paired && z0 == 0 && z1 == fp->Z)
+        // (launching the pairs as clusters of two, co-scheduled by construction, measured the same: 2.125 vs 2.116 ms)
+        k_crs_lincomb_wide<2><<<gw, 256, 0, st>>>(c->d_params, d_pidx, c->d_pntt, partial, d_zoff, slot_skip, fp->d_tptr,
+                                                  d_zoff + (fp->Z + 1) + (fp->n_out + 1), fp->n_paired);
       else k_crs_lincomb_wide<2><<<gw, 256, 0, st>>>(c->d_params, d_pidx, c->d_pntt, partial, d_zoff + z0, slot_skip, fp->d_tptr);
     } else if (lowreg) k_crs_lincomb_r64<<<grid, th, 0, st>>>(c->d_params, d_crs, d_term, d_pidx, fp->n_terms, 0u, c->d_pntt, partial, d_zoff + z0, slot_skip,
                                                        fp->d_tptr);
@@ -2806,6 +2857,7 @@ static int fast_run(rsg_context *c, FastPlan *fp, const FastTable &T, uint64_t *
     CUDA_TRY(cudaGetLastError());
   }
   c->st_lin_terms += fp->n_terms;
+  c->st_lin_shared += fp->shared_terms;
   c->st_lin_plain += T.n_slots;
   c->st_merged += T.nS ? 2 : 0;
   if (c->overlap_mode) {

@@ -35,12 +35,13 @@ MODES = {
     "fast_ntt_int": {"RSG_NTT": "int"},                                    # integer cluster transform also where the FP64 one applies
     "fast_ntt_int_single_cta": {"RSG_NTT": "int", "RSG_NTT_CLUSTER": "0"},
     "fast_enc_full": {"RSG_ENC_ROWS": "0"},                                # encode_body instead of the compact-row batch encode
+    "fast_lin_unpaired": {"RSG_LIN_PAIR": "0"},                            # plan order instead of the A / B splits side by side
 }
 
 
 def _set_mode(monkeypatch, mode):
     for k in ("RSG_FAST", "RSG_LIN", "RSG_OVERLAP", "RSG_LT_CTAS", "RSG_FAST_SPLITS", "RSG_OVERLAP_CHUNKS", "RSG_NTT_HALF", "RSG_NTT_CLUSTER",
-              "RSG_LIFT", "RSG_NTT", "RSG_ENC_ROWS"):
+              "RSG_LIFT", "RSG_NTT", "RSG_ENC_ROWS", "RSG_LIN_PAIR"):
         monkeypatch.delenv(k, raising=False)
     for k, v in MODES[mode].items():
         monkeypatch.setenv(k, v)

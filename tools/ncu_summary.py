@@ -96,6 +96,7 @@ def main():
     lines += ["", "## `ncu --set full --clock-control none` per launch (bench.py --steps 1 --warmup 1)", "",
               "| kernel | " + " | ".join(c[1] for c in cols) + " |", "|---|" + "---|" * len(cols)]
     lincomb = []
+    lincomb_name = "k_crs_lincomb"
     for r in rows:
         name = short(r["Kernel Name"])
         cells = []
@@ -109,8 +110,9 @@ def main():
             else:
                 cells.append(f"{num(v):.1f}" if "." in str(v) else str(v))
         lines.append(f"| {name} | " + " | ".join(cells) + " |")
-        if name == "k_crs_lincomb":
+        if name.startswith("k_crs_lincomb"):
             u = units["gpu__time_duration.sum"]
+            lincomb_name = name
             lincomb.append({"grid": r.get("launch__grid_size"),
                             "dram_read_bytes": to_bytes(r["dram__bytes_read.sum"], units["dram__bytes_read.sum"]),
                             "dram_write_bytes": to_bytes(r["dram__bytes_write.sum"], units["dram__bytes_write.sum"]),
@@ -120,7 +122,7 @@ def main():
         per_step = int(round(bench["work_per_step"]["lincomb_launches"]))
         first = lincomb[:per_step]                     # the launches of one proof, in order
         traffic = sum(x["dram_read_bytes"] + x["dram_write_bytes"] for x in first)
-        out = {"kernel": "k_crs_lincomb<2>", "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full --clock-control none, "
+        out = {"kernel": lincomb_name, "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full --clock-control none, "
                "bench.py --steps 1 --warmup 1, C4, 1x B200)", "per_launch": first, "launches_per_step": per_step,
                "dram_bytes_per_step": traffic, "algorithmic_bytes_per_step": bench["roofline"]["algorithmic_bytes_per_step"],
                "ratio": traffic / bench["roofline"]["algorithmic_bytes_per_step"]}
