@@ -377,7 +377,7 @@ def quotient_big(a, b, n, T):
 
 
 @pytest.mark.parametrize("n,TS", [(48, 64), (50, 64), (64, 64), (65, 64), (80, 64), (81, 64), (97, 64), (127, 64), (128, 64),
-                                  (150, 128), (256, 128), (300, 256)])
+                                  (150, 128), (256, 128), (300, 256), (600, 512), (1031, 1024), (1024, 512)])
 def test_blocked_model_matches_oracle(n, TS):
     random.seed(n * 7 + TS)
     T = tables_big(n, TS)
